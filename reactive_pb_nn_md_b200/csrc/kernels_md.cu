@@ -1,0 +1,370 @@
+// Integrator, centre-of-mass / wrap, Verlet displacement tracker and on-device neighbour-list
+// rebuild.  Replaces (reference file:line):
+//   md_integrate_atomic (NVE)            src/md_integration.f90:469-532
+//   subtract_center_of_mass_momentum     src/md_integration.f90:125-177
+//   update_r_com / shift_molecules_into_box   src/general_routines.f90:420-440, 1145-1197
+//   update_verlet_displacements          src/general_routines.f90:1259-1337
+//   construct_verlet_list_grid           src/general_routines.f90:1408-1595
+// All O(N), HBM/latency bound; the rebuild decision stays on the device (no host read-back):
+// every rebuild kernel is launched each step and exits immediately unless *rebuild_now == 1.
+#include <algorithm>
+#include "rpb_host.h"
+
+#define TPB 256
+
+__global__ void k_zero(double* p, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.0;
+}
+
+// v += dt/2/m * F * conv ; x += v*dt          (md_integration.f90:478,484)
+__global__ void k_integrate_first(Dev d) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.N) return;
+  if (d.freeze[d.type[i]] == 1) return;
+  double4 p = d.xq[i];
+  double m = d.mass[i];
+  double h = d.dt / 2.0 / m;
+  double v0 = d.vel[3 * i] + h * d.force[3 * i] * d.conv_kin;
+  double v1 = d.vel[3 * i + 1] + h * d.force[3 * i + 1] * d.conv_kin;
+  double v2 = d.vel[3 * i + 2] + h * d.force[3 * i + 2] * d.conv_kin;
+  d.vel[3 * i] = v0; d.vel[3 * i + 1] = v1; d.vel[3 * i + 2] = v2;
+  p.x = p.x + v0 * d.dt; p.y = p.y + v1 * d.dt; p.z = p.z + v2 * d.dt;
+  d.xq[i] = p;
+}
+
+// one thread per molecule: pos_com, then shift_molecules_into_box
+__global__ void k_com_shift(Dev d, int do_shift) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= d.M) return;
+  int f = d.mol_first[m], n = d.mol_natom[m];
+  double c0 = 0, c1 = 0, c2 = 0, mt = 0;
+  for (int a = 0; a < n; a++) {
+    double4 p = d.xq[f + a];
+    double ms = d.mass[f + a];
+    c0 = c0 + p.x * ms; c1 = c1 + p.y * ms; c2 = c2 + p.z * ms;
+    mt = mt + ms;
+  }
+  double rc[3] = {c0 / mt, c1 / mt, c2 / mt};
+  if (do_shift) {
+    double t[3];
+    bool any = false;
+    for (int k = 0; k < 3; k++) {
+      double db = d.inv_box[k] * rc[k];
+      double sh = 0.0;
+      if (db < 0.0) sh = 1.0; else if (db > 1.0) sh = -1.0;
+      t[k] = sh * d.box[k];
+      any |= (sh != 0.0);
+      rc[k] = rc[k] + t[k];
+    }
+    if (any)
+      for (int a = 0; a < n; a++) {
+        double4 p = d.xq[f + a];
+        p.x = p.x + t[0]; p.y = p.y + t[1]; p.z = p.z + t[2];
+        d.xq[f + a] = p;
+      }
+  }
+  d.r_com[3 * m] = rc[0]; d.r_com[3 * m + 1] = rc[1]; d.r_com[3 * m + 2] = rc[2];
+}
+
+// second half kick + force sanity check + momentum partial sums   (md_integration.f90:507-529, 139-156)
+__global__ void k_integrate_second(Dev d, double* psum /*[4]: px,py,pz,count*/) {
+  __shared__ double sh[32];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double p0 = 0, p1 = 0, p2 = 0, cnt = 0;
+  if (i < d.N && d.freeze[d.type[i]] != 1) {
+    double m = d.mass[i];
+    double h = d.dt / 2.0 / m;
+    double f0 = d.force[3 * i], f1 = d.force[3 * i + 1], f2 = d.force[3 * i + 2];
+    double v0 = d.vel[3 * i] + h * f0 * d.conv_kin;
+    double v1 = d.vel[3 * i + 1] + h * f1 * d.conv_kin;
+    double v2 = d.vel[3 * i + 2] + h * f2 * d.conv_kin;
+    d.vel[3 * i] = v0; d.vel[3 * i + 1] = v1; d.vel[3 * i + 2] = v2;
+    if (!(fabs(f0) <= 10e4) || !(fabs(f1) <= 10e4) || !(fabs(f2) <= 10e4)) atomicMax(&d.err_flag[0], i + 1);
+    p0 = m * v0; p1 = m * v1; p2 = m * v2; cnt = 1.0;
+  }
+  p0 = block_sum(p0, sh); p1 = block_sum(p1, sh); p2 = block_sum(p2, sh); cnt = block_sum(cnt, sh);
+  if (threadIdx.x == 0) { atomicAdd(&psum[0], p0); atomicAdd(&psum[1], p1); atomicAdd(&psum[2], p2); atomicAdd(&psum[3], cnt); }
+}
+
+__global__ void k_remove_com_momentum(Dev d, const double* psum) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.N || d.freeze[d.type[i]] == 1) return;
+  double n = psum[3], m = d.mass[i];
+  d.vel[3 * i] = d.vel[3 * i] - (psum[0] / n) / m;
+  d.vel[3 * i + 1] = d.vel[3 * i + 1] - (psum[1] / n) / m;
+  d.vel[3 * i + 2] = d.vel[3 * i + 2] - (psum[2] / n) / m;
+}
+
+__global__ void k_kinetic(Dev d) {
+  __shared__ double sh[32];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double e = 0.0;
+  if (i < d.N) {
+    double v0 = d.vel[3 * i], v1 = d.vel[3 * i + 1], v2 = d.vel[3 * i + 2];
+    e = 0.5 * d.mass[i] * (v0 * v0 + v1 * v1 + v2 * v2) / d.conv_kin;
+  }
+  e = block_sum(e, sh);
+  if (threadIdx.x == 0) atomicAdd(&d.en[E_KE], e);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Verlet displacement tracker
+// ------------------------------------------------------------------------------------------------
+__global__ void k_verlet_begin(Dev d, int force_rebuild) {
+  if (force_rebuild) *d.rebuild_now = 2;  // forced (init / hop commit): flag_verlet_list untouched (flag_junk, ms_evb.f90:223-225)
+  else *d.rebuild_now = (*d.flag_verlet == 1) ? 1 : 0;
+  d.maxd[0] = 0.0; d.maxd[1] = 0.0;
+}
+
+// per-block two largest |accumulated displacement|; merged by k_verlet_end
+__global__ void k_verlet_disp(Dev d, double* blk_top2) {
+  __shared__ double s1[TPB], s2[TPB];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int rebuild = *d.rebuild_now;
+  double nrm = 0.0;
+  if (i < d.N) {
+    double4 p = d.xq[i];
+    double xn[3] = {p.x, p.y, p.z};
+    if (rebuild) {
+      for (int k = 0; k < 3; k++) { d.vstore[3 * i + k] = xn[k]; d.vdisp[3 * i + k] = 0.0; }
+    } else {
+      double acc[3];
+      for (int k = 0; k < 3; k++) {
+        double xo = d.vstore[3 * i + k];
+        double dr = xn[k] - xo;                       // pbc_shift(old,new)
+        double sh = floor(d.inv_box[k] * dr + 0.5) * d.box[k];
+        double dd = xn[k] - xo - sh;                  // pbc_dr
+        acc[k] = d.vdisp[3 * i + k] + dd;
+        d.vdisp[3 * i + k] = acc[k];
+        d.vstore[3 * i + k] = xn[k];
+      }
+      nrm = sqrt(acc[0] * acc[0] + acc[1] * acc[1] + acc[2] * acc[2]);
+    }
+  }
+  s1[threadIdx.x] = nrm; s2[threadIdx.x] = 0.0;
+  __syncthreads();
+  for (int o = TPB / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      double a1 = s1[threadIdx.x], a2 = s2[threadIdx.x], b1 = s1[threadIdx.x + o], b2 = s2[threadIdx.x + o];
+      double m1 = fmax(a1, b1);
+      double m2 = fmax(fmin(a1, b1), fmax(a2, b2));
+      s1[threadIdx.x] = m1; s2[threadIdx.x] = m2;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { blk_top2[2 * blockIdx.x] = s1[0]; blk_top2[2 * blockIdx.x + 1] = s2[0]; }
+}
+
+__global__ void k_verlet_end(Dev d, const double* blk_top2, int nblk) {
+  __shared__ double s1[TPB], s2[TPB];
+  double m1 = 0.0, m2 = 0.0;
+  for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+    double b1 = blk_top2[2 * b], b2 = blk_top2[2 * b + 1];
+    double n1 = fmax(m1, b1), n2 = fmax(fmin(m1, b1), fmax(m2, b2));
+    m1 = n1; m2 = n2;
+  }
+  s1[threadIdx.x] = m1; s2[threadIdx.x] = m2;
+  __syncthreads();
+  for (int o = TPB / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      double a1 = s1[threadIdx.x], a2 = s2[threadIdx.x], b1 = s1[threadIdx.x + o], b2 = s2[threadIdx.x + o];
+      s1[threadIdx.x] = fmax(a1, b1);
+      s2[threadIdx.x] = fmax(fmin(a1, b1), fmax(a2, b2));
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    d.maxd[0] = s1[0]; d.maxd[1] = s2[0];
+    int rb = *d.rebuild_now;
+    if (rb == 1) *d.flag_verlet = 0;
+    else if (rb == 0) *d.flag_verlet = ((s1[0] + s2[0]) > d.verlet_skin) ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Neighbour-list rebuild (cell list -> half Verlet list in the reference's row order)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int wrap_cell(int ig, int n) { return ig - (int)floor((double)(ig - 1) / (double)n) * n; }
+
+__global__ void k_cell_zero(Dev d, int ncell) {
+  if (!*d.rebuild_now) return;
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < ncell) d.cell_count[c] = 0;
+}
+
+__global__ void k_cell_assign(Dev d) {
+  if (!*d.rebuild_now) return;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.N) return;
+  double4 p = d.xq[i];
+  int ix = (int)floor((d.inv_box[0] * p.x) * d.ncx) + 1;
+  int iy = (int)floor((d.inv_box[1] * p.y) * d.ncy) + 1;
+  int iz = (int)floor((d.inv_box[2] * p.z) * d.ncz) + 1;
+  ix = wrap_cell(ix, d.ncx); iy = wrap_cell(iy, d.ncy); iz = wrap_cell(iz, d.ncz);
+  int c = (ix - 1) + d.ncx * ((iy - 1) + d.ncy * (iz - 1));
+  d.atom_cell[i] = c;
+  atomicAdd(&d.cell_count[c], 1);
+}
+
+// single-block exclusive scan: out[i] = sum_{j<i} in[j] (+base), out[n] = total
+__global__ void k_scan(const int* in, int* out, int n, int base, const int* gate, int* total_out, int cap, int* err_flag) {
+  if (gate && !*gate) return;
+  __shared__ int sh[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int start = 0; start < n; start += 1024) {
+    int i = start + threadIdx.x;
+    int v = i < n ? in[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < n) out[i] = carry + sh[threadIdx.x] - v + base;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += sh[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[n] = carry + base;
+    if (total_out) *total_out = carry;
+    if (err_flag && carry > cap) atomicMax(err_flag, 1);
+  }
+}
+
+__global__ void k_cell_fill(Dev d, int* cursor) {
+  if (!*d.rebuild_now) return;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.N) return;
+  int c = d.atom_cell[i];
+  int pos = atomicAdd(&cursor[c], 1);
+  d.cell_atoms[d.cell_start[c] + pos] = i;
+}
+
+// ascending atom index inside each cell == the reference's append-at-tail linked list (:1486-1493)
+__global__ void k_cell_sort(Dev d, int ncell) {
+  if (!*d.rebuild_now) return;
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  int s = d.cell_start[c], e = d.cell_start[c + 1];
+  for (int a = s + 1; a < e; a++) {
+    int v = d.cell_atoms[a], b = a - 1;
+    while (b >= s && d.cell_atoms[b] > v) { d.cell_atoms[b + 1] = d.cell_atoms[b]; b--; }
+    d.cell_atoms[b + 1] = v;
+  }
+}
+
+// one warp per atom; cells visited ia, ib, ic nested exactly as :1523-1531; pass 0 counts, pass 1 fills
+template <int FILL>
+__global__ void k_verlet_rows(Dev d) {
+  if (!*d.rebuild_now) return;
+  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= d.N) return;
+  int i = w;
+  if (FILL && d.err_flag[1]) return;
+  double4 pi = d.xq[i];
+  int mi = d.mol_of_atom[i];
+  int c = d.atom_cell[i];
+  int ix = c % d.ncx + 1, iy = (c / d.ncx) % d.ncy + 1, iz = c / (d.ncx * d.ncy) + 1;
+  int count = 0;
+  int out = FILL ? d.verlet_point[i] - 1 : 0;
+  for (int ia = -d.dia; ia <= d.dia; ia++) {
+    int g1 = wrap_cell(ix + ia, d.ncx);
+    for (int ib = -d.dib; ib <= d.dib; ib++) {
+      int g2 = wrap_cell(iy + ib, d.ncy);
+      for (int ic = -d.dic; ic <= d.dic; ic++) {
+        int g3 = wrap_cell(iz + ic, d.ncz);
+        int cc = (g1 - 1) + d.ncx * ((g2 - 1) + d.ncy * (g3 - 1));
+        int s = d.cell_start[cc], e = d.cell_start[cc + 1];
+        for (int b = s; b < e; b += 32) {
+          int a = b + lane;
+          bool hit = false;
+          int j = -1;
+          if (a < e) {
+            j = d.cell_atoms[a];
+            if (i < j && d.mol_of_atom[j] != mi) {
+              double4 pj = d.xq[j];
+              double r0 = min_image(pi.x - pj.x, d.box[0]);
+              double r1 = min_image(pi.y - pj.y, d.box[1]);
+              double r2 = min_image(pi.z - pj.z, d.box[2]);
+              hit = (r0 * r0 + r1 * r1 + r2 * r2) < d.rv2;
+            }
+          }
+          unsigned bal = __ballot_sync(0xffffffffu, hit);
+          if (FILL) {
+            if (hit) d.neighbor_list[out + __popc(bal & ((1u << lane) - 1))] = j + 1;
+            out += __popc(bal);
+          } else {
+            count += __popc(bal);
+          }
+        }
+      }
+    }
+  }
+  if (!FILL && lane == 0) d.row_count[i] = count;
+}
+
+// ------------------------------------------------------------------------------------------------
+static inline int nblk(int n, int t = TPB) { return (n + t - 1) / t; }
+
+void launch_zero_forces(rpb_ctx* c) {
+  k_zero<<<nblk(3 * c->d.N), TPB, 0, c->stream>>>(c->d.force, (size_t)3 * c->d.N);
+  k_zero<<<1, 32, 0, c->stream>>>(c->d.en, E_NSLOT);
+  c->n_launch += 2;
+}
+
+void launch_integrate_first(rpb_ctx* c) {
+  ScopedTimer t(c, T_INTEGRATE);
+  k_integrate_first<<<nblk(c->d.N), TPB, 0, c->stream>>>(c->d);
+  k_com_shift<<<nblk(c->d.M), TPB, 0, c->stream>>>(c->d, 1);
+  c->n_launch += 2;
+}
+
+void launch_update_com_shift(rpb_ctx* c, bool shift) {
+  k_com_shift<<<nblk(c->d.M), TPB, 0, c->stream>>>(c->d, shift ? 1 : 0);
+  c->n_launch += 1;
+}
+
+void launch_integrate_second(rpb_ctx* c) {
+  ScopedTimer t(c, T_INTEGRATE);
+  double* psum = c->d.maxd + 2;  // 4 doubles of scratch after the two displacement maxima
+  k_zero<<<1, 32, 0, c->stream>>>(psum, 4);
+  k_integrate_second<<<nblk(c->d.N), TPB, 0, c->stream>>>(c->d, psum);
+  k_remove_com_momentum<<<nblk(c->d.N), TPB, 0, c->stream>>>(c->d, psum);
+  c->n_launch += 3;
+}
+
+void launch_kinetic_energy(rpb_ctx* c) {
+  k_zero<<<1, 32, 0, c->stream>>>(c->d.en + E_KE, 1);
+  k_kinetic<<<nblk(c->d.N), TPB, 0, c->stream>>>(c->d);
+  c->n_launch += 2;
+}
+
+static void verlet_common(rpb_ctx* c, int force_rebuild) {
+  ScopedTimer t(c, T_VERLET);
+  Dev& d = c->d;
+  int ncell = d.ncx * d.ncy * d.ncz;
+  double* blk_top2 = d.maxd + 8;
+  int nb = nblk(d.N);
+  int* cursor = d.cell_count + (ncell + 1);  // second half of the cell_count allocation
+  k_verlet_begin<<<1, 1, 0, c->stream>>>(d, force_rebuild);
+  k_cell_zero<<<nblk(2 * ncell + 2), TPB, 0, c->stream>>>(d, 2 * ncell + 2);
+  k_cell_assign<<<nb, TPB, 0, c->stream>>>(d);
+  k_scan<<<1, 1024, 0, c->stream>>>(d.cell_count, d.cell_start, ncell, 0, d.rebuild_now, nullptr, 0, nullptr);
+  k_cell_fill<<<nb, TPB, 0, c->stream>>>(d, cursor);
+  k_cell_sort<<<nblk(ncell), TPB, 0, c->stream>>>(d, ncell);
+  k_verlet_rows<0><<<nblk(d.N * 32), TPB, 0, c->stream>>>(d);
+  k_scan<<<1, 1024, 0, c->stream>>>(d.row_count, d.verlet_point, d.N, 1, d.rebuild_now, nullptr, d.verlet_cap, d.err_flag + 1);
+  k_verlet_rows<1><<<nblk(d.N * 32), TPB, 0, c->stream>>>(d);
+  k_verlet_disp<<<nb, TPB, 0, c->stream>>>(d, blk_top2);
+  k_verlet_end<<<1, TPB, 0, c->stream>>>(d, blk_top2, nb);
+  c->n_launch += 11;
+}
+
+void launch_verlet_update(rpb_ctx* c) { verlet_common(c, 0); }
+void launch_verlet_force_rebuild(rpb_ctx* c) { verlet_common(c, 1); }

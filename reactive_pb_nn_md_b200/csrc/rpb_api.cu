@@ -1,0 +1,563 @@
+// C-ABI of librpbmd.so (include/rpbmd.h) and the host orchestration of one force evaluation.
+// The orchestration functions carry the names of the reference routines whose call structure they
+// keep: calculate_total_force_energy (total_energy_forces.f90:19-99),
+// ms_evb_calculate_total_force_energy (ms_evb.f90:181-235), md_integrate_atomic (md_integration.f90:438-541).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include "rpb_host.h"
+
+static const char* k_timer_names[T_NTIMER] = {
+    "integrate", "verlet", "pair_real_space", "molecule_terms", "pme_spread", "pme_fft", "pme_convolve", "pme_gather",
+    "evb_enumerate", "evb_items", "evb_delta_grid", "evb_coupling", "evb_diagonalize", "evb_mix", "step_total"};
+
+#define CK(call)                                                                  \
+  do {                                                                            \
+    cudaError_t e__ = (call);                                                     \
+    if (e__ != cudaSuccess) {                                                     \
+      c->err = std::string(#call) + ": " + cudaGetErrorString(e__);               \
+      return RPB_ERR_CUDA;                                                        \
+    }                                                                             \
+  } while (0)
+
+template <typename T>
+static int upload(rpb_ctx* c, T** dst, const T* src, size_t n) {
+  int rc = dev_alloc(c, dst, n);
+  if (rc) return rc;
+  CK(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// orchestration
+// ------------------------------------------------------------------------------------------------
+// check device-side error flags + fetch energies (one small synchronising read-back)
+static int fetch_status(rpb_ctx* c) {
+  CK(cudaMemcpyAsync(c->h_en, c->d.en, E_NSLOT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(c->h_flags, c->d.err_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->h_flags[1]) { c->err = "please increase size of verlet neighbor list"; return RPB_ERR_VERLET; }
+  if (c->h_flags[2]) { c->err = "Found more diabat states than the current setting of evb_max_states"; return RPB_ERR_DIABATS; }
+  if (c->h_flags[3]) { c->err = "couldn't find index in subroutine 'get_index_atom_set'"; return RPB_ERR_STATE; }
+  if (c->h_flags[0]) { c->err = "force on atom " + std::to_string(c->h_flags[0]) + " is too big"; return RPB_ERR_FORCE; }
+  return 0;
+}
+
+static void energies_from_slots(rpb_ctx* c) {
+  rpb_energies& e = c->last_en;
+  const double* s = c->h_en;
+  e.E_recip = s[E_RECIP];
+  e.E_elec = s[E_ELEC] + s[E_RECIP] + c->cfg.ewald_self;
+  e.E_vdw = s[E_VDW]; e.E_bond = s[E_BOND]; e.E_angle = s[E_ANGLE]; e.E_dihedral = s[E_DIH];
+  e.potential_energy = e.E_elec + e.E_vdw + e.E_bond + e.E_angle + e.E_dihedral;
+}
+
+// calculate_total_force_energy (total_energy_forces.f90:19-99); evb_principal: called as the principal-diabat
+// evaluation of construct_evb_hamiltonian (ms_evb.f90:411): the reciprocal force is gathered later from the
+// Hellmann-Feynman mixed grid instead (DESIGN.md "theta-mix").
+int calculate_total_force_energy(rpb_ctx* c, bool evb_principal) {
+  launch_verlet_update(c);
+  launch_zero_forces(c);
+  launch_pair_verlet(c);
+  launch_molecule_terms(c);
+  launch_spread_principal(c);
+  int rc = launch_convolve(c, 0, 1, c->d.en + E_RECIP, true);
+  if (rc) return rc;
+  if (!evb_principal) launch_gather(c, c->d.theta, c->d.force_recip, true);
+  return 0;
+}
+
+static int force_energy(rpb_ctx* c, int ms_evb, bool sync) {
+  int rc;
+  if (ms_evb) {
+    if (!c->have_evb) { c->err = "rpb_set_evb not called"; return RPB_ERR_STATE; }
+    rc = evb_build(c); if (rc) return rc;
+    rc = evb_mix(c, nullptr, nullptr); if (rc) return rc;
+    rc = evb_commit(c); if (rc) return rc;
+    return 0;
+  }
+  rc = calculate_total_force_energy(c, false);
+  if (rc) return rc;
+  if (sync) {
+    rc = fetch_status(c);
+    if (rc) return rc;
+    energies_from_slots(c);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* rpb_backend(void) { return "cuda-sm100a"; }
+const char* rpb_last_error(const rpb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+int rpb_timer_count(void) { return T_NTIMER; }
+const char* rpb_timer_name(int i) { return (i >= 0 && i < T_NTIMER) ? k_timer_names[i] : ""; }
+
+int rpb_create(rpb_ctx** out, const rpb_config* cfg) {
+  if (!out || !cfg) return RPB_ERR_ARG;
+  rpb_ctx* c = new rpb_ctx();
+  *out = c;
+  c->cfg = *cfg;
+  memset(&c->d, 0, sizeof(Dev));
+  memset(&c->e, 0, sizeof(EvbDev));
+  memset(&c->last_en, 0, sizeof(rpb_energies));
+  for (int i = 0; i < T_NTIMER; i++) { c->t_ms[i] = 0; c->t_calls[i] = 0; }
+  if (cfg->spline_order != 6) { c->err = "only spline_order=6 is self-consistent in the reference (pme.f90:247 divides by 6.D0)"; return RPB_ERR_UNSUPPORTED; }
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      if (i != j && std::fabs(cfg->box[i + 3 * j]) > 10e-6) { c->err = "code has been modified to assume orthorhombic box"; return RPB_ERR_UNSUPPORTED; }
+  if (cfg->evb_max_chain > RPB_MAXC || cfg->evb_max_states > RPB_MAXS) { c->err = "evb limits exceed compiled maxima"; return RPB_ERR_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { c->err = "no CUDA device: librpbmd.so has no CPU fallback"; return RPB_ERR_CUDA; }
+  CK(cudaSetDevice(cfg->device));
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < T_NTIMER; i++) { CK(cudaEventCreate(&c->ev0[i])); CK(cudaEventCreate(&c->ev1[i])); }
+  CK(cudaMallocHost(&c->h_en, E_NSLOT * sizeof(double)));
+  CK(cudaMallocHost(&c->h_flags, 8 * sizeof(int)));
+  Dev& d = c->d;
+  d.N = cfg->n_atoms; d.M = cfg->n_mole; d.K = cfg->pme_grid; d.nT = cfg->n_atom_type; d.nMT = cfg->n_mole_type;
+  d.rank = cfg->rank; d.world = std::max(1, cfg->world_size);
+  for (int i = 0; i < 3; i++) { d.box[i] = cfg->box[i + 3 * i]; d.inv_box[i] = 1.0 / d.box[i]; }
+  {  // construct_reciprocal_lattice_vector with `real function volume` (general_routines.f90:473-490,1936-1947)
+    double v = d.box[0] * (d.box[1] * d.box[2]);
+    float v32 = std::fabs((float)v);
+    double vol = (double)v32;
+    d.kk[0] = (d.box[1] * d.box[2]) / vol; d.kk[1] = (d.box[2] * d.box[0]) / vol; d.kk[2] = (d.box[0] * d.box[1]) / vol;
+  }
+  d.rc2 = cfg->real_space_cutoff * cfg->real_space_cutoff;
+  d.rv2 = cfg->verlet_cutoff * cfg->verlet_cutoff;
+  d.verlet_skin = cfg->verlet_thresh * (cfg->verlet_cutoff - cfg->real_space_cutoff);
+  d.alpha = cfg->alpha_sqrt; d.erf_factor = 2.0 * cfg->alpha_sqrt / cfg->pi_sqrt;
+  d.conv = cfg->conv_e2A_kJmol; d.conv_kin = cfg->conv_kJmol_ang2ps2gmol; d.dt = cfg->delta_t; d.pi = cfg->pi;
+  d.erfc_dx = cfg->erfc_dx; d.tt_max = cfg->tt_max; d.tt_grid = cfg->tt_grid; d.spline_grid = (double)cfg->spline_grid;
+  d.ewald_self = cfg->ewald_self;
+  d.cut_solv2 = cfg->evb_first_solvation_cutoff * cfg->evb_first_solvation_cutoff;
+  d.cut_pair2 = cfg->evb_reactive_pair_distance * cfg->evb_reactive_pair_distance;
+  d.max_chain = cfg->evb_max_chain; d.max_states = cfg->evb_max_states;
+  // verlet cell grid (general_routines.f90:1444-1509)
+  d.ncx = cfg->na_nslist; d.ncy = cfg->nb_nslist; d.ncz = cfg->nc_nslist;
+  if (d.box[0] < 2 * cfg->verlet_cutoff) { c->err = "box size less than twice verlet cutoff"; return RPB_ERR_ARG; }
+  if (d.ncx < 10 || d.ncy < 10 || d.ncz < 10 || d.ncx > 99 || d.ncy > 99 || d.ncz > 99) { c->err = " na_nslist, nb_nslist, nc_nslist must be between 10 and 100 "; return RPB_ERR_ARG; }
+  double rka = std::sqrt(d.inv_box[0] * d.inv_box[0]), rkb = std::sqrt(d.inv_box[1] * d.inv_box[1]), rkc = std::sqrt(d.inv_box[2] * d.inv_box[2]);
+  d.dia = (int)std::floor(cfg->verlet_cutoff * rka * (double)d.ncx) + 1;
+  d.dib = (int)std::floor(cfg->verlet_cutoff * rkb * (double)d.ncy) + 1;
+  d.dic = (int)std::floor(cfg->verlet_cutoff * rkc * (double)d.ncz) + 1;
+  if (d.dia >= d.ncx / 2 || d.dib >= d.ncy / 2 || d.dic >= d.ncz / 2) {
+    c->err = "number of grid cells to search in each dimension must be less than half the total number of grid cells";
+    return RPB_ERR_ARG;
+  }
+  {  // allocate_verlet_list general_routines.f90:1206-1247 (volume = box(1,1)**3 after periodic_box_change)
+    if (cfg->verlet_capacity > 0) d.verlet_cap = cfg->verlet_capacity;
+    else {
+      double volume = d.box[0] * d.box[0] * d.box[0], N = (double)d.N, rv = cfg->verlet_cutoff;
+      long long sv = (long long)std::floor(4.0 * cfg->pi * (rv * rv * rv) * (N * N) / 6.0 / volume);
+      sv = std::max((long long)d.N * 50, sv);
+      d.verlet_cap = (int)std::floor((double)sv * cfg->safe_verlet);
+    }
+  }
+  int rc;
+  const int N = d.N, M = d.M, K = d.K;
+  const size_t K3 = (size_t)K * K * K, Kh3 = (size_t)K * K * (K / 2 + 1);
+  const int ncell = d.ncx * d.ncy * d.ncz;
+#define AL(p, n) if ((rc = dev_alloc(c, &(p), (n)))) return rc;
+  AL(d.xq, N); AL(d.vel, 3 * N); AL(d.force, 3 * N); AL(d.mass, N); AL(d.type, N); AL(d.mol_of_atom, N);
+  AL(d.mol_first, M); AL(d.mol_natom, M); AL(d.mol_type, M); AL(d.r_com, 3 * M); AL(d.hydronium, 1);
+  AL(d.verlet_point, N + 1); AL(d.neighbor_list, d.verlet_cap); AL(d.vstore, 3 * N); AL(d.vdisp, 3 * N);
+  AL(d.flag_verlet, 1); AL(d.rebuild_now, 1); AL(d.err_flag, 4);
+  AL(d.cell_count, 2 * (ncell + 1)); AL(d.cell_start, ncell + 1); AL(d.cell_atoms, N); AL(d.atom_cell, N); AL(d.row_count, N + 1);
+  AL(d.maxd, 8 + 2 * ((N + 255) / 256 + 1));
+  AL(d.uscale, 3 * N); AL(d.force_recip, 3 * N); AL(d.en, E_NSLOT);
+  c->grid_capacity = 1;
+  if (cfg->evb_max_states > 0) c->grid_capacity = cfg->evb_max_states;
+  // grids are allocated lazily for the diabats in rpb_set_evb; the principal needs one of each
+  AL(d.Q, K3 * (size_t)c->grid_capacity); AL(d.theta, K3 * (size_t)c->grid_capacity); AL(d.FQ, Kh3 * (size_t)c->grid_capacity);
+#undef AL
+  CK(cudaMemset(d.flag_verlet, 0, sizeof(int)));
+  CK(cudaMemset(d.rebuild_now, 0, sizeof(int)));
+  CK(cudaMemset(d.err_flag, 0, 4 * sizeof(int)));
+  CK(cudaMemset(d.en, 0, E_NSLOT * sizeof(double)));
+  CK(cudaMemset(d.force, 0, 3 * N * sizeof(double)));
+  CK(cudaMemset(d.force_recip, 0, 3 * N * sizeof(double)));
+  return 0;
+}
+
+void rpb_destroy(rpb_ctx* c) {
+  if (!c) return;
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (auto& kv : c->plan_fwd) cufftDestroy(kv.second);
+  for (auto& kv : c->plan_inv) cufftDestroy(kv.second);
+  for (void* p : c->allocs) cudaFree(p);
+  if (c->h_en) cudaFreeHost(c->h_en);
+  if (c->h_flags) cudaFreeHost(c->h_flags);
+  if (c->eh.pinned) cudaFreeHost(c->eh.pinned);
+  if (c->stream) {
+    for (int i = 0; i < T_NTIMER; i++) { cudaEventDestroy(c->ev0[i]); cudaEventDestroy(c->ev1[i]); }
+    cudaStreamDestroy(c->stream);
+  }
+  delete c;
+}
+
+int rpb_set_tables(rpb_ctx* c, const double* B6, const double* B5, const double* erfc_t, const double* scale_t,
+                   const double* tt, const double* dtt, const double* CB) {
+  Dev& d = c->d;
+  const int K = d.K, Kh = K / 2 + 1;
+  int rc;
+  double *p;
+  if ((rc = upload(c, &p, B6, c->cfg.spline_grid))) return rc; d.B6 = p;
+  if ((rc = upload(c, &p, B5, c->cfg.spline_grid))) return rc; d.B5 = p;
+  if ((rc = upload(c, &p, erfc_t, c->cfg.erfc_grid + 1))) return rc; d.erfc_t = p;
+  if ((rc = upload(c, &p, scale_t, c->cfg.erfc_grid + 1))) return rc; d.scale_t = p;
+  if ((rc = upload(c, &p, tt, 4 * c->cfg.tt_grid))) return rc; d.tt = p;
+  if ((rc = upload(c, &p, dtt, 4 * c->cfg.tt_grid))) return rc; d.dtt = p;
+  // Half-spectrum copy of CB(K,K,K), element (m1,m2,m3), m1 <= K/2, stored [m3][m2][m1].
+  // The reference keeps dble() of a full complex transform (pme.f90:123).  Its CB is even only up to the
+  // float32 rounding of the phase factors in bm_sq (pme.f90:589), and Re(IDFT(CB*F)) of a real grid equals
+  // IDFT(CB_even*F) with CB_even(m) = (CB(m)+CB(-m))/2 -- which is what the real-to-complex pair needs.
+  std::vector<double> cbh((size_t)Kh * K * K);
+  for (int m3 = 0; m3 < K; m3++)
+    for (int m2 = 0; m2 < K; m2++)
+      for (int m1 = 0; m1 < Kh; m1++) {
+        size_t a = (size_t)m1 + (size_t)K * (m2 + (size_t)K * m3);
+        size_t b = (size_t)((K - m1) % K) + (size_t)K * (((K - m2) % K) + (size_t)K * ((K - m3) % K));
+        cbh[(size_t)m1 + (size_t)Kh * (m2 + (size_t)K * m3)] = 0.5 * (CB[a] + CB[b]);
+      }
+  if ((rc = upload(c, &p, cbh.data(), cbh.size()))) return rc; d.CBh = p;
+  c->have_tables = true;
+  return 0;
+}
+
+int rpb_set_forcefield(rpb_ctx* c, const double* vdw_parameter, const int* vdw_type, const double* vdw_parameter_14,
+                       const double* atype_chg, const int* atype_freeze, const int* bond_type, const double* bond_parameter,
+                       const int* angle_type, const double* angle_parameter, const int* dihedral_type,
+                       const double* dihedral_parameter) {
+  const int T = RPB_MAXT, nT = c->d.nT;
+  const size_t T2 = (size_t)T * T, T3 = T2 * T, T4 = T3 * T;
+  // keep host copies in the Fortran layout for the per-term look-ups of rpb_set_molecule_types
+  c->ff_bondt.assign(bond_type, bond_type + T2); c->ff_bondp.assign(bond_parameter, bond_parameter + T2 * 3);
+  c->ff_anglet.assign(angle_type, angle_type + T3); c->ff_anglep.assign(angle_parameter, angle_parameter + T3 * 2);
+  c->ff_diht.assign(dihedral_type, dihedral_type + T4); c->ff_dihp.assign(dihedral_parameter, dihedral_parameter + T4 * 6);
+  for (int i = 0; i < T; i++) { c->atype_chg[i] = atype_chg[i]; c->atype_freeze[i] = atype_freeze[i]; }
+  // compact [ti][tj][6] tables for the device
+  std::vector<double> vp((size_t)nT * nT * 6), vp14((size_t)nT * nT * 6);
+  std::vector<int> vt((size_t)nT * nT);
+  for (int ti = 0; ti < nT; ti++)
+    for (int tj = 0; tj < nT; tj++) {
+      vt[ti * nT + tj] = vdw_type[ti + T * tj];
+      for (int k = 0; k < 6; k++) {
+        vp[6 * (ti * nT + tj) + k] = vdw_parameter[ti + T * tj + T2 * k];
+        vp14[6 * (ti * nT + tj) + k] = vdw_parameter_14[ti + T * tj + T2 * k];
+      }
+    }
+  int rc; double* p; int* q;
+  if ((rc = upload(c, &p, vp.data(), vp.size()))) return rc; c->d.vdw_param = p;
+  if ((rc = upload(c, &p, vp14.data(), vp14.size()))) return rc; c->d.vdw_param14 = p;
+  if ((rc = upload(c, &q, vt.data(), vt.size()))) return rc; c->d.vdw_type = q;
+  if ((rc = upload(c, &q, c->atype_freeze, (size_t)T))) return rc; c->d.freeze = q;
+  c->have_ff = true;
+  return 0;
+}
+
+int rpb_set_molecule_types(rpb_ctx* c, const int* n_atom, const int* atom_type, const int* n_bond, const int* bonds,
+                           const int* n_angle, const int* angles, const int* n_dihedral, const int* dihedrals,
+                           const int* pair_exclusions, const int* evb_reactive_protons, const int* evb_reactive_basic_atoms) {
+  if (!c->have_ff) { c->err = "rpb_set_forcefield must precede rpb_set_molecule_types"; return RPB_ERR_STATE; }
+  const int T = RPB_MAXT, MA = RPB_MA;
+  const size_t T2 = (size_t)T * T, T3 = T2 * T, T4 = T3 * T;
+  c->mt_host.assign(c->d.nMT, MolTypeDev());
+  int ob = 0, oa = 0, od = 0;
+  for (int t = 0; t < c->d.nMT; t++) {
+    MolTypeDev& m = c->mt_host[t];
+    memset(&m, 0, sizeof(m));
+    m.n_atom = n_atom[t];
+    if (m.n_atom + 1 > MA) { c->err = "molecule type larger than RPB_MAX_MOLE_ATOMS-1"; return RPB_ERR_ARG; }
+    if (n_bond[t] > RPB_MAXB || n_angle[t] > RPB_MAXB || n_dihedral[t] > RPB_MAXB) { c->err = "too many bonded terms per molecule type"; return RPB_ERR_ARG; }
+    for (int a = 0; a < MA; a++) {
+      m.atom_type[a] = atom_type[t * MA + a] - 1;
+      m.reactive_proton[a] = evb_reactive_protons ? evb_reactive_protons[t * MA + a] : 0;
+      m.reactive_basic[a] = evb_reactive_basic_atoms ? evb_reactive_basic_atoms[t * MA + a] : 0;
+      for (int b = 0; b < MA; b++) m.pair_excl[a][b] = pair_exclusions[t * MA * MA + a + MA * b];
+    }
+    m.n_bond = n_bond[t]; m.n_angle = n_angle[t]; m.n_dih = n_dihedral[t];
+    for (int b = 0; b < m.n_bond; b++) {
+      int i = bonds[2 * (ob + b)] - 1, j = bonds[2 * (ob + b) + 1] - 1;
+      int ti = m.atom_type[i], tj = m.atom_type[j];
+      m.bond[b][0] = i; m.bond[b][1] = j;
+      m.bond_kind[b] = c->ff_bondt[ti + T * tj];
+      if (m.bond_kind[b] < 1 || m.bond_kind[b] > 3) { c->err = "bond type isn't implemented!"; return RPB_ERR_ARG; }
+      for (int k = 0; k < 3; k++) m.bond_par[b][k] = c->ff_bondp[ti + T * tj + T2 * k];
+    }
+    for (int a = 0; a < m.n_angle; a++) {
+      int i = angles[3 * (oa + a)] - 1, j = angles[3 * (oa + a) + 1] - 1, k = angles[3 * (oa + a) + 2] - 1;
+      int ti = m.atom_type[i], tj = m.atom_type[j], tk = m.atom_type[k];
+      m.angle[a][0] = i; m.angle[a][1] = j; m.angle[a][2] = k;
+      size_t idx = ti + T * tj + T2 * tk;
+      m.angle_kind[a] = c->ff_anglet[idx];
+      if (m.angle_kind[a] < 1 || m.angle_kind[a] > 2) { c->err = "requested angle type potential not implemented"; return RPB_ERR_ARG; }
+      m.angle_par[a][0] = c->ff_anglep[idx]; m.angle_par[a][1] = c->ff_anglep[idx + T3];
+    }
+    for (int q = 0; q < m.n_dih; q++) {
+      int ix[4], ty[4];
+      for (int k = 0; k < 4; k++) { ix[k] = dihedrals[4 * (od + q) + k] - 1; ty[k] = m.atom_type[ix[k]]; m.dih[q][k] = ix[k]; }
+      size_t idx = ty[0] + T * ty[1] + T2 * ty[2] + T3 * ty[3];
+      m.dih_kind[q] = c->ff_diht[idx];
+      for (int k = 0; k < 6; k++) m.dih_par[q][k] = c->ff_dihp[idx + T4 * k];
+      if (m.dih_kind[q] == 1) {  // "undefined dihedral force" guard of intra_bonded_interactions.f90:434-441 needs phase 0 or pi
+        double xi0 = m.dih_par[q][0];
+        if (!(std::fabs(xi0) < 1e-4 || std::fabs(xi0 - c->cfg.pi) < 1e-4)) { /* handled at run time only when sin != 0 */ }
+      }
+    }
+    ob += n_bond[t]; oa += n_angle[t]; od += n_dihedral[t];
+    // find_bonded_atom_hydrogen general_routines.f90:575-602
+    for (int a = 0; a < MA; a++) {
+      int heavy = -1, count = 0;
+      for (int b = 0; b < m.n_bond; b++) {
+        if (m.bond[b][0] == a) { heavy = m.bond[b][1]; count++; }
+        else if (m.bond[b][1] == a) { heavy = m.bond[b][0]; count++; }
+      }
+      m.bonded_heavy[a] = count == 1 ? heavy : -1;
+    }
+    m.heavy_acid_atom = m.heavy_base_atom = -1;
+  }
+  c->have_mt = true;
+  if (!c->d.mt) {
+    MolTypeDev* p;
+    int rc = dev_alloc(c, &p, (size_t)c->d.nMT);
+    if (rc) return rc;
+    c->d.mt = p;
+  }
+  CK(cudaMemcpy((void*)c->d.mt, c->mt_host.data(), c->mt_host.size() * sizeof(MolTypeDev), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int rpb_set_evb(rpb_ctx* c, const int* da_i, const double* da_p, const int* pa_i, const double* pa_p, const int* dc_i,
+                const double* dc_p, const int* dc_t, const double* ex_a, const double* ex_p, const int* acid,
+                const int* basic, const int* conj_pairs, const int* conj_atom, const double* ref_e, const int* proton_index,
+                const int* heavy_acid_index) {
+  if (!c->have_mt) { c->err = "rpb_set_molecule_types must precede rpb_set_evb"; return RPB_ERR_STATE; }
+  EvbTables& e = c->evb_host;
+  const int MI = RPB_MAXI, MM = RPB_MAXM, T = RPB_MAXT;
+  for (int i = 0; i < MI; i++) {
+    for (int j = 0; j < 3; j++) { e.da_int[i][j] = da_i[i + MI * j] - 1; e.dc_int[i][j] = dc_i[i + MI * j] - 1; }
+    for (int j = 0; j < 2; j++) e.pa_int[i][j] = pa_i[i + MI * j] - 1;
+    for (int j = 0; j < 6; j++) e.da_par[i][j] = da_p[i + MI * j];
+    for (int j = 0; j < 5; j++) e.pa_par[i][j] = pa_p[i + MI * j];
+    for (int j = 0; j < 10; j++) e.dc_par[i][j] = dc_p[i + MI * j];
+    e.dc_type[i] = dc_t[i];
+  }
+  for (int i = 0; i < T; i++) { e.exch_atomic[i] = ex_a[i]; e.conj_atom[i] = conj_atom[i] - 1; e.atype_chg[i] = c->atype_chg[i]; }
+  for (int i = 0; i < MM; i++) {
+    for (int j = 0; j < MM; j++) e.exch_proton[i][j] = ex_p[i + MM * j];
+    e.conj_pairs[i] = conj_pairs[i] - 1; e.ref_energy[i] = ref_e[i];
+    e.proton_index[i] = proton_index[i] - 1; e.heavy_acid_index[i] = heavy_acid_index[i] - 1;
+  }
+  (void)acid; (void)basic;
+  // get_heavy_atom_transfer_acid / _base (ms_evb.f90:2888-2938), resolved per molecule type
+  auto heavy_acid = [&](int t) {
+    if (t < 0 || t >= c->d.nMT) return -1;
+    int th = e.heavy_acid_index[t];
+    if (th < 0) return -1;
+    for (int a = 0; a < c->mt_host[t].n_atom; a++) if (c->mt_host[t].atom_type[a] == th) return a;
+    return -1;
+  };
+  for (int t = 0; t < c->d.nMT; t++) {
+    c->mt_host[t].heavy_acid_atom = heavy_acid(t);
+    c->mt_host[t].heavy_base_atom = heavy_acid(e.conj_pairs[t]);
+  }
+  CK(cudaMemcpy((void*)c->d.mt, c->mt_host.data(), c->mt_host.size() * sizeof(MolTypeDev), cudaMemcpyHostToDevice));
+  if (!c->d.evb) {
+    EvbTables* p;
+    int rc = dev_alloc(c, &p, 1);
+    if (rc) return rc;
+    c->d.evb = p;
+  }
+  CK(cudaMemcpy((void*)c->d.evb, &e, sizeof(EvbTables), cudaMemcpyHostToDevice));
+  int rc = evb_alloc(c);
+  if (rc) return rc;
+  c->have_evb = true;
+  return 0;
+}
+
+int rpb_upload_state(rpb_ctx* c, const double* xyz, const double* velocity, const double* mass, const double* charge,
+                     const int* atom_type_index, const int* mol_first_atom, const int* mol_n_atom, const int* mol_type,
+                     int hydronium_mol) {
+  const int N = c->d.N, M = c->d.M;
+  std::vector<double4> xq(N);
+  std::vector<int> ty(N), moa(N);
+  for (int i = 0; i < N; i++) { xq[i] = make_double4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], charge[i]); ty[i] = atom_type_index[i] - 1; }
+  c->mol_first.resize(M); c->mol_natom.resize(M); c->mol_type.resize(M);
+  int expect = 0;
+  for (int m = 0; m < M; m++) {
+    c->mol_first[m] = mol_first_atom[m] - 1; c->mol_natom[m] = mol_n_atom[m]; c->mol_type[m] = mol_type[m] - 1;
+    if (c->mol_first[m] != expect) { c->err = "molecules must be contiguous ascending atom ranges"; return RPB_ERR_ARG; }
+    for (int a = 0; a < mol_n_atom[m]; a++) moa[expect + a] = m;
+    expect += mol_n_atom[m];
+  }
+  if (expect != N) { c->err = "molecule table does not cover all atoms"; return RPB_ERR_ARG; }
+  c->hydronium_mol = hydronium_mol - 1;
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(c->d.xq, xq.data(), N * sizeof(double4), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d.vel, velocity, 3 * N * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d.mass, mass, N * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d.type, ty.data(), N * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d.mol_of_atom, moa.data(), N * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d.mol_first, c->mol_first.data(), M * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d.mol_natom, c->mol_natom.data(), M * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d.mol_type, c->mol_type.data(), M * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d.hydronium, &c->hydronium_mol, sizeof(int), cudaMemcpyHostToDevice));
+  c->have_state = true;
+  return 0;
+}
+
+int rpb_initialize(rpb_ctx* c) {
+  if (!(c->have_tables && c->have_ff && c->have_mt && c->have_state)) { c->err = "tables/forcefield/molecule types/state must be set first"; return RPB_ERR_STATE; }
+  launch_update_com_shift(c, true);
+  launch_verlet_force_rebuild(c);
+  int rc = fetch_status(c);
+  if (rc) return rc;
+  c->initialized = true;
+  return 0;
+}
+
+int rpb_force_energy(rpb_ctx* c, int ms_evb) {
+  if (!c->initialized) { c->err = "rpb_initialize not called"; return RPB_ERR_STATE; }
+  if (ms_evb && c->d.world > 1) { c->err = "world_size>1: use the phase calls"; return RPB_ERR_STATE; }
+  return force_energy(c, ms_evb, true);
+}
+
+int rpb_step_begin(rpb_ctx* c) { launch_integrate_first(c); return 0; }
+int rpb_step_end(rpb_ctx* c) {
+  launch_integrate_second(c);
+  int rc = fetch_status(c);
+  return rc;
+}
+int rpb_evb_phase_build(rpb_ctx* c) { return evb_build(c); }
+int rpb_evb_phase_mix(rpb_ctx* c) { return evb_mix(c, nullptr, nullptr); }
+int rpb_evb_phase_commit(rpb_ctx* c) { return evb_commit(c); }
+int rpb_evb_exchange_h(rpb_ctx* c, void** ptr, int* n) { *ptr = c->e.h_diag; *n = 2 * RPB_MAXS; return 0; }
+int rpb_evb_exchange_f(rpb_ctx* c, void** ptr, int* n) { *ptr = c->e.f_mix; *n = 3 * c->d.N; return 0; }
+
+int rpb_step(rpb_ctx* c, int n_steps, int ms_evb) {
+  if (!c->initialized) { c->err = "rpb_initialize not called"; return RPB_ERR_STATE; }
+  if (ms_evb && c->d.world > 1) { c->err = "world_size>1: use the phase calls"; return RPB_ERR_STATE; }
+  for (int s = 0; s < n_steps; s++) {
+    launch_integrate_first(c);
+    int rc = force_energy(c, ms_evb, false);
+    if (rc) return rc;
+    launch_integrate_second(c);
+  }
+  int rc = fetch_status(c);
+  if (rc) return rc;
+  if (!ms_evb) energies_from_slots(c);
+  return 0;
+}
+
+int rpb_get_energies(rpb_ctx* c, rpb_energies* e) {
+  launch_kinetic_energy(c);
+  CK(cudaMemcpyAsync(c->h_en, c->d.en, E_NSLOT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->last_en.kinetic_energy = c->h_en[E_KE];
+  *e = c->last_en;
+  return 0;
+}
+
+int rpb_download_state(rpb_ctx* c, double* xyz, double* velocity, double* force, double* mass, double* charge,
+                       int* atom_type_index, int* mol_first_atom, int* mol_n_atom, int* mol_type, int* hydronium_mol) {
+  const int N = c->d.N, M = c->d.M;
+  CK(cudaStreamSynchronize(c->stream));
+  if (xyz || charge) {
+    std::vector<double4> xq(N);
+    CK(cudaMemcpy(xq.data(), c->d.xq, N * sizeof(double4), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < N; i++) {
+      if (xyz) { xyz[3 * i] = xq[i].x; xyz[3 * i + 1] = xq[i].y; xyz[3 * i + 2] = xq[i].z; }
+      if (charge) charge[i] = xq[i].w;
+    }
+  }
+  if (velocity) CK(cudaMemcpy(velocity, c->d.vel, 3 * N * sizeof(double), cudaMemcpyDeviceToHost));
+  if (force) CK(cudaMemcpy(force, c->d.force, 3 * N * sizeof(double), cudaMemcpyDeviceToHost));
+  if (mass) CK(cudaMemcpy(mass, c->d.mass, N * sizeof(double), cudaMemcpyDeviceToHost));
+  if (atom_type_index) {
+    CK(cudaMemcpy(atom_type_index, c->d.type, N * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < N; i++) atom_type_index[i] += 1;
+  }
+  for (int m = 0; m < M; m++) {
+    if (mol_first_atom) mol_first_atom[m] = c->mol_first[m] + 1;
+    if (mol_n_atom) mol_n_atom[m] = c->mol_natom[m];
+    if (mol_type) mol_type[m] = c->mol_type[m] + 1;
+  }
+  if (hydronium_mol) *hydronium_mol = c->hydronium_mol + 1;
+  return 0;
+}
+
+int rpb_get_r_com(rpb_ctx* c, double* r_com) {
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(r_com, c->d.r_com, 3 * c->d.M * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int rpb_get_neighbor_list(rpb_ctx* c, int* verlet_point, int* neighbor_list, int capacity, int* n_pairs, int* flag) {
+  const int N = c->d.N;
+  CK(cudaStreamSynchronize(c->stream));
+  int last = 0, fl = 0;
+  CK(cudaMemcpy(&last, c->d.verlet_point + N, sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&fl, c->d.flag_verlet, sizeof(int), cudaMemcpyDeviceToHost));
+  int np = last - 1;
+  if (n_pairs) *n_pairs = np;
+  if (flag) *flag = fl;
+  if (verlet_point) CK(cudaMemcpy(verlet_point, c->d.verlet_point, (N + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+  if (neighbor_list) {
+    if (capacity < np) { c->err = "neighbor_list buffer too small"; return RPB_ERR_ARG; }
+    CK(cudaMemcpy(neighbor_list, c->d.neighbor_list, (size_t)np * sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+int rpb_get_pme(rpb_ctx* c, int state, double* Q_grid, double* theta, double* force_recip) {
+  const int K = c->d.K;
+  const size_t K3 = (size_t)K * K * K;
+  if (state < 1 || state > c->grid_capacity) { c->err = "diabat grid not available"; return RPB_ERR_ARG; }
+  CK(cudaStreamSynchronize(c->stream));
+  if (Q_grid) {
+    if (state > 1 || c->eh.built) { c->err = "Q grids are consumed in place by the batched FFT in MS-EVB mode; only theta is kept"; }
+    CK(cudaMemcpy(Q_grid, c->d.Q + K3 * (state - 1), K3 * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  if (theta) CK(cudaMemcpy(theta, c->d.theta + K3 * (state - 1), K3 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (force_recip) CK(cudaMemcpy(force_recip, c->d.force_recip, 3 * c->d.N * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int rpb_get_evb(rpb_ctx* c, int* n_states, double* hamiltonian, double* eigenvector, int* proton_log, int* coupling_matrix,
+                int* principal_diabat, int* new_hydronium_mol, double* adiabatic_potential) {
+  EvbHost& h = c->eh;
+  const int S = h.n_states;
+  if (n_states) *n_states = S;
+  if (hamiltonian) for (int i = 0; i < RPB_MAXS; i++) for (int j = 0; j < RPB_MAXS; j++) hamiltonian[i + RPB_MAXS * j] = h.hamiltonian[i][j];
+  if (eigenvector) for (int s = 0; s < S; s++) eigenvector[s] = h.evec[s];
+  if (proton_log)
+    for (int s = 0; s < RPB_MAXS; s++) for (int k = 0; k < RPB_MAXC; k++) for (int f = 0; f < 5; f++) {
+      int v = (s < S) ? h.proton_log[s][k][f] : -1;
+      proton_log[s + RPB_MAXS * k + RPB_MAXS * RPB_MAXC * f] = v < 0 ? -1 : v + 1;
+    }
+  if (coupling_matrix) for (int s = 0; s < RPB_MAXS; s++) coupling_matrix[s] = (s < S && h.parent[s] >= 0) ? h.parent[s] + 1 : -1;
+  if (principal_diabat) *principal_diabat = h.principal_diabat + 1;
+  if (new_hydronium_mol) *new_hydronium_mol = h.new_hydronium + 1;
+  if (adiabatic_potential) *adiabatic_potential = h.adiabatic_potential;
+  return 0;
+}
+
+int rpb_debug_mix_forces(rpb_ctx* c, const double* coeff, double* force) { return evb_mix(c, coeff, force); }
+
+int rpb_get_launch_counts(rpb_ctx* c, long long* own, long long* fft) {
+  if (own) *own = c->n_launch;
+  if (fft) *fft = c->n_fft;
+  return 0;
+}
+int rpb_timers_enable(rpb_ctx* c, int on) { c->timers_on = on != 0; return 0; }
+int rpb_timers_reset(rpb_ctx* c) { for (int i = 0; i < T_NTIMER; i++) { c->t_ms[i] = 0; c->t_calls[i] = 0; } return 0; }
+int rpb_timers_get(rpb_ctx* c, double* ms, long long* calls) {
+  for (int i = 0; i < T_NTIMER; i++) { ms[i] = c->t_ms[i]; calls[i] = c->t_calls[i]; }
+  return 0;
+}
+void* rpb_get_stream(rpb_ctx* c) { return (void*)c->stream; }
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+// Host-side context of librpbmd.so and the launcher prototypes of every kernel file.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+#include "rpb_dev.cuh"
+#include "rpb_evb.cuh"
+
+enum {
+  T_INTEGRATE = 0, T_VERLET, T_PAIR, T_INTRA, T_SPREAD, T_FFT, T_CONV, T_GATHER, T_EVB_ENUM, T_EVB_ITEMS,
+  T_EVB_GRID, T_EVB_COUPLING, T_EVB_DIAG, T_EVB_MIX, T_STEP, T_NTIMER
+};
+
+struct rpb_ctx {
+  rpb_config cfg;
+  std::string err;
+  bool have_tables = false, have_ff = false, have_mt = false, have_evb = false, have_state = false, initialized = false;
+  cudaStream_t stream = nullptr;
+  Dev d;                       // device pointer table (host copy, passed by value to kernels)
+  std::vector<void*> allocs;   // everything cudaMalloc'ed (freed in rpb_destroy)
+  // host copies of small tables
+  std::vector<MolTypeDev> mt_host;
+  EvbTables evb_host;
+  std::vector<double> ff_vdw, ff_vdw14, ff_bondp, ff_anglep, ff_dihp;
+  std::vector<int> ff_vdwt, ff_bondt, ff_anglet, ff_diht;
+  double atype_chg[RPB_MAXT]; int atype_freeze[RPB_MAXT];
+  // host mirror of the molecule table (kept in sync on hop commit)
+  std::vector<int> mol_first, mol_natom, mol_type;
+  int hydronium_mol = -1;
+  // cuFFT
+  std::map<int, cufftHandle> plan_fwd, plan_inv;
+  // EVB
+  EvbDev e;                    // device pointers of the EVB working set
+  EvbHost eh;                  // pinned host read-back area + per-step host state
+  int grid_capacity = 0;       // number of K^3 grids allocated in d.Q / d.theta
+  // pinned scratch
+  double* h_en = nullptr;      // [E_NSLOT]
+  int* h_flags = nullptr;      // [8]
+  // measurement
+  long long n_launch = 0, n_fft = 0;
+  bool timers_on = false;
+  cudaEvent_t ev0[T_NTIMER], ev1[T_NTIMER];
+  double t_ms[T_NTIMER];
+  long long t_calls[T_NTIMER];
+  rpb_energies last_en;
+};
+
+template <typename T>
+int dev_alloc(rpb_ctx* ctx, T** p, size_t n) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+  if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return RPB_ERR_CUDA; }
+  ctx->allocs.push_back(q);
+  *p = (T*)q;
+  return 0;
+}
+
+struct ScopedTimer {
+  rpb_ctx* c; int id;
+  ScopedTimer(rpb_ctx* c_, int id_) : c(c_), id(id_) { if (c->timers_on) cudaEventRecord(c->ev0[id], c->stream); }
+  ~ScopedTimer() {
+    if (c->timers_on) {
+      cudaEventRecord(c->ev1[id], c->stream);
+      cudaEventSynchronize(c->ev1[id]);
+      float ms = 0; cudaEventElapsedTime(&ms, c->ev0[id], c->ev1[id]);
+      c->t_ms[id] += ms; c->t_calls[id]++;
+    }
+  }
+};
+
+// ---- rpb_api.cu
+int calculate_total_force_energy(rpb_ctx*, bool evb_principal);   // total_energy_forces.f90:19-99
+// ---- kernels_md.cu
+void launch_integrate_first(rpb_ctx*);      // md_integration.f90:469-491
+void launch_integrate_second(rpb_ctx*);     // md_integration.f90:507-532
+void launch_update_com_shift(rpb_ctx*, bool shift);
+void launch_verlet_update(rpb_ctx*);        // total_energy_forces.f90:30-39
+void launch_verlet_force_rebuild(rpb_ctx*); // construct_verlet_list + displacement init
+void launch_zero_forces(rpb_ctx*);
+void launch_kinetic_energy(rpb_ctx*);
+// ---- kernels_pair.cu
+void launch_pair_verlet(rpb_ctx*);          // pair_int_real_space.f90:135-371
+void launch_molecule_terms(rpb_ctx*);       // pair_int_real_space.f90:386-588 + intra_bonded_interactions.f90:17-552
+// ---- kernels_pme.cu
+int pme_get_plans(rpb_ctx*, int batch, cufftHandle* fwd, cufftHandle* inv);
+void launch_scaled_coords(rpb_ctx*);
+void launch_spread_principal(rpb_ctx*);     // pme.f90:184-264
+int launch_convolve(rpb_ctx*, int first_grid, int n_grids, double* e_recip_dev, bool inverse);  // pme.f90:73-129
+void launch_gather(rpb_ctx*, const double* theta, double* out_force, bool add_to_force);       // pme.f90:346-498
+// ---- kernels_evb.cu
+int evb_alloc(rpb_ctx*);
+int evb_build(rpb_ctx*);
+int evb_mix(rpb_ctx*, const double* coeff_override_host, double* force_out_host);
+int evb_commit(rpb_ctx*);
