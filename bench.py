@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- MS-EVB steps/s (and ns/day) of the per-timestep force path on synthetic water/acid boxes.
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path (this repo)
+    python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference algorithm, all host threads
+
+Workload (config.workload): BASELINE.json configs[2] "c3": H3O+ in 2999 flexible waters (9001 atoms, L=44.81 A,
+PME 48^3, r_c=10, r_v=12, dt=0.5 fs), MS-EVB with ~20 diabatic states.  At N>1 the diabatic states are sharded
+round-robin across the ranks and combined with two all-reduces per step (H elements, HF forces):
+total work is fixed -> "scaling": "strong".  `--workload c2|c3|c4` selects the other single-GPU configs.
+
+One "step" = md_integrate_atomic: half-kick/drift, COM+wrap, MS-EVB force (principal diabat, enumeration, all
+diabats' matrix elements with batched PME, Jacobi, Hellmann-Feynman mixing), half-kick, COM momentum removal.
+Timing: CUDA events on the library's stream around every step, L2 flushed (256 MiB write) between steps outside
+the timed intervals, barrier + synchronize on both sides, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DT_PS = 0.0005
+WORKLOADS = {
+    "c2": dict(desc="3375 flexible H2O, non-reactive (BASELINE configs[1])", pme_grid=48, ms_evb=False),
+    "c3": dict(desc="H3O+ + 2999 H2O, MS-EVB (BASELINE configs[2])", pme_grid=48, ms_evb=True),
+    "c4": dict(desc="H3O+ + 9999 H2O, MS-EVB, 64^3 PME (BASELINE configs[3], single excess proton)", pme_grid=64, ms_evb=True),
+}
+
+
+def build_system(name):
+    from reactive_pb_nn_md_b200 import system
+    return {"c2": system.config_c2, "c3": system.config_c3, "c4": system.config_c4}[name]()
+
+
+def params_for(name, n_threads=1):
+    from reactive_pb_nn_md_b200 import engine
+    return engine.SimulationParameters(delta_t=DT_PS, real_space_cutoff=10.0, verlet_cutoff=12.0, na_nslist=10,
+                                       nb_nslist=10, nc_nslist=10, alpha_sqrt=0.3,
+                                       pme_grid=WORKLOADS[name]["pme_grid"], spline_order=6, n_threads=n_threads)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.stop_flag = False
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smax.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement of the reference algorithm (oracle/) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from reactive_pb_nn_md_b200 import engine
+    from reactive_pb_nn_md_b200._binding import Library
+    cores = os.cpu_count() or 1
+    lib = Library(os.path.join(ROOT, "oracle", "librpbmd_oracle.so"))
+    wl = WORKLOADS[args.workload]
+    s = build_system(args.workload)
+    sim = engine.Simulation(s, params_for(args.workload, n_threads=cores), library=lib)
+    evb = wl["ms_evb"]
+    (sim.ms_evb_calculate_total_force_energy if evb else sim.calculate_total_force_energy)()
+    sim.md_integrate_atomic(args.warmup, ms_evb=evb)
+    t0 = time.perf_counter()
+    sim.md_integrate_atomic(args.steps, ms_evb=evb)
+    dt = time.perf_counter() - t0
+    sps = args.steps / dt
+    n_states = sim.evb()["n_states"] if evb else 1
+    line = {
+        "impl": "reference", "metric": "ms_evb_steps_per_s", "value": sps, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "ns_per_day": sps * DT_PS * 86.4,
+        "config": {"workload": args.workload, "description": wl["desc"], "n_atoms": s.n_atoms, "pme_grid": wl["pme_grid"],
+                   "n_states": n_states, "delta_t_ps": DT_PS},
+        "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
+                         "sample": "%d full MD steps of the same workload, CPU restatement of the reference algorithm "
+                                   "(g++ -O2 -fopenmp, %d threads); the Fortran/MKL reference cannot be built in this image"
+                                   % (args.steps, cores)},
+        "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def algorithmic_model(name, N, K, S, n_own, pairs_listed, pairs_cut):
+    """ALGORITHMIC bytes / flops per launch for each timed kernel."""
+    K3 = K ** 3
+    m = {
+        "pme_spread": ("hbm", 32 * N + 8 * K3),
+        "pme_gather": ("hbm", 8 * K3 + 32 * N + 24 * N),
+        "pme_convolve": ("hbm", 2 * 16 * (K // 2 + 1) * K * K * 1 + 8 * (K // 2 + 1) * K * K),
+        "evb_grid_broadcast": ("hbm", 8 * K3 + 8 * K3 * n_own),
+        "evb_theta_mix": ("hbm", 8 * K3 * (n_own + 1) + 8 * K3),
+        "evb_mix_forces": ("hbm", 24 * N * (2 * n_own + 1) + 24 * N),
+        "evb_gather_mix": ("hbm", 8 * K3 + 32 * N + 24 * N),
+        "pair_real_space": ("fp64", 24 * pairs_listed + 56 * pairs_cut),
+    }
+    return m
+
+
+def run_ours(args):
+    import torch
+    from reactive_pb_nn_md_b200 import engine
+    from reactive_pb_nn_md_b200._binding import Library, load_cuda
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        pg = dist.group.WORLD
+    lib = load_cuda()
+    wl = WORKLOADS[args.workload]
+    evb = wl["ms_evb"]
+    s = build_system(args.workload)
+    sim = engine.Simulation(s, params_for(args.workload), library=lib, device=local_rank, rank=rank if evb else 0,
+                            world_size=world if evb else 1, process_group=pg)
+    first = sim.ms_evb_calculate_total_force_energy if evb else sim.calculate_total_force_energy
+    first()
+    step = lambda n=1: sim.md_integrate_atomic(n, ms_evb=evb)
+    stream = torch.cuda.ExternalStream(sim.dll.rpb_get_stream(sim.ctx), device=torch.device("cuda", local_rank))
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    own0, fft0 = sim.launch_counts()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(float(k))                     # L2 flush (256 MiB > 126 MB L2), outside the timed interval
+        torch.cuda.synchronize()
+        evs[k][0].record(stream)
+        step()
+        evs[k][1].record(stream)
+    barrier()
+    wall = time.perf_counter() - wall0
+    ms_total = sum(a.elapsed_time(b) for a, b in evs)
+    own1, fft1 = sim.launch_counts()
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    clocks = sampler.finish() if rank == 0 else None
+    sps = args.steps / (ms_total * 1e-3)
+
+    # ---- per-kernel pass (events recorded inside the library on its own stream; separate from the headline loop)
+    sim.timers_enable(True)
+    sim.timers(reset=True)
+    n_prof = min(args.steps, 20)
+    for k in range(n_prof):
+        flush.fill_(float(k)); torch.cuda.synchronize()
+        step()
+    tm = sim.timers()
+    sim.timers_enable(False)
+    n_states = sim.evb()["n_states"] if evb else 1
+    n_own = len([x for x in range(1, n_states) if (x - 1) % world == rank]) if evb else 0
+    vp, nl, _ = sim.neighbor_list()
+    pairs_listed = len(nl)
+    model = algorithmic_model(args.workload, s.n_atoms, wl["pme_grid"], n_states, n_own, pairs_listed, int(0.58 * pairs_listed))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    fp64_peak = sim.fp64_peak_tflops()
+    kernels = {}
+    step_ms = tm.get("step_total", (0.0, 0))[0] / max(n_prof, 1)
+    for name, (ms, calls) in tm.items():
+        if calls == 0 or name == "step_total":
+            continue
+        per_launch = ms / calls
+        ent = {"ms_per_step": ms / n_prof, "launches_per_step": calls / n_prof, "share_of_step": (ms / n_prof) / step_ms if step_ms else None}
+        if name in model:
+            bound, work = model[name]
+            if bound == "hbm":
+                ach = work / (per_launch * 1e-3) / 1e9
+                ent.update({"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "algorithmic_bytes": work})
+            else:
+                ach = work / (per_launch * 1e-3) / 1e12
+                ent.update({"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak, "algorithmic_flops": work})
+        kernels[name] = ent
+    single = {k: v for k, v in kernels.items() if "bound" in v}
+    dom = max(single, key=lambda k: single[k]["ms_per_step"]) if single else None
+    roofline = None
+    if dom:
+        r = single[dom]
+        roofline = {"kernel": dom, "bound": r["bound"], "achieved": r["achieved"], "peak": r["peak"], "unit": r["unit"],
+                    "frac": r["frac"], "traffic": None,
+                    "peak_source": hbm_src if r["bound"] == "hbm" else "fp64 FMA micro-benchmark run inside this bench (8 DFMA chains/thread)"}
+
+    # ---- end-to-end through the reference-facing call with HOST buffers: upload x,v -> step -> download x,v,F + energies
+    e2e = None
+    cpu_baseline = None
+    if world == 1:
+        st = sim.download_state()
+        xyz = torch.from_numpy(st["xyz"]).pin_memory().numpy()
+        vel = torch.from_numpy(st["velocity"]).pin_memory().numpy()
+        n_e2e = min(args.steps, 50)
+        N = s.n_atoms
+        h2d = 2 * 3 * N * 8 + 2 * N * 8 + N * 4 + 3 * s.n_mole * 4
+        d2h = 3 * 3 * N * 8 + 8 * 8
+        for _ in range(3):
+            sim.upload_state(xyz, vel, st); step(); st = sim.download_state(); xyz[:] = st["xyz"]; vel[:] = st["velocity"]; sim.energies()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            sim.upload_state(xyz, vel, st)          # host buffers -> device (positions, velocities, topology)
+            step()
+            st = sim.download_state()               # device -> host: x, v, F, topology after possible hops
+            xyz[:] = st["xyz"]; vel[:] = st["velocity"]
+            sim.energies()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        e2e = {"value": n_e2e / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "call": "rpb_upload_state + rpb_step(1) + rpb_download_state + rpb_get_energies (host buffers)"}
+        # ---- CPU baseline: bounded sample of the same workload on the host cores (oracle = port of the reference algorithm)
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            olib = Library(os.path.join(ROOT, "oracle", "librpbmd_oracle.so"))
+            so = engine.Simulation(s, params_for(args.workload, n_threads=cores), library=olib)
+            (so.ms_evb_calculate_total_force_energy if evb else so.calculate_total_force_energy)()
+            so.md_integrate_atomic(2, ms_evb=evb)
+            n_cpu = args.cpu_steps
+            t0 = time.perf_counter()
+            so.md_integrate_atomic(n_cpu, ms_evb=evb)
+            cdt = time.perf_counter() - t0
+            cpu_baseline = {"value": n_cpu / cdt, "unit": "steps/s", "cores": cores, "kind": "port",
+                            "sample": "%d full MD steps of the same workload with the CPU restatement of the reference "
+                                      "algorithm (oracle/, g++ -O2 -fopenmp)" % n_cpu}
+    if rank == 0:
+        line = {
+            "metric": "ms_evb_steps_per_s", "value": sps, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "ns_per_day": sps * DT_PS * 86.4,
+            "config": {"workload": args.workload, "description": wl["desc"], "n_atoms": s.n_atoms, "pme_grid": wl["pme_grid"],
+                       "n_states": n_states, "delta_t_ps": DT_PS, "parallelism": "diabatic-state sharding x%d" % world,
+                       "l2": "flushed between timed steps (256 MiB write)", "timing": "cuda events per step on the library stream, max over ranks"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(own1 - own0), "cufft_execs": int(fft1 - fft0),
+            "roofline": roofline, "kernels": kernels, "fp64_peak_tflops_measured": fp64_peak,
+            "cpu_baseline": cpu_baseline, "wall_s_timed_region": wall,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

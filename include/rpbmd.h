@@ -211,6 +211,8 @@ const char* rpb_timer_name(int i);
 int rpb_timers_get(rpb_ctx*, double* ms /*rpb_timer_count()*/, long long* calls);
 /* stream the library launches on (cudaStream_t as void*), for external event timing */
 void* rpb_get_stream(rpb_ctx*);
+/* measured fp64 FMA peak of the device (TFLOP/s): denominator for the FP64-pipe-bound pair kernels */
+int rpb_measure_fp64_peak(rpb_ctx*, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -259,5 +259,6 @@ int rpb_timer_count(void) { return 0; }
 const char* rpb_timer_name(int) { return ""; }
 int rpb_timers_get(rpb_ctx*, double*, long long*) { return 0; }
 void* rpb_get_stream(rpb_ctx*) { return nullptr; }
+int rpb_measure_fp64_peak(rpb_ctx*, double* t) { if (t) *t = 0.0; return 0; }
 
 }  // extern "C"

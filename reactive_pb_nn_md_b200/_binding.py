@@ -90,6 +90,7 @@ _PROTOS = {
     "rpb_timer_name": (C.c_char_p, [C.c_int]),
     "rpb_timers_get": (C.c_int, [_vp, _dp, C.POINTER(C.c_longlong)]),
     "rpb_get_stream": (_vp, [_vp]),
+    "rpb_measure_fp64_peak": (C.c_int, [_vp, _dp]),
 }
 
 ABI_SYMBOLS = tuple(sorted(_PROTOS))

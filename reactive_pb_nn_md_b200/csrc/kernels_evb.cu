@@ -1128,7 +1128,6 @@ int evb_build(rpb_ctx* c) {
   CKE(cudaMemcpyAsync(sc.slot_state, slot_state.data(), MAXS * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   CKE(cudaMemcpyAsync(sc.state_list, state_list.data(), MAXS * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   {
-    ScopedTimer t(c, T_EVB_ITEMS);
     CKE(cudaMemsetAsync(e.item_energy, 0, (RPB_MAX_ITEMS + 1) * sizeof(double), c->stream));
     CKE(cudaMemsetAsync(e.vex, 0, MAXS * sizeof(double), c->stream));
     CKE(cudaMemsetAsync(e.e_recip, 0, MAXS * sizeof(double), c->stream));
@@ -1136,15 +1135,15 @@ int evb_build(rpb_ctx* c) {
     CKE(cudaMemsetAsync(e.Foff, 0, (size_t)S * n3 * sizeof(double), c->stream));
     k_evb_snapshots<<<(S + 31) / 32, 32, 0, c->stream>>>(d, e, -1);
     dim3 g(h.n_items, (N + ITEM_TPB - 1) / ITEM_TPB);
-    k_evb_items_background<<<g, ITEM_TPB, 0, c->stream>>>(d, e, h.n_items);
-    k_evb_items_chain<<<(h.n_items + 31) / 32, 32, 0, c->stream>>>(d, e, h.n_items);
+    { ScopedTimer t(c, T_EVB_ITEMS_BG); k_evb_items_background<<<g, ITEM_TPB, 0, c->stream>>>(d, e, h.n_items); }
+    { ScopedTimer t(c, T_EVB_ITEMS_CHAIN); k_evb_items_chain<<<(h.n_items + 31) / 32, 32, 0, c->stream>>>(d, e, h.n_items); }
     c->n_launch += 3;
   }
   if (n_own > 0) {
     {
-      ScopedTimer t(c, T_EVB_GRID);
-      k_evb_broadcast_grid<<<(unsigned)((K3 / 2 + 255) / 256), 256, 0, c->stream>>>(d.Q, d.Q + K3, K3, n_own);
+      { ScopedTimer t(c, T_EVB_BCAST); k_evb_broadcast_grid<<<(unsigned)((K3 / 2 + 255) / 256), 256, 0, c->stream>>>(d.Q, d.Q + K3, K3, n_own); }
       int warps = h.n_items * 2 * MA;
+      ScopedTimer t(c, T_EVB_PATCH);
       k_evb_item_pme<<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(d, e, h.n_items, sc.slot_of_state, 0);
       c->n_launch += 2;
     }
@@ -1152,7 +1151,7 @@ int evb_build(rpb_ctx* c) {
     rc = launch_convolve(c, 1, n_own, e.e_recip, true);
     if (rc) return rc;
     {
-      ScopedTimer t(c, T_EVB_GRID);
+      ScopedTimer t(c, T_EVB_CORR);
       int warps = h.n_items * 2 * MA;
       k_evb_item_pme<<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(d, e, h.n_items, sc.slot_of_state, 1);
       c->n_launch += 1;
@@ -1200,13 +1199,12 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
     c->n_launch++;
   }
   {
-    ScopedTimer t(c, T_EVB_MIX);
     int include_principal = (d.rank == 0) ? 1 : 0;
     // slot 0 (principal theta) only contributes on rank 0: mask it on the other ranks through slot_state
     if (!include_principal) { int m1 = -1; CKE(cudaMemcpyAsync(sc.slot_state, &m1, sizeof(int), cudaMemcpyHostToDevice, c->stream)); }
-    k_evb_theta_mix<<<(unsigned)((K3 / 2 + 255) / 256), 256, 0, c->stream>>>(d, e, sc.slot_state, n_own + 1);
-    k_evb_mix_forces<<<(unsigned)((n3 + 255) / 256), 256, 0, c->stream>>>(d, e, sc.state_list, n_own, include_principal);
-    k_evb_gather_mix<<<(N * 32 + 255) / 256, 256, 0, c->stream>>>(d, e);
+    { ScopedTimer t(c, T_EVB_THETAMIX); k_evb_theta_mix<<<(unsigned)((K3 / 2 + 255) / 256), 256, 0, c->stream>>>(d, e, sc.slot_state, n_own + 1); }
+    { ScopedTimer t(c, T_EVB_MIXF); k_evb_mix_forces<<<(unsigned)((n3 + 255) / 256), 256, 0, c->stream>>>(d, e, sc.state_list, n_own, include_principal); }
+    { ScopedTimer t(c, T_EVB_GATHERMIX); k_evb_gather_mix<<<(N * 32 + 255) / 256, 256, 0, c->stream>>>(d, e); }
     c->n_launch += 3;
   }
   if (coeff_override_host) {

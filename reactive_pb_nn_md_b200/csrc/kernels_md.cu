@@ -368,3 +368,37 @@ static void verlet_common(rpb_ctx* c, int force_rebuild) {
 
 void launch_verlet_update(rpb_ctx* c) { verlet_common(c, 0); }
 void launch_verlet_force_rebuild(rpb_ctx* c) { verlet_common(c, 1); }
+
+// ------------------------------------------------------------------------------------------------
+// fp64 FMA peak of this device (roofline denominator for the FP64-pipe-bound pair kernels): 8 independent
+// DFMA chains per thread, 148*8 CTAs of 256 threads.
+__global__ void k_fp64_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, cc = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, b, cc); a1 = fma(a1, b, cc); a2 = fma(a2, b, cc); a3 = fma(a3, b, cc);
+    a4 = fma(a4, b, cc); a5 = fma(a5, b, cc); a6 = fma(a6, b, cc); a7 = fma(a7, b, cc);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int measure_fp64_peak(rpb_ctx* c, double* tflops) {
+  const int blocks = 148 * 8, threads = 256, iters = 1 << 14;
+  double* buf = nullptr;
+  if (cudaMalloc(&buf, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) { c->err = "cudaMalloc failed"; return RPB_ERR_CUDA; }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0, c->stream);
+    k_fp64_peak<<<blocks, threads, 0, c->stream>>>(buf, iters);
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+    best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+  *tflops = best;
+  return 0;
+}

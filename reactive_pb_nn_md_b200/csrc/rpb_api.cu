@@ -9,7 +9,8 @@
 
 static const char* k_timer_names[T_NTIMER] = {
     "integrate", "verlet", "pair_real_space", "molecule_terms", "pme_spread", "pme_fft", "pme_convolve", "pme_gather",
-    "evb_enumerate", "evb_items", "evb_delta_grid", "evb_coupling", "evb_diagonalize", "evb_mix", "step_total"};
+    "evb_enumerate", "evb_items_background", "evb_items_chain", "evb_grid_broadcast", "evb_grid_patch", "evb_recip_corr",
+    "evb_coupling", "evb_jacobi", "evb_theta_mix", "evb_mix_forces", "evb_gather_mix", "step_total"};
 
 #define CK(call)                                                                  \
   do {                                                                            \
@@ -112,7 +113,6 @@ int rpb_create(rpb_ctx** out, const rpb_config* cfg) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { c->err = "no CUDA device: librpbmd.so has no CPU fallback"; return RPB_ERR_CUDA; }
   CK(cudaSetDevice(cfg->device));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  for (int i = 0; i < T_NTIMER; i++) { CK(cudaEventCreate(&c->ev0[i])); CK(cudaEventCreate(&c->ev1[i])); }
   CK(cudaMallocHost(&c->h_en, E_NSLOT * sizeof(double)));
   CK(cudaMallocHost(&c->h_flags, 8 * sizeof(int)));
   Dev& d = c->d;
@@ -192,7 +192,7 @@ void rpb_destroy(rpb_ctx* c) {
   if (c->h_flags) cudaFreeHost(c->h_flags);
   if (c->eh.pinned) cudaFreeHost(c->eh.pinned);
   if (c->stream) {
-    for (int i = 0; i < T_NTIMER; i++) { cudaEventDestroy(c->ev0[i]); cudaEventDestroy(c->ev1[i]); }
+    for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
   }
   delete c;
@@ -441,6 +441,7 @@ int rpb_step(rpb_ctx* c, int n_steps, int ms_evb) {
   if (!c->initialized) { c->err = "rpb_initialize not called"; return RPB_ERR_STATE; }
   if (ms_evb && c->d.world > 1) { c->err = "world_size>1: use the phase calls"; return RPB_ERR_STATE; }
   for (int s = 0; s < n_steps; s++) {
+    ScopedTimer t(c, T_STEP);
     launch_integrate_first(c);
     int rc = force_energy(c, ms_evb, false);
     if (rc) return rc;
@@ -552,12 +553,32 @@ int rpb_get_launch_counts(rpb_ctx* c, long long* own, long long* fft) {
   if (fft) *fft = c->n_fft;
   return 0;
 }
-int rpb_timers_enable(rpb_ctx* c, int on) { c->timers_on = on != 0; return 0; }
-int rpb_timers_reset(rpb_ctx* c) { for (int i = 0; i < T_NTIMER; i++) { c->t_ms[i] = 0; c->t_calls[i] = 0; } return 0; }
+static void timers_resolve(rpb_ctx* c) {
+  if (c->ev_used == 0) return;
+  cudaStreamSynchronize(c->stream);
+  for (int k = 0; k < c->ev_used; k++) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev_pool[2 * k], c->ev_pool[2 * k + 1]) == cudaSuccess) { c->t_ms[c->ev_id[k]] += ms; c->t_calls[c->ev_id[k]]++; }
+  }
+  c->ev_used = 0;
+}
+int rpb_timers_enable(rpb_ctx* c, int on) {
+  if (on && c->ev_pool.empty()) {
+    c->ev_pool.resize(2 * 8192);
+    c->ev_id.resize(8192);
+    for (auto& ev : c->ev_pool) if (cudaEventCreate(&ev) != cudaSuccess) { c->err = "cudaEventCreate failed"; return RPB_ERR_CUDA; }
+  }
+  if (!on) timers_resolve(c);
+  c->timers_on = on != 0;
+  return 0;
+}
+int rpb_timers_reset(rpb_ctx* c) { timers_resolve(c); for (int i = 0; i < T_NTIMER; i++) { c->t_ms[i] = 0; c->t_calls[i] = 0; } return 0; }
 int rpb_timers_get(rpb_ctx* c, double* ms, long long* calls) {
+  timers_resolve(c);
   for (int i = 0; i < T_NTIMER; i++) { ms[i] = c->t_ms[i]; calls[i] = c->t_calls[i]; }
   return 0;
 }
 void* rpb_get_stream(rpb_ctx* c) { return (void*)c->stream; }
+int rpb_measure_fp64_peak(rpb_ctx* c, double* tflops) { return measure_fp64_peak(c, tflops); }
 
 }  // extern "C"

@@ -7,8 +7,9 @@
 #include "rpb_evb.cuh"
 
 enum {
-  T_INTEGRATE = 0, T_VERLET, T_PAIR, T_INTRA, T_SPREAD, T_FFT, T_CONV, T_GATHER, T_EVB_ENUM, T_EVB_ITEMS,
-  T_EVB_GRID, T_EVB_COUPLING, T_EVB_DIAG, T_EVB_MIX, T_STEP, T_NTIMER
+  T_INTEGRATE = 0, T_VERLET, T_PAIR, T_INTRA, T_SPREAD, T_FFT, T_CONV, T_GATHER, T_EVB_ENUM, T_EVB_ITEMS_BG,
+  T_EVB_ITEMS_CHAIN, T_EVB_BCAST, T_EVB_PATCH, T_EVB_CORR, T_EVB_COUPLING, T_EVB_DIAG, T_EVB_THETAMIX, T_EVB_MIXF,
+  T_EVB_GATHERMIX, T_STEP, T_NTIMER
 };
 
 struct rpb_ctx {
@@ -39,7 +40,9 @@ struct rpb_ctx {
   // measurement
   long long n_launch = 0, n_fft = 0;
   bool timers_on = false;
-  cudaEvent_t ev0[T_NTIMER], ev1[T_NTIMER];
+  std::vector<cudaEvent_t> ev_pool;   // 2 events per recorded interval
+  std::vector<int> ev_id;
+  int ev_used = 0;
   double t_ms[T_NTIMER];
   long long t_calls[T_NTIMER];
   rpb_energies last_en;
@@ -55,17 +58,18 @@ int dev_alloc(rpb_ctx* ctx, T** p, size_t n) {
   return 0;
 }
 
+// Per-phase CUDA-event timers.  Events are only RECORDED on the launching stream while a step runs (no
+// synchronisation, so enabling them does not serialise the step); rpb_timers_get resolves them afterwards.
 struct ScopedTimer {
-  rpb_ctx* c; int id;
-  ScopedTimer(rpb_ctx* c_, int id_) : c(c_), id(id_) { if (c->timers_on) cudaEventRecord(c->ev0[id], c->stream); }
-  ~ScopedTimer() {
-    if (c->timers_on) {
-      cudaEventRecord(c->ev1[id], c->stream);
-      cudaEventSynchronize(c->ev1[id]);
-      float ms = 0; cudaEventElapsedTime(&ms, c->ev0[id], c->ev1[id]);
-      c->t_ms[id] += ms; c->t_calls[id]++;
+  rpb_ctx* c; int id; int slot;
+  ScopedTimer(rpb_ctx* c_, int id_) : c(c_), id(id_), slot(-1) {
+    if (c->timers_on && c->ev_used < (int)c->ev_pool.size() / 2) {
+      slot = c->ev_used++;
+      c->ev_id[slot] = id;
+      cudaEventRecord(c->ev_pool[2 * slot], c->stream);
     }
   }
+  ~ScopedTimer() { if (slot >= 0) cudaEventRecord(c->ev_pool[2 * slot + 1], c->stream); }
 };
 
 // ---- rpb_api.cu
@@ -78,6 +82,7 @@ void launch_verlet_update(rpb_ctx*);        // total_energy_forces.f90:30-39
 void launch_verlet_force_rebuild(rpb_ctx*); // construct_verlet_list + displacement init
 void launch_zero_forces(rpb_ctx*);
 void launch_kinetic_energy(rpb_ctx*);
+int measure_fp64_peak(rpb_ctx*, double* tflops);
 // ---- kernels_pair.cu
 void launch_pair_verlet(rpb_ctx*);          // pair_int_real_space.f90:135-371
 void launch_molecule_terms(rpb_ctx*);       // pair_int_real_space.f90:386-588 + intra_bonded_interactions.f90:17-552

@@ -134,13 +134,18 @@ class Simulation:
         except Exception:
             pass
 
-    def upload_state(self, xyz, velocity):
+    def upload_state(self, xyz, velocity, topology=None):
+        """atom_data / molecule_data -> library.  `topology` (a dict as returned by download_state) carries the
+        per-atom and per-molecule arrays after proton hops have permuted them; default: the initial system."""
         s = self.system
+        t = topology if topology is not None else dict(
+            mass=s.mass, charge=s.charge, atom_type=s.atom_type, mol_first_atom=s.mol_first_atom,
+            mol_n_atom=s.mol_n_atom, mol_type=s.mol_type, hydronium_mol=s.hydronium_mol)
         xyz = np.ascontiguousarray(xyz, np.float64)
         velocity = np.ascontiguousarray(velocity, np.float64)
         self._check(self.dll.rpb_upload_state(
-            self.ctx, dptr(xyz), dptr(velocity), dptr(s.mass), dptr(s.charge), iptr(s.atom_type),
-            iptr(s.mol_first_atom), iptr(s.mol_n_atom), iptr(s.mol_type), int(s.hydronium_mol)))
+            self.ctx, dptr(xyz), dptr(velocity), dptr(t["mass"]), dptr(t["charge"]), iptr(t["atom_type"]),
+            iptr(t["mol_first_atom"]), iptr(t["mol_n_atom"]), iptr(t["mol_type"]), int(t["hydronium_mol"])))
 
     # -- the reference interface ------------------------------------------------------------
     def calculate_total_force_energy(self):
@@ -181,7 +186,13 @@ class Simulation:
     def _allreduce(self, which):
         import torch.distributed as dist
         t = self._exchange_tensor(which)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
+        if t.is_cuda:
+            import torch
+            torch.cuda.synchronize()          # library stream -> NCCL stream
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
+            torch.cuda.synchronize()          # NCCL stream -> library stream
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
 
     # -- results ----------------------------------------------------------------------------
     def energies(self):
@@ -254,6 +265,14 @@ class Simulation:
         a, b = C.c_longlong(), C.c_longlong()
         self._check(self.dll.rpb_get_launch_counts(self.ctx, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def timers_enable(self, on=True):
+        self._check(self.dll.rpb_timers_enable(self.ctx, int(on)))
+
+    def fp64_peak_tflops(self):
+        t = C.c_double()
+        self._check(self.dll.rpb_measure_fp64_peak(self.ctx, C.byref(t)))
+        return t.value
 
     def timers(self, reset=False):
         n = self.dll.rpb_timer_count()
