@@ -405,7 +405,8 @@ __global__ void __launch_bounds__(ITEM_TPB) k_evb_items_background(Dev d, EvbDev
   __shared__ ItemShared sh;
   __shared__ double red[32];
   __shared__ double facc[ITEM_TPB / 32][3 * MA][3];   // per-warp force accumulators: donor | acceptor | hydronium
-  const EvbItem it = e.items[blockIdx.x];
+  const int item_id = e.real_list[blockIdx.x];
+  const EvbItem it = e.items[item_id];
   const Snapshot& S = e.snap[it.state * NLEV + it.level];
   if (threadIdx.x == 0) fill_item_shared(d, S, it, sh);
   for (int k = threadIdx.x; k < (ITEM_TPB / 32) * 3 * MA * 3; k += blockDim.x) (&facc[0][0][0])[k] = 0.0;
@@ -471,7 +472,7 @@ __global__ void __launch_bounds__(ITEM_TPB) k_evb_items_background(Dev d, EvbDev
     atomicAdd(&outF[3 * j], sign * fj[0]); atomicAdd(&outF[3 * j + 1], sign * fj[1]); atomicAdd(&outF[3 * j + 2], sign * fj[2]);
   }
   en = block_sum(en, red);
-  if (threadIdx.x == 0 && en != 0.0) atomicAdd(&e.item_energy[blockIdx.x], en);
+  if (threadIdx.x == 0 && en != 0.0) atomicAdd(&e.item_energy[item_id], en);
   __syncthreads();
   // fold the per-warp accumulators and push the image-atom forces out
   for (int k = threadIdx.x; k < 3 * MA * 3; k += blockDim.x) {
@@ -490,8 +491,9 @@ __global__ void __launch_bounds__(ITEM_TPB) k_evb_items_background(Dev d, EvbDev
 // one thread per item: everything that involves only chain atoms (intramolecular terms of donor and acceptor,
 // pairs among the chain molecules, repulsion with chain atoms, reference energy)
 __global__ void k_evb_items_chain(Dev d, EvbDev e, int n_items) {
-  int ii = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ii >= n_items) return;
+  int ir = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ir >= n_items) return;
+  const int ii = e.real_list[ir];
   const EvbItem it = e.items[ii];
   const Snapshot& S = e.snap[it.state * NLEV + it.level];
   const EvbTables& E = *d.evb;
@@ -593,9 +595,14 @@ __global__ void k_evb_item_pme(Dev d, EvbDev e, int n_items, const int* __restri
   } else {
     double F[3];
     gather_atom_warp(d, d.theta + K3 * slot, u, q, lane, F);
-    if (lane < 3) {
+    // slot of this atom in the diabat's chain-atom table (level-0 snapshot order)
+    const Snapshot& S0 = e.snap[it.state * NLEV];
+    int slot = -1, cnt = 0;
+    for (int k = 0; k < S0.n_mol; k++) for (int b = 0; b < S0.m[k].n_atom; b++) { if (S0.m[k].atom[b] == I.atom[a]) slot = cnt; cnt++; }
+    if (lane < 3 && slot >= 0) {
       double v = lane == 0 ? F[0] : (lane == 1 ? F[1] : F[2]);
-      atomicAdd(&e.dF[(size_t)it.state * 3 * d.N + 3 * I.atom[a] + lane], it.sign * v);
+      atomicAdd(&e.corr_f[((size_t)it.state * CM * MA + slot) * 3 + lane], it.sign * v);
+      if (lane == 0) e.corr_atom[it.state * CM * MA + slot] = I.atom[a];
     }
   }
 }
@@ -789,127 +796,156 @@ __global__ void k_evb_assemble(Dev d, EvbDev e, const CouplingGeo* geo, int n_it
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   int S = *e.n_states;
   if (s >= MAXS) return;
-  e.h_diag[s] = 0.0; e.h_diag[MAXS + s] = 0.0;
+  e.h_diag[s] = 0.0; e.h_diag[MAXS + s] = 0.0; e.h_diag[2 * MAXS + s] = 0.0;
   if (s >= S || !state_owned(s, d.rank, d.world)) return;
-  // principal energy: calculate_total_force_energy + repulsion + reference (ms_evb.f90:411-436)
-  double E_elec = d.en[E_ELEC] + d.en[E_RECIP] + d.ewald_self;
-  double H11 = E_elec + d.en[E_VDW] + d.en[E_BOND] + d.en[E_ANGLE] + d.en[E_DIH];
-  double Hs = H11;
+  if (s == 0) {
+    // principal energy: calculate_total_force_energy + repulsion + reference (ms_evb.f90:411-436)
+    double E_elec = d.en[E_ELEC] + d.en[E_RECIP] + d.ewald_self;
+    double H11 = E_elec + d.en[E_VDW] + d.en[E_BOND] + d.en[E_ANGLE] + d.en[E_DIH];
+    for (int ii = 0; ii < n_items; ii++) if (e.items[ii].state == 0) H11 = H11 + e.item_energy[ii];
+    e.h_diag[0] = H11;
+    return;
+  }
+  // energy delta of the last hop: acceptor-topology item minus donor-topology item (ms_evb.f90:1546)
+  double dE = 0.0;
   for (int ii = 0; ii < n_items; ii++) {
     const EvbItem& it = e.items[ii];
-    if (it.state == 0) { Hs = Hs + e.item_energy[ii]; }
+    if (it.state == s && it.real && it.sign > 0) dE = e.item_energy[ii] - e.item_energy[ii - 1];
   }
-  if (s > 0) {
-    // items are ordered (hop, donor-topology, acceptor-topology) for each diabat
-    for (int ii = 0; ii < n_items; ii++) {
-      const EvbItem& it = e.items[ii];
-      if (it.state == s && it.sign > 0) Hs = Hs + e.item_energy[ii] - e.item_energy[ii - 1];
-    }
-    Hs = Hs + (e.e_recip[slot_of_state[s]] - e.e_recip[0]);
-    const CouplingGeo& G = geo[s];
-    double pref = G.Vconst + e.vex[s];
-    e.h_diag[MAXS + s] = pref * G.A;
-    double* Fo = e.Foff + (size_t)s * 3 * d.N;
-    for (int c = 0; c < 3; c++) {
-      atomicAdd(&Fo[3 * G.atom_Od + c], -pref * G.dA[0][c]);
-      atomicAdd(&Fo[3 * G.atom_Oa + c], -pref * G.dA[1][c]);
-      atomicAdd(&Fo[3 * G.atom_H + c], -pref * G.dA[2][c]);
-    }
+  e.h_diag[s] = dE;
+  e.h_diag[2 * MAXS + s] = e.e_recip[slot_of_state[s]] - e.e_recip[0];
+  const CouplingGeo& G = geo[s];
+  double pref = G.Vconst + e.vex[s];
+  e.h_diag[MAXS + s] = pref * G.A;
+  double* Fo = e.Foff + (size_t)s * 3 * d.N;
+  for (int c = 0; c < 3; c++) {
+    atomicAdd(&Fo[3 * G.atom_Od + c], -pref * G.dA[0][c]);
+    atomicAdd(&Fo[3 * G.atom_Oa + c], -pref * G.dA[1][c]);
+    atomicAdd(&Fo[3 * G.atom_H + c], -pref * G.dA[2][c]);
   }
-  e.h_diag[s] = Hs;
 }
 
 // ================================================================================================
-// K12: cyclic Jacobi (Numerical Recipes order, general_routines.f90:2013-2088) by ONE warp:
-// the rotation sequence is the reference's; each rotation's row/column updates run across the lanes.
+// K12: block-level Jacobi eigensolver for the (<= 80 x 80) EVB Hamiltonian, one CTA, matrix in shared memory.
+// Same rotation formulas, thresholds and stopping logic as the reference's Numerical-Recipes routine
+// (general_routines.f90:2035-2074), but the n/2 disjoint rotations of a round-robin round are applied
+// concurrently (rows, then columns) instead of one (ip,iq) at a time; the ground-state eigenvector is unique up
+// to sign, so only the rounding-level path differs.  Followed by the reference's selections (ms_evb.f90:279-328):
+// ground state = first minimum eigenvalue, principal diabat = first maximum |c_i|.
 // ================================================================================================
-__global__ void k_evb_jacobi(Dev d, EvbDev e, const double* coeff_override) {
+#define JAC_TPB 256
+__global__ void __launch_bounds__(JAC_TPB) k_evb_jacobi(Dev d, EvbDev e, const double* coeff_override) {
   extern __shared__ double smem[];
   const int S = *e.n_states;
-  const int lane = threadIdx.x;
-  double* a = smem;              // [S*S] column-major
-  double* v = a + S * S;
-  double* dd = v + S * S;        // d, b, z
-  double* b = dd + S; double* z = b + S;
-  __shared__ double s_s, s_tau;
-  __shared__ int s_rot;
+  const int n = S + (S & 1);          // padded to even for the round-robin pairing (dummy row/column stays zero)
+  const int tid = threadIdx.x, nth = blockDim.x;
+  double* a = smem;                   // [n*n] column-major, full symmetric
+  double* v = a + n * n;              // [n*n]
+  double* rc = v + n * n;             // [n/2] cos
+  double* rs = rc + n / 2;            // [n/2] sin
+  int* rp = (int*)(rs + n / 2);       // [n/2] p
+  int* rq = rp + n / 2;               // [n/2] q   (q < 0: no rotation)
+  __shared__ double red[32];
+  __shared__ double s_sm;
+  __shared__ int s_nrot;
   if (coeff_override) {
-    for (int i = lane; i < S; i += 32) e.evec[i] = coeff_override[i];
+    for (int i = tid; i < S; i += nth) e.evec[i] = coeff_override[i];
   } else {
-    for (int k = lane; k < S * S; k += 32) { a[k] = 0.0; v[k] = 0.0; }
-    __syncwarp();
-    for (int i = lane; i < S; i += 32) {
-      a[i + S * i] = e.h_diag[i];
-      if (i > 0) { int p = e.parent[i]; a[p + S * i] = e.h_diag[MAXS + i]; a[i + S * p] = e.h_diag[MAXS + i]; }
-      v[i + S * i] = 1.0;
+    for (int k = tid; k < n * n; k += nth) { a[k] = 0.0; v[k] = 0.0; }
+    __syncthreads();
+    for (int i = tid; i < n; i += nth) {
+      v[i + n * i] = 1.0;
+      if (i < S) {
+        // H_ss = H_11 + sum of the hop deltas along the chain (root first) + (E_rec(s) - E_rec(1))   ms_evb.f90:1546, 2083
+        int chain[MAXC + 1], nc = 0;
+        for (int t = i; t > 0 && nc <= MAXC; t = e.parent[t]) chain[nc++] = t;
+        double Hs = e.h_diag[0];
+        for (int k = nc - 1; k >= 0; k--) Hs = Hs + e.h_diag[chain[k]];
+        Hs = Hs + e.h_diag[2 * MAXS + i];
+        a[i + n * i] = Hs;
+        e.h_full[i] = Hs; e.h_full[MAXS + i] = (i > 0) ? e.h_diag[MAXS + i] : 0.0;
+        if (i > 0) { int p = e.parent[i]; a[p + n * i] = e.h_diag[MAXS + i]; a[i + n * p] = e.h_diag[MAXS + i]; }
+      }
     }
-    __syncwarp();
-    for (int i = lane; i < S; i += 32) { b[i] = a[i + S * i]; dd[i] = b[i]; z[i] = 0.0; }
-    __syncwarp();
+    __syncthreads();
     int status = 1;
     for (int it = 1; it <= 50; it++) {
       double sm = 0.0;
-      for (int k = lane; k < S * S; k += 32) { int i = k % S, j = k / S; if (i < j) sm += fabs(a[k]); }
-      sm = warp_sum(sm);
-      sm = __shfl_sync(0xffffffffu, sm, 0);
+      for (int k = tid; k < n * n; k += nth) { int i = k % n, j = k / n; if (i < j) sm += fabs(a[k]); }
+      sm = block_sum(sm, red);
+      if (tid == 0) { s_sm = sm; s_nrot = 0; }
+      __syncthreads();
+      sm = s_sm;
       if (sm == 0.0) { status = 0; break; }
-      double tresh = (it < 4) ? 0.2 * sm / (double)(S * S) : 0.0;
-      for (int ip = 0; ip < S - 1; ip++) {
-        for (int iq = ip + 1; iq < S; iq++) {
-          if (lane == 0) {
-            s_rot = 0;
-            double apq = a[ip + S * iq];
+      const double tresh = (it < 4) ? 0.2 * sm / (double)(S * S) : 0.0;
+      for (int r = 0; r < n - 1; r++) {
+        // ---- phase A: rotation parameters of the n/2 disjoint pairs of this round
+        if (tid < n / 2) {
+          int t = tid, p, q;
+          if (t == 0) { p = r; q = n - 1; }
+          else { p = (r + t) % (n - 1); q = (r - t + (n - 1)) % (n - 1); }
+          if (p > q) { int x = p; p = q; q = x; }
+          double apq = a[p + n * q];
+          int rot = 0;
+          double cc = 1.0, sn = 0.0;
+          if (apq != 0.0) {
+            double app = a[p + n * p], aqq = a[q + n * q];
             double g = 100.0 * fabs(apq);
-            if (it > 4 && (fabs(dd[ip]) + g == fabs(dd[ip])) && (fabs(dd[iq]) + g == fabs(dd[iq]))) {
-              a[ip + S * iq] = 0.0;
+            if (it > 4 && (fabs(app) + g == fabs(app)) && (fabs(aqq) + g == fabs(aqq))) {
+              a[p + n * q] = 0.0; a[q + n * p] = 0.0;
             } else if (fabs(apq) > tresh) {
-              double h = dd[iq] - dd[ip], t;
-              if (fabs(h) + g == fabs(h)) t = apq / h;
+              double h = aqq - app, tt;
+              if (fabs(h) + g == fabs(h)) tt = apq / h;
               else {
                 double theta = 0.5 * h / apq;
-                t = 1.0 / (fabs(theta) + sqrt(1.0 + theta * theta));
-                if (theta < 0.0) t = -t;
+                tt = 1.0 / (fabs(theta) + sqrt(1.0 + theta * theta));
+                if (theta < 0.0) tt = -tt;
               }
-              double cc = 1.0 / sqrt(1 + t * t), sn = t * cc;
-              s_s = sn; s_tau = sn / (1.0 + cc);
-              h = t * apq;
-              z[ip] = z[ip] - h; z[iq] = z[iq] + h; dd[ip] = dd[ip] - h; dd[iq] = dd[iq] + h;
-              a[ip + S * iq] = 0.0;
-              s_rot = 1;
+              cc = 1.0 / sqrt(1 + tt * tt); sn = tt * cc;
+              rot = 1;
             }
           }
-          __syncwarp();
-          if (s_rot) {
-            double sn = s_s, tau = s_tau;
-            for (int k = lane; k < S; k += 32) {
-              // a: three index ranges of jrotate (:2063-2065)
-              if (k != ip && k != iq) {
-                double* p1 = (k < ip) ? &a[k + S * ip] : &a[ip + S * k];
-                double* p2 = (k < iq) ? &a[k + S * iq] : &a[iq + S * k];
-                double w1 = *p1, w2 = *p2;
-                *p1 = w1 - sn * (w2 + w1 * tau);
-                *p2 = w2 + sn * (w1 - w2 * tau);
-              }
-              double* q1 = &v[k + S * ip]; double* q2 = &v[k + S * iq];
-              double u1 = *q1, u2 = *q2;
-              *q1 = u1 - sn * (u2 + u1 * tau);
-              *q2 = u2 + sn * (u1 - u2 * tau);
-            }
-          }
-          __syncwarp();
+          rc[t] = cc; rs[t] = sn; rp[t] = p; rq[t] = rot ? q : -1;
+          if (rot) atomicAdd(&s_nrot, 1);
         }
+        __syncthreads();
+        // ---- phase B: rows p,q of A <- J^T A
+        for (int w = tid; w < (n / 2) * n; w += nth) {
+          int t = w / n, k = w - t * n, q = rq[t];
+          if (q < 0) continue;
+          int p = rp[t];
+          double cc = rc[t], sn = rs[t];
+          double x = a[p + n * k], y = a[q + n * k];
+          a[p + n * k] = cc * x - sn * y;
+          a[q + n * k] = sn * x + cc * y;
+        }
+        __syncthreads();
+        // ---- phase C: columns p,q of A <- A J ; V <- V J
+        for (int w = tid; w < (n / 2) * n; w += nth) {
+          int t = w / n, k = w - t * n, q = rq[t];
+          if (q < 0) continue;
+          int p = rp[t];
+          double cc = rc[t], sn = rs[t];
+          double x = a[k + n * p], y = a[k + n * q];
+          double xn = cc * x - sn * y, yn = sn * x + cc * y;
+          if (k == p) yn = 0.0;       // a(p,q) = 0 exactly, as in the reference (:2062)
+          if (k == q) xn = 0.0;
+          a[k + n * p] = xn; a[k + n * q] = yn;
+          double vx = v[k + n * p], vy = v[k + n * q];
+          v[k + n * p] = cc * vx - sn * vy;
+          v[k + n * q] = sn * vx + cc * vy;
+        }
+        __syncthreads();
       }
-      for (int i = lane; i < S; i += 32) { b[i] = b[i] + z[i]; dd[i] = b[i]; z[i] = 0.0; }
-      __syncwarp();
     }
-    if (lane == 0) {
+    if (tid == 0) {
       int ground = 0;
-      double e0 = dd[0];
-      for (int i = 1; i < S; i++) if (dd[i] < e0) { e0 = dd[i]; ground = i; }
+      double e0 = a[0];
+      for (int i = 1; i < S; i++) if (a[i + n * i] < e0) { e0 = a[i + n * i]; ground = i; }
       *e.e_ground = e0;
       int pd = 0;
-      double coef = fabs(v[0 + S * ground]);
-      for (int i = 0; i < S; i++) if (coef < fabs(v[i + S * ground])) { coef = fabs(v[i + S * ground]); pd = i; }
+      double coef = fabs(v[0 + n * ground]);
+      for (int i = 0; i < S; i++) if (coef < fabs(v[i + n * ground])) { coef = fabs(v[i + n * ground]); pd = i; }
       int newh = *d.hydronium;
       for (int h = 0; h < d.max_chain; h++) {
         if (e.proton_log[(pd * MAXC + h) * 5] < 0) break;
@@ -917,17 +953,22 @@ __global__ void k_evb_jacobi(Dev d, EvbDev e, const double* coeff_override) {
       }
       e.result[0] = pd; e.result[1] = newh; e.result[2] = status; e.result[3] = ground;
     }
-    __syncwarp();
+    __syncthreads();
     int ground = e.result[3];
-    for (int i = lane; i < S; i += 32) e.evec[i] = v[i + S * ground];
+    for (int i = tid; i < S; i += nth) e.evec[i] = v[i + n * ground];
   }
-  __syncwarp();
+  __syncthreads();
   // Hellmann-Feynman weights: c_s^2 (diagonal) and 2 c_parent c_s (coupling)   ms_evb.f90:298-303
-  for (int i = lane; i < MAXS; i += 32) {
+  for (int i = tid; i < MAXS; i += nth) {
     double ci = i < S ? e.evec[i] : 0.0;
     e.coef2[i] = ci * ci;
     e.coef2[MAXS + i] = (i > 0 && i < S) ? 2.0 * e.evec[e.parent[i]] * ci : 0.0;
+    e.coef2[2 * MAXS + i] = ci * ci;
   }
+  __syncthreads();
+  // weight of the last-hop force delta of diabat s = sum of c_t^2 over every diabat whose chain passes through s
+  // (DFS pre-order => parent(s) < s, so one descending pass accumulates the subtrees)
+  if (tid == 0) for (int i = S - 1; i >= 1; i--) e.coef2[2 * MAXS + e.parent[i]] += e.coef2[2 * MAXS + i];
 }
 
 // ================================================================================================
@@ -957,10 +998,21 @@ __global__ void k_evb_mix_forces(Dev d, EvbDev e, const int* __restrict__ state_
   double f = include_principal ? e.dF[i] : 0.0;   // dF slot 0 holds the principal-diabat force (without F_rec)
   for (int k = 0; k < n_list; k++) {
     int s = state_list[k];
-    f = fma(e.coef2[s], e.dF[(size_t)s * n3 + i], f);
+    f = fma(e.coef2[2 * MAXS + s], e.dF[(size_t)s * n3 + i], f);
     f = fma(e.coef2[MAXS + s], e.Foff[(size_t)s * n3 + i], f);
   }
   e.f_mix[i] = f;
+}
+
+// + sum_s c_s^2 * (reciprocal-space corrections of the chain atoms of diabat s)   ms_evb.f90:2103-2248
+__global__ void k_evb_add_corr(Dev d, EvbDev e, const int* __restrict__ state_list, int n_list) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_list * CM * MA) return;
+  int s = state_list[t / (CM * MA)], slot = t % (CM * MA);
+  int atom = e.corr_atom[s * CM * MA + slot];
+  if (atom < 0) return;
+  double w = e.coef2[s];
+  for (int c = 0; c < 3; c++) atomicAdd(&e.f_mix[3 * atom + c], w * e.corr_f[((size_t)s * CM * MA + slot) * 3 + c]);
 }
 
 __global__ void k_evb_gather_mix(Dev d, EvbDev e) {
@@ -1045,8 +1097,9 @@ int evb_alloc(rpb_ctx* c) {
 #define AL(p, n) if ((rc = dev_alloc(c, &(p), (size_t)(n)))) return rc;
   AL(e.n_states, 1); AL(e.proton_log, MAXS * MAXC * 5); AL(e.parent, MAXS); AL(e.n_hops, MAXS);
   AL(e.snap, MAXS * NLEV); AL(e.items, RPB_MAX_ITEMS + 1); AL(e.n_items, 1); AL(e.item_energy, RPB_MAX_ITEMS + 1);
+  AL(e.real_list, RPB_MAX_ITEMS + 1); AL(e.n_real, 1); AL(e.corr_f, (size_t)MAXS * CM * MA * 3); AL(e.corr_atom, MAXS * CM * MA); AL(e.h_full, 2 * MAXS);
   AL(e.dF, (size_t)MAXS * 3 * N); AL(e.Foff, (size_t)MAXS * 3 * N);
-  AL(e.vex, MAXS); AL(e.e_recip, MAXS); AL(e.h_diag, 2 * MAXS); AL(e.f_mix, 3 * N); AL(e.evec, MAXS); AL(e.coef2, 2 * MAXS);
+  AL(e.vex, MAXS); AL(e.e_recip, MAXS); AL(e.h_diag, 3 * MAXS); AL(e.f_mix, 3 * N); AL(e.evec, MAXS); AL(e.coef2, 3 * MAXS);
   AL(e.e_ground, 1); AL(e.result, 8); AL(e.theta_mix, K3);
   EvbScratch s;
   AL(s.geo, MAXS); AL(s.slot_of_state, MAXS); AL(s.slot_state, MAXS); AL(s.state_list, MAXS); AL(s.coeff_dev, MAXS);
@@ -1062,7 +1115,7 @@ int evb_alloc(rpb_ctx* c) {
 static void host_items(rpb_ctx* c, std::vector<EvbItem>& items) {
   EvbHost& h = c->eh;
   items.clear();
-  EvbItem p; p.state = 0; p.level = 0; p.donor_slot = -1; p.acceptor_slot = -1; p.sign = 1.0;
+  EvbItem p; p.state = 0; p.level = 0; p.donor_slot = -1; p.acceptor_slot = -1; p.sign = 1.0; p.real = 1; p.pad = 0;
   items.push_back(p);   // principal diabat: EVB repulsion + reference energy (ms_evb.f90:418-426)
   for (int s = 1; s < h.n_states; s++) {
     if (!state_owned(s, c->d.rank, c->d.world)) continue;
@@ -1078,7 +1131,8 @@ static void host_items(rpb_ctx* c, std::vector<EvbItem>& items) {
     for (int k = 0; k < h.n_hops[s]; k++) {
       int a = h.proton_log[s][k][3], as = 0;
       for (int q = 0; q < nm; q++) if (mols[q] == a) as = q;
-      EvbItem it; it.state = s; it.donor_slot = cur; it.acceptor_slot = as;
+      EvbItem it; it.state = s; it.donor_slot = cur; it.acceptor_slot = as; it.pad = 0;
+      it.real = (k == h.n_hops[s] - 1) ? 1 : 0;   // earlier hops' real-space deltas are the ancestors' (same images, same background)
       it.level = k; it.sign = -1.0; items.push_back(it);
       it.level = k + 1; it.sign = 1.0; items.push_back(it);
       cur = as;
@@ -1116,6 +1170,10 @@ int evb_build(rpb_ctx* c) {
   std::vector<EvbItem> items;
   host_items(c, items);
   h.n_items = (int)items.size();
+  std::vector<int> real_list;
+  for (int i = 0; i < h.n_items; i++) if (items[i].real) real_list.push_back(i);
+  const int n_real = (int)real_list.size();
+  CKE(cudaMemcpyAsync(e.real_list, real_list.data(), n_real * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   std::vector<int> slot_of_state(MAXS, 0), slot_state(MAXS, -1), state_list;
   slot_state[0] = 0;   // slot 0 = principal grid on every rank
   for (int s = 1; s < S; s++)
@@ -1134,9 +1192,11 @@ int evb_build(rpb_ctx* c) {
     CKE(cudaMemsetAsync(e.dF, 0, (size_t)S * n3 * sizeof(double), c->stream));
     CKE(cudaMemsetAsync(e.Foff, 0, (size_t)S * n3 * sizeof(double), c->stream));
     k_evb_snapshots<<<(S + 31) / 32, 32, 0, c->stream>>>(d, e, -1);
-    dim3 g(h.n_items, (N + ITEM_TPB - 1) / ITEM_TPB);
-    { ScopedTimer t(c, T_EVB_ITEMS_BG); k_evb_items_background<<<g, ITEM_TPB, 0, c->stream>>>(d, e, h.n_items); }
-    { ScopedTimer t(c, T_EVB_ITEMS_CHAIN); k_evb_items_chain<<<(h.n_items + 31) / 32, 32, 0, c->stream>>>(d, e, h.n_items); }
+    CKE(cudaMemsetAsync(e.corr_f, 0, (size_t)S * CM * MA * 3 * sizeof(double), c->stream));
+    CKE(cudaMemsetAsync(e.corr_atom, 0xff, (size_t)S * CM * MA * sizeof(int), c->stream));
+    dim3 g(n_real, (N + ITEM_TPB - 1) / ITEM_TPB);
+    { ScopedTimer t(c, T_EVB_ITEMS_BG); k_evb_items_background<<<g, ITEM_TPB, 0, c->stream>>>(d, e, n_real); }
+    { ScopedTimer t(c, T_EVB_ITEMS_CHAIN); k_evb_items_chain<<<(n_real + 31) / 32, 32, 0, c->stream>>>(d, e, n_real); }
     c->n_launch += 3;
   }
   if (n_own > 0) {
@@ -1193,9 +1253,10 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
   }
   {
     ScopedTimer t(c, T_EVB_DIAG);
-    size_t shmem = ((size_t)2 * S * S + 3 * S) * sizeof(double);
+    const int np = S + (S & 1);
+    size_t shmem = ((size_t)2 * np * np + 2 * np) * sizeof(double);
     if (shmem > 48 * 1024) cudaFuncSetAttribute(k_evb_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
-    k_evb_jacobi<<<1, 32, shmem, c->stream>>>(d, e, coeff_dev);
+    k_evb_jacobi<<<1, JAC_TPB, shmem, c->stream>>>(d, e, coeff_dev);
     c->n_launch++;
   }
   {
@@ -1203,7 +1264,8 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
     // slot 0 (principal theta) only contributes on rank 0: mask it on the other ranks through slot_state
     if (!include_principal) { int m1 = -1; CKE(cudaMemcpyAsync(sc.slot_state, &m1, sizeof(int), cudaMemcpyHostToDevice, c->stream)); }
     { ScopedTimer t(c, T_EVB_THETAMIX); k_evb_theta_mix<<<(unsigned)((K3 / 2 + 255) / 256), 256, 0, c->stream>>>(d, e, sc.slot_state, n_own + 1); }
-    { ScopedTimer t(c, T_EVB_MIXF); k_evb_mix_forces<<<(unsigned)((n3 + 255) / 256), 256, 0, c->stream>>>(d, e, sc.state_list, n_own, include_principal); }
+    { ScopedTimer t(c, T_EVB_MIXF); k_evb_mix_forces<<<(unsigned)((n3 + 255) / 256), 256, 0, c->stream>>>(d, e, sc.state_list, n_own, include_principal);
+      if (n_own > 0) { k_evb_add_corr<<<(n_own * CM * MA + 127) / 128, 128, 0, c->stream>>>(d, e, sc.state_list, n_own); c->n_launch++; } }
     { ScopedTimer t(c, T_EVB_GATHERMIX); k_evb_gather_mix<<<(N * 32 + 255) / 256, 256, 0, c->stream>>>(d, e); }
     c->n_launch += 3;
   }
@@ -1217,7 +1279,7 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
   CKE(cudaMemcpyAsync(h.pinned + 1, e.result, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CKE(cudaMemcpyAsync(pd, e.e_ground, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CKE(cudaMemcpyAsync(pd + 1, e.evec, MAXS * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CKE(cudaMemcpyAsync(pd + 1 + MAXS, e.h_diag, 2 * MAXS * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CKE(cudaMemcpyAsync(pd + 1 + MAXS, e.h_full, 2 * MAXS * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CKE(cudaMemcpyAsync(c->h_flags, d.err_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CKE(cudaMemcpyAsync(c->h_en, d.en, E_NSLOT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CKE(cudaStreamSynchronize(c->stream));

@@ -434,7 +434,7 @@ int rpb_step_end(rpb_ctx* c) {
 int rpb_evb_phase_build(rpb_ctx* c) { return evb_build(c); }
 int rpb_evb_phase_mix(rpb_ctx* c) { return evb_mix(c, nullptr, nullptr); }
 int rpb_evb_phase_commit(rpb_ctx* c) { return evb_commit(c); }
-int rpb_evb_exchange_h(rpb_ctx* c, void** ptr, int* n) { *ptr = c->e.h_diag; *n = 2 * RPB_MAXS; return 0; }
+int rpb_evb_exchange_h(rpb_ctx* c, void** ptr, int* n) { *ptr = c->e.h_diag; *n = 3 * RPB_MAXS; return 0; }
 int rpb_evb_exchange_f(rpb_ctx* c, void** ptr, int* n) { *ptr = c->e.f_mix; *n = 3 * c->d.N; return 0; }
 
 int rpb_step(rpb_ctx* c, int n_steps, int ms_evb) {

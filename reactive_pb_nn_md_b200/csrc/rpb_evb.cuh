@@ -34,6 +34,8 @@ struct EvbItem {
   int level;                  // snapshot level
   int donor_slot, acceptor_slot;
   double sign;
+  int real;                   // 1: this hop is the LAST hop of its diabat (or the principal item): real-space/chain terms are evaluated
+  int pad;
 };
 
 #define RPB_MAX_ITEMS (2 * RPB_MAXS * RPB_MAXC)
@@ -47,14 +49,17 @@ struct EvbDev {
   EvbItem* items;             // [RPB_MAX_ITEMS]
   int* n_items;
   double* item_energy;        // [RPB_MAX_ITEMS] : E_ref + E_intra + E_real + E_rep of the item's topology
-  double* dF;                 // [MAXS][3N] diagonal force deltas (index 0 unused)
+  int* real_list; int* n_real; // item indices with real==1
+  double* dF;                 // [MAXS][3N]: slot 0 principal-diabat force; slot s: force delta of the LAST hop of diabat s
+  double* corr_f; int* corr_atom; // [MAXS][CM*MA][3], [MAXS][CM*MA]: reciprocal-space corrections of the chain atoms of diabat s
   double* Foff;               // [MAXS][3N] off-diagonal coupling forces
   double* vex;                // [MAXS]
   double* e_recip;            // [MAXS] E_rec of each diabat grid
-  double* h_diag;             // exchange buffer [2*MAXS]: H_ss | H_parent(s),s
+  double* h_diag;             // exchange buffer [3*MAXS]: (H_11, dE_s of the last hop) | H_parent(s),s | E_rec(s)-E_rec(1)
+  double* h_full;             // [2*MAXS] assembled H_ss | H_parent(s),s (after the exchange)
   double* f_mix;              // exchange buffer [3N]
   double* evec;               // ground-state eigenvector [MAXS]
-  double* coef2;              // c_s^2 / 2 c_p c_s weights [2*MAXS]
+  double* coef2;              // [3*MAXS] c_s^2 | 2 c_parent c_s | sum of c_t^2 over the DFS subtree of s
   double* e_ground;           // adiabatic potential
   int* result;                // [0] principal diabat (0-based) [1] new hydronium molecule (0-based) [2] jacobi status
   double* coupling_geo;       // [MAXS][16] A, Vconst, dA[3][3], atoms...
