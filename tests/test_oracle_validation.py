@@ -1,0 +1,134 @@
+"""Self-validation of the oracle (the reference ships no golden vectors and cannot be compiled here: parity is
+UNPINNED).  Physics invariants the restatement must satisfy, each checked on the raw fp64 buffers."""
+import numpy as np
+import pytest
+
+from reactive_pb_nn_md_b200 import engine, system, tables
+from reactive_pb_nn_md_b200.forcefield import load_forcefield
+from tests.util import rel_rms, small_params, water_system
+
+NACL_PMT = """solute_species
+header
+2
+Na   1.0  0.0  0.0  0
+Cl  -1.0  0.0  0.0  0
+
+cross_terms
+0
+"""
+NACL_TOP = """[ bondtypes ]
+
+[ angletypes ]
+
+[ dihedraltypes ]
+
+[ moleculetype ]
+na 3
+[ atoms ]
+1 Na 22.99
+[ bonds ]
+[ angles ]
+[ dihedrals ]
+[ exclusions ]
+
+[ moleculetype ]
+cl 3
+[ atoms ]
+1 Cl 35.45
+[ bonds ]
+[ angles ]
+[ dihedrals ]
+[ exclusions ]
+"""
+
+
+def test_madelung_constant_rock_salt(oracle_lib):
+    """PME reciprocal + table real space + Ewald self must reproduce the NaCl Madelung energy."""
+    ff = load_forcefield(NACL_PMT, NACL_TOP, "opls", 3, ("na", "cl"))
+    n, d = 8, 3.8
+    names, xyz = [], []
+    for i in range(n):
+        for j in range(n):
+            for k in range(n):
+                names.append("na" if (i + j + k) % 2 == 0 else "cl")
+                xyz.append([(i + 0.25) * d, (j + 0.25) * d, (k + 0.25) * d])
+    s = system.System(ff, n * d, names, np.array(xyz))
+    sim = engine.Simulation(s, small_params(pme_grid=48), library=oracle_lib)
+    sim.calculate_total_force_energy()
+    e = sim.energies()
+    madelung = 1.747564594633
+    expect = -(n ** 3) / 2.0 * madelung * tables.CONV_E2A_KJMOL / d
+    assert abs(e["E_elec"] - expect) / abs(expect) < 2e-4, (e["E_elec"], expect)
+    assert np.abs(sim.forces()).max() < 1e-2 * abs(expect) / (n ** 3) / d     # perfect lattice: forces vanish
+
+
+def test_ewald_split_independent_of_alpha(oracle_lib):
+    s = water_system(10)
+    es = []
+    for alpha, K in ((0.3, 48), (0.34, 60)):
+        sim = engine.Simulation(s, small_params(alpha_sqrt=alpha, pme_grid=K), library=oracle_lib)
+        sim.calculate_total_force_energy()
+        es.append(sim.energies()["E_elec"])
+    assert abs(es[0] - es[1]) < 2e-3 * abs(es[0])
+
+
+def test_forces_are_energy_derivatives(oracle_lib):
+    """central differences; the B-spline / erfc tables make E piecewise (nearest-above look-ups), hence the loose
+    tolerance and the large step"""
+    s = water_system(10)
+    sim = engine.Simulation(s, small_params(), library=oracle_lib)
+    sim.calculate_total_force_energy()
+    f = sim.forces()
+    st = sim.download_state()
+    x0, h = st["xyz"].copy(), 1e-2
+    for ia, dim in ((7, 0), (100, 2), (1501, 1), (2222, 0)):
+        es = []
+        for sg in (1, -1):
+            x = x0.copy(); x[ia, dim] += sg * h
+            sim.upload_state(x, st["velocity"]); sim.calculate_total_force_energy()
+            es.append(sim.energies()["potential_energy"])
+        fd = -(es[0] - es[1]) / (2 * h)
+        assert abs(fd - f[ia, dim]) < 2e-2 * max(abs(f[ia, dim]), 10.0), (ia, dim, fd, f[ia, dim])
+
+
+def test_translation_by_box_vector_is_exact_symmetry(oracle_lib):
+    s = water_system(10)
+    p = small_params()
+    a = engine.Simulation(s, p, library=oracle_lib); a.calculate_total_force_energy()
+    s2 = system.System(s.ff, s.box_length, ["h2o"] * s.n_mole, s.xyz + np.array([s.box_length, 0.0, 0.0]), s.velocity)
+    b = engine.Simulation(s2, p, library=oracle_lib); b.calculate_total_force_energy()
+    # x+L-L is not bit-identical to x, and the nearest-above B-spline look-ups (pme.f90:247) turn a 1-ulp change of
+    # a scaled coordinate into a ~1e-5 jump of a weight: the symmetry holds to table resolution only
+    assert abs(a.energies()["potential_energy"] - b.energies()["potential_energy"]) < 5e-3
+    assert rel_rms(a.forces(), b.forces()) < 1e-4
+
+
+def test_newton_third_law_and_nve_conservation(oracle_lib):
+    s = water_system(10)
+    sim = engine.Simulation(s, small_params(n_threads=8), library=oracle_lib)
+    sim.calculate_total_force_energy()
+    # real-space and bonded forces sum to zero exactly; PME reciprocal forces only to interpolation accuracy
+    assert np.abs(sim.forces().sum(axis=0)).max() < 0.2
+    e0 = sim.energies(); E0 = e0["potential_energy"] + e0["kinetic_energy"]
+    sim.md_integrate_atomic(40)
+    e1 = sim.energies(); E1 = e1["potential_energy"] + e1["kinetic_energy"]
+    assert abs(E1 - E0) < 1e-2 * e0["kinetic_energy"], (E0, E1)   # strained synthetic lattice, dt = 0.5 fs, flexible water
+    p = (sim.download_state()["mass"][:, None] * sim.download_state()["velocity"]).sum(axis=0)
+    assert np.abs(p).max() < 1e-8          # subtract_center_of_mass_momentum
+
+
+def test_verlet_list_is_complete_half_list(oracle_lib):
+    s = water_system(10)
+    sim = engine.Simulation(s, small_params(), library=oracle_lib)
+    vp, nl, flag = sim.neighbor_list()
+    x = sim.download_state()["xyz"]
+    L = s.box_length
+    rows = rng_rows = [5, 1234, 2990]
+    mol = np.repeat(np.arange(s.n_mole), 3)
+    for i in rows:
+        d = x[i] - x
+        d -= L * np.floor(d / L + 0.5)
+        within = np.where(((d ** 2).sum(axis=1) < 144.0) & (np.arange(len(x)) > i) & (mol != mol[i]))[0] + 1
+        got = nl[vp[i] - 1: vp[i + 1] - 1]
+        assert sorted(got) == sorted(within)
+    assert flag == 0 and vp[0] == 1 and vp[-1] - 1 == len(nl)
