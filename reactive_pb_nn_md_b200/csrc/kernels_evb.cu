@@ -16,6 +16,8 @@
 //   After the (optional) all-reduce of H: warp-level cyclic Jacobi -> theta_mix = sum c_s^2 theta_s (streaming)
 //   -> ONE gather for all atoms -> F = sum c_i c_j F_ij.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "rpb_host.h"
 #include "rpb_bonded.cuh"
@@ -34,111 +36,195 @@ __host__ __device__ inline bool state_owned(int s, int rank, int world) {
 }
 
 // ================================================================================================
-// K8: diabat enumeration, pre-order DFS exactly as evb_conduct_proton_transfer_recursive
+// K8: diabat enumeration.  The reference walks a pre-order DFS (evb_conduct_proton_transfer_recursive,
+// ms_evb.f90:498-607) and runs find_evb_reactive_neighbors (:702-764) for every (donor, proton) it meets.  That
+// search depends only on (molecule, proton) -- always principal-topology coordinates -- so it is memoised and done
+// with the whole CTA, level by level (depth < max_chain):
+//   1. compact the molecules whose centre of mass lies within max_chain * first-solvation cutoff of the hydronium
+//      (nothing farther can ever be an acceptor);
+//   2. per level:  a) (molecule of the level) x (compact molecule): the reference's centre-of-mass test -> short
+//      "near" lists;  b) (molecule, reactive proton, near molecule): the proton-acceptor distance test on the basic
+//      atoms -> hit lists;  c) hits sorted into the reference's (molecule, atom) loop order and truncated at
+//      evb_max_neighbors;  d) unseen acceptors join the next level;
+//   3. one thread replays the DFS over the memoised lists (shared memory only) and writes the hop logs.
 // ================================================================================================
-struct Frame { int mol, diabat, count, i_atom, n_nb, cursor; int nb[RPB_EVB_MAX_NEIGHBORS][2]; };
+#define ENUM_TPB 512
+#define ENUM_MAXMOL RPB_MAXS   // distinct molecules whose protons are searched (each is the acceptor of some diabat)
+#define ENUM_MAXP 4            // reactive protons per molecule
+#define ENUM_NEAR 40           // molecules inside the first-solvation cutoff of one molecule (~17 in water at 5 A)
+#define ENUM_HITS 12           // acceptor atoms inside the reactive-pair distance of one proton (10 are kept)
+#define ENUM_COMPACT 2048
+struct EnumFrame { int mol, v, diabat, count, ip, cursor; int log[MAXC][5]; };
 
-__global__ void k_evb_enumerate(Dev d, EvbDev e) {
-  __shared__ Frame fr[MAXC + 2];
-  __shared__ int depth, op, s_count, n_hit;
-  __shared__ int hits[64][2];
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    for (int i = 0; i < MAXS * MAXC * 5; i++) e.proton_log[i] = -1;
-    for (int i = 0; i < MAXS; i++) { e.parent[i] = -1; e.n_hops[i] = 0; }
-    s_count = 1;
-    depth = 0;
-    fr[0].mol = *d.hydronium; fr[0].diabat = 0; fr[0].count = 0; fr[0].i_atom = -1; fr[0].n_nb = 0; fr[0].cursor = 0;
-    op = 0;
+__global__ void __launch_bounds__(ENUM_TPB) k_evb_enumerate(Dev d, EvbDev e) {
+  __shared__ int compact[ENUM_COMPACT];
+  __shared__ int vis_mol[ENUM_MAXMOL];
+  __shared__ unsigned char prot_n[ENUM_MAXMOL], prot[ENUM_MAXMOL][ENUM_MAXP], heavy[ENUM_MAXMOL][ENUM_MAXP];
+  __shared__ int near_n[ENUM_MAXMOL];
+  __shared__ int near_mol[ENUM_MAXMOL][ENUM_NEAR];
+  __shared__ int nb_n[ENUM_MAXMOL][ENUM_MAXP];
+  __shared__ int nb[ENUM_MAXMOL][ENUM_MAXP][ENUM_HITS];          // acceptor molecule * 16 + acceptor atom
+  __shared__ unsigned char nb_v[ENUM_MAXMOL][ENUM_MAXP][RPB_EVB_MAX_NEIGHBORS];
+  __shared__ int s_ncomp, s_nvis, s_fail;
+  __shared__ EnumFrame fr[MAXC + 1];
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int hyd = *d.hydronium;
+  for (int i = tid; i < MAXS * MAXC * 5; i += nth) e.proton_log[i] = -1;
+  for (int i = tid; i < MAXS; i += nth) { e.parent[i] = -1; e.n_hops[i] = 0; }
+  for (int i = tid; i < ENUM_MAXMOL * ENUM_MAXP; i += nth) (&nb_n[0][0])[i] = 0;
+  for (int i = tid; i < ENUM_MAXMOL; i += nth) near_n[i] = 0;
+  if (tid == 0) { s_ncomp = 0; s_nvis = 1; vis_mol[0] = hyd; s_fail = 0; }
+  __syncthreads();
+  // ---- 1. compact list (superset: min-image COM distance below max_chain * cutoff + 0.5 A)
+  {
+    double R = (double)d.max_chain * sqrt(d.cut_solv2) + 0.5;
+    double R2 = R * R;
+    double c0 = d.r_com[3 * hyd], c1 = d.r_com[3 * hyd + 1], c2 = d.r_com[3 * hyd + 2];
+    for (int jm = tid; jm < d.M; jm += nth) {
+      double a0 = min_image(d.r_com[3 * jm] - c0, d.box[0]), a1 = min_image(d.r_com[3 * jm + 1] - c1, d.box[1]),
+             a2 = min_image(d.r_com[3 * jm + 2] - c2, d.box[2]);
+      if (a0 * a0 + a1 * a1 + a2 * a2 < R2) {
+        int slot = atomicAdd(&s_ncomp, 1);
+        if (slot < ENUM_COMPACT) compact[slot] = jm;
+      }
+    }
   }
   __syncthreads();
-  const int hyd = *d.hydronium;
-  while (true) {
-    if (tid == 0) {
-      op = 0;
-      while (true) {
-        if (depth < 0) { op = 2; break; }
-        Frame& f = fr[depth];
-        if (f.count >= d.max_chain) { depth--; continue; }       // "if ( count < evb_max_chain )" :538
-        if (f.cursor < f.n_nb) {
-          int acc_mol = f.nb[f.cursor][0], acc_atom = f.nb[f.cursor][1];
-          f.cursor++;
-          if (s_count >= d.max_states) { atomicMax(&d.err_flag[2], 1); op = 2; break; }
-          int da = s_count++;
-          e.parent[da] = f.diabat;
-          for (int h = 0; h < f.count; h++)
-            for (int q = 0; q < 5; q++) e.proton_log[(da * MAXC + h) * 5 + q] = e.proton_log[(f.diabat * MAXC + h) * 5 + q];
-          const MolTypeDev& T = d.mt[d.mol_type[f.mol]];
-          int* L = &e.proton_log[(da * MAXC + f.count) * 5];
-          L[0] = f.mol; L[1] = f.i_atom; L[2] = T.bonded_heavy[f.i_atom]; L[3] = acc_mol; L[4] = acc_atom;
-          if (L[2] < 0) atomicMax(&d.err_flag[3], 1);
-          e.n_hops[da] = f.count + 1;
-          if (acc_mol != hyd) {                                     // flag_cycle :573,596
-            Frame& g = fr[depth + 1];
-            g.mol = acc_mol; g.diabat = da; g.count = f.count + 1; g.i_atom = -1; g.n_nb = 0; g.cursor = 0;
-            depth++;
-          }
-          continue;
-        }
-        // next reactive proton of this donor (principal-topology molecule type) :542-546
-        const MolTypeDev& T = d.mt[d.mol_type[f.mol]];
-        int ia = f.i_atom + 1, n = d.mol_natom[f.mol];
-        while (ia < n && T.reactive_proton[ia] != 1) ia++;
-        if (ia >= n) { depth--; continue; }
-        f.i_atom = ia; f.n_nb = 0; f.cursor = 0;
-        n_hit = 0;
-        op = 1;
-        break;
-      }
-    }
-    __syncthreads();
-    if (op == 2) break;
-    // find_evb_reactive_neighbors for (fr[depth].mol, fr[depth].i_atom)  :702-764
-    {
-      const Frame& f = fr[depth];
-      int im = f.mol;
-      double rci[3] = {d.r_com[3 * im], d.r_com[3 * im + 1], d.r_com[3 * im + 2]};
-      double4 ph = d.xq[d.mol_first[im] + f.i_atom];
-      double xh[3] = {ph.x, ph.y, ph.z};
-      for (int jm = tid; jm < d.M; jm += blockDim.x) {
-        if (jm == im) continue;
-        double shift[3], dc[3];
-        for (int k = 0; k < 3; k++) {
-          double dr = d.r_com[3 * jm + k] - rci[k];
-          shift[k] = floor(d.inv_box[k] * dr + 0.5) * d.box[k];
-          dc[k] = d.r_com[3 * jm + k] - rci[k] - shift[k];
-        }
-        if (dc[0] * dc[0] + dc[1] * dc[1] + dc[2] * dc[2] < d.cut_solv2) {
-          const MolTypeDev& TJ = d.mt[d.mol_type[jm]];
-          int fj = d.mol_first[jm], nj = d.mol_natom[jm];
-          for (int ja = 0; ja < nj; ja++) {
-            if (TJ.reactive_basic[ja] != 1) continue;
-            double4 pj = d.xq[fj + ja];
-            double r0 = pj.x - xh[0] - shift[0], r1 = pj.y - xh[1] - shift[1], r2 = pj.z - xh[2] - shift[2];
-            if (r0 * r0 + r1 * r1 + r2 * r2 < d.cut_pair2) {
-              int slot = atomicAdd(&n_hit, 1);
-              if (slot < 64) { hits[slot][0] = jm; hits[slot][1] = ja; }
-            }
-          }
-        }
-      }
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int n = min(n_hit, 64);
-      for (int a = 1; a < n; a++) {   // ascending (molecule, atom) == the reference's loop order
-        int m0 = hits[a][0], a0 = hits[a][1], b = a - 1;
-        while (b >= 0 && (hits[b][0] > m0 || (hits[b][0] == m0 && hits[b][1] > a0))) { hits[b + 1][0] = hits[b][0]; hits[b + 1][1] = hits[b][1]; b--; }
-        hits[b + 1][0] = m0; hits[b + 1][1] = a0;
-      }
-      Frame& f = fr[depth];
-      f.n_nb = min(n, RPB_EVB_MAX_NEIGHBORS);   // evb_neighbor_list(evb_max_neighbors,2)
-      for (int a = 0; a < f.n_nb; a++) { f.nb[a][0] = hits[a][0]; f.nb[a][1] = hits[a][1]; }
-      f.cursor = 0;
-    }
-    __syncthreads();
+  if (s_ncomp > ENUM_COMPACT) {
+    if (tid == 0) { atomicMax(&d.err_flag[3], 9); *e.n_states = 1; }
+    return;
   }
-  if (tid == 0) *e.n_states = s_count;
+  const int ncomp = s_ncomp;
+  // ---- 2. memoised neighbour searches, level by level
+  int lvl_begin = 0, lvl_end = 1;
+  for (int L = 0; L < d.max_chain; L++) {
+    const int nlvl = lvl_end - lvl_begin;
+    // reactive protons of the molecules of this level (principal-topology molecule type, ms_evb.f90:542-546)
+    for (int vv = lvl_begin + tid; vv < lvl_end; vv += nth) {
+      int mol = vis_mol[vv];
+      const MolTypeDev& T = d.mt[d.mol_type[mol]];
+      int n = d.mol_natom[mol], np = 0;
+      for (int ia = 0; ia < n; ia++)
+        if (T.reactive_proton[ia] == 1) {
+          if (np >= ENUM_MAXP) { s_fail = 2; break; }
+          prot[vv][np] = (unsigned char)ia;
+          int hv = T.bonded_heavy[ia];
+          heavy[vv][np] = (unsigned char)(hv < 0 ? 255 : hv);
+          np++;
+        }
+      prot_n[vv] = (unsigned char)np;
+    }
+    // a) centre-of-mass test of find_evb_reactive_neighbors (:724-733), flattened over (molecule, compact entry)
+    for (int idx = tid; idx < nlvl * ncomp; idx += nth) {
+      const int vv = lvl_begin + idx / ncomp, jm = compact[idx % ncomp], im = vis_mol[vv];
+      if (jm == im) continue;
+      double dc2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        double dr = d.r_com[3 * jm + k] - d.r_com[3 * im + k];
+        double shift = floor(d.inv_box[k] * dr + 0.5) * d.box[k];
+        double dc = d.r_com[3 * jm + k] - d.r_com[3 * im + k] - shift;
+        dc2 = k == 0 ? dc * dc : dc2 + dc * dc;
+      }
+      if (dc2 < d.cut_solv2) {
+        int slot = atomicAdd(&near_n[vv], 1);
+        if (slot < ENUM_NEAR) near_mol[vv][slot] = jm; else s_fail = 3;
+      }
+    }
+    __syncthreads();
+    // b) proton -> basic-atom distance test (:734-754), flattened over (molecule, proton, near molecule)
+    for (int idx = tid; idx < nlvl * ENUM_MAXP * ENUM_NEAR; idx += nth) {
+      const int vv = lvl_begin + idx / (ENUM_MAXP * ENUM_NEAR), ip = (idx / ENUM_NEAR) % ENUM_MAXP, kn = idx % ENUM_NEAR;
+      if (ip >= prot_n[vv] || kn >= min(near_n[vv], ENUM_NEAR)) continue;
+      const int im = vis_mol[vv], jm = near_mol[vv][kn];
+      double4 ph = d.xq[d.mol_first[im] + prot[vv][ip]];
+      double shift[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        double dr = d.r_com[3 * jm + k] - d.r_com[3 * im + k];
+        shift[k] = floor(d.inv_box[k] * dr + 0.5) * d.box[k];
+      }
+      const MolTypeDev& TJ = d.mt[d.mol_type[jm]];
+      const int fj = d.mol_first[jm], nj = d.mol_natom[jm];
+      for (int ja = 0; ja < nj; ja++) {
+        if (TJ.reactive_basic[ja] != 1) continue;
+        double4 pj = d.xq[fj + ja];
+        double r0 = pj.x - ph.x - shift[0], r1 = pj.y - ph.y - shift[1], r2 = pj.z - ph.z - shift[2];
+        if (r0 * r0 + r1 * r1 + r2 * r2 < d.cut_pair2) {
+          int slot = atomicAdd(&nb_n[vv][ip], 1);
+          if (slot < ENUM_HITS) nb[vv][ip][slot] = jm * 16 + ja; else s_fail = 3;
+        }
+      }
+    }
+    __syncthreads();
+    // c) ascending (molecule, atom) == the reference's loop order; keep evb_max_neighbors   (evb_neighbor_list(10,2))
+    for (int idx = tid; idx < nlvl * ENUM_MAXP; idx += nth) {
+      const int vv = lvl_begin + idx / ENUM_MAXP, ip = idx % ENUM_MAXP;
+      int n = min(nb_n[vv][ip], ENUM_HITS);
+      for (int a = 1; a < n; a++) {
+        int key = nb[vv][ip][a], b2 = a - 1;
+        while (b2 >= 0 && nb[vv][ip][b2] > key) { nb[vv][ip][b2 + 1] = nb[vv][ip][b2]; b2--; }
+        nb[vv][ip][b2 + 1] = key;
+      }
+      nb_n[vv][ip] = min(n, RPB_EVB_MAX_NEIGHBORS);
+    }
+    __syncthreads();
+    // d) next level: acceptors not seen before (their protons are searched only if a diabat can still hop from them)
+    if (tid == 0 && L + 1 < d.max_chain) {
+      int nv = s_nvis;
+      for (int vv = lvl_begin; vv < lvl_end; vv++)
+        for (int ip = 0; ip < prot_n[vv]; ip++)
+          for (int k = 0; k < nb_n[vv][ip]; k++) {
+            int acc = nb[vv][ip][k] >> 4, at = -1;
+            if (acc == hyd) { nb_v[vv][ip][k] = 0; continue; }
+            for (int q = 0; q < nv; q++) if (vis_mol[q] == acc) { at = q; break; }
+            if (at < 0) {
+              if (nv >= ENUM_MAXMOL) { s_fail = 1; at = 0; }
+              else { vis_mol[nv] = acc; at = nv++; }
+            }
+            nb_v[vv][ip][k] = (unsigned char)at;
+          }
+      s_nvis = nv;
+    }
+    __syncthreads();
+    lvl_begin = lvl_end; lvl_end = s_nvis;
+  }
+  // ---- 3. DFS replay (pre-order; new diabat id = ++counter, :557)
+  if (tid == 0) {
+    int s_count = 1, depth = 0;
+    if (s_fail == 1) { atomicMax(&d.err_flag[2], 1); depth = -1; }            // more molecules than evb_max_states diabats
+    else if (s_fail) { atomicMax(&d.err_flag[3], 9); depth = -1; }            // compiled enumeration limits exceeded
+    fr[0].mol = hyd; fr[0].v = 0; fr[0].diabat = 0; fr[0].count = 0; fr[0].ip = -1; fr[0].cursor = 0;
+    while (depth >= 0) {
+      EnumFrame& f = fr[depth];
+      if (f.ip >= 0 && f.cursor < nb_n[f.v][f.ip]) {
+        const int pk = nb[f.v][f.ip][f.cursor];
+        const int acc_mol = pk >> 4, acc_atom = pk & 15;
+        const int acc_v = nb_v[f.v][f.ip][f.cursor];
+        f.cursor++;
+        if (s_count >= d.max_states) { atomicMax(&d.err_flag[2], 1); break; }
+        const int da = s_count++;
+        e.parent[da] = f.diabat;
+        int row[5] = {f.mol, (int)prot[f.v][f.ip], (int)heavy[f.v][f.ip], acc_mol, acc_atom};
+        if (row[2] == 255) { atomicMax(&d.err_flag[3], 1); row[2] = -1; }   // find_bonded_atom_hydrogen failed
+        for (int h = 0; h < f.count; h++)
+          for (int q = 0; q < 5; q++) e.proton_log[(da * MAXC + h) * 5 + q] = f.log[h][q];
+        for (int q = 0; q < 5; q++) e.proton_log[(da * MAXC + f.count) * 5 + q] = row[q];
+        e.n_hops[da] = f.count + 1;
+        if (acc_mol != hyd && f.count + 1 < d.max_chain) {          // flag_cycle :573,596 ; "if ( count < evb_max_chain )" :538
+          EnumFrame& g = fr[depth + 1];
+          g.mol = acc_mol; g.v = acc_v; g.diabat = da; g.count = f.count + 1; g.ip = -1; g.cursor = 0;
+          for (int h = 0; h < f.count; h++) for (int q = 0; q < 5; q++) g.log[h][q] = f.log[h][q];
+          for (int q = 0; q < 5; q++) g.log[f.count][q] = row[q];
+          depth++;
+        }
+        continue;
+      }
+      if (f.ip + 1 < prot_n[f.v]) { f.ip++; f.cursor = 0; }   // next reactive proton of this donor
+      else depth--;
+    }
+    *e.n_states = s_count;
+  }
 }
 
 // ================================================================================================
@@ -222,35 +308,71 @@ __device__ void image_proton_transfer(const Dev& d, MolImage& D, MolImage& A, in
   }
 }
 
+// warp-cooperative copy of a struct whose size is a multiple of 8 bytes
+template <typename T>
+__device__ __forceinline__ void warp_copy_struct(T* dst, const T* src, int lane) {
+  static_assert(sizeof(T) % 8 == 0, "struct size must be a multiple of 8");
+  const double* s = reinterpret_cast<const double*>(src);
+  double* t = reinterpret_cast<double*>(dst);
+  for (int k = lane; k < (int)(sizeof(T) / 8); k += 32) t[k] = s[k];
+}
+
+// One warp per diabat, working copy in shared memory: the lanes load the principal images of the chain molecules
+// and store every level's snapshot cooperatively; lane 0 replays the hops on the shared copy.
 // only_state >= 0: build that diabat regardless of ownership (hop commit needs the new principal's images on every rank)
-__global__ void k_evb_snapshots(Dev d, EvbDev e, int only_state) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  int S = *e.n_states;
+#define SNAP_WPB 4
+__global__ void __launch_bounds__(32 * SNAP_WPB) k_evb_snapshots(Dev d, EvbDev e, int only_state) {
+  static_assert(CM * MA == 32, "one lane per (chain molecule, atom)");
+  __shared__ Snapshot Wsh[SNAP_WPB];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int s = blockIdx.x * SNAP_WPB + w;
+  const int S = *e.n_states;
   if (only_state >= 0) { if (s != 0) return; s = only_state; }
   else if (s >= S || !(s == 0 || state_owned(s, d.rank, d.world))) return;
-  Snapshot W;
+  Snapshot& W = Wsh[w];
   const int* L = &e.proton_log[s * MAXC * 5];
-  int nh = e.n_hops[s];
-  int m0 = *d.hydronium;
-  W.n_mol = 1;
-  load_principal_image(d, m0, W.m[0]);
-  for (int h = 0; h < nh; h++) {
-    int a = L[h * 5 + 3];
-    bool found = false;
-    for (int k = 0; k < W.n_mol; k++) found |= (W.m[k].mol == a);
-    if (!found) { load_principal_image(d, a, W.m[W.n_mol]); W.n_mol++; }
+  const int nh = e.n_hops[s];
+  if (lane == 0) {
+    int nm = 1;
+    W.m[0].mol = *d.hydronium;
+    for (int h = 0; h < nh; h++) {
+      int a = L[h * 5 + 3];
+      bool found = false;
+      for (int k = 0; k < nm; k++) found |= (W.m[k].mol == a);
+      if (!found) W.m[nm++].mol = a;
+    }
+    for (int k = nm; k < CM; k++) { W.m[k].mol = -1; W.m[k].n_atom = 0; W.m[k].mtype = 0; }
+    W.n_mol = nm; W.hydronium = 0;
   }
-  for (int k = W.n_mol; k < CM; k++) { W.m[k].mol = -1; W.m[k].n_atom = 0; W.m[k].mtype = 0; }
-  W.hydronium = 0;
-  e.snap[s * NLEV + 0] = W;
+  __syncwarp();
+  {
+    const int k = lane / MA, a = lane % MA;
+    if (k < W.n_mol) {
+      MolImage& im = W.m[k];
+      const int mol = im.mol, f = d.mol_first[mol], n = d.mol_natom[mol];
+      if (a == 0) { im.n_atom = n; im.mtype = d.mol_type[mol]; for (int c = 0; c < 3; c++) im.r_com[c] = d.r_com[3 * mol + c]; }
+      if (a < n) {
+        double4 p = d.xq[f + a];
+        im.atom[a] = f + a; im.type[a] = d.type[f + a]; im.q[a] = p.w; im.mass[a] = d.mass[f + a];
+        im.x[a][0] = p.x; im.x[a][1] = p.y; im.x[a][2] = p.z;
+      }
+    }
+  }
+  __syncwarp();
+  warp_copy_struct(&e.snap[s * NLEV + 0], &W, lane);
   int cur = 0;  // slot of the current hydronium (= donor of the next hop)
   for (int h = 0; h < nh; h++) {
-    int a = L[h * 5 + 3], as = 0;
+    __syncwarp();
+    int as = 0;
+    const int a = L[h * 5 + 3];
     for (int k = 0; k < W.n_mol; k++) if (W.m[k].mol == a) as = k;
-    image_proton_transfer(d, W.m[cur], W.m[as], L[h * 5 + 1], L[h * 5 + 4]);
-    W.hydronium = as;
+    if (lane == 0) {
+      image_proton_transfer(d, W.m[cur], W.m[as], L[h * 5 + 1], L[h * 5 + 4]);
+      W.hydronium = as;
+    }
     cur = as;
-    e.snap[s * NLEV + h + 1] = W;
+    __syncwarp();
+    warp_copy_struct(&e.snap[s * NLEV + h + 1], &W, lane);
   }
 }
 
@@ -269,35 +391,41 @@ struct ItemShared {
   int pa_row[MA][RPB_MAXT];             // Born-Mayer row per (hydronium atom, solvent atom type)
 };
 
-__device__ void fill_item_shared(const Dev& d, const Snapshot& S, const EvbItem& it, ItemShared& sh) {
-  // executed by thread 0
-  sh.n_chain = 0;
-  for (int k = 0; k < S.n_mol; k++)
-    for (int a = 0; a < S.m[k].n_atom; a++) sh.chain_atoms[sh.n_chain++] = S.m[k].atom[a];
-  sh.nd = sh.na = 0;
-  if (it.donor_slot >= 0) {
-    const MolImage& D = S.m[it.donor_slot];
-    sh.nd = D.n_atom;
-    for (int a = 0; a < D.n_atom; a++) { sh.d_atom[a] = D.atom[a]; sh.d_type[a] = D.type[a]; sh.d_q[a] = D.q[a]; for (int k = 0; k < 3; k++) sh.d_x[a][k] = D.x[a][k]; }
-  }
-  if (it.acceptor_slot >= 0) {
-    const MolImage& A = S.m[it.acceptor_slot];
-    sh.na = A.n_atom;
-    for (int a = 0; a < A.n_atom; a++) { sh.a_atom[a] = A.atom[a]; sh.a_type[a] = A.type[a]; sh.a_q[a] = A.q[a]; for (int k = 0; k < 3; k++) sh.a_x[a][k] = A.x[a][k]; }
-  }
+// executed by the whole CTA (tid 0 copies the images, threads t < RPB_MAXT resolve the parameter rows); caller syncs
+__device__ void fill_item_shared(const Dev& d, const Snapshot& S, const EvbItem& it, ItemShared& sh, int tid) {
   const MolImage& H = S.m[S.hydronium];
   const EvbTables& E = *d.evb;
-  sh.nh = H.n_atom;
-  for (int a = 0; a < H.n_atom; a++) { sh.h_atom[a] = H.atom[a]; sh.h_type[a] = H.type[a]; for (int k = 0; k < 3; k++) sh.h_x[a][k] = H.x[a][k]; }
-  sh.h_heavy = d.mt[H.mtype].heavy_acid_atom;
-  if (sh.h_heavy < 0) { atomicMax(&d.err_flag[3], 3); sh.h_heavy = 0; }
-  sh.h_type_H = H.type[H.n_atom - 1];
-  sh.h_type_heavy = H.type[sh.h_heavy];
-  for (int t = 0; t < RPB_MAXT; t++) {
+  if (tid == 0) {
+    sh.n_chain = 0;
+    for (int k = 0; k < S.n_mol; k++)
+      for (int a = 0; a < S.m[k].n_atom; a++) sh.chain_atoms[sh.n_chain++] = S.m[k].atom[a];
+    sh.nd = sh.na = 0;
+    if (it.donor_slot >= 0) {
+      const MolImage& D = S.m[it.donor_slot];
+      sh.nd = D.n_atom;
+      for (int a = 0; a < D.n_atom; a++) { sh.d_atom[a] = D.atom[a]; sh.d_type[a] = D.type[a]; sh.d_q[a] = D.q[a]; for (int k = 0; k < 3; k++) sh.d_x[a][k] = D.x[a][k]; }
+    }
+    if (it.acceptor_slot >= 0) {
+      const MolImage& A = S.m[it.acceptor_slot];
+      sh.na = A.n_atom;
+      for (int a = 0; a < A.n_atom; a++) { sh.a_atom[a] = A.atom[a]; sh.a_type[a] = A.type[a]; sh.a_q[a] = A.q[a]; for (int k = 0; k < 3; k++) sh.a_x[a][k] = A.x[a][k]; }
+    }
+    sh.nh = H.n_atom;
+    for (int a = 0; a < H.n_atom; a++) { sh.h_atom[a] = H.atom[a]; sh.h_type[a] = H.type[a]; for (int k = 0; k < 3; k++) sh.h_x[a][k] = H.x[a][k]; }
+    sh.h_heavy = d.mt[H.mtype].heavy_acid_atom;
+    if (sh.h_heavy < 0) { atomicMax(&d.err_flag[3], 3); sh.h_heavy = 0; }
+    sh.h_type_H = H.type[H.n_atom - 1];
+    sh.h_type_heavy = H.type[sh.h_heavy];
+  }
+  if (tid >= 32 && tid < 32 + RPB_MAXT) {
+    const int t = tid - 32;
+    int hv = d.mt[H.mtype].heavy_acid_atom;
+    if (hv < 0) hv = 0;
+    const int tH = H.type[H.n_atom - 1], tO = H.type[hv];
     int row = -1;
     for (int i = 0; i < RPB_MAXI; i++) {            // get_index_atom_set general_routines.f90:613-637
       if (E.da_int[i][0] < 0) break;
-      if (E.da_int[i][0] == t && E.da_int[i][1] == sh.h_type_heavy && E.da_int[i][2] == sh.h_type_H) { row = i; break; }
+      if (E.da_int[i][0] == t && E.da_int[i][1] == tO && E.da_int[i][2] == tH) { row = i; break; }
     }
     sh.da_row[t] = row;
     for (int a = 0; a < H.n_atom; a++) {
@@ -400,166 +528,232 @@ __device__ inline double repulsion_with_atom(const Dev& d, const ItemShared& sh,
 }
 
 #define ITEM_TPB 256
-// grid = (n_items, ceil(N/ITEM_TPB)): image atoms of one item against the background (non-chain) atoms
-__global__ void __launch_bounds__(ITEM_TPB) k_evb_items_background(Dev d, EvbDev e, int n_items) {
-  __shared__ ItemShared sh;
-  __shared__ double red[32];
-  __shared__ double facc[ITEM_TPB / 32][3 * MA][3];   // per-warp force accumulators: donor | acceptor | hydronium
-  const int item_id = e.real_list[blockIdx.x];
-  const EvbItem it = e.items[item_id];
-  const Snapshot& S = e.snap[it.state * NLEV + it.level];
-  if (threadIdx.x == 0) fill_item_shared(d, S, it, sh);
-  for (int k = threadIdx.x; k < (ITEM_TPB / 32) * 3 * MA * 3; k += blockDim.x) (&facc[0][0][0])[k] = 0.0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  double* outF = (it.state == 0) ? d.force : e.dF + (size_t)it.state * 3 * d.N;
-  const double sign = it.sign;
-  int j = blockIdx.y * blockDim.x + threadIdx.x;
-  bool active = j < d.N;
-  double xj[3] = {0, 0, 0}, qj = 0.0;
-  int tj = 0;
-  if (active) {
-    for (int k = 0; k < sh.n_chain; k++) active &= (sh.chain_atoms[k] != j);
+#define CAND_CAP 2048        // atoms inside the candidate radius of one chain atom (~420 at 10 A in water)
+#define CAND_SLOTS 1024      // distinct chain atoms over all diabats of a step
+
+// ---- candidate lists: for every distinct chain atom g (principal index; the host lists them from the hop log)
+// the atoms j whose minimum-image distance from g is below the candidate radius (real-space cutoff + margin, or the
+// EVB repulsion reach if that is larger), from the CURRENT positions -- so the set is exact, unlike a Verlet row
+// between rebuilds (the reference scans all N atoms per image atom, ms_evb.f90:1629-1841).  The item kernel applies
+// the reference's own cutoff test to the image position; this pass only removes the ~95 % of atoms that are far away,
+// once per chain atom instead of once per (diabat, topology, image atom).
+// grid = (ceil(N/256), n_unique)
+__global__ void __launch_bounds__(256) k_evb_candidates(Dev d, const int* __restrict__ uniq_atom, double r2cand,
+                                                        int* __restrict__ chain_slot, int* __restrict__ cand, int* __restrict__ cand_n) {
+  const int slot = blockIdx.y, g = uniq_atom[slot];
+  const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) chain_slot[g] = slot;
+  const double4 pg = d.xq[g];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  bool hit = false;
+  if (j < d.N && j != g) {
+    double4 pj = d.xq[j];
+    double dx = min_image(pg.x - pj.x, d.box[0]), dy = min_image(pg.y - pj.y, d.box[1]), dz = min_image(pg.z - pj.z, d.box[2]);
+    hit = dx * dx + dy * dy + dz * dz < r2cand;
   }
-  if (active) { double4 p = d.xq[j]; xj[0] = p.x; xj[1] = p.y; xj[2] = p.z; qj = p.w; tj = d.type[j]; }
-  double en = 0.0, fj[3] = {0, 0, 0};
-  // ---- real-space pairs (ms_evb.f90:1629-1841)
-  for (int side = 0; side < 2; side++) {
-    int n = side == 0 ? sh.nd : sh.na;
-    for (int a = 0; a < n; a++) {
-      const double* xi = side == 0 ? sh.d_x[a] : sh.a_x[a];
-      double f[3] = {0, 0, 0};
-      bool hit = false;
-      if (active) {
-        double dr[3] = {min_image(xi[0] - xj[0], d.box[0]), min_image(xi[1] - xj[1], d.box[1]), min_image(xi[2] - xj[2], d.box[2])};
-        double dr2 = dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2];
-        if (dr2 < d.rc2) {
-          int ti = side == 0 ? sh.d_type[a] : sh.a_type[a];
-          double qi = side == 0 ? sh.d_q[a] : sh.a_q[a];
-          int pidx = ti * d.nT + tj;
-          double ee, ev;
-          pair_terms(d, dr, dr2, qi * qj, d.vdw_type[pidx], &d.vdw_param[6 * pidx], true, ee, ev, f);
-          en += ee + ev;
-          fj[0] -= f[0]; fj[1] -= f[1]; fj[2] -= f[2];
-          hit = true;
-        }
-      }
-      if (__any_sync(0xffffffffu, hit)) {
-        double s0 = warp_sum(f[0]), s1 = warp_sum(f[1]), s2 = warp_sum(f[2]);
-        if (lane == 0) { double* t = facc[w][side * MA + a]; t[0] += s0; t[1] += s1; t[2] += s2; }
-      }
-    }
-  }
-  // ---- EVB repulsion of the hydronium image (ms_evb.f90:2259-2478)
-  {
-    double fh[MA][3];
-    for (int a = 0; a < MA; a++) fh[a][0] = fh[a][1] = fh[a][2] = 0.0;
-    bool hit = false;
-    if (active && (sh.da_row[tj] >= 0 || true)) {
-      double e0 = repulsion_with_atom(d, sh, xj, tj, fh, fj);
-      hit = (e0 != 0.0);
-      for (int a = 0; a < sh.nh && !hit; a++) hit |= (fh[a][0] != 0.0 || fh[a][1] != 0.0 || fh[a][2] != 0.0);
-      en += e0;
-    }
-    if (__any_sync(0xffffffffu, hit)) {
-      for (int a = 0; a < sh.nh; a++) {
-        double s0 = warp_sum(fh[a][0]), s1 = warp_sum(fh[a][1]), s2 = warp_sum(fh[a][2]);
-        if (lane == 0) { double* t = facc[w][2 * MA + a]; t[0] += s0; t[1] += s1; t[2] += s2; }
-      }
-    }
-  }
-  if (active && (fj[0] != 0.0 || fj[1] != 0.0 || fj[2] != 0.0)) {
-    atomicAdd(&outF[3 * j], sign * fj[0]); atomicAdd(&outF[3 * j + 1], sign * fj[1]); atomicAdd(&outF[3 * j + 2], sign * fj[2]);
-  }
-  en = block_sum(en, red);
-  if (threadIdx.x == 0 && en != 0.0) atomicAdd(&e.item_energy[item_id], en);
-  __syncthreads();
-  // fold the per-warp accumulators and push the image-atom forces out
-  for (int k = threadIdx.x; k < 3 * MA * 3; k += blockDim.x) {
-    int grp = k / (MA * 3), a = (k / 3) % MA, c = k % 3;
-    int n = grp == 0 ? sh.nd : (grp == 1 ? sh.na : sh.nh);
-    if (a >= n) continue;
-    double s = 0.0;
-    for (int ww = 0; ww < ITEM_TPB / 32; ww++) s += facc[ww][grp * MA + a][c];
-    if (s != 0.0) {
-      int atom = grp == 0 ? sh.d_atom[a] : (grp == 1 ? sh.a_atom[a] : sh.h_atom[a]);
-      atomicAdd(&outF[3 * atom + c], sign * s);
+  unsigned m = __ballot_sync(0xffffffffu, hit);
+  if (m) {
+    int leader = __ffs(m) - 1, base = 0;
+    if (lane == leader) base = atomicAdd(&cand_n[slot], __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (hit) {
+      int p = base + __popc(m & ((1u << lane) - 1u));
+      if (p < CAND_CAP) cand[(size_t)slot * CAND_CAP + p] = j;
     }
   }
 }
 
-// one thread per item: everything that involves only chain atoms (intramolecular terms of donor and acceptor,
-// pairs among the chain molecules, repulsion with chain atoms, reference energy)
-__global__ void k_evb_items_chain(Dev d, EvbDev e, int n_items) {
-  int ir = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ir >= n_items) return;
-  const int ii = e.real_list[ir];
-  const EvbItem it = e.items[ii];
+#define ITEM_SPLIT 4          // CTAs per item (the candidate chunks of an item are dealt round-robin to 4 x 8 warps)
+struct ItemBlock {
+  ItemShared sh;
+  int d_ci[MA], a_ci[MA], h_ci[MA];       // position of every image atom in sh.chain_atoms
+  int task_first[2 * MA + 1];             // prefix sum of 32-candidate chunks per image atom
+  double fl[CM * MA][3];                  // force accumulators of the chain atoms (shared-memory atomics)
+  double red[32];
+};
+
+// ITEM_SPLIT CTAs per (diabat, last hop, topology) item.
+//   every warp of every CTA : (image atom, 32-candidate chunk) tasks -- real-space pairs of the donor/acceptor image atoms
+//                             with the background atoms (ms_evb.f90:1629-1841); the chunks of the hydronium's heavy atom
+//                             also carry the EVB repulsion (ms_evb.f90:2259-2478)
+//   CTA 0 only, thread 0/32 : bonded + intramolecular terms of donor / acceptor   (ms_evb.f90:1472, 1849-1855)
+//   CTA 0 only, threads 64+ : pairs among the chain molecules                      (ms_evb.f90:1629-1841 restricted to chain atoms)
+//   CTA 0 only, warp 7      : repulsion of the hydronium image with chain atoms    (ms_evb.f90:2259-2478)
+__global__ void __launch_bounds__(ITEM_TPB) k_evb_items(Dev d, EvbDev e, const int* __restrict__ chain_slot,
+                                                        const int* __restrict__ cand, const int* __restrict__ cand_n,
+                                                        double rcand, double rep_reach) {
+  __shared__ ItemBlock B;
+  ItemShared& sh = B.sh;
+  const int item_id = e.real_list[blockIdx.x];
+  const EvbItem it = e.items[item_id];
   const Snapshot& S = e.snap[it.state * NLEV + it.level];
   const EvbTables& E = *d.evb;
-  double* outF = (it.state == 0) ? d.force : e.dF + (size_t)it.state * 3 * d.N;
-  double en = 0.0;
-  double fl[CM][MA][3];
-  for (int k = 0; k < CM; k++) for (int a = 0; a < MA; a++) fl[k][a][0] = fl[k][a][1] = fl[k][a][2] = 0.0;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int part = blockIdx.y, nparts = gridDim.y;
+  fill_item_shared(d, S, it, sh, tid);
+  for (int k = tid; k < CM * MA * 3; k += blockDim.x) (&B.fl[0][0])[k] = 0.0;
+  __syncthreads();
   const int ds = it.donor_slot, as = it.acceptor_slot;
-  if (ds >= 0) {
-    // reference energy of the acid of this topology (ms_evb.f90:1478,1520)
-    en += (it.sign < 0) ? E.ref_energy[S.m[ds].mtype] : E.ref_energy[S.m[as].mtype];
-    // intramolecular bonded + non-bonded of donor and acceptor (:1472, 1849-1855)
-    for (int w = 0; w < 2; w++) {
-      int sl = w == 0 ? ds : as;
-      const MolImage& I = S.m[sl];
-      MolEnergies ME;
-      molecule_terms(d, d.mt[I.mtype], I.n_atom, I.x, I.type, I.q, fl[sl], ME, true, true);
-      en += ME.e_bond + ME.e_angle + ME.e_dih + ME.e_elec + ME.e_vdw;
-    }
-    // pairs: donor atoms vs all other chain molecules; acceptor atoms vs chain molecules other than donor, acceptor
-    for (int w = 0; w < 2; w++) {
-      int sl = w == 0 ? ds : as;
-      const MolImage& I = S.m[sl];
-      for (int k = 0; k < S.n_mol; k++) {
-        if (k == ds || (w == 1 && k == as)) continue;
-        const MolImage& J = S.m[k];
-        for (int a = 0; a < I.n_atom; a++)
-          for (int b = 0; b < J.n_atom; b++) {
-            double dr[3] = {min_image(I.x[a][0] - J.x[b][0], d.box[0]), min_image(I.x[a][1] - J.x[b][1], d.box[1]),
-                            min_image(I.x[a][2] - J.x[b][2], d.box[2])};
-            double dr2 = dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2];
-            if (dr2 < d.rc2) {
-              int pidx = I.type[a] * d.nT + J.type[b];
-              double ee, ev, f[3];
-              pair_terms(d, dr, dr2, I.q[a] * J.q[b], d.vdw_type[pidx], &d.vdw_param[6 * pidx], true, ee, ev, f);
-              en += ee + ev;
-              for (int c = 0; c < 3; c++) { fl[sl][a][c] += f[c]; fl[k][b][c] -= f[c]; }
-            }
-          }
+  const bool hyd_is_donor = (ds >= 0 && S.hydronium == ds);
+  // image list: donor atoms, acceptor atoms (principal item: the hydronium atoms, repulsion only)
+  const int n_img = (ds >= 0) ? sh.nd + sh.na : sh.nh;
+  if (tid < 3 * MA) {   // position of every image atom in sh.chain_atoms
+    int grp = tid / MA, a = tid % MA;
+    int n = grp == 0 ? sh.nd : (grp == 1 ? sh.na : sh.nh);
+    if (a < n) {
+      int g = grp == 0 ? sh.d_atom[a] : (grp == 1 ? sh.a_atom[a] : sh.h_atom[a]), ci = 0;
+      for (int k = 0; k < sh.n_chain; k++) if (sh.chain_atoms[k] == g) ci = k;
+      (grp == 0 ? B.d_ci : (grp == 1 ? B.a_ci : B.h_ci))[a] = ci;
+      if (grp == 2) {   // the heavy atom's candidate list must cover the reach of the repulsion terms of every hydronium atom
+        const double* xo = sh.h_x[sh.h_heavy];
+        double dx = sh.h_x[a][0] - xo[0], dy = sh.h_x[a][1] - xo[1], dz = sh.h_x[a][2] - xo[2];
+        if (sqrt(dx * dx + dy * dy + dz * dz) + rep_reach > rcand) atomicMax(&d.err_flag[3], 8);
       }
     }
-  } else {
+  }
+  if (tid == 32) {
+    int acc = 0;
+    for (int ia = 0; ia < n_img; ia++) {
+      B.task_first[ia] = acc;
+      int g = (ds >= 0) ? (ia < sh.nd ? sh.d_atom[ia] : sh.a_atom[ia - sh.nd]) : sh.h_atom[ia];
+      if (ds < 0 && ia != sh.h_heavy) continue;       // principal item: only the EVB repulsion, centred on the heavy atom
+      int nc = cand_n[chain_slot[g]];
+      if (nc > CAND_CAP) { atomicMax(&d.err_flag[3], 7); nc = CAND_CAP; }
+      acc += (nc + 31) >> 5;
+    }
+    B.task_first[n_img] = acc;
+  }
+  __syncthreads();
+  double* outF = (it.state == 0) ? d.force : e.dF + (size_t)it.state * 3 * d.N;
+  const double sign = it.sign;
+  double en = 0.0;
+
+  // ---------------- image atoms x candidate atoms ----------------
+  const int n_tasks = B.task_first[n_img];
+  for (int t = part * (ITEM_TPB / 32) + w; t < n_tasks; t += nparts * (ITEM_TPB / 32)) {
+    int ia = 0;
+    while (t >= B.task_first[ia + 1]) ia++;
+    int side, a;
+    if (ds >= 0) { side = ia < sh.nd ? 0 : 1; a = side == 0 ? ia : ia - sh.nd; } else { side = 2; a = ia; }
+    const double* xi = side == 0 ? sh.d_x[a] : (side == 1 ? sh.a_x[a] : sh.h_x[a]);
+    const int g = side == 0 ? sh.d_atom[a] : (side == 1 ? sh.a_atom[a] : sh.h_atom[a]);
+    const int ti = side == 0 ? sh.d_type[a] : (side == 1 ? sh.a_type[a] : sh.h_type[a]);
+    const double qi = side == 0 ? sh.d_q[a] : (side == 1 ? sh.a_q[a] : 0.0);
+    const int ci = side == 0 ? B.d_ci[a] : (side == 1 ? B.a_ci[a] : B.h_ci[a]);
+    // is this image atom the heavy atom of the hydronium image?
+    const bool in_hyd = (side == 2) || (side == 0 && hyd_is_donor) || (side == 1 && !hyd_is_donor);
+    const bool heavy = in_hyd && (a == sh.h_heavy);
+    const int slot = chain_slot[g];
+    const int nc = min(cand_n[slot], CAND_CAP);
+    const int c = (t - B.task_first[ia]) * 32 + lane;
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    double fh[MA][3];
+    if (heavy) for (int q = 0; q < MA; q++) fh[q][0] = fh[q][1] = fh[q][2] = 0.0;
+    bool live = c < nc;
+    int j = 0;
+    if (live) {
+      j = cand[(size_t)slot * CAND_CAP + c];
+      for (int k = 0; k < sh.n_chain; k++) live &= (sh.chain_atoms[k] != j);
+    }
+    if (live) {
+      double4 pj = d.xq[j];
+      int tj = d.type[j];
+      double xj[3] = {pj.x, pj.y, pj.z};
+      double fj[3] = {0.0, 0.0, 0.0};
+      if (side != 2) {
+        double dr[3] = {min_image(xi[0] - xj[0], d.box[0]), min_image(xi[1] - xj[1], d.box[1]), min_image(xi[2] - xj[2], d.box[2])};
+        double dr2 = dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2];
+        if (dr2 < d.rc2) {
+          int pidx = ti * d.nT + tj;
+          double ee, ev, f[3];
+          pair_terms(d, dr, dr2, qi * pj.w, d.vdw_type[pidx], &d.vdw_param[6 * pidx], true, ee, ev, f);
+          en += ee + ev;
+          fx += f[0]; fy += f[1]; fz += f[2];
+          fj[0] -= f[0]; fj[1] -= f[1]; fj[2] -= f[2];
+        }
+      }
+      if (heavy) en += repulsion_with_atom(d, sh, xj, tj, fh, fj);
+      if (fj[0] != 0.0 || fj[1] != 0.0 || fj[2] != 0.0) {
+        atomicAdd(&outF[3 * j], sign * fj[0]); atomicAdd(&outF[3 * j + 1], sign * fj[1]); atomicAdd(&outF[3 * j + 2], sign * fj[2]);
+      }
+    }
+    fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
+    if (lane == 0) { atomicAdd(&B.fl[ci][0], fx); atomicAdd(&B.fl[ci][1], fy); atomicAdd(&B.fl[ci][2], fz); }
+    if (heavy) {
+      for (int q = 0; q < sh.nh; q++) {
+        double s0 = warp_sum(fh[q][0]), s1 = warp_sum(fh[q][1]), s2 = warp_sum(fh[q][2]);
+        if (lane == 0) { int cq = B.h_ci[q]; atomicAdd(&B.fl[cq][0], s0); atomicAdd(&B.fl[cq][1], s1); atomicAdd(&B.fl[cq][2], s2); }
+      }
+    }
+  }
+
+  // ---------------- chain-internal terms (first CTA of the item) ----------------
+  if (part != 0) {
+    // nothing
+  } else if (ds >= 0) {
+    if (tid == 0) en += (sign < 0) ? E.ref_energy[S.m[ds].mtype] : E.ref_energy[S.m[as].mtype];   // ms_evb.f90:1478,1520
+    if (tid == 0 || tid == 32) {
+      int sl = tid == 0 ? ds : as;
+      const MolImage& I = S.m[sl];
+      const int* cidx = tid == 0 ? B.d_ci : B.a_ci;
+      double f[MA][3];
+      for (int q = 0; q < MA; q++) f[q][0] = f[q][1] = f[q][2] = 0.0;
+      MolEnergies ME;
+      molecule_terms(d, d.mt[I.mtype], I.n_atom, I.x, I.type, I.q, f, ME, true, true);
+      en += ME.e_bond + ME.e_angle + ME.e_dih + ME.e_elec + ME.e_vdw;
+      for (int q = 0; q < I.n_atom; q++) for (int c = 0; c < 3; c++) atomicAdd(&B.fl[cidx[q]][c], f[q][c]);
+    }
+    if (tid >= 64) {
+      // donor atoms vs every other chain molecule; acceptor atoms vs chain molecules other than donor and acceptor
+      const int per = CM * MA * MA;
+      for (int t = tid - 64; t < 2 * per; t += ITEM_TPB - 64) {
+        int wv = t / per, r = t % per, k = r / (MA * MA), a = (r / MA) % MA, b2 = r % MA;
+        int sl = wv == 0 ? ds : as;
+        if (k >= S.n_mol || k == ds || (wv == 1 && k == as)) continue;
+        const MolImage& I = S.m[sl];
+        const MolImage& J = S.m[k];
+        if (a >= I.n_atom || b2 >= J.n_atom) continue;
+        double dr[3] = {min_image(I.x[a][0] - J.x[b2][0], d.box[0]), min_image(I.x[a][1] - J.x[b2][1], d.box[1]),
+                        min_image(I.x[a][2] - J.x[b2][2], d.box[2])};
+        double dr2 = dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2];
+        if (dr2 < d.rc2) {
+          int pidx = I.type[a] * d.nT + J.type[b2];
+          double ee, ev, f[3];
+          pair_terms(d, dr, dr2, I.q[a] * J.q[b2], d.vdw_type[pidx], &d.vdw_param[6 * pidx], true, ee, ev, f);
+          en += ee + ev;
+          int c1 = (wv == 0 ? B.d_ci : B.a_ci)[a], c2 = 0;
+          for (int q = 0; q < sh.n_chain; q++) if (sh.chain_atoms[q] == J.atom[b2]) c2 = q;
+          for (int c = 0; c < 3; c++) { atomicAdd(&B.fl[c1][c], f[c]); atomicAdd(&B.fl[c2][c], -f[c]); }
+        }
+      }
+    }
+  } else if (tid == 0) {
     en += E.ref_energy[S.m[S.hydronium].mtype];   // principal diabat: E_reference (ms_evb.f90:424)
   }
-  // repulsion of the hydronium image with the other chain molecules' atoms
-  {
-    // build the small lookup locally (same code path as the background kernel, without shared memory)
-    static_assert(sizeof(ItemShared) < 8192, "ItemShared too large for local use");
-    ItemShared L;
-    fill_item_shared(d, S, it, L);
+  if (part == 0 && w == 7) {
+    // repulsion of the hydronium image with the atoms of the other chain molecules
     int hs = S.hydronium;
-    for (int k = 0; k < S.n_mol; k++) {
-      if (k == hs) continue;
+    for (int t = lane; t < S.n_mol * MA; t += 32) {
+      int k = t / MA, b2 = t % MA;
+      if (k == hs || b2 >= S.m[k].n_atom) continue;
       const MolImage& J = S.m[k];
-      for (int b = 0; b < J.n_atom; b++) {
-        double fj[3] = {0, 0, 0};
-        en += repulsion_with_atom(d, L, J.x[b], J.type[b], fl[hs], fj);
-        for (int c = 0; c < 3; c++) fl[k][b][c] += fj[c];
-      }
+      double fh[MA][3], fj[3] = {0.0, 0.0, 0.0};
+      for (int q = 0; q < MA; q++) fh[q][0] = fh[q][1] = fh[q][2] = 0.0;
+      en += repulsion_with_atom(d, sh, J.x[b2], J.type[b2], fh, fj);
+      int c2 = 0;
+      for (int q = 0; q < sh.n_chain; q++) if (sh.chain_atoms[q] == J.atom[b2]) c2 = q;
+      for (int c = 0; c < 3; c++) if (fj[c] != 0.0) atomicAdd(&B.fl[c2][c], fj[c]);
+      for (int q = 0; q < sh.nh; q++) for (int c = 0; c < 3; c++) if (fh[q][c] != 0.0) atomicAdd(&B.fl[B.h_ci[q]][c], fh[q][c]);
     }
   }
-  atomicAdd(&e.item_energy[ii], en);
-  for (int k = 0; k < S.n_mol; k++)
-    for (int a = 0; a < S.m[k].n_atom; a++)
-      for (int c = 0; c < 3; c++)
-        if (fl[k][a][c] != 0.0) atomicAdd(&outF[3 * S.m[k].atom[a] + c], it.sign * fl[k][a][c]);
+  en = block_sum(en, B.red);
+  if (tid == 0 && en != 0.0) atomicAdd(&e.item_energy[item_id], en);
+  __syncthreads();
+  for (int t = tid; t < sh.n_chain * 3; t += blockDim.x) {
+    int k = t / 3, c = t % 3;
+    double v = B.fl[k][c];
+    if (v != 0.0) atomicAdd(&outF[3 * sh.chain_atoms[k] + c], sign * v);
+  }
 }
 
 // ================================================================================================
@@ -656,91 +850,113 @@ __device__ void coupling_function(double& A, double& Vc, double dA[3][3], int ft
   }
 }
 
-// one thread per owned diabat s>=1: geometric factor, Zundel sites, and the Vex terms of the OTHER chain molecules
-__global__ void k_evb_coupling_geo(Dev d, EvbDev e, CouplingGeo* geo) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  int S = *e.n_states;
+// one warp per owned diabat s>=1: geometric factor and Zundel sites (lane 0, on a shared-memory copy of the final-level
+// snapshot), then the Vex terms of the OTHER chain molecules with (atom, site) pairs dealt to the lanes
+#define GEO_WPB 4
+__global__ void __launch_bounds__(32 * GEO_WPB) k_evb_coupling_geo(Dev d, EvbDev e, CouplingGeo* geo) {
+  __shared__ Snapshot Ssh[GEO_WPB];
+  __shared__ CouplingGeo Gsh[GEO_WPB];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * GEO_WPB + w;
+  const int S = *e.n_states;
   if (s >= S) return;
-  CouplingGeo& G = geo[s];
-  G.valid = 0;
-  if (s == 0 || !state_owned(s, d.rank, d.world)) return;
+  if (s == 0 || !state_owned(s, d.rank, d.world)) { if (lane == 0) geo[s].valid = 0; return; }
   const EvbTables& E = *d.evb;
-  int nh = e.n_hops[s];
-  const Snapshot& Sn = e.snap[s * NLEV + nh];
-  const Snapshot& Sp = e.snap[s * NLEV + nh - 1];
-  int as = Sn.hydronium, ds = Sp.hydronium;    // last acceptor / last donor
+  const int nh = e.n_hops[s];
+  Snapshot& Sn = Ssh[w];
+  CouplingGeo& G = Gsh[w];
+  warp_copy_struct(&Sn, &e.snap[s * NLEV + nh], lane);
+  const int ds = e.snap[s * NLEV + nh - 1].hydronium;    // last donor
+  __syncwarp();
+  const int as = Sn.hydronium;                            // last acceptor
   const MolImage& D = Sn.m[ds];
   const MolImage& A = Sn.m[as];
-  int iOd = d.mt[D.mtype].heavy_base_atom, iOa = d.mt[A.mtype].heavy_acid_atom, iH = A.n_atom - 1;
-  if (iOd < 0 || iOa < 0) { atomicMax(&d.err_flag[3], 4); return; }
-  // ---- geometric factor (ms_evb.f90:1117-1174)
-  double rO1[3], rO2[3], rH[3], shift[3], rOO[3], q[3];
-  for (int k = 0; k < 3; k++) {
-    rO1[k] = D.x[iOd][k];
-    double dr = A.x[iOa][k] - rO1[k];
-    shift[k] = floor(d.inv_box[k] * dr + 0.5) * d.box[k];
-    rO2[k] = rO1[k] + (A.x[iOa][k] - rO1[k] - shift[k]);
-    rH[k] = rO1[k] + (A.x[iH][k] - rO1[k] - shift[k]);
-    rOO[k] = rO1[k] - rO2[k];
-    q[k] = (rO1[k] + rO2[k]) / 2.0 - rH[k];
-  }
-  int row = -1;
-  for (int i = 0; i < RPB_MAXI; i++) {
-    if (E.dc_int[i][0] < 0) break;
-    if (E.dc_int[i][0] == D.type[iOd] && E.dc_int[i][1] == A.type[iOa] && E.dc_int[i][2] == A.type[iH]) { row = i; break; }
-  }
-  if (row < 0) { atomicMax(&d.err_flag[3], 5); return; }
-  coupling_function(G.A, G.Vconst, G.dA, E.dc_type[row], E.dc_par[row], q, rOO);
-  G.atom_Od = D.atom[iOd]; G.atom_Oa = A.atom[iOa]; G.atom_H = A.atom[iH];
-  // ---- Zundel centre of mass and exchange-charge sites (ms_evb.f90:2946-2982, 1340-1392)
-  double tmd = 0, tma = 0;
-  for (int a = 0; a < D.n_atom; a++) tmd = tmd + D.mass[a];
-  for (int a = 0; a < A.n_atom; a++) tma = tma + A.mass[a];
-  double shifta[3];
-  for (int k = 0; k < 3; k++) {
-    double dr = A.r_com[k] - D.r_com[k];
-    shifta[k] = floor(d.inv_box[k] * dr + 0.5) * d.box[k];
-    double rca = D.r_com[k] + (A.r_com[k] - D.r_com[k] - shifta[k]);
-    G.rz[k] = (tmd * D.r_com[k] + tma * rca) / (tmd + tma);
-  }
-  double qx = E.exch_proton[A.mtype][D.mtype];
-  G.n_site = 0;
-  for (int a = 0; a < D.n_atom; a++) {
-    int n = G.n_site++;
-    G.site_atom[n] = D.atom[a]; G.site_q[n] = E.exch_atomic[D.type[a]];
-    for (int k = 0; k < 3; k++) { double dr = D.x[a][k] - G.rz[k] - 0.0; G.site_x[n][k] = G.rz[k] + dr; }
-  }
-  for (int a = 0; a < A.n_atom; a++) {
-    int n = G.n_site++;
-    G.site_atom[n] = A.atom[a]; G.site_q[n] = (a == A.n_atom - 1) ? qx : E.exch_atomic[A.type[a]];
-    for (int k = 0; k < 3; k++) { double dr = A.x[a][k] - G.rz[k] - shifta[k]; G.site_x[n][k] = G.rz[k] + dr; }
-  }
-  G.n_chain = 0;
-  for (int k = 0; k < Sn.n_mol; k++) for (int a = 0; a < Sn.m[k].n_atom; a++) G.chain_atoms[G.n_chain++] = Sn.m[k].atom[a];
-  // ---- Vex with the other chain molecules (final-level charges, positions, centres of mass)
-  double vex = 0.0;
-  double* Fo = e.Foff + (size_t)s * 3 * d.N;
-  for (int km = 0; km < Sn.n_mol; km++) {
-    if (km == ds || km == as) continue;
-    const MolImage& J = Sn.m[km];
-    double sh[3];
-    for (int k = 0; k < 3; k++) sh[k] = floor(d.inv_box[k] * (J.r_com[k] - G.rz[k]) + 0.5) * d.box[k];
-    for (int b = 0; b < J.n_atom; b++)
-      for (int n = 0; n < G.n_site; n++) {
-        double r[3];
-        for (int k = 0; k < 3; k++) r[k] = -(J.x[b][k] - G.site_x[n][k] - sh[k]);
-        double rm = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
-        double qq = G.site_q[n] * J.q[b];
-        vex += qq / rm * d.conv;
-        for (int k = 0; k < 3; k++) {
-          double dV = -qq / (rm * rm * rm) * r[k] * d.conv;
-          atomicAdd(&Fo[3 * G.site_atom[n] + k], -G.A * dV);
-          atomicAdd(&Fo[3 * J.atom[b] + k], G.A * dV);
-        }
+  if (lane == 0) {
+    G.valid = 0;
+    int iOd = d.mt[D.mtype].heavy_base_atom, iOa = d.mt[A.mtype].heavy_acid_atom, iH = A.n_atom - 1;
+    if (iOd < 0 || iOa < 0) atomicMax(&d.err_flag[3], 4);
+    else {
+      // ---- geometric factor (ms_evb.f90:1117-1174)
+      double rO1[3], rO2[3], rH[3], shift[3], rOO[3], q[3];
+      for (int k = 0; k < 3; k++) {
+        rO1[k] = D.x[iOd][k];
+        double dr = A.x[iOa][k] - rO1[k];
+        shift[k] = floor(d.inv_box[k] * dr + 0.5) * d.box[k];
+        rO2[k] = rO1[k] + (A.x[iOa][k] - rO1[k] - shift[k]);
+        rH[k] = rO1[k] + (A.x[iH][k] - rO1[k] - shift[k]);
+        rOO[k] = rO1[k] - rO2[k];
+        q[k] = (rO1[k] + rO2[k]) / 2.0 - rH[k];
       }
+      int row = -1;
+      for (int i = 0; i < RPB_MAXI; i++) {
+        if (E.dc_int[i][0] < 0) break;
+        if (E.dc_int[i][0] == D.type[iOd] && E.dc_int[i][1] == A.type[iOa] && E.dc_int[i][2] == A.type[iH]) { row = i; break; }
+      }
+      if (row < 0) atomicMax(&d.err_flag[3], 5);
+      else {
+        coupling_function(G.A, G.Vconst, G.dA, E.dc_type[row], E.dc_par[row], q, rOO);
+        G.atom_Od = D.atom[iOd]; G.atom_Oa = A.atom[iOa]; G.atom_H = A.atom[iH];
+        // ---- Zundel centre of mass and exchange-charge sites (ms_evb.f90:2946-2982, 1340-1392)
+        double tmd = 0, tma = 0;
+        for (int a = 0; a < D.n_atom; a++) tmd = tmd + D.mass[a];
+        for (int a = 0; a < A.n_atom; a++) tma = tma + A.mass[a];
+        double shifta[3];
+        for (int k = 0; k < 3; k++) {
+          double dr = A.r_com[k] - D.r_com[k];
+          shifta[k] = floor(d.inv_box[k] * dr + 0.5) * d.box[k];
+          double rca = D.r_com[k] + (A.r_com[k] - D.r_com[k] - shifta[k]);
+          G.rz[k] = (tmd * D.r_com[k] + tma * rca) / (tmd + tma);
+        }
+        double qx = E.exch_proton[A.mtype][D.mtype];
+        int ns = 0;
+        for (int a = 0; a < D.n_atom; a++) {
+          int n = ns++;
+          G.site_atom[n] = D.atom[a]; G.site_q[n] = E.exch_atomic[D.type[a]];
+          for (int k = 0; k < 3; k++) { double dr = D.x[a][k] - G.rz[k] - 0.0; G.site_x[n][k] = G.rz[k] + dr; }
+        }
+        for (int a = 0; a < A.n_atom; a++) {
+          int n = ns++;
+          G.site_atom[n] = A.atom[a]; G.site_q[n] = (a == A.n_atom - 1) ? qx : E.exch_atomic[A.type[a]];
+          for (int k = 0; k < 3; k++) { double dr = A.x[a][k] - G.rz[k] - shifta[k]; G.site_x[n][k] = G.rz[k] + dr; }
+        }
+        G.n_site = ns;
+        int ncn = 0;
+        for (int k = 0; k < Sn.n_mol; k++) for (int a = 0; a < Sn.m[k].n_atom; a++) G.chain_atoms[ncn++] = Sn.m[k].atom[a];
+        G.n_chain = ncn;
+        G.valid = 1;
+      }
+    }
   }
-  atomicAdd(&e.vex[s], vex);
-  G.valid = 1;
+  __syncwarp();
+  if (G.valid) {
+    // ---- Vex with the other chain molecules (final-level charges, positions, centres of mass)
+    double vex = 0.0;
+    double* Fo = e.Foff + (size_t)s * 3 * d.N;
+    const int nsite = G.n_site;
+    for (int t = lane; t < CM * MA * nsite; t += 32) {
+      const int km = t / (MA * nsite), b = (t / nsite) % MA, n = t % nsite;
+      if (km >= Sn.n_mol || km == ds || km == as) continue;
+      const MolImage& J = Sn.m[km];
+      if (b >= J.n_atom) continue;
+      double r[3];
+      for (int k = 0; k < 3; k++) {
+        double sh = floor(d.inv_box[k] * (J.r_com[k] - G.rz[k]) + 0.5) * d.box[k];
+        r[k] = -(J.x[b][k] - G.site_x[n][k] - sh);
+      }
+      double rm = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+      double qq = G.site_q[n] * J.q[b];
+      vex += qq / rm * d.conv;
+      for (int k = 0; k < 3; k++) {
+        double dV = -qq / (rm * rm * rm) * r[k] * d.conv;
+        atomicAdd(&Fo[3 * G.site_atom[n] + k], -G.A * dV);
+        atomicAdd(&Fo[3 * J.atom[b] + k], G.A * dV);
+      }
+    }
+    vex = warp_sum(vex);
+    if (lane == 0) atomicAdd(&e.vex[s], vex);
+  }
+  __syncwarp();
+  warp_copy_struct(&geo[s], &G, lane);
 }
 
 // grid = (n_owned states list, ceil(N/256)): Vex between the Zundel sites and the background atoms
@@ -792,7 +1008,7 @@ __global__ void __launch_bounds__(256) k_evb_coupling_vex(Dev d, EvbDev e, const
 }
 
 // one thread per owned diabat: H_ss, H_parent,s and the geometric part of the coupling force
-__global__ void k_evb_assemble(Dev d, EvbDev e, const CouplingGeo* geo, int n_items, const int* slot_of_state) {
+__global__ void k_evb_assemble(Dev d, EvbDev e, const CouplingGeo* geo, const int* __restrict__ last_item, const int* slot_of_state) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   int S = *e.n_states;
   if (s >= MAXS) return;
@@ -802,16 +1018,13 @@ __global__ void k_evb_assemble(Dev d, EvbDev e, const CouplingGeo* geo, int n_it
     // principal energy: calculate_total_force_energy + repulsion + reference (ms_evb.f90:411-436)
     double E_elec = d.en[E_ELEC] + d.en[E_RECIP] + d.ewald_self;
     double H11 = E_elec + d.en[E_VDW] + d.en[E_BOND] + d.en[E_ANGLE] + d.en[E_DIH];
-    for (int ii = 0; ii < n_items; ii++) if (e.items[ii].state == 0) H11 = H11 + e.item_energy[ii];
+    H11 = H11 + e.item_energy[0];     // item 0 = the principal diabat's EVB repulsion + reference energy
     e.h_diag[0] = H11;
     return;
   }
   // energy delta of the last hop: acceptor-topology item minus donor-topology item (ms_evb.f90:1546)
-  double dE = 0.0;
-  for (int ii = 0; ii < n_items; ii++) {
-    const EvbItem& it = e.items[ii];
-    if (it.state == s && it.real && it.sign > 0) dE = e.item_energy[ii] - e.item_energy[ii - 1];
-  }
+  const int ii = last_item[s];      // acceptor-topology item of the last hop; the donor-topology item precedes it
+  double dE = e.item_energy[ii] - e.item_energy[ii - 1];
   e.h_diag[s] = dE;
   e.h_diag[2 * MAXS + s] = e.e_recip[slot_of_state[s]] - e.e_recip[0];
   const CouplingGeo& G = geo[s];
@@ -825,29 +1038,243 @@ __global__ void k_evb_assemble(Dev d, EvbDev e, const CouplingGeo* geo, int n_it
   }
 }
 
+// Hellmann-Feynman weights from the ground-state vector e.evec (whole CTA; caller has synchronised):
+// c_s^2 (diagonal), 2 c_parent c_s (coupling) (ms_evb.f90:298-303), and the subtree sums used by the hop-tree
+// de-duplication of the real-space deltas.
+__device__ void hellmann_feynman_weights(EvbDev& e, int S, int tid, int nth) {
+  for (int i = tid; i < MAXS; i += nth) {
+    double ci = i < S ? e.evec[i] : 0.0;
+    e.coef2[i] = ci * ci;
+    e.coef2[MAXS + i] = (i > 0 && i < S) ? 2.0 * e.evec[e.parent[i]] * ci : 0.0;
+    e.coef2[2 * MAXS + i] = ci * ci;
+  }
+  __syncthreads();
+  // weight of the last-hop force delta of diabat s = sum of c_t^2 over every diabat whose chain passes through s
+  // (DFS pre-order => parent(s) < s, so one descending pass accumulates the subtrees)
+  if (tid == 0) for (int i = S - 1; i >= 1; i--) e.coef2[2 * MAXS + e.parent[i]] += e.coef2[2 * MAXS + i];
+}
+
 // ================================================================================================
-// K12: block-level Jacobi eigensolver for the (<= 80 x 80) EVB Hamiltonian, one CTA, matrix in shared memory.
-// Same rotation formulas, thresholds and stopping logic as the reference's Numerical-Recipes routine
+// K12a: ground state of the EVB Hamiltonian from its TREE structure (default solver).
+// A diabat couples only to its DFS parent (ms_evb.f90:675-681), so H is a symmetric tree matrix of depth
+// <= evb_max_chain: diagonal H_ss, one off-diagonal beta_s = H_parent(s),s per diabat.  Eliminating the leaves first,
+// the pivots of H - x are   d_s(x) = delta_s - x - sum_{children c} beta_c^2 / d_c(x)   (delta_s = H_ss - H_11, formed
+// from the hop deltas directly, so the 1e5 kJ/mol common offset never enters the arithmetic), every level of the tree
+// in parallel.  det(H - x) = prod d_s, and all d_s > 0 exactly when x is below the lowest eigenvalue (Sylvester), so:
+//   * lowest eigenvalue: Laguerre's iteration on the characteristic polynomial through sum d'/d and its derivative
+//     (d', d'' by the same recurrence), started left of the spectrum (Gershgorin, or the previous step's value):
+//     monotone from the left, cubic, every pivot stays positive -- 4-6 evaluations; a step that rounding pushes onto
+//     the root retreats geometrically;
+//   * eigenvector: inverse iteration with the factorisation at the converged (valid) shift, 2-3 tree solves;
+//   * energy: Rayleigh quotient of that vector.
+// One evaluation costs ~(depth+1) dependent divisions, independent of S; the whole solve is ~10 us where the cyclic
+// Jacobi sweeps (K12b, kept as the general-purpose cross-check, RPB_EVB_SOLVER=jacobi) need 100-300 us of barriers.
+// Same selections afterwards as the reference (ms_evb.f90:279-328): principal diabat = first maximum |c_i|.
+// ================================================================================================
+#define TREE_TPB 96
+static_assert(MAXS <= TREE_TPB, "one thread per diabat");
+struct TreeShared {
+  double delta[MAXS], beta[MAXS], b2[MAXS], dv[MAXS], d1[MAXS], d2[MAXS], invd[MAXS], y[MAXS], b[MAXS];
+  int parent[MAXS], level[MAXS], child_start[MAXS + 1], child[MAXS];
+  double red[2][4];
+};
+
+// sums two values over the CTA; every thread returns the same (deterministically ordered) totals
+__device__ __forceinline__ void tree_sum2(TreeShared& T, double& a, double& b, int tid) {
+  a = warp_sum(a); b = warp_sum(b);
+  __syncthreads();
+  if ((tid & 31) == 0) { T.red[0][tid >> 5] = a; T.red[1][tid >> 5] = b; }
+  __syncthreads();
+  a = T.red[0][0] + T.red[0][1] + T.red[0][2];
+  b = T.red[1][0] + T.red[1][1] + T.red[1][2];
+}
+
+// pivots (and their first two derivatives) of H - x, leaves first; returns true when every pivot is positive
+__device__ __forceinline__ bool tree_pivots(TreeShared& T, int S, int maxlev, int i, double x) {
+  for (int L = maxlev; L >= 0; L--) {
+    if (i < S && T.level[i] == L) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+      for (int k = T.child_start[i]; k < T.child_start[i + 1]; k++) {
+        const int c = T.child[k];
+        const double r = T.invd[c], br = T.b2[c] * r, q = T.d1[c] * r;
+        s0 += br; s1 += br * q; s2 += br * (T.d2[c] * r - 2.0 * q * q);
+      }
+      const double di = T.delta[i] - x - s0;
+      T.dv[i] = di; T.d1[i] = -1.0 + s1; T.d2[i] = s2; T.invd[i] = 1.0 / di;
+    }
+    __syncthreads();
+  }
+  return __syncthreads_and(i >= S || T.dv[i] > 0.0) != 0;
+}
+
+__global__ void __launch_bounds__(TREE_TPB) k_evb_tree_solver(Dev d, EvbDev e, const double* coeff_override) {
+  __shared__ TreeShared T;
+  const int S = *e.n_states;
+  const int tid = threadIdx.x, nth = blockDim.x, i = tid;
+  if (coeff_override) {
+    for (int k = tid; k < S; k += nth) e.evec[k] = coeff_override[k];
+    __syncthreads();
+    hellmann_feynman_weights(e, S, tid, nth);
+    return;
+  }
+  if (i < S) {
+    // H_ss = H_11 + sum of the hop deltas along the chain (root first) + (E_rec(s) - E_rec(1))   ms_evb.f90:1546, 2083
+    int chain[MAXC + 1], nc = 0;
+    for (int t = i; t > 0 && nc <= MAXC; t = e.parent[t]) chain[nc++] = t;
+    double Hs = e.h_diag[0], dl = 0.0;
+    for (int k = nc - 1; k >= 0; k--) { Hs = Hs + e.h_diag[chain[k]]; dl = dl + e.h_diag[chain[k]]; }
+    Hs = Hs + e.h_diag[2 * MAXS + i]; dl = dl + e.h_diag[2 * MAXS + i];
+    e.h_full[i] = Hs; e.h_full[MAXS + i] = (i > 0) ? e.h_diag[MAXS + i] : 0.0;
+    T.delta[i] = (i > 0) ? dl : 0.0;
+    T.beta[i] = (i > 0) ? e.h_diag[MAXS + i] : 0.0;
+    T.b2[i] = T.beta[i] * T.beta[i];
+    T.parent[i] = (i > 0) ? e.parent[i] : -1;
+    T.level[i] = nc;
+    T.y[i] = 1.0;
+  }
+  __syncthreads();
+  if (tid == 0) {   // children in ascending order (deterministic summation)
+    for (int k = 0; k <= S; k++) T.child_start[k] = 0;
+    for (int k = 1; k < S; k++) T.child_start[T.parent[k] + 1]++;
+    for (int k = 0; k < S; k++) T.child_start[k + 1] += T.child_start[k];
+    int fill[MAXS];
+    for (int k = 0; k < S; k++) fill[k] = T.child_start[k];
+    for (int k = 1; k < S; k++) T.child[fill[T.parent[k]]++] = k;
+  }
+  __syncthreads();
+  int mlev = 0;
+  for (int k = 0; k < S; k++) mlev = max(mlev, T.level[k]);
+  // Gershgorin lower bound of the spectrum and the magnitude of the problem
+  double gers = 1e300, mag = 0.0;
+  for (int k = 0; k < S; k++) {
+    double g = T.delta[k] - fabs(T.beta[k]);
+    for (int q = T.child_start[k]; q < T.child_start[k + 1]; q++) g -= fabs(T.beta[T.child[q]]);
+    gers = fmin(gers, g); mag = fmax(mag, fabs(T.delta[k]));
+  }
+  double lo = gers - 1e-3 * (1.0 + fabs(gers)), hi = 1e300;
+  const double tol = 1e-10 * fmax(fmax(mag, fabs(lo)), 1.0);   // the inverse iteration + Rayleigh quotient finish the job
+  double x = lo;
+  const double warm = e.tree_mu[0];
+  bool warm_try = (e.tree_mu[1] == 1.0) && (warm - 2.0 > lo);
+  if (warm_try) x = warm - 2.0;
+  int n_eval = 0, retreat = 0, status = 1;
+  if (S == 1) { status = 0; x = 0.0; }
+  else {
+    for (int it = 0; it < 120; it++) {
+      const bool ok = tree_pivots(T, S, mlev, i, x);
+      n_eval++;
+      if (!ok) {
+        if (warm_try && it == 0) { x = lo; warm_try = false; continue; }    // the previous value is no lower bound any more
+        hi = fmin(hi, x);
+        if (hi - lo <= tol) { x = lo; tree_pivots(T, S, mlev, i, x); n_eval++; status = 0; break; }
+        x = fmax(hi - 0.5 * tol * pow(8.0, (double)retreat), 0.5 * (lo + hi));
+        retreat++;
+        continue;
+      }
+      lo = x;
+      if (hi - lo <= tol) { status = 0; break; }
+      double G = 0.0, S2 = 0.0;
+      if (i < S) { const double q = T.d1[i] * T.invd[i]; G = q; S2 = T.d2[i] * T.invd[i] - q * q; }
+      tree_sum2(T, G, S2, tid);
+      const double n = (double)S;
+      const double disc = fmax((n - 1.0) * (n * (-S2) - G * G), 0.0);
+      const double a = n / (G - sqrt(disc));          // G < 0 left of the spectrum: a < 0, the step goes right
+      double xn = x - a;
+      if (xn - x <= tol) { status = 0; break; }
+      if (!(xn < hi)) xn = 0.5 * (lo + hi);
+      x = xn;
+    }
+  }
+  // ---- eigenvector: inverse iteration with the factorisation at the (valid) shift x
+  double mu = 0.0;
+  if (S > 1) {
+    for (int rep = 0; rep < 4; rep++) {
+      if (i < S) T.b[i] = T.y[i];
+      __syncthreads();
+      for (int L = mlev; L >= 0; L--) {        // forward elimination, leaves first
+        if (i < S && T.level[i] == L) {
+          double acc = T.b[i];
+          for (int k = T.child_start[i]; k < T.child_start[i + 1]; k++) { const int c = T.child[k]; acc -= T.beta[c] * (T.b[c] * T.invd[c]); }
+          T.b[i] = acc;
+        }
+        __syncthreads();
+      }
+      for (int L = 0; L <= mlev; L++) {        // back substitution, root first
+        if (i < S && T.level[i] == L) T.b[i] = (T.b[i] - (i > 0 ? T.beta[i] * T.b[T.parent[i]] : 0.0)) * T.invd[i];
+        __syncthreads();
+      }
+      double nrm = (i < S) ? T.b[i] * T.b[i] : 0.0, zero = 0.0;
+      tree_sum2(T, nrm, zero, tid);
+      const double inv = rsqrt(nrm);
+      double change = 0.0;
+      if (i < S) { const double yn = T.b[i] * inv; change = fabs(fabs(yn) - fabs(T.y[i])); T.y[i] = yn; }
+      n_eval++;
+      if (__syncthreads_and(change < 1e-15)) break;
+    }
+    double r1 = 0.0, r2 = 0.0;
+    if (i < S) { r1 = T.delta[i] * T.y[i] * T.y[i]; if (i > 0) r2 = 2.0 * T.beta[i] * T.y[i] * T.y[T.parent[i]]; }
+    tree_sum2(T, r1, r2, tid);
+    mu = r1 + r2;
+  }
+  if (i < S) e.evec[i] = T.y[i];
+  if (tid == 0) {
+    *e.e_ground = e.h_diag[0] + mu;
+    int pd = 0;
+    double coef = fabs(T.y[0]);
+    for (int k = 0; k < S; k++) if (coef < fabs(T.y[k])) { coef = fabs(T.y[k]); pd = k; }
+    int newh = *d.hydronium;
+    for (int h = 0; h < d.max_chain; h++) {
+      if (e.proton_log[(pd * MAXC + h) * 5] < 0) break;
+      newh = e.proton_log[(pd * MAXC + h) * 5 + 3];
+    }
+    e.result[0] = pd; e.result[1] = newh; e.result[2] = status; e.result[3] = 0; e.result[4] = n_eval;
+    e.tree_mu[0] = mu; e.tree_mu[1] = (status == 0) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  hellmann_feynman_weights(e, S, tid, nth);
+}
+
+// ================================================================================================
+// K12b: block-level Jacobi eigensolver for the (<= 80 x 80) EVB Hamiltonian, one CTA, matrix in shared memory.
+// Same rotation definition, thresholds and stopping logic as the reference's Numerical-Recipes routine
 // (general_routines.f90:2035-2074), but the n/2 disjoint rotations of a round-robin round are applied
-// concurrently (rows, then columns) instead of one (ip,iq) at a time; the ground-state eigenvector is unique up
-// to sign, so only the rounding-level path differs.  Followed by the reference's selections (ms_evb.f90:279-328):
-// ground state = first minimum eigenvalue, principal diabat = first maximum |c_i|.
+// concurrently.  A round is two phases:
+//   A  one thread per pair (p,q): rotation parameters and the 2x2 diagonal block (a_pp -= t a_pq, a_qq += t a_pq,
+//      a_pq = 0, :2056-2062).  The parameters use the hypot form of the same angle, t = sgn(z) b / (|z| + sqrt(z^2+b^2))
+//      with z = (a_qq-a_pp)/2, b = a_pq, and (c, s) = (u, sgn(z) b) / sqrt(u^2+b^2), u = |z| + sqrt(z^2+b^2): two
+//      dependent long-latency operations (rsqrt) instead of five (div, sqrt, div, sqrt, div) -- this serial chain, not
+//      the arithmetic volume, is what a round costs;
+//   B  one thread per off-diagonal 2x2 block above the diagonal, A_IJ <- R_I^T A_IJ R_J (mirrored into the lower
+//      triangle), and one thread per 2x2 block of V <- V R_J.
+// The ground-state eigenvector is unique up to sign, so only the rounding-level path differs from the serial sweep.
+// Followed by the reference's selections (ms_evb.f90:279-328): ground state = first minimum eigenvalue,
+// principal diabat = first maximum |c_i|.
 // ================================================================================================
-#define JAC_TPB 256
+#define JAC_TPB 512
+__device__ __forceinline__ void jac_pair(int t, int r, int n, int& p, int& q) {
+  if (t == 0) { p = r; q = n - 1; }
+  else {
+    p = r + t; if (p >= n - 1) p -= n - 1;
+    q = r - t; if (q < 0) q += n - 1;
+  }
+  if (p > q) { int x = p; p = q; q = x; }
+}
+
 __global__ void __launch_bounds__(JAC_TPB) k_evb_jacobi(Dev d, EvbDev e, const double* coeff_override) {
   extern __shared__ double smem[];
   const int S = *e.n_states;
   const int n = S + (S & 1);          // padded to even for the round-robin pairing (dummy row/column stays zero)
+  const int nb = n / 2;
   const int tid = threadIdx.x, nth = blockDim.x;
   double* a = smem;                   // [n*n] column-major, full symmetric
   double* v = a + n * n;              // [n*n]
-  double* rc = v + n * n;             // [n/2] cos
-  double* rs = rc + n / 2;            // [n/2] sin
-  int* rp = (int*)(rs + n / 2);       // [n/2] p
-  int* rq = rp + n / 2;               // [n/2] q   (q < 0: no rotation)
+  double* tmp = v + n * n;            // [n*n] warm-start scratch
+  double* rc = tmp + n * n;           // [nb] cos
+  double* rs = rc + nb;               // [nb] sin
+  int* rp = (int*)(rs + nb);          // [nb] p
+  int* rq = rp + nb;                  // [nb] q
   __shared__ double red[32];
   __shared__ double s_sm;
-  __shared__ int s_nrot;
   if (coeff_override) {
     for (int i = tid; i < S; i += nth) e.evec[i] = coeff_override[i];
   } else {
@@ -868,72 +1295,109 @@ __global__ void __launch_bounds__(JAC_TPB) k_evb_jacobi(Dev d, EvbDev e, const d
       }
     }
     __syncthreads();
-    int status = 1;
+    // ---- warm start: when the diabat set is the one of the previous call (same hop logs), H changed by one MD step
+    // only, so it is first rotated into the previous eigenbasis, A = V_prev^T H V_prev (nearly diagonal), and the
+    // sweeps start from V = V_prev.  Same solver, same stopping rule; about half the sweeps.
+    {
+      const int chain_len = e.jac_sig[1 + MAXS * MAXC * 5];   // consecutive warm starts: bounded, so that the rounding-level
+      int same = (e.jac_sig[0] == S) && chain_len < 64;         // loss of orthogonality of V_prev cannot accumulate
+      if (same) for (int k = tid; k < S * MAXC * 5; k += nth) same &= (e.jac_sig[1 + k] == e.proton_log[k]);
+      same = __syncthreads_and(same);
+      if (same) {
+        for (int k = tid; k < n * n; k += nth) v[k] = e.jac_v[k];
+        __syncthreads();
+        for (int k = tid; k < n * n; k += nth) {       // tmp = H V
+          const int i = k % n, j = k / n;
+          double acc = 0.0;
+          for (int m = 0; m < n; m++) acc = fma(a[i + n * m], v[m + n * j], acc);
+          tmp[k] = acc;
+        }
+        __syncthreads();
+        for (int k = tid; k < n * n; k += nth) {       // A = V^T tmp, upper triangle mirrored
+          const int i = k % n, j = k / n;
+          if (i > j) continue;
+          double acc = 0.0;
+          for (int m = 0; m < n; m++) acc = fma(v[m + n * i], tmp[m + n * j], acc);
+          a[i + n * j] = acc; a[j + n * i] = acc;
+        }
+        __syncthreads();
+      } else {
+        for (int k = tid; k < S * MAXC * 5; k += nth) e.jac_sig[1 + k] = e.proton_log[k];
+        if (tid == 0) e.jac_sig[0] = S;
+      }
+      __syncthreads();
+      if (tid == 0) e.jac_sig[1 + MAXS * MAXC * 5] = same ? chain_len + 1 : 0;
+    }
+    const int n_upper = nb * (nb - 1) / 2;
+    int status = 1, sweeps = 0;
     for (int it = 1; it <= 50; it++) {
       double sm = 0.0;
       for (int k = tid; k < n * n; k += nth) { int i = k % n, j = k / n; if (i < j) sm += fabs(a[k]); }
       sm = block_sum(sm, red);
-      if (tid == 0) { s_sm = sm; s_nrot = 0; }
+      if (tid == 0) s_sm = sm;
       __syncthreads();
       sm = s_sm;
       if (sm == 0.0) { status = 0; break; }
+      sweeps = it;
       const double tresh = (it < 4) ? 0.2 * sm / (double)(S * S) : 0.0;
       for (int r = 0; r < n - 1; r++) {
-        // ---- phase A: rotation parameters of the n/2 disjoint pairs of this round
-        if (tid < n / 2) {
-          int t = tid, p, q;
-          if (t == 0) { p = r; q = n - 1; }
-          else { p = (r + t) % (n - 1); q = (r - t + (n - 1)) % (n - 1); }
-          if (p > q) { int x = p; p = q; q = x; }
-          double apq = a[p + n * q];
-          int rot = 0;
+        // ---- phase A: parameters + diagonal block of every pair
+        if (tid < nb) {
+          int p, q;
+          jac_pair(tid, r, n, p, q);
           double cc = 1.0, sn = 0.0;
+          const double apq = a[p + n * q];
           if (apq != 0.0) {
-            double app = a[p + n * p], aqq = a[q + n * q];
-            double g = 100.0 * fabs(apq);
-            if (it > 4 && (fabs(app) + g == fabs(app)) && (fabs(aqq) + g == fabs(aqq))) {
-              a[p + n * q] = 0.0; a[q + n * p] = 0.0;
+            const double app = a[p + n * p], aqq = a[q + n * q];
+            const double g = 100.0 * fabs(apq);
+            // (the reference applies this flush only after four sweeps, :2043; it is a no-op at working precision
+            //  whenever its condition holds, and applying it from the first sweep lets a warm-started solve stop early)
+            if ((fabs(app) + g == fabs(app)) && (fabs(aqq) + g == fabs(aqq))) {
+              a[p + n * q] = 0.0; a[q + n * p] = 0.0;                                  // :2044-2045
             } else if (fabs(apq) > tresh) {
-              double h = aqq - app, tt;
-              if (fabs(h) + g == fabs(h)) tt = apq / h;
-              else {
-                double theta = 0.5 * h / apq;
-                tt = 1.0 / (fabs(theta) + sqrt(1.0 + theta * theta));
-                if (theta < 0.0) tt = -tt;
-              }
-              cc = 1.0 / sqrt(1 + tt * tt); sn = tt * cc;
-              rot = 1;
+              const double z = 0.5 * (aqq - app), az = fabs(z);
+              const double h2 = az * az + apq * apq;
+              const double u = az + h2 * rsqrt(h2);
+              const double sb = z < 0.0 ? -apq : apq;
+              const double tt = sb / u;
+              const double w = rsqrt(u * u + apq * apq);
+              cc = u * w; sn = sb * w;
+              a[p + n * p] = app - tt * apq; a[q + n * q] = aqq + tt * apq;            // :2056-2062
+              a[p + n * q] = 0.0; a[q + n * p] = 0.0;
             }
           }
-          rc[t] = cc; rs[t] = sn; rp[t] = p; rq[t] = rot ? q : -1;
-          if (rot) atomicAdd(&s_nrot, 1);
+          rc[tid] = cc; rs[tid] = sn; rp[tid] = p; rq[tid] = q;
         }
         __syncthreads();
-        // ---- phase B: rows p,q of A <- J^T A
-        for (int w = tid; w < (n / 2) * n; w += nth) {
-          int t = w / n, k = w - t * n, q = rq[t];
-          if (q < 0) continue;
-          int p = rp[t];
-          double cc = rc[t], sn = rs[t];
-          double x = a[p + n * k], y = a[q + n * k];
-          a[p + n * k] = cc * x - sn * y;
-          a[q + n * k] = sn * x + cc * y;
-        }
-        __syncthreads();
-        // ---- phase C: columns p,q of A <- A J ; V <- V J
-        for (int w = tid; w < (n / 2) * n; w += nth) {
-          int t = w / n, k = w - t * n, q = rq[t];
-          if (q < 0) continue;
-          int p = rp[t];
-          double cc = rc[t], sn = rs[t];
-          double x = a[k + n * p], y = a[k + n * q];
-          double xn = cc * x - sn * y, yn = sn * x + cc * y;
-          if (k == p) yn = 0.0;       // a(p,q) = 0 exactly, as in the reference (:2062)
-          if (k == q) xn = 0.0;
-          a[k + n * p] = xn; a[k + n * q] = yn;
-          double vx = v[k + n * p], vy = v[k + n * q];
-          v[k + n * p] = cc * vx - sn * vy;
-          v[k + n * q] = sn * vx + cc * vy;
+        // ---- phase B: off-diagonal blocks of A (upper triangle of the block grid, mirrored) and V
+        for (int b = tid; b < n_upper + nb * nb; b += nth) {
+          if (b < n_upper) {
+            // (I,J), I < J, from the linear index of the strict upper triangle
+            int I = 0, rem = b;
+            while (rem >= nb - 1 - I) { rem -= nb - 1 - I; I++; }
+            const int J = I + 1 + rem;
+            const double cI = rc[I], sI = rs[I], cJ = rc[J], sJ = rs[J];
+            if (sI == 0.0 && sJ == 0.0) continue;
+            const int pI = rp[I], qI = rq[I], pJ = rp[J], qJ = rq[J];
+            const double x00 = a[pI + n * pJ], x10 = a[qI + n * pJ], x01 = a[pI + n * qJ], x11 = a[qI + n * qJ];
+            const double y00 = cI * x00 - sI * x10, y10 = sI * x00 + cI * x10;   // rows p_I, q_I <- R_I^T A
+            const double y01 = cI * x01 - sI * x11, y11 = sI * x01 + cI * x11;
+            const double z00 = cJ * y00 - sJ * y01, z01 = sJ * y00 + cJ * y01;   // columns p_J, q_J <- A R_J
+            const double z10 = cJ * y10 - sJ * y11, z11 = sJ * y10 + cJ * y11;
+            a[pI + n * pJ] = z00; a[pJ + n * pI] = z00; a[pI + n * qJ] = z01; a[qJ + n * pI] = z01;
+            a[qI + n * pJ] = z10; a[pJ + n * qI] = z10; a[qI + n * qJ] = z11; a[qJ + n * qI] = z11;
+          } else {
+            const int bb = b - n_upper, I = bb / nb, J = bb - I * nb;
+            const double cJ = rc[J], sJ = rs[J];
+            if (sJ == 0.0) continue;
+            const int pJ = rp[J], qJ = rq[J];
+#pragma unroll
+            for (int k = 2 * I; k < 2 * I + 2; k++) {
+              const double vx = v[k + n * pJ], vy = v[k + n * qJ];
+              v[k + n * pJ] = cJ * vx - sJ * vy;
+              v[k + n * qJ] = sJ * vx + cJ * vy;
+            }
+          }
         }
         __syncthreads();
       }
@@ -951,24 +1415,16 @@ __global__ void __launch_bounds__(JAC_TPB) k_evb_jacobi(Dev d, EvbDev e, const d
         if (e.proton_log[(pd * MAXC + h) * 5] < 0) break;
         newh = e.proton_log[(pd * MAXC + h) * 5 + 3];
       }
-      e.result[0] = pd; e.result[1] = newh; e.result[2] = status; e.result[3] = ground;
+      e.result[0] = pd; e.result[1] = newh; e.result[2] = status; e.result[3] = ground; e.result[4] = sweeps;
     }
     __syncthreads();
     int ground = e.result[3];
     for (int i = tid; i < S; i += nth) e.evec[i] = v[i + n * ground];
+    if (status == 0) for (int k = tid; k < n * n; k += nth) e.jac_v[k] = v[k];
+    else if (tid == 0) e.jac_sig[0] = -1;
   }
   __syncthreads();
-  // Hellmann-Feynman weights: c_s^2 (diagonal) and 2 c_parent c_s (coupling)   ms_evb.f90:298-303
-  for (int i = tid; i < MAXS; i += nth) {
-    double ci = i < S ? e.evec[i] : 0.0;
-    e.coef2[i] = ci * ci;
-    e.coef2[MAXS + i] = (i > 0 && i < S) ? 2.0 * e.evec[e.parent[i]] * ci : 0.0;
-    e.coef2[2 * MAXS + i] = ci * ci;
-  }
-  __syncthreads();
-  // weight of the last-hop force delta of diabat s = sum of c_t^2 over every diabat whose chain passes through s
-  // (DFS pre-order => parent(s) < s, so one descending pass accumulates the subtrees)
-  if (tid == 0) for (int i = S - 1; i >= 1; i--) e.coef2[2 * MAXS + e.parent[i]] += e.coef2[2 * MAXS + i];
+  hellmann_feynman_weights(e, S, tid, nth);
 }
 
 // ================================================================================================
@@ -1068,13 +1524,26 @@ __global__ void k_evb_commit_patch(Dev d, EvbDev e, int state, int level, const 
 // ================================================================================================
 // host orchestration
 // ================================================================================================
+// layout of the packed per-step upload (bytes)
+#define ENUM_BLOCK_INTS (16 + MAXS * (2 + MAXC * 5))
+#define PACK_OFF_ITEMS 0
+#define PACK_OFF_REAL (PACK_OFF_ITEMS + (RPB_MAX_ITEMS + 1) * (int)sizeof(EvbItem))
+#define PACK_OFF_SLOT_OF (PACK_OFF_REAL + (RPB_MAX_ITEMS + 1) * 4)
+#define PACK_OFF_SLOT_STATE (PACK_OFF_SLOT_OF + MAXS * 4)
+#define PACK_OFF_STATE_LIST (PACK_OFF_SLOT_STATE + MAXS * 4)
+#define PACK_OFF_UNIQ (PACK_OFF_STATE_LIST + MAXS * 4)
+#define PACK_OFF_LAST (PACK_OFF_UNIQ + CAND_SLOTS * 4)
+#define PACK_BYTES (PACK_OFF_LAST + MAXS * 4)
+
 struct EvbScratch {   // device scratch owned by the context (allocated in evb_alloc)
+  char* pack_dev; char* pack_host;
   CouplingGeo* geo;
   int* slot_of_state;   // [MAXS]
   int* slot_state;      // [MAXS] inverse map (slot -> state), -1 unused
   int* state_list;      // [MAXS] owned diabats s>=1
   double* coeff_dev;    // [MAXS]
   int* perm; int* new_first;
+  int* chain_slot; int* cand; int* cand_n; int* uniq_atom; int* last_item;
   double4* xq2; double* vel2; double* force2; double* mass2; int* type2; int* moa2;
 };
 static std::map<rpb_ctx*, EvbScratch> g_scratch;
@@ -1095,21 +1564,48 @@ int evb_alloc(rpb_ctx* c) {
   const size_t K3 = (size_t)c->d.K * c->d.K * c->d.K;
   int rc;
 #define AL(p, n) if ((rc = dev_alloc(c, &(p), (size_t)(n)))) return rc;
-  AL(e.n_states, 1); AL(e.proton_log, MAXS * MAXC * 5); AL(e.parent, MAXS); AL(e.n_hops, MAXS);
-  AL(e.snap, MAXS * NLEV); AL(e.items, RPB_MAX_ITEMS + 1); AL(e.n_items, 1); AL(e.item_energy, RPB_MAX_ITEMS + 1);
-  AL(e.real_list, RPB_MAX_ITEMS + 1); AL(e.n_real, 1); AL(e.corr_f, (size_t)MAXS * CM * MA * 3); AL(e.corr_atom, MAXS * CM * MA); AL(e.h_full, 2 * MAXS);
+  {  // enumeration results are read back every step: one contiguous block, one copy (layout == EvbHost::pinned)
+    int* blk;
+    AL(blk, ENUM_BLOCK_INTS);
+    e.n_states = blk; e.n_hops = blk + 16; e.parent = blk + 16 + MAXS; e.proton_log = blk + 16 + 2 * MAXS;
+  }
+  AL(e.snap, MAXS * NLEV); AL(e.n_items, 1); AL(e.item_energy, RPB_MAX_ITEMS + 1);
+  AL(e.n_real, 1); AL(e.corr_f, (size_t)MAXS * CM * MA * 3); AL(e.corr_atom, MAXS * CM * MA); AL(e.h_full, 2 * MAXS);
   AL(e.dF, (size_t)MAXS * 3 * N); AL(e.Foff, (size_t)MAXS * 3 * N);
   AL(e.vex, MAXS); AL(e.e_recip, MAXS); AL(e.h_diag, 3 * MAXS); AL(e.f_mix, 3 * N); AL(e.evec, MAXS); AL(e.coef2, 3 * MAXS);
-  AL(e.e_ground, 1); AL(e.result, 8); AL(e.theta_mix, K3);
+  AL(e.e_ground, 1); AL(e.result, 8); AL(e.theta_mix, K3); AL(e.jac_v, MAXS * MAXS); AL(e.jac_sig, 2 + MAXS * MAXC * 5); AL(e.tree_mu, 2);
   EvbScratch s;
-  AL(s.geo, MAXS); AL(s.slot_of_state, MAXS); AL(s.slot_state, MAXS); AL(s.state_list, MAXS); AL(s.coeff_dev, MAXS);
+  AL(s.geo, MAXS); AL(s.coeff_dev, MAXS);
+  // per-step host -> device tables travel as ONE packed copy from pinned memory (see PackLayout)
+  AL(s.pack_dev, PACK_BYTES);
+  CKE(cudaMallocHost(&s.pack_host, PACK_BYTES));
+  e.items = (EvbItem*)(s.pack_dev + PACK_OFF_ITEMS); e.real_list = (int*)(s.pack_dev + PACK_OFF_REAL);
+  s.slot_of_state = (int*)(s.pack_dev + PACK_OFF_SLOT_OF); s.slot_state = (int*)(s.pack_dev + PACK_OFF_SLOT_STATE);
+  s.state_list = (int*)(s.pack_dev + PACK_OFF_STATE_LIST); s.uniq_atom = (int*)(s.pack_dev + PACK_OFF_UNIQ);
+  s.last_item = (int*)(s.pack_dev + PACK_OFF_LAST);
   AL(s.perm, N); AL(s.new_first, CM);
+  AL(s.chain_slot, N); AL(s.cand, (size_t)CAND_SLOTS * CAND_CAP); AL(s.cand_n, CAND_SLOTS + 2);
   AL(s.xq2, N); AL(s.vel2, 3 * N); AL(s.force2, 3 * N); AL(s.mass2, N); AL(s.type2, N); AL(s.moa2, N);
 #undef AL
   g_scratch[c] = s;
+  // every FFT batch size this context can meet (no plan is built inside a step)
+  for (int b = 1; b <= c->grid_capacity; b++) {
+    cufftHandle pf, pi;
+    if ((rc = pme_get_plans(c, b, &pf, &pi))) return rc;
+  }
   CKE(cudaMallocHost(&c->eh.pinned, (16 + MAXS * (2 + MAXC * 5)) * sizeof(int) + 4 * MAXS * sizeof(double)));
-  CKE(cudaMemset(e.n_states, 0, sizeof(int)));
+  CKE(cudaMemset(e.n_states, 0, ENUM_BLOCK_INTS * sizeof(int)));
+  CKE(cudaMemset(e.jac_sig, 0xff, (2 + MAXS * MAXC * 5) * sizeof(int)));
+  CKE(cudaMemset(e.tree_mu, 0, 2 * sizeof(double)));
+  { const char* sv = getenv("RPB_EVB_SOLVER"); c->evb_solver = (sv && std::string(sv) == "jacobi") ? 1 : 0; }
   return 0;
+}
+
+void evb_free(rpb_ctx* c) {
+  auto it = g_scratch.find(c);
+  if (it == g_scratch.end()) return;
+  if (it->second.pack_host) cudaFreeHost(it->second.pack_host);
+  g_scratch.erase(it);
 }
 
 static void host_items(rpb_ctx* c, std::vector<EvbItem>& items) {
@@ -1145,17 +1641,14 @@ int evb_build(rpb_ctx* c) {
   EvbScratch& sc = g_scratch[c];
   const int N = d.N;
   const size_t K3 = (size_t)d.K * d.K * d.K, n3 = (size_t)3 * N;
-  int rc = calculate_total_force_energy(c, true);
+  int rc = calculate_total_force_energy(c, true);   // principal diabat; its FFT convolution joins the batch below
   if (rc) return rc;
   {
     ScopedTimer t(c, T_EVB_ENUM);
-    k_evb_enumerate<<<1, 256, 0, c->stream>>>(d, e);
+    k_evb_enumerate<<<1, ENUM_TPB, 0, c->stream>>>(d, e);
     c->n_launch++;
     int* pin = h.pinned;
-    CKE(cudaMemcpyAsync(pin, e.n_states, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CKE(cudaMemcpyAsync(pin + 16, e.n_hops, MAXS * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CKE(cudaMemcpyAsync(pin + 16 + MAXS, e.parent, MAXS * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CKE(cudaMemcpyAsync(pin + 16 + 2 * MAXS, e.proton_log, MAXS * MAXC * 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CKE(cudaMemcpyAsync(pin, e.n_states, ENUM_BLOCK_INTS * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CKE(cudaMemcpyAsync(c->h_flags, d.err_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CKE(cudaStreamSynchronize(c->stream));
     if (c->h_flags[1]) { c->err = "please increase size of verlet neighbor list"; return RPB_ERR_VERLET; }
@@ -1170,46 +1663,72 @@ int evb_build(rpb_ctx* c) {
   std::vector<EvbItem> items;
   host_items(c, items);
   h.n_items = (int)items.size();
-  std::vector<int> real_list;
-  for (int i = 0; i < h.n_items; i++) if (items[i].real) real_list.push_back(i);
-  const int n_real = (int)real_list.size();
-  CKE(cudaMemcpyAsync(e.real_list, real_list.data(), n_real * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  std::vector<int> slot_of_state(MAXS, 0), slot_state(MAXS, -1), state_list;
-  slot_state[0] = 0;   // slot 0 = principal grid on every rank
+  int* real_list = (int*)(sc.pack_host + PACK_OFF_REAL);
+  int n_real = 0;
+  int* last_item = (int*)(sc.pack_host + PACK_OFF_LAST);
+  for (int i = 0; i < MAXS; i++) last_item[i] = 1;
+  for (int i = 0; i < h.n_items; i++)
+    if (items[i].real) {
+      real_list[n_real++] = i;
+      if (items[i].sign > 0 && items[i].state > 0) last_item[items[i].state] = i;
+    }
+  memcpy(sc.pack_host + PACK_OFF_ITEMS, items.data(), items.size() * sizeof(EvbItem));
+  // distinct chain atoms of the owned diabats (principal indices, from the host mirror of the molecule table)
+  int* uniq_atom = (int*)(sc.pack_host + PACK_OFF_UNIQ);
+  int n_uniq = 0;
+  {
+    std::vector<int> um(1, c->hydronium_mol);
+    for (int s = 1; s < S; s++) {
+      if (!state_owned(s, d.rank, d.world)) continue;
+      for (int k = 0; k < h.n_hops[s]; k++) {
+        int a = h.proton_log[s][k][3];
+        if (std::find(um.begin(), um.end(), a) == um.end()) um.push_back(a);
+      }
+    }
+    for (int m : um)
+      for (int a = 0; a < c->mol_natom[m]; a++) {
+        if (n_uniq >= CAND_SLOTS) { c->err = "more distinct chain atoms than CAND_SLOTS"; return RPB_ERR_DIABATS; }
+        uniq_atom[n_uniq++] = c->mol_first[m] + a;
+      }
+  }
+  int* slot_of_state = (int*)(sc.pack_host + PACK_OFF_SLOT_OF);
+  int* slot_state = (int*)(sc.pack_host + PACK_OFF_SLOT_STATE);
+  int* state_list = (int*)(sc.pack_host + PACK_OFF_STATE_LIST);
+  for (int i = 0; i < MAXS; i++) { slot_of_state[i] = 0; slot_state[i] = -1; state_list[i] = 0; }
+  slot_state[0] = (d.rank == 0) ? 0 : -1;   // slot 0 = principal grid on every rank; it enters theta_mix on rank 0 only
+  int n_own = 0;
   for (int s = 1; s < S; s++)
-    if (state_owned(s, d.rank, d.world)) { state_list.push_back(s); slot_of_state[s] = (int)state_list.size(); slot_state[state_list.size()] = s; }
-  const int n_own = (int)state_list.size();
+    if (state_owned(s, d.rank, d.world)) { state_list[n_own++] = s; slot_of_state[s] = n_own; slot_state[n_own] = s; }
   if (n_own + 1 > c->grid_capacity) { c->err = "grid capacity exceeded"; return RPB_ERR_DIABATS; }
-  state_list.resize(MAXS, 0);
-  CKE(cudaMemcpyAsync(e.items, items.data(), items.size() * sizeof(EvbItem), cudaMemcpyHostToDevice, c->stream));
-  CKE(cudaMemcpyAsync(sc.slot_of_state, slot_of_state.data(), MAXS * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  CKE(cudaMemcpyAsync(sc.slot_state, slot_state.data(), MAXS * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  CKE(cudaMemcpyAsync(sc.state_list, state_list.data(), MAXS * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CKE(cudaMemcpyAsync(sc.pack_dev, sc.pack_host, PACK_BYTES, cudaMemcpyHostToDevice, c->stream));
   {
     CKE(cudaMemsetAsync(e.item_energy, 0, (RPB_MAX_ITEMS + 1) * sizeof(double), c->stream));
     CKE(cudaMemsetAsync(e.vex, 0, MAXS * sizeof(double), c->stream));
-    CKE(cudaMemsetAsync(e.e_recip, 0, MAXS * sizeof(double), c->stream));
     CKE(cudaMemsetAsync(e.dF, 0, (size_t)S * n3 * sizeof(double), c->stream));
     CKE(cudaMemsetAsync(e.Foff, 0, (size_t)S * n3 * sizeof(double), c->stream));
-    k_evb_snapshots<<<(S + 31) / 32, 32, 0, c->stream>>>(d, e, -1);
+    { ScopedTimer t(c, T_EVB_SNAP); k_evb_snapshots<<<(S + SNAP_WPB - 1) / SNAP_WPB, 32 * SNAP_WPB, 0, c->stream>>>(d, e, -1); }
     CKE(cudaMemsetAsync(e.corr_f, 0, (size_t)S * CM * MA * 3 * sizeof(double), c->stream));
     CKE(cudaMemsetAsync(e.corr_atom, 0xff, (size_t)S * CM * MA * sizeof(int), c->stream));
-    dim3 g(n_real, (N + ITEM_TPB - 1) / ITEM_TPB);
-    { ScopedTimer t(c, T_EVB_ITEMS_BG); k_evb_items_background<<<g, ITEM_TPB, 0, c->stream>>>(d, e, n_real); }
-    { ScopedTimer t(c, T_EVB_ITEMS_CHAIN); k_evb_items_chain<<<(n_real + 31) / 32, 32, 0, c->stream>>>(d, e, n_real); }
+    {
+      ScopedTimer t(c, T_EVB_CAND);
+      CKE(cudaMemsetAsync(sc.cand_n, 0, CAND_SLOTS * sizeof(int), c->stream));
+      dim3 g((N + 255) / 256, n_uniq);
+      k_evb_candidates<<<g, 256, 0, c->stream>>>(d, sc.uniq_atom, c->evb_rcand * c->evb_rcand, sc.chain_slot, sc.cand, sc.cand_n);
+    }
+    { ScopedTimer t(c, T_EVB_ITEMS_BG); k_evb_items<<<dim3(n_real, ITEM_SPLIT), ITEM_TPB, 0, c->stream>>>(d, e, sc.chain_slot, sc.cand, sc.cand_n, c->evb_rcand, c->evb_rep_reach); }
     c->n_launch += 3;
   }
   if (n_own > 0) {
-    {
-      { ScopedTimer t(c, T_EVB_BCAST); k_evb_broadcast_grid<<<(unsigned)((K3 / 2 + 255) / 256), 256, 0, c->stream>>>(d.Q, d.Q + K3, K3, n_own); }
-      int warps = h.n_items * 2 * MA;
-      ScopedTimer t(c, T_EVB_PATCH);
-      k_evb_item_pme<<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(d, e, h.n_items, sc.slot_of_state, 0);
-      c->n_launch += 2;
-    }
-    // e_recip[0] = principal E_rec (already in d.en[E_RECIP]); slots 1..n_own batched
-    rc = launch_convolve(c, 1, n_own, e.e_recip, true);
-    if (rc) return rc;
+    { ScopedTimer t(c, T_EVB_BCAST); k_evb_broadcast_grid<<<(unsigned)((K3 / 2 + 255) / 256), 256, 0, c->stream>>>(d.Q, d.Q + K3, K3, n_own); }
+    int warps = h.n_items * 2 * MA;
+    ScopedTimer t(c, T_EVB_PATCH);
+    k_evb_item_pme<<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(d, e, h.n_items, sc.slot_of_state, 0);
+    c->n_launch += 2;
+  }
+  // ONE batched D2Z -> (x CB, E_rec) -> Z2D over the principal grid (slot 0) and every owned diabat (slots 1..n_own)
+  rc = launch_convolve(c, 0, n_own + 1, e.e_recip, true);
+  if (rc) return rc;
+  if (n_own > 0) {
     {
       ScopedTimer t(c, T_EVB_CORR);
       int warps = h.n_items * 2 * MA;
@@ -1218,16 +1737,20 @@ int evb_build(rpb_ctx* c) {
     }
   }
   {
-    ScopedTimer t(c, T_EVB_COUPLING);
-    k_copy<<<1, 32, 0, c->stream>>>(e.e_recip, d.en + E_RECIP, 1);
-    k_evb_coupling_geo<<<(S + 31) / 32, 32, 0, c->stream>>>(d, e, sc.geo);
-    c->n_launch += 2;
+    {
+      ScopedTimer t(c, T_EVB_COUPLING_GEO);
+      k_copy<<<1, 32, 0, c->stream>>>(d.en + E_RECIP, e.e_recip, 1);   // E_rec of the principal diabat (pme.f90:127)
+      k_evb_coupling_geo<<<(S + GEO_WPB - 1) / GEO_WPB, 32 * GEO_WPB, 0, c->stream>>>(d, e, sc.geo);
+      c->n_launch += 2;
+    }
     if (n_own > 0) {
+      ScopedTimer t(c, T_EVB_COUPLING);
       dim3 g(n_own, (N + 255) / 256);
       k_evb_coupling_vex<<<g, 256, 0, c->stream>>>(d, e, sc.geo, sc.state_list);
       c->n_launch += 1;
     }
-    k_evb_assemble<<<(MAXS + 31) / 32, 32, 0, c->stream>>>(d, e, sc.geo, h.n_items, sc.slot_of_state);
+    ScopedTimer t(c, T_EVB_ASSEMBLE);
+    k_evb_assemble<<<(MAXS + 31) / 32, 32, 0, c->stream>>>(d, e, sc.geo, sc.last_item, sc.slot_of_state);
     c->n_launch += 1;
   }
   // keep the principal-diabat force (incl. EVB repulsion, without reciprocal part) in dF slot 0: d.force is
@@ -1253,16 +1776,22 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
   }
   {
     ScopedTimer t(c, T_EVB_DIAG);
+    if (c->evb_solver == 0) {
+      k_evb_tree_solver<<<1, TREE_TPB, 0, c->stream>>>(d, e, coeff_dev);
+      c->n_launch++;
+    } else {
     const int np = S + (S & 1);
-    size_t shmem = ((size_t)2 * np * np + 2 * np) * sizeof(double);
+    size_t shmem = ((size_t)3 * np * np + 2 * np) * sizeof(double);
     if (shmem > 48 * 1024) cudaFuncSetAttribute(k_evb_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
-    k_evb_jacobi<<<1, JAC_TPB, shmem, c->stream>>>(d, e, coeff_dev);
+    const int nbp = np / 2, work = nbp * (nbp - 1) / 2 + nbp * nbp;   // 2x2 blocks of A (upper) and V per round
+    const int nthr = std::min(JAC_TPB, std::max(64, (work + 31) / 32 * 32));
+    k_evb_jacobi<<<1, nthr, shmem, c->stream>>>(d, e, coeff_dev);
     c->n_launch++;
+    }
   }
   {
     int include_principal = (d.rank == 0) ? 1 : 0;
     // slot 0 (principal theta) only contributes on rank 0: mask it on the other ranks through slot_state
-    if (!include_principal) { int m1 = -1; CKE(cudaMemcpyAsync(sc.slot_state, &m1, sizeof(int), cudaMemcpyHostToDevice, c->stream)); }
     { ScopedTimer t(c, T_EVB_THETAMIX); k_evb_theta_mix<<<(unsigned)((K3 / 2 + 255) / 256), 256, 0, c->stream>>>(d, e, sc.slot_state, n_own + 1); }
     { ScopedTimer t(c, T_EVB_MIXF); k_evb_mix_forces<<<(unsigned)((n3 + 255) / 256), 256, 0, c->stream>>>(d, e, sc.state_list, n_own, include_principal);
       if (n_own > 0) { k_evb_add_corr<<<(n_own * CM * MA + 127) / 128, 128, 0, c->stream>>>(d, e, sc.state_list, n_own); c->n_launch++; } }
@@ -1276,7 +1805,7 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
   }
   // read back what the host needs for the commit decision and the accessors
   double* pd = (double*)(h.pinned + 16 + MAXS * (2 + MAXC * 5));
-  CKE(cudaMemcpyAsync(h.pinned + 1, e.result, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CKE(cudaMemcpyAsync(h.pinned + 1, e.result, 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CKE(cudaMemcpyAsync(pd, e.e_ground, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CKE(cudaMemcpyAsync(pd + 1, e.evec, MAXS * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CKE(cudaMemcpyAsync(pd + 1 + MAXS, e.h_full, 2 * MAXS * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1285,6 +1814,8 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
   CKE(cudaStreamSynchronize(c->stream));
   if (c->h_flags[3]) { c->err = "couldn't find index in subroutine 'get_index_atom_set' (code " + std::to_string(c->h_flags[3]) + ")"; return RPB_ERR_STATE; }
   if (h.pinned[3]) { c->err = "too many iterations in jacobi"; return RPB_ERR_STATE; }
+  static const bool dbg_jacobi = getenv("RPB_DEBUG_JACOBI") != nullptr;
+  if (dbg_jacobi) fprintf(stderr, "[evb solver %s] S=%d %s=%d\n", c->evb_solver ? "jacobi" : "tree", S, c->evb_solver ? "sweeps" : "evaluations", h.pinned[5]);
   h.principal_diabat = h.pinned[1]; h.new_hydronium = h.pinned[2];
   h.adiabatic_potential = pd[0];
   memcpy(h.evec, pd + 1, MAXS * sizeof(double));

@@ -202,7 +202,7 @@ __global__ void k_cell_assign(Dev d) {
   int iy = (int)floor((d.inv_box[1] * p.y) * d.ncy) + 1;
   int iz = (int)floor((d.inv_box[2] * p.z) * d.ncz) + 1;
   ix = wrap_cell(ix, d.ncx); iy = wrap_cell(iy, d.ncy); iz = wrap_cell(iz, d.ncz);
-  int c = (ix - 1) + d.ncx * ((iy - 1) + d.ncy * (iz - 1));
+  int c = (iz - 1) + d.ncz * ((iy - 1) + d.ncy * (ix - 1));   // z fastest: a column of the cell walk is contiguous in cell_atoms
   d.atom_cell[i] = c;
   atomicAdd(&d.cell_count[c], 1);
 }
@@ -259,54 +259,74 @@ __global__ void k_cell_sort(Dev d, int ncell) {
   }
 }
 
-// one warp per atom; cells visited ia, ib, ic nested exactly as :1523-1531; pass 0 counts, pass 1 fills
+// One warp per atom.  The reference visits the cells ia, ib, ic nested (:1523-1531) and, inside a cell, ascending atom
+// index; cells are stored z-fastest here, so the innermost ic loop of one (ia, ib) column is ONE contiguous range of
+// cell_atoms (two when the column wraps around the box), which the warp sweeps 32 atoms at a time with
+// ballot-ordered appends -- same row order, ~3x fewer and fuller iterations than cell by cell.
+// Both lists come out of the same walk: the reference's half list (j > i, 1-based) and the symmetric list (j != i,
+// 0-based) of the atomic-free pair kernel.  Pass 0 counts, pass 1 fills.
+// The minimum-image shift uses the reciprocal box: it can differ from the reference's division only for |dr| ~ L/2,
+// where the pair is outside r_v <= L/2 with either shift; dr - L*k itself is evaluated as in the reference.
 template <int FILL>
 __global__ void k_verlet_rows(Dev d) {
   if (!*d.rebuild_now) return;
   int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= d.N) return;
-  int i = w;
+  const int i = w;
   if (FILL && d.err_flag[1]) return;
-  double4 pi = d.xq[i];
-  int mi = d.mol_of_atom[i];
-  int c = d.atom_cell[i];
-  int ix = c % d.ncx + 1, iy = (c / d.ncx) % d.ncy + 1, iz = c / (d.ncx * d.ncy) + 1;
-  int count = 0;
-  int out = FILL ? d.verlet_point[i] - 1 : 0;
+  const double4 pi = d.xq[i];
+  const int mi = d.mol_of_atom[i];
+  const int c = d.atom_cell[i];
+  const int iz = c % d.ncz + 1, iy = (c / d.ncz) % d.ncy + 1, ix = c / (d.ncz * d.ncy) + 1;
+  int n_half = 0, n_full = 0;
+  int out_h = FILL ? d.verlet_point[i] - 1 : 0, out_f = FILL ? d.full_point[i] : 0;
+  // z segments of a column: [iz-dic, iz+dic] wrapped into 1..ncz, in the order the reference meets them
+  int seg0[2], seg1[2], nseg = 1;
+  {
+    int zl = iz - d.dic, zh = iz + d.dic;
+    if (zl < 1) { seg0[0] = zl + d.ncz; seg1[0] = d.ncz; seg0[1] = 1; seg1[1] = zh; nseg = 2; }
+    else if (zh > d.ncz) { seg0[0] = zl; seg1[0] = d.ncz; seg0[1] = 1; seg1[1] = zh - d.ncz; nseg = 2; }
+    else { seg0[0] = zl; seg1[0] = zh; }
+  }
   for (int ia = -d.dia; ia <= d.dia; ia++) {
-    int g1 = wrap_cell(ix + ia, d.ncx);
+    const int g1 = wrap_cell(ix + ia, d.ncx);
     for (int ib = -d.dib; ib <= d.dib; ib++) {
-      int g2 = wrap_cell(iy + ib, d.ncy);
-      for (int ic = -d.dic; ic <= d.dic; ic++) {
-        int g3 = wrap_cell(iz + ic, d.ncz);
-        int cc = (g1 - 1) + d.ncx * ((g2 - 1) + d.ncy * (g3 - 1));
-        int s = d.cell_start[cc], e = d.cell_start[cc + 1];
+      const int g2 = wrap_cell(iy + ib, d.ncy);
+      const int col = d.ncz * ((g2 - 1) + d.ncy * (g1 - 1));
+      for (int sg = 0; sg < nseg; sg++) {
+        const int s = d.cell_start[col + seg0[sg] - 1], e = d.cell_start[col + seg1[sg]];
         for (int b = s; b < e; b += 32) {
-          int a = b + lane;
+          const int a = b + lane;
           bool hit = false;
           int j = -1;
           if (a < e) {
             j = d.cell_atoms[a];
-            if (i < j && d.mol_of_atom[j] != mi) {
-              double4 pj = d.xq[j];
-              double r0 = min_image(pi.x - pj.x, d.box[0]);
-              double r1 = min_image(pi.y - pj.y, d.box[1]);
-              double r2 = min_image(pi.z - pj.z, d.box[2]);
+            if (i != j && d.mol_of_atom[j] != mi) {
+              const double4 pj = d.xq[j];
+              double r0 = pi.x - pj.x, r1 = pi.y - pj.y, r2 = pi.z - pj.z;
+              r0 = r0 - d.box[0] * floor(r0 * d.inv_box[0] + 0.5);
+              r1 = r1 - d.box[1] * floor(r1 * d.inv_box[1] + 0.5);
+              r2 = r2 - d.box[2] * floor(r2 * d.inv_box[2] + 0.5);
               hit = (r0 * r0 + r1 * r1 + r2 * r2) < d.rv2;
             }
           }
-          unsigned bal = __ballot_sync(0xffffffffu, hit);
+          const unsigned bal_f = __ballot_sync(0xffffffffu, hit);
+          const unsigned bal_h = __ballot_sync(0xffffffffu, hit && i < j);
+          const unsigned below = (1u << lane) - 1u;
           if (FILL) {
-            if (hit) d.neighbor_list[out + __popc(bal & ((1u << lane) - 1))] = j + 1;
-            out += __popc(bal);
+            if (hit) {
+              d.full_list[out_f + __popc(bal_f & below)] = j;
+              if (i < j) d.neighbor_list[out_h + __popc(bal_h & below)] = j + 1;
+            }
+            out_f += __popc(bal_f); out_h += __popc(bal_h);
           } else {
-            count += __popc(bal);
+            n_full += __popc(bal_f); n_half += __popc(bal_h);
           }
         }
       }
     }
   }
-  if (!FILL && lane == 0) d.row_count[i] = count;
+  if (!FILL && lane == 0) { d.row_count[i] = n_half; d.row_count_full[i] = n_full; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -360,10 +380,11 @@ static void verlet_common(rpb_ctx* c, int force_rebuild) {
   k_cell_sort<<<nblk(ncell), TPB, 0, c->stream>>>(d, ncell);
   k_verlet_rows<0><<<nblk(d.N * 32), TPB, 0, c->stream>>>(d);
   k_scan<<<1, 1024, 0, c->stream>>>(d.row_count, d.verlet_point, d.N, 1, d.rebuild_now, nullptr, d.verlet_cap, d.err_flag + 1);
+  k_scan<<<1, 1024, 0, c->stream>>>(d.row_count_full, d.full_point, d.N, 0, d.rebuild_now, nullptr, 2 * d.verlet_cap, d.err_flag + 1);
   k_verlet_rows<1><<<nblk(d.N * 32), TPB, 0, c->stream>>>(d);
   k_verlet_disp<<<nb, TPB, 0, c->stream>>>(d, blk_top2);
   k_verlet_end<<<1, TPB, 0, c->stream>>>(d, blk_top2, nb);
-  c->n_launch += 11;
+  c->n_launch += 12;
 }
 
 void launch_verlet_update(rpb_ctx* c) { verlet_common(c, 0); }

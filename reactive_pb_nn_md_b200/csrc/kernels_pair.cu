@@ -5,59 +5,85 @@
 //   intra_molecular_pairwise_energy_force src/pair_int_real_space.f90:386-588
 //   intra_molecular_energy_force          src/intra_bonded_interactions.f90:17-552
 //
-// Pair kernel: one warp per i-atom, lanes stride over the CSR row (coalesced neighbour indices,
-// 32-byte xq gathers that stay in L2), fp64 throughout; F_i is reduced in registers and shuffles,
-// F_j goes out as fp64 RED atomics.  Bound by the FP64 pipe (div/sqrt sequences) -- see DESIGN.md.
+// Pair kernel: one warp per i-atom over its row of the SYMMETRIC list (both directions of every listed pair, built
+// next to the reference-ordered half list at every rebuild): each pair is evaluated from both of its atoms, F_i is
+// reduced in registers + shuffles and stored once -- no atomics, so the forces are reproducible run to run -- and the
+// energies are halved.  Per listed pair: minimum image with a reciprocal box (the shift can only differ from the
+// reference's division for |dr| ~ L/2, far outside the cutoff) and the cutoff test.  Per in-cutoff pair: ONE rsqrt
+// replaces the sqrt and the six divisions of pair_int_real_space.f90:621-645,698-759 (relative differences ~1e-16,
+// the interpolated tables are continuous across bins), and the erfc / ewaldscale tables are read interleaved.
+// Bound by the FP64 pipe -- see DESIGN.md.
 #include "rpb_host.h"
 #include "rpb_bonded.cuh"
 
 #define PAIR_TPB 256
 
-__global__ void __launch_bounds__(PAIR_TPB) k_pair_verlet(Dev d) {
+__global__ void __launch_bounds__(PAIR_TPB, 3) k_pair_verlet(Dev d) {
   extern __shared__ double sh_par[];           // [nT*nT][6] vdw parameters
-  __shared__ int sh_vt[RPB_MAXT * RPB_MAXT];
+  __shared__ int sh_vt[RPB_MAXT * RPB_MAXT];   // atype_vdw_type; 2 = SAPT row with all-zero coefficients (contributes exactly 0)
   __shared__ double sh_red[32];
   for (int k = threadIdx.x; k < d.nT * d.nT * 6; k += blockDim.x) sh_par[k] = d.vdw_param[k];
-  for (int k = threadIdx.x; k < d.nT * d.nT; k += blockDim.x) sh_vt[k] = d.vdw_type[k];
+  for (int k = threadIdx.x; k < d.nT * d.nT; k += blockDim.x) {
+    int vt = d.vdw_type[k];
+    if (vt == 1) {
+      const double* P = &d.vdw_param[6 * k];
+      if (P[0] == 0.0 && P[2] == 0.0 && P[3] == 0.0 && P[4] == 0.0 && P[5] == 0.0) vt = 2;
+    }
+    sh_vt[k] = vt;
+  }
   __syncthreads();
-  int lane = threadIdx.x & 31;
-  int nwarp_total = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nwarp_total = (gridDim.x * blockDim.x) >> 5;
+  const double ibx = d.inv_box[0], iby = d.inv_box[1], ibz = d.inv_box[2];
+  const double bx = d.box[0], by = d.box[1], bz = d.box[2];
   double e_el = 0.0, e_vdw = 0.0;
   for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < d.N; i += nwarp_total) {
-    int vs = d.verlet_point[i] - 1, vf = d.verlet_point[i + 1] - 1;
-    if (vf <= vs) continue;
-    double4 pi = d.xq[i];
-    int ti = d.type[i];
+    const int vs = d.full_point[i], vf = d.full_point[i + 1];
+    const double4 pi = d.xq[i];
+    const int ti = d.type[i] * d.nT;
     double fx = 0.0, fy = 0.0, fz = 0.0;
     for (int v = vs + lane; v < vf; v += 32) {
-      int j = d.neighbor_list[v] - 1;
-      double4 pj = d.xq[j];
-      double dr[3];
-      dr[0] = min_image(pi.x - pj.x, d.box[0]);
-      dr[1] = min_image(pi.y - pj.y, d.box[1]);
-      dr[2] = min_image(pi.z - pj.z, d.box[2]);
-      double dr2 = dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2];
+      const int j = d.full_list[v];
+      const double4 pj = d.xq[j];
+      double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+      dx = fma(-bx, floor(fma(dx, ibx, 0.5)), dx);
+      dy = fma(-by, floor(fma(dy, iby, 0.5)), dy);
+      dz = fma(-bz, floor(fma(dz, ibz, 0.5)), dz);
+      const double dr2 = fma(dz, dz, fma(dy, dy, dx * dx));
       if (dr2 < d.rc2) {
-        int pidx = ti * d.nT + d.type[j];
-        double ee, ev, f[3];
-        pair_terms(d, dr, dr2, pi.w * pj.w, sh_vt[pidx], &sh_par[6 * pidx], true, ee, ev, f);
-        e_el += ee; e_vdw += ev;
-        fx += f[0]; fy += f[1]; fz += f[2];
-        atomicAdd(&d.force[3 * j], -f[0]);
-        atomicAdd(&d.force[3 * j + 1], -f[1]);
-        atomicAdd(&d.force[3 * j + 2], -f[2]);
+        const int pidx = ti + d.type[j];
+        const int vt = sh_vt[pidx];
+        const double inv_r = rsqrt(dr2);
+        const double r = dr2 * inv_r, inv_r2 = inv_r * inv_r;
+        // linear_interpolation_ewald_tables  pair_int_real_space.f90:740-759
+        const double x1 = r * d.inv_erfc_dx;
+        const double ci = ceil(x1);
+        const int it = (int)ci;
+        const double c2 = (x1 + 1.0) - ci, c1 = 1.0 - c2;
+        const double2 t0 = __ldg(&d.es_t[it - 1]), t1 = __ldg(&d.es_t[it]);
+        const double qr = (pi.w * pj.w) * inv_r;
+        e_el = fma(qr, fma(c2, t1.x, c1 * t0.x), e_el);
+        double fs = (qr * inv_r2) * fma(c2, t1.y, c1 * t0.y);
+        if (vt == 0) {                       // pairwise_real_space_LJ :621-645
+          const double c12 = sh_par[6 * pidx], c6 = sh_par[6 * pidx + 1];
+          const double r6 = inv_r2 * inv_r2 * inv_r2, c12r6 = c12 * r6;
+          e_vdw = fma(r6, c12r6 - c6, e_vdw);
+          fs = fma(inv_r2 * r6, 12.0 * c12r6 - 6.0 * c6, fs);
+        } else if (vt == 1) {                // pairwise_real_space_sapt :651-690 (generic path)
+          double dr[3] = {dx, dy, dz}, ee, ev, f[3];
+          pair_terms(d, dr, dr2, 0.0, 1, &sh_par[6 * pidx], false, ee, ev, f);
+          e_vdw += ev;
+          fx += f[0]; fy += f[1]; fz += f[2];
+        }
+        fx = fma(dx, fs, fx); fy = fma(dy, fs, fy); fz = fma(dz, fs, fz);
       }
     }
     fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
-    if (lane == 0) {
-      atomicAdd(&d.force[3 * i], fx);
-      atomicAdd(&d.force[3 * i + 1], fy);
-      atomicAdd(&d.force[3 * i + 2], fz);
-    }
+    if (lane == 0) { d.force[3 * i] += fx; d.force[3 * i + 1] += fy; d.force[3 * i + 2] += fz; }   // this warp owns atom i
   }
   e_el = block_sum(e_el, sh_red);
   e_vdw = block_sum(e_vdw, sh_red);
-  if (threadIdx.x == 0) { atomicAdd(&d.en[E_ELEC], e_el); atomicAdd(&d.en[E_VDW], e_vdw); }
+  if (threadIdx.x == 0) { atomicAdd(&d.en[E_ELEC], 0.5 * e_el); atomicAdd(&d.en[E_VDW], 0.5 * e_vdw); }
 }
 
 // one thread per molecule: intramolecular non-bonded (exclusion correction, 1-4) + bonds/angles/dihedrals

@@ -64,21 +64,44 @@ __global__ void k_gather(Dev d, const double* __restrict__ theta, double* out, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// cuFFT plans are cached per batch size; batch sizes are rounded up to a multiple of 4 (the spare grids behind the
+// last owned diabat are transformed too and ignored) so that a run whose number of diabats changes from step to step
+// never builds a plan inside the step: rpb_set_evb pre-creates every size.  All plans share one work area (they run
+// on one stream).
+int pme_round_batch(int batch) { return batch <= 1 ? 1 : (batch + 3) / 4 * 4; }
+
 int pme_get_plans(rpb_ctx* ctx, int batch, cufftHandle* fwd, cufftHandle* inv) {
+  batch = pme_round_batch(batch);
   auto it = ctx->plan_fwd.find(batch);
   if (it == ctx->plan_fwd.end()) {
     int K = ctx->d.K;
     int n[3] = {K, K, K};
     cufftHandle pf, pi;
-    if (cufftPlanMany(&pf, 3, n, nullptr, 1, K * K * K, nullptr, 1, K * K * (K / 2 + 1), CUFFT_D2Z, batch) != CUFFT_SUCCESS ||
-        cufftPlanMany(&pi, 3, n, nullptr, 1, K * K * (K / 2 + 1), nullptr, 1, K * K * K, CUFFT_Z2D, batch) != CUFFT_SUCCESS) {
-      ctx->err = "cufftPlanMany failed";
+    size_t wf = 0, wi = 0;
+    if (cufftCreate(&pf) != CUFFT_SUCCESS || cufftCreate(&pi) != CUFFT_SUCCESS || cufftSetAutoAllocation(pf, 0) != CUFFT_SUCCESS ||
+        cufftSetAutoAllocation(pi, 0) != CUFFT_SUCCESS ||
+        cufftMakePlanMany(pf, 3, n, nullptr, 1, K * K * K, nullptr, 1, K * K * (K / 2 + 1), CUFFT_D2Z, batch, &wf) != CUFFT_SUCCESS ||
+        cufftMakePlanMany(pi, 3, n, nullptr, 1, K * K * (K / 2 + 1), nullptr, 1, K * K * K, CUFFT_Z2D, batch, &wi) != CUFFT_SUCCESS) {
+      ctx->err = "cufftMakePlanMany failed";
       return RPB_ERR_CUDA;
     }
     cufftSetStream(pf, ctx->stream);
     cufftSetStream(pi, ctx->stream);
     ctx->plan_fwd[batch] = pf;
     ctx->plan_inv[batch] = pi;
+    size_t need = std::max(wf, wi);
+    if (need > ctx->fft_work_bytes) {
+      cudaStreamSynchronize(ctx->stream);
+      char* w = nullptr;
+      int rc = dev_alloc(ctx, &w, need);
+      if (rc) return rc;
+      ctx->fft_work = w; ctx->fft_work_bytes = need;
+      for (auto& kv : ctx->plan_fwd) cufftSetWorkArea(kv.second, w);
+      for (auto& kv : ctx->plan_inv) cufftSetWorkArea(kv.second, w);
+    } else {
+      cufftSetWorkArea(pf, ctx->fft_work);
+      cufftSetWorkArea(pi, ctx->fft_work);
+    }
   }
   *fwd = ctx->plan_fwd[batch];
   *inv = ctx->plan_inv[batch];

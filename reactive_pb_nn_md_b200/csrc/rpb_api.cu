@@ -9,8 +9,9 @@
 
 static const char* k_timer_names[T_NTIMER] = {
     "integrate", "verlet", "pair_real_space", "molecule_terms", "pme_spread", "pme_fft", "pme_convolve", "pme_gather",
-    "evb_enumerate", "evb_items_background", "evb_items_chain", "evb_grid_broadcast", "evb_grid_patch", "evb_recip_corr",
-    "evb_coupling", "evb_jacobi", "evb_theta_mix", "evb_mix_forces", "evb_gather_mix", "step_total"};
+    "evb_enumerate", "evb_items", "evb_candidates", "evb_grid_broadcast", "evb_grid_patch", "evb_recip_corr",
+    "evb_coupling_vex", "evb_jacobi", "evb_theta_mix", "evb_mix_forces", "evb_gather_mix", "evb_snapshots", "evb_coupling_geo",
+    "evb_assemble", "step_total"};
 
 #define CK(call)                                                                  \
   do {                                                                            \
@@ -62,9 +63,10 @@ int calculate_total_force_energy(rpb_ctx* c, bool evb_principal) {
   launch_pair_verlet(c);
   launch_molecule_terms(c);
   launch_spread_principal(c);
+  if (evb_principal) return 0;
   int rc = launch_convolve(c, 0, 1, c->d.en + E_RECIP, true);
   if (rc) return rc;
-  if (!evb_principal) launch_gather(c, c->d.theta, c->d.force_recip, true);
+  launch_gather(c, c->d.theta, c->d.force_recip, true);
   return 0;
 }
 
@@ -163,16 +165,18 @@ int rpb_create(rpb_ctx** out, const rpb_config* cfg) {
 #define AL(p, n) if ((rc = dev_alloc(c, &(p), (n)))) return rc;
   AL(d.xq, N); AL(d.vel, 3 * N); AL(d.force, 3 * N); AL(d.mass, N); AL(d.type, N); AL(d.mol_of_atom, N);
   AL(d.mol_first, M); AL(d.mol_natom, M); AL(d.mol_type, M); AL(d.r_com, 3 * M); AL(d.hydronium, 1);
-  AL(d.verlet_point, N + 1); AL(d.neighbor_list, d.verlet_cap); AL(d.vstore, 3 * N); AL(d.vdisp, 3 * N);
+  AL(d.verlet_point, N + 1); AL(d.neighbor_list, d.verlet_cap); AL(d.full_point, N + 1); AL(d.full_list, 2 * (size_t)d.verlet_cap); AL(d.vstore, 3 * N); AL(d.vdisp, 3 * N);
   AL(d.flag_verlet, 1); AL(d.rebuild_now, 1); AL(d.err_flag, 4);
-  AL(d.cell_count, 2 * (ncell + 1)); AL(d.cell_start, ncell + 1); AL(d.cell_atoms, N); AL(d.atom_cell, N); AL(d.row_count, N + 1);
+  AL(d.cell_count, 2 * (ncell + 1)); AL(d.cell_start, ncell + 1); AL(d.cell_atoms, N); AL(d.atom_cell, N); AL(d.row_count, N + 1); AL(d.row_count_full, N + 1);
   AL(d.maxd, 8 + 2 * ((N + 255) / 256 + 1));
   AL(d.uscale, 3 * N); AL(d.force_recip, 3 * N); AL(d.en, E_NSLOT);
   c->grid_capacity = 1;
   if (cfg->evb_max_states > 0) c->grid_capacity = cfg->evb_max_states;
   // grids are allocated lazily for the diabats in rpb_set_evb; the principal needs one of each
-  AL(d.Q, K3 * (size_t)c->grid_capacity); AL(d.theta, K3 * (size_t)c->grid_capacity); AL(d.FQ, Kh3 * (size_t)c->grid_capacity);
+  const size_t n_grids = (size_t)c->grid_capacity + 4;
+  AL(d.Q, K3 * n_grids); AL(d.theta, K3 * n_grids); AL(d.FQ, Kh3 * n_grids);
 #undef AL
+  CK(cudaMemset(d.Q, 0, K3 * n_grids * sizeof(double)));
   CK(cudaMemset(d.flag_verlet, 0, sizeof(int)));
   CK(cudaMemset(d.rebuild_now, 0, sizeof(int)));
   CK(cudaMemset(d.err_flag, 0, 4 * sizeof(int)));
@@ -185,6 +189,7 @@ int rpb_create(rpb_ctx** out, const rpb_config* cfg) {
 void rpb_destroy(rpb_ctx* c) {
   if (!c) return;
   if (c->stream) cudaStreamSynchronize(c->stream);
+  evb_free(c);
   for (auto& kv : c->plan_fwd) cufftDestroy(kv.second);
   for (auto& kv : c->plan_inv) cufftDestroy(kv.second);
   for (void* p : c->allocs) cudaFree(p);
@@ -208,6 +213,13 @@ int rpb_set_tables(rpb_ctx* c, const double* B6, const double* B5, const double*
   if ((rc = upload(c, &p, B5, c->cfg.spline_grid))) return rc; d.B5 = p;
   if ((rc = upload(c, &p, erfc_t, c->cfg.erfc_grid + 1))) return rc; d.erfc_t = p;
   if ((rc = upload(c, &p, scale_t, c->cfg.erfc_grid + 1))) return rc; d.scale_t = p;
+  {  // interleaved copy for the Verlet pair kernel; two spare points behind the end keep a rounded-up index in bounds
+    std::vector<double2> es((size_t)c->cfg.erfc_grid + 3);
+    for (int i = 0; i < c->cfg.erfc_grid + 3; i++) { int k = std::min(i, c->cfg.erfc_grid); es[i] = make_double2(erfc_t[k], scale_t[k]); }
+    double2* q;
+    if ((rc = upload(c, &q, es.data(), es.size()))) return rc;
+    d.es_t = q; d.inv_erfc_dx = 1.0 / c->cfg.erfc_dx;
+  }
   if ((rc = upload(c, &p, tt, 4 * c->cfg.tt_grid))) return rc; d.tt = p;
   if ((rc = upload(c, &p, dtt, 4 * c->cfg.tt_grid))) return rc; d.dtt = p;
   // Half-spectrum copy of CB(K,K,K), element (m1,m2,m3), m1 <= K/2, stored [m3][m2][m1].
@@ -352,6 +364,16 @@ int rpb_set_evb(rpb_ctx* c, const int* da_i, const double* da_p, const int* pa_i
     e.proton_index[i] = proton_index[i] - 1; e.heavy_acid_index[i] = heavy_acid_index[i] - 1;
   }
   (void)acid; (void)basic;
+  {  // candidate radius of the diabat real-space deltas: the real-space cutoff (+ margin for the rounding of image
+     // positions that were made whole), or the reach of the EVB repulsion terms if that is larger
+    double da_rc = 0.0, pa_rc = 0.0;
+    for (int i = 0; i < MI; i++) {
+      if (e.da_int[i][0] >= 0) da_rc = std::max(da_rc, e.da_par[i][5]);
+      if (e.pa_int[i][0] >= 0) pa_rc = std::max(pa_rc, e.pa_par[i][4]);
+    }
+    c->evb_rep_reach = pa_rc;
+    c->evb_rcand = std::max(c->cfg.real_space_cutoff + 1e-3, std::max(da_rc, pa_rc + 4.0) + 1e-3);
+  }
   // get_heavy_atom_transfer_acid / _base (ms_evb.f90:2888-2938), resolved per molecule type
   auto heavy_acid = [&](int t) {
     if (t < 0 || t >= c->d.nMT) return -1;

@@ -77,12 +77,15 @@ struct Dev {
   const EvbTables* evb;
   // tables
   const double *B6, *B5, *erfc_t, *scale_t, *tt, *dtt, *CBh;
+  const double2* es_t;   // {erfc_t[i], scale_t[i]} interleaved (one 16-byte load per table point)
+  double inv_erfc_dx;
   // verlet
   int* verlet_point; int* neighbor_list; int verlet_cap;
+  int* full_point; int* full_list;   // symmetric (both directions) copy of the list, 0-based, for the atomic-free pair kernel
   double* vstore; double* vdisp; int* flag_verlet; int* rebuild_now;
   int* err_flag;  // [0] atom with |F|>1e5 (1-based, 0 none)  [1] verlet overflow  [2] too many diabats  [3] evb lookup failure
   int ncx, ncy, ncz, dia, dib, dic;
-  int* cell_count; int* cell_start; int* cell_atoms; int* atom_cell; int* row_count;
+  int* cell_count; int* cell_start; int* cell_atoms; int* atom_cell; int* row_count; int* row_count_full;
   double* maxd;  // two largest displacements
   // PME
   double* uscale; double* Q; double* theta; cufftDoubleComplex* FQ; double* force_recip;

@@ -64,6 +64,8 @@ struct EvbDev {
   int* result;                // [0] principal diabat (0-based) [1] new hydronium molecule (0-based) [2] jacobi status
   double* coupling_geo;       // [MAXS][16] A, Vconst, dA[3][3], atoms...
   double* theta_mix;          // K^3
+  double* tree_mu;            // [0] lowest eigenvalue (relative to H_11) of the previous tree solve, [1] 1.0 if valid
+  double* jac_v; int* jac_sig; // eigenvector matrix and diabat-set signature (S, hop logs) of the previous Jacobi solve
 };
 
 struct EvbHost {

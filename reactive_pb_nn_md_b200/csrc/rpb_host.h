@@ -8,8 +8,8 @@
 
 enum {
   T_INTEGRATE = 0, T_VERLET, T_PAIR, T_INTRA, T_SPREAD, T_FFT, T_CONV, T_GATHER, T_EVB_ENUM, T_EVB_ITEMS_BG,
-  T_EVB_ITEMS_CHAIN, T_EVB_BCAST, T_EVB_PATCH, T_EVB_CORR, T_EVB_COUPLING, T_EVB_DIAG, T_EVB_THETAMIX, T_EVB_MIXF,
-  T_EVB_GATHERMIX, T_STEP, T_NTIMER
+  T_EVB_CAND, T_EVB_BCAST, T_EVB_PATCH, T_EVB_CORR, T_EVB_COUPLING, T_EVB_DIAG, T_EVB_THETAMIX, T_EVB_MIXF,
+  T_EVB_GATHERMIX, T_EVB_SNAP, T_EVB_COUPLING_GEO, T_EVB_ASSEMBLE, T_STEP, T_NTIMER
 };
 
 struct rpb_ctx {
@@ -29,11 +29,15 @@ struct rpb_ctx {
   std::vector<int> mol_first, mol_natom, mol_type;
   int hydronium_mol = -1;
   // cuFFT
-  std::map<int, cufftHandle> plan_fwd, plan_inv;
+  std::map<int, cufftHandle> plan_fwd, plan_inv;   // keyed by (rounded) batch size
+  char* fft_work = nullptr; size_t fft_work_bytes = 0;   // work area shared by every plan
   // EVB
   EvbDev e;                    // device pointers of the EVB working set
   EvbHost eh;                  // pinned host read-back area + per-step host state
-  int grid_capacity = 0;       // number of K^3 grids allocated in d.Q / d.theta
+  int grid_capacity = 0;       // number of K^3 grids usable in d.Q / d.theta (4 spare ones follow for the rounded FFT batch)
+  int evb_solver = 0;          // 0: tree-structured ground-state solver (default)  1: block Jacobi (RPB_EVB_SOLVER=jacobi)
+  double evb_rcand = 0.0;      // candidate-list radius of the diabat real-space deltas
+  double evb_rep_reach = 0.0;  // largest cutoff of the EVB proton-acceptor repulsion
   // pinned scratch
   double* h_en = nullptr;      // [E_NSLOT]
   int* h_flags = nullptr;      // [8]
@@ -87,6 +91,7 @@ int measure_fp64_peak(rpb_ctx*, double* tflops);
 void launch_pair_verlet(rpb_ctx*);          // pair_int_real_space.f90:135-371
 void launch_molecule_terms(rpb_ctx*);       // pair_int_real_space.f90:386-588 + intra_bonded_interactions.f90:17-552
 // ---- kernels_pme.cu
+int pme_round_batch(int batch);
 int pme_get_plans(rpb_ctx*, int batch, cufftHandle* fwd, cufftHandle* inv);
 void launch_scaled_coords(rpb_ctx*);
 void launch_spread_principal(rpb_ctx*);     // pme.f90:184-264
@@ -94,6 +99,7 @@ int launch_convolve(rpb_ctx*, int first_grid, int n_grids, double* e_recip_dev, 
 void launch_gather(rpb_ctx*, const double* theta, double* out_force, bool add_to_force);       // pme.f90:346-498
 // ---- kernels_evb.cu
 int evb_alloc(rpb_ctx*);
+void evb_free(rpb_ctx*);
 int evb_build(rpb_ctx*);
 int evb_mix(rpb_ctx*, const double* coeff_override_host, double* force_out_host);
 int evb_commit(rpb_ctx*);

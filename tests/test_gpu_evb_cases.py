@@ -124,3 +124,32 @@ def test_full_size_c3_properties(cuda_lib):
     assert np.count_nonzero(np.triu(H, 1)) == S - 1                   # tree: one coupling per non-principal diabat
     # linearity of the Hellmann-Feynman mix in c_i c_j: F(c) for the ground state equals the stored adiabatic force
     assert rel_rms(sim.debug_mix_forces(ev["eigenvector"]), sim.forces()) < 1e-12
+
+
+def test_tree_solver_matches_block_jacobi(cuda_lib, oracle_lib, monkeypatch):
+    """The default ground-state solver exploits the tree structure of the EVB Hamiltonian; the block-level Jacobi
+    kernel (RPB_EVB_SOLVER=jacobi) and the oracle's Numerical-Recipes Jacobi (general_routines.f90:2013-2088) must
+    give the same ground state, principal diabat and Hellmann-Feynman forces."""
+    s = water_system(10, with_hydronium=True)
+    p = small_params()
+    monkeypatch.delenv("RPB_EVB_SOLVER", raising=False)
+    st = engine.Simulation(s, p, library=cuda_lib)
+    monkeypatch.setenv("RPB_EVB_SOLVER", "jacobi")
+    sj = engine.Simulation(s, p, library=cuda_lib)
+    monkeypatch.delenv("RPB_EVB_SOLVER", raising=False)
+    so = engine.Simulation(s, p, library=oracle_lib)
+    for sim in (st, sj, so):
+        sim.ms_evb_calculate_total_force_energy()
+    et, ej, eo = st.evb(), sj.evb(), so.evb()
+    assert et["n_states"] == ej["n_states"] == eo["n_states"] > 1
+    for a in (et, ej):
+        assert abs(a["adiabatic_potential"] - eo["adiabatic_potential"]) <= 1e-12 * abs(eo["adiabatic_potential"])
+        c = a["eigenvector"] * np.sign(np.dot(a["eigenvector"], eo["eigenvector"]))
+        assert np.abs(c - eo["eigenvector"]).max() < 1e-10
+        assert a["principal_diabat"] == eo["principal_diabat"]
+    assert rel_rms(st.forces(), sj.forces()) < 1e-12
+    # a few steps of dynamics: the warm-started solves stay on the oracle's trajectory
+    for sim in (st, sj, so):
+        sim.md_integrate_atomic(5, ms_evb=True)
+    assert np.abs(st.download_state()["xyz"] - so.download_state()["xyz"]).max() < 1e-9
+    assert np.abs(sj.download_state()["xyz"] - so.download_state()["xyz"]).max() < 1e-9
