@@ -1521,6 +1521,19 @@ __global__ void k_evb_commit_patch(Dev d, EvbDev e, int state, int level, const 
   *d.hydronium = S.m[S.hydronium].mol;
 }
 
+// zero (or -1) every accumulator evb_build adds into: item energies, Vex, candidate counters, chain-atom corrections,
+// and the per-diabat force deltas / coupling forces of the S diabats in flight
+__global__ void k_evb_clear(Dev d, EvbDev e, int* cand_n, int S) {
+  const size_t n3 = (size_t)3 * d.N, nbig = (size_t)S * n3;
+  const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  for (size_t k = tid; k < nbig; k += nth) { e.dF[k] = 0.0; e.Foff[k] = 0.0; }
+  for (size_t k = tid; k < (size_t)S * CM * MA * 3; k += nth) e.corr_f[k] = 0.0;
+  for (size_t k = tid; k < (size_t)S * CM * MA; k += nth) e.corr_atom[k] = -1;
+  for (size_t k = tid; k < RPB_MAX_ITEMS + 1; k += nth) e.item_energy[k] = 0.0;
+  for (size_t k = tid; k < MAXS; k += nth) e.vex[k] = 0.0;
+  for (size_t k = tid; k < CAND_SLOTS; k += nth) cand_n[k] = 0;
+}
+
 // ================================================================================================
 // host orchestration
 // ================================================================================================
@@ -1636,22 +1649,48 @@ static void host_items(rpb_ctx* c, std::vector<EvbItem>& items) {
   }
 }
 
+// host-side wall clock of the orchestration phases (RPB_DEBUG_HOST=1): where the CPU thread spends a step
+#include <chrono>
+struct HostClock {
+  static bool on() { static const bool v = getenv("RPB_DEBUG_HOST") != nullptr; return v; }
+  static double now() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+  static double acc[8]; static long n;
+  static void report() {
+    if (!on() || ++n % 20) return;
+    fprintf(stderr, "[host us/step] principal-launch %.0f | wait-enumerate %.0f | build-launch %.0f | mix-launch %.0f | wait-mix %.0f | commit %.0f\n",
+            acc[0] / 20, acc[1] / 20, acc[2] / 20, acc[3] / 20, acc[4] / 20, acc[5] / 20);
+    for (int k = 0; k < 8; k++) acc[k] = 0;
+  }
+};
+double HostClock::acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+long HostClock::n = 0;
+
+int evb_enumerate_async(rpb_ctx* c) {
+  Dev& d = c->d; EvbDev& e = c->e; EvbHost& h = c->eh;
+  {
+    ScopedTimer t(c, T_EVB_ENUM);
+    k_evb_enumerate<<<1, ENUM_TPB, 0, c->stream>>>(d, e);
+    c->n_launch++;
+  }
+  CKE(cudaMemcpyAsync(h.pinned, e.n_states, ENUM_BLOCK_INTS * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CKE(cudaMemcpyAsync(c->h_flags, d.err_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CKE(cudaEventRecord(c->ev_enum, c->stream));
+  return 0;
+}
+
 int evb_build(rpb_ctx* c) {
   Dev& d = c->d; EvbDev& e = c->e; EvbHost& h = c->eh;
   EvbScratch& sc = g_scratch[c];
   const int N = d.N;
   const size_t K3 = (size_t)d.K * d.K * d.K, n3 = (size_t)3 * N;
-  int rc = calculate_total_force_energy(c, true);   // principal diabat; its FFT convolution joins the batch below
+  double hc0 = HostClock::now();
+  int rc = calculate_total_force_energy(c, true);   // principal diabat (+ enumeration); its FFT convolution joins the batch below
   if (rc) return rc;
+  double hc1 = HostClock::now();
   {
-    ScopedTimer t(c, T_EVB_ENUM);
-    k_evb_enumerate<<<1, ENUM_TPB, 0, c->stream>>>(d, e);
-    c->n_launch++;
     int* pin = h.pinned;
-    CKE(cudaMemcpyAsync(pin, e.n_states, ENUM_BLOCK_INTS * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CKE(cudaMemcpyAsync(c->h_flags, d.err_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CKE(cudaStreamSynchronize(c->stream));
-    if (c->h_flags[1]) { c->err = "please increase size of verlet neighbor list"; return RPB_ERR_VERLET; }
+    CKE(cudaEventSynchronize(c->ev_enum));           // only the enumeration: the pair forces etc. are still running
+    HostClock::acc[0] += hc1 - hc0; hc0 = HostClock::now(); HostClock::acc[1] += hc0 - hc1;
     if (c->h_flags[2]) { c->err = "Found more diabat states than the current setting of evb_max_states"; return RPB_ERR_DIABATS; }
     if (c->h_flags[3]) { c->err = "error in subroutine find_bonded_atom_hydrogen"; return RPB_ERR_STATE; }
     h.n_states = pin[0];
@@ -1701,35 +1740,32 @@ int evb_build(rpb_ctx* c) {
     if (state_owned(s, d.rank, d.world)) { state_list[n_own++] = s; slot_of_state[s] = n_own; slot_state[n_own] = s; }
   if (n_own + 1 > c->grid_capacity) { c->err = "grid capacity exceeded"; return RPB_ERR_DIABATS; }
   CKE(cudaMemcpyAsync(sc.pack_dev, sc.pack_host, PACK_BYTES, cudaMemcpyHostToDevice, c->stream));
+  k_evb_clear<<<148 * 4, 256, 0, c->stream>>>(d, e, sc.cand_n, S);   // every accumulator of the build, one launch
+  c->n_launch += 1;
+  { ScopedTimer t(c, T_EVB_SNAP); k_evb_snapshots<<<(S + SNAP_WPB - 1) / SNAP_WPB, 32 * SNAP_WPB, 0, c->stream>>>(d, e, -1); }
+  c->n_launch += 1;
+  // Three independent branches from here (joined before the Hamiltonian is assembled):
+  //   main   : candidate lists -> real-space / repulsion / bonded deltas of every (diabat, last hop, topology)
+  //   aux[0] : off-diagonal couplings (geometry factor, Vex with all atoms)
+  //   aux[1] : reciprocal space -- delta grids, ONE batched D2Z -> (x CB, E_rec) -> Z2D over the principal grid
+  //            (slot 0, spread on this stream by calculate_total_force_energy) and every owned diabat, chain-atom
+  //            force corrections
+  stream_depend(c, 4, c->main_stream, c->aux[0]);
+  stream_depend(c, 5, c->main_stream, c->aux[1]);
   {
-    CKE(cudaMemsetAsync(e.item_energy, 0, (RPB_MAX_ITEMS + 1) * sizeof(double), c->stream));
-    CKE(cudaMemsetAsync(e.vex, 0, MAXS * sizeof(double), c->stream));
-    CKE(cudaMemsetAsync(e.dF, 0, (size_t)S * n3 * sizeof(double), c->stream));
-    CKE(cudaMemsetAsync(e.Foff, 0, (size_t)S * n3 * sizeof(double), c->stream));
-    { ScopedTimer t(c, T_EVB_SNAP); k_evb_snapshots<<<(S + SNAP_WPB - 1) / SNAP_WPB, 32 * SNAP_WPB, 0, c->stream>>>(d, e, -1); }
-    CKE(cudaMemsetAsync(e.corr_f, 0, (size_t)S * CM * MA * 3 * sizeof(double), c->stream));
-    CKE(cudaMemsetAsync(e.corr_atom, 0xff, (size_t)S * CM * MA * sizeof(int), c->stream));
-    {
-      ScopedTimer t(c, T_EVB_CAND);
-      CKE(cudaMemsetAsync(sc.cand_n, 0, CAND_SLOTS * sizeof(int), c->stream));
-      dim3 g((N + 255) / 256, n_uniq);
-      k_evb_candidates<<<g, 256, 0, c->stream>>>(d, sc.uniq_atom, c->evb_rcand * c->evb_rcand, sc.chain_slot, sc.cand, sc.cand_n);
+    StreamScope ss(c, c->aux[1]);
+    if (n_own > 0) {
+      { ScopedTimer t(c, T_EVB_BCAST); k_evb_broadcast_grid<<<(unsigned)((K3 / 2 + 255) / 256), 256, 0, c->stream>>>(d.Q, d.Q + K3, K3, n_own); }
+      int warps = h.n_items * 2 * MA;
+      ScopedTimer t(c, T_EVB_PATCH);
+      k_evb_item_pme<<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(d, e, h.n_items, sc.slot_of_state, 0);
+      c->n_launch += 2;
     }
-    { ScopedTimer t(c, T_EVB_ITEMS_BG); k_evb_items<<<dim3(n_real, ITEM_SPLIT), ITEM_TPB, 0, c->stream>>>(d, e, sc.chain_slot, sc.cand, sc.cand_n, c->evb_rcand, c->evb_rep_reach); }
-    c->n_launch += 3;
-  }
-  if (n_own > 0) {
-    { ScopedTimer t(c, T_EVB_BCAST); k_evb_broadcast_grid<<<(unsigned)((K3 / 2 + 255) / 256), 256, 0, c->stream>>>(d.Q, d.Q + K3, K3, n_own); }
-    int warps = h.n_items * 2 * MA;
-    ScopedTimer t(c, T_EVB_PATCH);
-    k_evb_item_pme<<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(d, e, h.n_items, sc.slot_of_state, 0);
-    c->n_launch += 2;
-  }
-  // ONE batched D2Z -> (x CB, E_rec) -> Z2D over the principal grid (slot 0) and every owned diabat (slots 1..n_own)
-  rc = launch_convolve(c, 0, n_own + 1, e.e_recip, true);
-  if (rc) return rc;
-  if (n_own > 0) {
-    {
+    rc = launch_convolve(c, 0, n_own + 1, e.e_recip, true);
+    if (rc) return rc;
+    k_copy<<<1, 32, 0, c->stream>>>(d.en + E_RECIP, e.e_recip, 1);   // E_rec of the principal diabat (pme.f90:127)
+    c->n_launch += 1;
+    if (n_own > 0) {
       ScopedTimer t(c, T_EVB_CORR);
       int warps = h.n_items * 2 * MA;
       k_evb_item_pme<<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(d, e, h.n_items, sc.slot_of_state, 1);
@@ -1737,11 +1773,11 @@ int evb_build(rpb_ctx* c) {
     }
   }
   {
+    StreamScope ss(c, c->aux[0]);
     {
       ScopedTimer t(c, T_EVB_COUPLING_GEO);
-      k_copy<<<1, 32, 0, c->stream>>>(d.en + E_RECIP, e.e_recip, 1);   // E_rec of the principal diabat (pme.f90:127)
       k_evb_coupling_geo<<<(S + GEO_WPB - 1) / GEO_WPB, 32 * GEO_WPB, 0, c->stream>>>(d, e, sc.geo);
-      c->n_launch += 2;
+      c->n_launch += 1;
     }
     if (n_own > 0) {
       ScopedTimer t(c, T_EVB_COUPLING);
@@ -1749,6 +1785,19 @@ int evb_build(rpb_ctx* c) {
       k_evb_coupling_vex<<<g, 256, 0, c->stream>>>(d, e, sc.geo, sc.state_list);
       c->n_launch += 1;
     }
+  }
+  {
+    {
+      ScopedTimer t(c, T_EVB_CAND);
+      dim3 g((N + 255) / 256, n_uniq);
+      k_evb_candidates<<<g, 256, 0, c->stream>>>(d, sc.uniq_atom, c->evb_rcand * c->evb_rcand, sc.chain_slot, sc.cand, sc.cand_n);
+    }
+    { ScopedTimer t(c, T_EVB_ITEMS_BG); k_evb_items<<<dim3(n_real, ITEM_SPLIT), ITEM_TPB, 0, c->stream>>>(d, e, sc.chain_slot, sc.cand, sc.cand_n, c->evb_rcand, c->evb_rep_reach); }
+    c->n_launch += 2;
+  }
+  stream_depend(c, 6, c->aux[0], c->main_stream);
+  stream_depend(c, 7, c->aux[1], c->main_stream);
+  {
     ScopedTimer t(c, T_EVB_ASSEMBLE);
     k_evb_assemble<<<(MAXS + 31) / 32, 32, 0, c->stream>>>(d, e, sc.geo, sc.last_item, sc.slot_of_state);
     c->n_launch += 1;
@@ -1758,6 +1807,7 @@ int evb_build(rpb_ctx* c) {
   k_copy<<<(unsigned)((n3 + 255) / 256), 256, 0, c->stream>>>(e.dF, d.force, n3);
   c->n_launch++;
   h.built = true;
+  HostClock::acc[2] += HostClock::now() - hc0;
   return 0;
 }
 
@@ -1765,6 +1815,7 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
   Dev& d = c->d; EvbDev& e = c->e; EvbHost& h = c->eh;
   EvbScratch& sc = g_scratch[c];
   if (!h.built) { c->err = "evb_mix before evb_build"; return RPB_ERR_STATE; }
+  double hm0 = HostClock::now();
   const int N = d.N, S = h.n_states;
   const size_t K3 = (size_t)d.K * d.K * d.K, n3 = (size_t)3 * N;
   int n_own = 0;
@@ -1789,6 +1840,18 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
     c->n_launch++;
     }
   }
+  double* pd = (double*)(h.pinned + 16 + MAXS * (2 + MAXC * 5));
+  if (!coeff_override_host) {
+  // read back what the host needs for the commit decision and the accessors right behind the solver: the host waits
+  // for THIS event only, while the mixing kernels queued below are still running
+  CKE(cudaMemcpyAsync(h.pinned + 1, e.result, 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CKE(cudaMemcpyAsync(pd, e.e_ground, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CKE(cudaMemcpyAsync(pd + 1, e.evec, MAXS * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CKE(cudaMemcpyAsync(pd + 1 + MAXS, e.h_full, 2 * MAXS * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CKE(cudaMemcpyAsync(c->h_flags, d.err_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CKE(cudaMemcpyAsync(c->h_en, d.en, E_NSLOT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CKE(cudaEventRecord(c->ev_enum, c->stream));
+  }
   {
     int include_principal = (d.rank == 0) ? 1 : 0;
     // slot 0 (principal theta) only contributes on rank 0: mask it on the other ranks through slot_state
@@ -1803,15 +1866,10 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
     CKE(cudaMemcpy(force_out_host, e.f_mix, n3 * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
   }
-  // read back what the host needs for the commit decision and the accessors
-  double* pd = (double*)(h.pinned + 16 + MAXS * (2 + MAXC * 5));
-  CKE(cudaMemcpyAsync(h.pinned + 1, e.result, 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CKE(cudaMemcpyAsync(pd, e.e_ground, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CKE(cudaMemcpyAsync(pd + 1, e.evec, MAXS * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CKE(cudaMemcpyAsync(pd + 1 + MAXS, e.h_full, 2 * MAXS * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CKE(cudaMemcpyAsync(c->h_flags, d.err_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CKE(cudaMemcpyAsync(c->h_en, d.en, E_NSLOT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CKE(cudaStreamSynchronize(c->stream));
+  double hm1 = HostClock::now();
+  CKE(cudaEventSynchronize(c->ev_enum));
+  HostClock::acc[3] += hm1 - hm0; HostClock::acc[4] += HostClock::now() - hm1;
+  if (c->h_flags[1]) { c->err = "please increase size of verlet neighbor list"; return RPB_ERR_VERLET; }
   if (c->h_flags[3]) { c->err = "couldn't find index in subroutine 'get_index_atom_set' (code " + std::to_string(c->h_flags[3]) + ")"; return RPB_ERR_STATE; }
   if (h.pinned[3]) { c->err = "too many iterations in jacobi"; return RPB_ERR_STATE; }
   static const bool dbg_jacobi = getenv("RPB_DEBUG_JACOBI") != nullptr;
@@ -1841,6 +1899,7 @@ static void host_shift(std::vector<int>& perm, std::vector<int>& first, std::vec
 }
 
 int evb_commit(rpb_ctx* c) {
+  HostClock::report();
   Dev& d = c->d; EvbDev& e = c->e; EvbHost& h = c->eh;
   EvbScratch& sc = g_scratch[c];
   const int N = d.N, M = d.M;

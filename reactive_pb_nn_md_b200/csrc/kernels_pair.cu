@@ -13,10 +13,30 @@
 // replaces the sqrt and the six divisions of pair_int_real_space.f90:621-645,698-759 (relative differences ~1e-16,
 // the interpolated tables are continuous across bins), and the erfc / ewaldscale tables are read interleaved.
 // Bound by the FP64 pipe -- see DESIGN.md.
+#include <cstdlib>
 #include "rpb_host.h"
 #include "rpb_bonded.cuh"
 
-#define PAIR_TPB 256
+#define PAIR_TPB 128
+#define PAIR_B 4        // neighbours in flight per lane
+
+// cold path of the pair kernel: a SAPT row with non-zero coefficients (pairwise_real_space_sapt :651-690; the example
+// force field has none).  Out of line and fed with scalars so that it costs the hot loop no registers.
+__device__ __noinline__ void sapt_pair(const double* __restrict__ tt_t, const double* __restrict__ dtt_t, double tt_max, int tt_grid,
+                                       double dr2, const double* par, double& e_vdw, double& fs) {
+  const double A = par[0], B = par[1], C6 = par[2], C8 = par[3], C10 = par[4], C12 = par[5];
+  const double r = sqrt(dr2);
+  const double dr6 = dr2 * dr2 * dr2, dr8 = dr6 * dr2, dr10 = dr8 * dr2, dr12 = dr10 * dr2;
+  const int idx = (int)ceil(B * r / tt_max * (double)tt_grid);
+  const double* tt = &tt_t[4 * (idx - 1)];
+  const double* dt = &dtt_t[4 * (idx - 1)];
+  const double ex = exp(-1 * B * r);
+  e_vdw += A * ex - tt[0] * C6 / dr6 - tt[1] * C8 / dr8 - tt[2] * C10 / dr10 - tt[3] * C12 / dr12;
+  const double fac = r * A * B * ex + r * (B * dt[0]) * C6 / dr6 - tt[0] * 6.0 * C6 / dr6 + r * (B * dt[1]) * C8 / dr8 -
+                     tt[1] * 8.0 * C8 / dr8 + r * (B * dt[2]) * C10 / dr10 - tt[2] * 10.0 * C10 / dr10 +
+                     r * (B * dt[3]) * C12 / dr12 - tt[3] * 12.0 * C12 / dr12;
+  fs += fac / dr2;
+}
 
 __global__ void __launch_bounds__(PAIR_TPB, 3) k_pair_verlet(Dev d) {
   extern __shared__ double sh_par[];           // [nT*nT][6] vdw parameters
@@ -36,50 +56,75 @@ __global__ void __launch_bounds__(PAIR_TPB, 3) k_pair_verlet(Dev d) {
   const int nwarp_total = (gridDim.x * blockDim.x) >> 5;
   const double ibx = d.inv_box[0], iby = d.inv_box[1], ibz = d.inv_box[2];
   const double bx = d.box[0], by = d.box[1], bz = d.box[2];
+  const int* __restrict__ L = d.full_list;
   double e_el = 0.0, e_vdw = 0.0;
   for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < d.N; i += nwarp_total) {
     const int vs = d.full_point[i], vf = d.full_point[i + 1];
     const double4 pi = d.xq[i];
     const int ti = d.type[i] * d.nT;
     double fx = 0.0, fy = 0.0, fz = 0.0;
-    for (int v = vs + lane; v < vf; v += 32) {
-      const int j = d.full_list[v];
-      const double4 pj = d.xq[j];
-      double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-      dx = fma(-bx, floor(fma(dx, ibx, 0.5)), dx);
-      dy = fma(-by, floor(fma(dy, iby, 0.5)), dy);
-      dz = fma(-bz, floor(fma(dz, ibz, 0.5)), dz);
-      const double dr2 = fma(dz, dz, fma(dy, dy, dx * dx));
-      if (dr2 < d.rc2) {
-        const int pidx = ti + d.type[j];
+    // The loop is bound by memory latency, not arithmetic: a warp issues in order and stalls at the first USE of a
+    // pending load, so every lane works on PAIR_B neighbours at once -- PAIR_B list entries, then PAIR_B 32-byte
+    // coordinate gathers, then PAIR_B 32-byte table gathers are issued back to back (one exposed latency per batch and
+    // stage instead of one per neighbour), and the list entries of the next batch are fetched a full batch ahead.
+    // (Measured on B200, C3: 107 us one neighbour at a time -> 59 us with PAIR_B = 4; staging the gathers through
+    // shared memory with cp.async was slower, 142 us -- twice the L1 wavefronts for 16-byte copies.)
+    int jn[PAIR_B];
+#pragma unroll
+    for (int k = 0; k < PAIR_B; k++) { const int v = vs + 32 * k + lane; jn[k] = v < vf ? L[v] : -1; }
+    for (int base = vs; base < vf; base += 32 * PAIR_B) {
+      int j[PAIR_B];
+      double4 p[PAIR_B];
+#pragma unroll
+      for (int k = 0; k < PAIR_B; k++) { j[k] = jn[k]; p[k] = make_double4(0.0, 0.0, 0.0, 0.0); if (j[k] >= 0) p[k] = ldg256(&d.xq[j[k] & 0xffffff]); }
+#pragma unroll
+      for (int k = 0; k < PAIR_B; k++) { const int v = base + 32 * (PAIR_B + k) + lane; jn[k] = v < vf ? L[v] : -1; }
+      double sdx[PAIR_B], sdy[PAIR_B], sdz[PAIR_B], sinv[PAIR_B], sc2[PAIR_B], sqq[PAIR_B];
+      double4 tb[PAIR_B];       // {erfc[i-1], scale[i-1], erfc[i], scale[i]}
+      bool in[PAIR_B];
+#pragma unroll
+      for (int k = 0; k < PAIR_B; k++) {   // minimum image, cutoff, table index, table load
+        double dx = pi.x - p[k].x, dy = pi.y - p[k].y, dz = pi.z - p[k].z;
+        dx = fma(-bx, floor(fma(dx, ibx, 0.5)), dx);
+        dy = fma(-by, floor(fma(dy, iby, 0.5)), dy);
+        dz = fma(-bz, floor(fma(dz, ibz, 0.5)), dz);
+        const double dr2 = fma(dz, dz, fma(dy, dy, dx * dx));
+        in[k] = j[k] >= 0 && dr2 < d.rc2;
+        tb[k] = make_double4(0.0, 0.0, 0.0, 0.0);
+        sdx[k] = dx; sdy[k] = dy; sdz[k] = dz; sqq[k] = pi.w * p[k].w;
+        sinv[k] = 1.0; sc2[k] = 0.0;
+        if (in[k]) {
+          const double inv_r = rsqrt(dr2);
+          // linear_interpolation_ewald_tables  pair_int_real_space.f90:740-759
+          const double x1 = (dr2 * inv_r) * d.inv_erfc_dx;
+          const double ci = ceil(x1);
+          tb[k] = ldg256(&d.es2_t[(int)ci]);
+          sc2[k] = (x1 + 1.0) - ci;
+          sinv[k] = inv_r;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < PAIR_B; k++) {   // energies and force of the in-cutoff pairs
+        if (!in[k]) continue;
+        const int pidx = ti + (j[k] >> 24);
+        const double inv_r = sinv[k], inv_r2 = inv_r * inv_r, c1 = 1.0 - sc2[k];
+        const double qr = sqq[k] * inv_r;
+        e_el = fma(qr, fma(sc2[k], tb[k].z, c1 * tb[k].x), e_el);
+        double fs = (qr * inv_r2) * fma(sc2[k], tb[k].w, c1 * tb[k].y);
         const int vt = sh_vt[pidx];
-        const double inv_r = rsqrt(dr2);
-        const double r = dr2 * inv_r, inv_r2 = inv_r * inv_r;
-        // linear_interpolation_ewald_tables  pair_int_real_space.f90:740-759
-        const double x1 = r * d.inv_erfc_dx;
-        const double ci = ceil(x1);
-        const int it = (int)ci;
-        const double c2 = (x1 + 1.0) - ci, c1 = 1.0 - c2;
-        const double2 t0 = __ldg(&d.es_t[it - 1]), t1 = __ldg(&d.es_t[it]);
-        const double qr = (pi.w * pj.w) * inv_r;
-        e_el = fma(qr, fma(c2, t1.x, c1 * t0.x), e_el);
-        double fs = (qr * inv_r2) * fma(c2, t1.y, c1 * t0.y);
         if (vt == 0) {                       // pairwise_real_space_LJ :621-645
           const double c12 = sh_par[6 * pidx], c6 = sh_par[6 * pidx + 1];
           const double r6 = inv_r2 * inv_r2 * inv_r2, c12r6 = c12 * r6;
           e_vdw = fma(r6, c12r6 - c6, e_vdw);
           fs = fma(inv_r2 * r6, 12.0 * c12r6 - 6.0 * c6, fs);
         } else if (vt == 1) {                // pairwise_real_space_sapt :651-690 (generic path)
-          double dr[3] = {dx, dy, dz}, ee, ev, f[3];
-          pair_terms(d, dr, dr2, 0.0, 1, &sh_par[6 * pidx], false, ee, ev, f);
-          e_vdw += ev;
-          fx += f[0]; fy += f[1]; fz += f[2];
+          sapt_pair(d.tt, d.dtt, d.tt_max, d.tt_grid, 1.0 / inv_r2, &sh_par[6 * pidx], e_vdw, fs);
         }
-        fx = fma(dx, fs, fx); fy = fma(dy, fs, fy); fz = fma(dz, fs, fz);
+        fx = fma(sdx[k], fs, fx); fy = fma(sdy[k], fs, fy); fz = fma(sdz[k], fs, fz);
       }
     }
     fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
-    if (lane == 0) { d.force[3 * i] += fx; d.force[3 * i + 1] += fy; d.force[3 * i + 2] += fz; }   // this warp owns atom i
+    if (lane == 0) { atomicAdd(&d.force[3 * i], fx); atomicAdd(&d.force[3 * i + 1], fy); atomicAdd(&d.force[3 * i + 2], fz); }   // one RED per component: the bonded branch adds to d.force concurrently
   }
   e_el = block_sum(e_el, sh_red);
   e_vdw = block_sum(e_vdw, sh_red);
@@ -116,9 +161,9 @@ __global__ void k_molecule_terms(Dev d) {
 
 void launch_pair_verlet(rpb_ctx* c) {
   ScopedTimer t(c, T_PAIR);
-  int warps_per_block = PAIR_TPB / 32;
-  int blocks = std::min((c->d.N + warps_per_block - 1) / warps_per_block, 148 * 8);
-  size_t shmem = (size_t)c->d.nT * c->d.nT * 6 * sizeof(double);
+  const int warps_per_block = PAIR_TPB / 32;
+  const int blocks = (c->d.N + warps_per_block - 1) / warps_per_block;
+  const size_t shmem = (size_t)c->d.nT * c->d.nT * 6 * sizeof(double);
   k_pair_verlet<<<blocks, PAIR_TPB, shmem, c->stream>>>(c->d);
   c->n_launch += 1;
 }

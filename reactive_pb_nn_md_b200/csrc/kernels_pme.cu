@@ -131,6 +131,7 @@ int launch_convolve(rpb_ctx* c, int first_grid, int n_grids, double* e_recip_dev
   size_t K3 = (size_t)K * K * K, Kh3 = (size_t)K * K * (K / 2 + 1);
   {
     ScopedTimer t(c, T_FFT);
+    cufftSetStream(pf, c->stream);
     if (cufftExecD2Z(pf, c->d.Q + K3 * first_grid, c->d.FQ + Kh3 * first_grid) != CUFFT_SUCCESS) { c->err = "cufftExecD2Z failed"; return RPB_ERR_CUDA; }
     c->n_fft += 1;
   }
@@ -143,6 +144,7 @@ int launch_convolve(rpb_ctx* c, int first_grid, int n_grids, double* e_recip_dev
   }
   if (inverse) {
     ScopedTimer t(c, T_FFT);
+    cufftSetStream(pi, c->stream);
     if (cufftExecZ2D(pi, c->d.FQ + Kh3 * first_grid, c->d.theta + K3 * first_grid) != CUFFT_SUCCESS) { c->err = "cufftExecZ2D failed"; return RPB_ERR_CUDA; }
     c->n_fft += 1;
   }

@@ -57,15 +57,29 @@ static void energies_from_slots(rpb_ctx* c) {
 // calculate_total_force_energy (total_energy_forces.f90:19-99); evb_principal: called as the principal-diabat
 // evaluation of construct_evb_hamiltonian (ms_evb.f90:411): the reciprocal force is gathered later from the
 // Hellmann-Feynman mixed grid instead (DESIGN.md "theta-mix").
+// Three independent branches run concurrently: [Verlet update -> pair forces] on the main stream, the per-molecule
+// bonded / intramolecular terms on aux[0], and the PME reciprocal branch (scaled coordinates, spreading, FFT) on
+// aux[1].  In MS-EVB mode aux[1] is NOT joined here: evb_build keeps using it for the batched diabat grids.
 int calculate_total_force_energy(rpb_ctx* c, bool evb_principal) {
-  launch_verlet_update(c);
   launch_zero_forces(c);
-  launch_pair_verlet(c);
-  launch_molecule_terms(c);
-  launch_spread_principal(c);
-  if (evb_principal) return 0;
-  int rc = launch_convolve(c, 0, 1, c->d.en + E_RECIP, true);
+  stream_depend(c, 0, c->main_stream, c->aux[0]);
+  stream_depend(c, 1, c->main_stream, c->aux[1]);
+  { StreamScope sc(c, c->aux[0]); launch_molecule_terms(c); }
+  int rc = 0;
+  {
+    StreamScope sc(c, c->aux[1]);
+    launch_spread_principal(c);
+    if (!evb_principal) rc = launch_convolve(c, 0, 1, c->d.en + E_RECIP, true);
+  }
   if (rc) return rc;
+  // MS-EVB: the diabat enumeration needs positions and centres of mass only; it goes first on the main stream so that
+  // the host learns the number of diabats (which sizes the later launches) while the GPU is busy with the pair forces
+  if (evb_principal && (rc = evb_enumerate_async(c))) return rc;
+  launch_verlet_update(c);
+  launch_pair_verlet(c);
+  stream_depend(c, 2, c->aux[0], c->main_stream);
+  if (evb_principal) return 0;
+  stream_depend(c, 3, c->aux[1], c->main_stream);
   launch_gather(c, c->d.theta, c->d.force_recip, true);
   return 0;
 }
@@ -110,11 +124,16 @@ int rpb_create(rpb_ctx** out, const rpb_config* cfg) {
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++)
       if (i != j && std::fabs(cfg->box[i + 3 * j]) > 10e-6) { c->err = "code has been modified to assume orthorhombic box"; return RPB_ERR_UNSUPPORTED; }
+  if (cfg->n_atoms >= (1 << 24)) { c->err = "more than 2^24 atoms: the symmetric neighbour list packs the atom type into the top byte"; return RPB_ERR_UNSUPPORTED; }
   if (cfg->evb_max_chain > RPB_MAXC || cfg->evb_max_states > RPB_MAXS) { c->err = "evb limits exceed compiled maxima"; return RPB_ERR_ARG; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { c->err = "no CUDA device: librpbmd.so has no CPU fallback"; return RPB_ERR_CUDA; }
   CK(cudaSetDevice(cfg->device));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->main_stream = c->stream;
+  for (int k = 0; k < 2; k++) CK(cudaStreamCreateWithFlags(&c->aux[k], cudaStreamNonBlocking));
+  for (int k = 0; k < 8; k++) CK(cudaEventCreateWithFlags(&c->ev_sync[k], cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_enum, cudaEventDisableTiming));
   CK(cudaMallocHost(&c->h_en, E_NSLOT * sizeof(double)));
   CK(cudaMallocHost(&c->h_flags, 8 * sizeof(int)));
   Dev& d = c->d;
@@ -165,8 +184,9 @@ int rpb_create(rpb_ctx** out, const rpb_config* cfg) {
 #define AL(p, n) if ((rc = dev_alloc(c, &(p), (n)))) return rc;
   AL(d.xq, N); AL(d.vel, 3 * N); AL(d.force, 3 * N); AL(d.mass, N); AL(d.type, N); AL(d.mol_of_atom, N);
   AL(d.mol_first, M); AL(d.mol_natom, M); AL(d.mol_type, M); AL(d.r_com, 3 * M); AL(d.hydronium, 1);
-  AL(d.verlet_point, N + 1); AL(d.neighbor_list, d.verlet_cap); AL(d.full_point, N + 1); AL(d.full_list, 2 * (size_t)d.verlet_cap); AL(d.vstore, 3 * N); AL(d.vdisp, 3 * N);
-  AL(d.flag_verlet, 1); AL(d.rebuild_now, 1); AL(d.err_flag, 4);
+  AL(d.verlet_point, N + 1); AL(d.neighbor_list, d.verlet_cap); AL(d.full_point, N + 1); AL(d.full_list, 2 * (size_t)d.verlet_cap);
+  AL(d.vrow_tmp, (size_t)N * 1024); AL(d.vsort_xq, N); AL(d.vsort_mol, N); AL(d.vsort_entry, N); AL(d.vstore, 3 * N); AL(d.vdisp, 3 * N);
+  AL(d.flag_verlet, 1); AL(d.rebuild_now, 1); AL(d.err_flag, 4); AL(d.vdone, 1);
   AL(d.cell_count, 2 * (ncell + 1)); AL(d.cell_start, ncell + 1); AL(d.cell_atoms, N); AL(d.atom_cell, N); AL(d.row_count, N + 1); AL(d.row_count_full, N + 1);
   AL(d.maxd, 8 + 2 * ((N + 255) / 256 + 1));
   AL(d.uscale, 3 * N); AL(d.force_recip, 3 * N); AL(d.en, E_NSLOT);
@@ -179,6 +199,7 @@ int rpb_create(rpb_ctx** out, const rpb_config* cfg) {
   CK(cudaMemset(d.Q, 0, K3 * n_grids * sizeof(double)));
   CK(cudaMemset(d.flag_verlet, 0, sizeof(int)));
   CK(cudaMemset(d.rebuild_now, 0, sizeof(int)));
+  CK(cudaMemset(d.vdone, 0, sizeof(int)));
   CK(cudaMemset(d.err_flag, 0, 4 * sizeof(int)));
   CK(cudaMemset(d.en, 0, E_NSLOT * sizeof(double)));
   CK(cudaMemset(d.force, 0, 3 * N * sizeof(double)));
@@ -198,6 +219,9 @@ void rpb_destroy(rpb_ctx* c) {
   if (c->eh.pinned) cudaFreeHost(c->eh.pinned);
   if (c->stream) {
     for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
+    for (int k = 0; k < 8; k++) if (c->ev_sync[k]) cudaEventDestroy(c->ev_sync[k]);
+    if (c->ev_enum) cudaEventDestroy(c->ev_enum);
+    for (int k = 0; k < 2; k++) if (c->aux[k]) { cudaStreamSynchronize(c->aux[k]); cudaStreamDestroy(c->aux[k]); }
     cudaStreamDestroy(c->stream);
   }
   delete c;
@@ -214,11 +238,12 @@ int rpb_set_tables(rpb_ctx* c, const double* B6, const double* B5, const double*
   if ((rc = upload(c, &p, erfc_t, c->cfg.erfc_grid + 1))) return rc; d.erfc_t = p;
   if ((rc = upload(c, &p, scale_t, c->cfg.erfc_grid + 1))) return rc; d.scale_t = p;
   {  // interleaved copy for the Verlet pair kernel; two spare points behind the end keep a rounded-up index in bounds
-    std::vector<double2> es((size_t)c->cfg.erfc_grid + 3);
-    for (int i = 0; i < c->cfg.erfc_grid + 3; i++) { int k = std::min(i, c->cfg.erfc_grid); es[i] = make_double2(erfc_t[k], scale_t[k]); }
-    double2* q;
+    const int G = c->cfg.erfc_grid;
+    std::vector<double4> es((size_t)G + 3);
+    for (int i = 0; i < G + 3; i++) { int k0 = std::min(std::max(i - 1, 0), G), k1 = std::min(i, G); es[i] = make_double4(erfc_t[k0], scale_t[k0], erfc_t[k1], scale_t[k1]); }
+    double4* q;
     if ((rc = upload(c, &q, es.data(), es.size()))) return rc;
-    d.es_t = q; d.inv_erfc_dx = 1.0 / c->cfg.erfc_dx;
+    d.es2_t = q; d.inv_erfc_dx = 1.0 / c->cfg.erfc_dx;
   }
   if ((rc = upload(c, &p, tt, 4 * c->cfg.tt_grid))) return rc; d.tt = p;
   if ((rc = upload(c, &p, dtt, 4 * c->cfg.tt_grid))) return rc; d.dtt = p;

@@ -77,16 +77,18 @@ struct Dev {
   const EvbTables* evb;
   // tables
   const double *B6, *B5, *erfc_t, *scale_t, *tt, *dtt, *CBh;
-  const double2* es_t;   // {erfc_t[i], scale_t[i]} interleaved (one 16-byte load per table point)
+  const double4* es2_t;  // es2_t[i] = {erfc_t[i-1], scale_t[i-1], erfc_t[i], scale_t[i]}: both table points of an interpolation in ONE 32-byte load
   double inv_erfc_dx;
   // verlet
   int* verlet_point; int* neighbor_list; int verlet_cap;
+  int* vrow_tmp; double4* vsort_xq; int* vsort_mol; int* vsort_entry;   // rebuild scratch: fixed-capacity rows, cell-sorted copies
   int* full_point; int* full_list;   // symmetric (both directions) copy of the list, 0-based, for the atomic-free pair kernel
   double* vstore; double* vdisp; int* flag_verlet; int* rebuild_now;
   int* err_flag;  // [0] atom with |F|>1e5 (1-based, 0 none)  [1] verlet overflow  [2] too many diabats  [3] evb lookup failure
   int ncx, ncy, ncz, dia, dib, dic;
   int* cell_count; int* cell_start; int* cell_atoms; int* atom_cell; int* row_count; int* row_count_full;
   double* maxd;  // two largest displacements
+  int* vdone;    // arrival counter of the displacement kernel's blocks
   // PME
   double* uscale; double* Q; double* theta; cufftDoubleComplex* FQ; double* force_recip;
   // energies
@@ -103,6 +105,13 @@ struct Dev {
   } while (0)
 
 #ifdef __CUDACC__
+// one 256-bit read-only load (LDG.E.ENL2.256): a 32-byte-aligned double4 costs one L1 wavefront per distinct line
+// instead of the two of a pair of LDG.128 -- the scattered gathers of the pair kernel are bound by exactly that
+__device__ __forceinline__ double4 ldg256(const double4* p) {
+  double4 v;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
 // ---- strict fp64 helpers (the library is compiled with --fmad=false; fma() is used explicitly
 //      only where the summation order is free) ----
 __device__ __forceinline__ double min_image(double d, double L) { return d - L * floor(d / L + 0.5); }

@@ -16,7 +16,11 @@ struct rpb_ctx {
   rpb_config cfg;
   std::string err;
   bool have_tables = false, have_ff = false, have_mt = false, have_evb = false, have_state = false, initialized = false;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;        // stream the launchers use (normally the main stream; see StreamScope)
+  cudaStream_t main_stream = nullptr;   // the library's main stream: host synchronisation and timing happen here
+  cudaStream_t aux[2] = {nullptr, nullptr};   // side streams for the independent branches of a force evaluation
+  cudaEvent_t ev_sync[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // fork / join points
+  cudaEvent_t ev_enum = nullptr;        // enumeration results have reached pinned host memory
   Dev d;                       // device pointer table (host copy, passed by value to kernels)
   std::vector<void*> allocs;   // everything cudaMalloc'ed (freed in rpb_destroy)
   // host copies of small tables
@@ -62,6 +66,18 @@ int dev_alloc(rpb_ctx* ctx, T** p, size_t n) {
   return 0;
 }
 
+// Launchers always use ctx->stream; a StreamScope redirects them to a side stream for the lifetime of the scope.
+struct StreamScope {
+  rpb_ctx* c; cudaStream_t saved;
+  StreamScope(rpb_ctx* c_, cudaStream_t s) : c(c_), saved(c_->stream) { c->stream = s; }
+  ~StreamScope() { c->stream = saved; }
+};
+// `to` waits for everything queued on `from` so far (fork or join, depending on the direction)
+inline void stream_depend(rpb_ctx* c, int ev, cudaStream_t from, cudaStream_t to) {
+  cudaEventRecord(c->ev_sync[ev], from);
+  cudaStreamWaitEvent(to, c->ev_sync[ev], 0);
+}
+
 // Per-phase CUDA-event timers.  Events are only RECORDED on the launching stream while a step runs (no
 // synchronisation, so enabling them does not serialise the step); rpb_timers_get resolves them afterwards.
 struct ScopedTimer {
@@ -100,6 +116,7 @@ void launch_gather(rpb_ctx*, const double* theta, double* out_force, bool add_to
 // ---- kernels_evb.cu
 int evb_alloc(rpb_ctx*);
 void evb_free(rpb_ctx*);
+int evb_enumerate_async(rpb_ctx*);   // launched early in the principal evaluation; evb_build waits for its read-back
 int evb_build(rpb_ctx*);
 int evb_mix(rpb_ctx*, const double* coeff_override_host, double* force_out_host);
 int evb_commit(rpb_ctx*);

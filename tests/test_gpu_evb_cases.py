@@ -130,7 +130,7 @@ def test_tree_solver_matches_block_jacobi(cuda_lib, oracle_lib, monkeypatch):
     """The default ground-state solver exploits the tree structure of the EVB Hamiltonian; the block-level Jacobi
     kernel (RPB_EVB_SOLVER=jacobi) and the oracle's Numerical-Recipes Jacobi (general_routines.f90:2013-2088) must
     give the same ground state, principal diabat and Hellmann-Feynman forces."""
-    s = water_system(10, with_hydronium=True)
+    s = water_system(10, hydronium=True)
     p = small_params()
     monkeypatch.delenv("RPB_EVB_SOLVER", raising=False)
     st = engine.Simulation(s, p, library=cuda_lib)
