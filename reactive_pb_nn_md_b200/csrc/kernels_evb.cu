@@ -1008,8 +1008,7 @@ __global__ void __launch_bounds__(256) k_evb_coupling_vex(Dev d, EvbDev e, const
 }
 
 // one thread per owned diabat: H_ss, H_parent,s and the geometric part of the coupling force
-__global__ void k_evb_assemble(Dev d, EvbDev e, const CouplingGeo* geo, const int* __restrict__ last_item, const int* slot_of_state) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ void assemble_state(const Dev& d, EvbDev& e, const CouplingGeo* geo, const int* __restrict__ last_item, const int* slot_of_state, int s) {
   int S = *e.n_states;
   if (s >= MAXS) return;
   e.h_diag[s] = 0.0; e.h_diag[MAXS + s] = 0.0; e.h_diag[2 * MAXS + s] = 0.0;
@@ -1037,11 +1036,17 @@ __global__ void k_evb_assemble(Dev d, EvbDev e, const CouplingGeo* geo, const in
     atomicAdd(&Fo[3 * G.atom_H + c], -pref * G.dA[2][c]);
   }
 }
+__global__ void k_evb_assemble(Dev d, EvbDev e, const CouplingGeo* geo, const int* __restrict__ last_item, const int* slot_of_state) {
+  assemble_state(d, e, geo, last_item, slot_of_state, blockIdx.x * blockDim.x + threadIdx.x);
+}
 
 // Hellmann-Feynman weights from the ground-state vector e.evec (whole CTA; caller has synchronised):
 // c_s^2 (diagonal), 2 c_parent c_s (coupling) (ms_evb.f90:298-303), and the subtree sums used by the hop-tree
 // de-duplication of the real-space deltas.
-__device__ void hellmann_feynman_weights(EvbDev& e, int S, int tid, int nth) {
+__device__ void hellmann_feynman_weights(const Dev& d, EvbDev& e, int S, int tid, int nth) {
+  // error flags and energy slots ride along in the solver's read-back block
+  if (tid < 4) e.status_copy[tid] = (double)d.err_flag[tid];
+  if (tid < E_NSLOT) e.status_copy[4 + tid] = d.en[tid];
   for (int i = tid; i < MAXS; i += nth) {
     double ci = i < S ? e.evec[i] : 0.0;
     e.coef2[i] = ci * ci;
@@ -1107,14 +1112,20 @@ __device__ __forceinline__ bool tree_pivots(TreeShared& T, int S, int maxlev, in
   return __syncthreads_and(i >= S || T.dv[i] > 0.0) != 0;
 }
 
-__global__ void __launch_bounds__(TREE_TPB) k_evb_tree_solver(Dev d, EvbDev e, const double* coeff_override) {
+// geo != nullptr (single rank): the Hamiltonian elements are assembled here first (one launch less on the critical path)
+__global__ void __launch_bounds__(TREE_TPB) k_evb_tree_solver(Dev d, EvbDev e, const double* coeff_override, const CouplingGeo* geo,
+                                                                const int* __restrict__ last_item, const int* slot_of_state) {
   __shared__ TreeShared T;
   const int S = *e.n_states;
   const int tid = threadIdx.x, nth = blockDim.x, i = tid;
+  if (geo) {
+    assemble_state(d, e, geo, last_item, slot_of_state, tid);
+    __syncthreads();     // h_diag is read back below by the same CTA
+  }
   if (coeff_override) {
     for (int k = tid; k < S; k += nth) e.evec[k] = coeff_override[k];
     __syncthreads();
-    hellmann_feynman_weights(e, S, tid, nth);
+    hellmann_feynman_weights(d, e, S, tid, nth);
     return;
   }
   if (i < S) {
@@ -1231,7 +1242,7 @@ __global__ void __launch_bounds__(TREE_TPB) k_evb_tree_solver(Dev d, EvbDev e, c
     e.tree_mu[0] = mu; e.tree_mu[1] = (status == 0) ? 1.0 : 0.0;
   }
   __syncthreads();
-  hellmann_feynman_weights(e, S, tid, nth);
+  hellmann_feynman_weights(d, e, S, tid, nth);
 }
 
 // ================================================================================================
@@ -1424,7 +1435,7 @@ __global__ void __launch_bounds__(JAC_TPB) k_evb_jacobi(Dev d, EvbDev e, const d
     else if (tid == 0) e.jac_sig[0] = -1;
   }
   __syncthreads();
-  hellmann_feynman_weights(e, S, tid, nth);
+  hellmann_feynman_weights(d, e, S, tid, nth);
 }
 
 // ================================================================================================
@@ -1447,31 +1458,35 @@ __global__ void k_evb_theta_mix(Dev d, EvbDev e, const int* __restrict__ slot_st
 }
 
 // f_mix = [rank 0: principal force] + sum_s c_s^2 dF_s + 2 c_p c_s Foff_s   over owned diabats
-__global__ void k_evb_mix_forces(Dev d, EvbDev e, const int* __restrict__ state_list, int n_list, int include_principal) {
+// in_place (single rank, ground-state mix): the principal-diabat force is still in d.force; it is saved to dF slot 0
+// (the per-state debug accessors need it later) and d.force receives the mixed force -- no copies before or after.
+__global__ void k_evb_mix_forces(Dev d, EvbDev e, const int* __restrict__ state_list, int n_list, int include_principal, int in_place) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   size_t n3 = (size_t)3 * d.N;
   if (i >= n3) return;
-  double f = include_principal ? e.dF[i] : 0.0;   // dF slot 0 holds the principal-diabat force (without F_rec)
+  double f = 0.0;
+  if (in_place) { f = d.force[i]; e.dF[i] = f; }
+  else if (include_principal) f = e.dF[i];        // dF slot 0 holds the principal-diabat force (without F_rec)
   for (int k = 0; k < n_list; k++) {
     int s = state_list[k];
     f = fma(e.coef2[2 * MAXS + s], e.dF[(size_t)s * n3 + i], f);
     f = fma(e.coef2[MAXS + s], e.Foff[(size_t)s * n3 + i], f);
   }
-  e.f_mix[i] = f;
+  (in_place ? d.force : e.f_mix)[i] = f;
 }
 
 // + sum_s c_s^2 * (reciprocal-space corrections of the chain atoms of diabat s)   ms_evb.f90:2103-2248
-__global__ void k_evb_add_corr(Dev d, EvbDev e, const int* __restrict__ state_list, int n_list) {
+__global__ void k_evb_add_corr(Dev d, EvbDev e, const int* __restrict__ state_list, int n_list, double* __restrict__ out) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_list * CM * MA) return;
   int s = state_list[t / (CM * MA)], slot = t % (CM * MA);
   int atom = e.corr_atom[s * CM * MA + slot];
   if (atom < 0) return;
   double w = e.coef2[s];
-  for (int c = 0; c < 3; c++) atomicAdd(&e.f_mix[3 * atom + c], w * e.corr_f[((size_t)s * CM * MA + slot) * 3 + c]);
+  for (int c = 0; c < 3; c++) atomicAdd(&out[3 * atom + c], w * e.corr_f[((size_t)s * CM * MA + slot) * 3 + c]);
 }
 
-__global__ void k_evb_gather_mix(Dev d, EvbDev e) {
+__global__ void k_evb_gather_mix(Dev d, EvbDev e, double* __restrict__ out) {
   int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= d.N) return;
   double u[3] = {d.uscale[3 * w], d.uscale[3 * w + 1], d.uscale[3 * w + 2]};
@@ -1479,7 +1494,7 @@ __global__ void k_evb_gather_mix(Dev d, EvbDev e) {
   gather_atom_warp(d, e.theta_mix, u, d.xq[w].w, lane, F);
   if (lane < 3) {
     double v = lane == 0 ? F[0] : (lane == 1 ? F[1] : F[2]);
-    e.f_mix[3 * w + lane] += v;
+    out[3 * w + lane] += v;
   }
 }
 
@@ -1523,7 +1538,14 @@ __global__ void k_evb_commit_patch(Dev d, EvbDev e, int state, int level, const 
 
 // zero (or -1) every accumulator evb_build adds into: item energies, Vex, candidate counters, chain-atom corrections,
 // and the per-diabat force deltas / coupling forces of the S diabats in flight
-__global__ void k_evb_clear(Dev d, EvbDev e, int* cand_n, int S) {
+#define CLEAR_MARGIN 8
+// s_end < 0: launched BEFORE the enumeration of the step, it clears the diabats [0, previous S + CLEAR_MARGIN) -- the
+// host repeats the rule and issues a second launch for [that bound, S) in the rare step that gains more diabats
+__global__ void k_evb_clear(Dev d, EvbDev e, int* cand_n, int s_begin, int s_end) {
+  if (s_end < 0) s_end = min(MAXS, *e.n_states + CLEAR_MARGIN);
+  const int S = s_end - s_begin;
+  e.dF += (size_t)s_begin * 3 * d.N; e.Foff += (size_t)s_begin * 3 * d.N;
+  e.corr_f += (size_t)s_begin * CM * MA * 3; e.corr_atom += (size_t)s_begin * CM * MA;
   const size_t n3 = (size_t)3 * d.N, nbig = (size_t)S * n3;
   const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
   for (size_t k = tid; k < nbig; k += nth) { e.dF[k] = 0.0; e.Foff[k] = 0.0; }
@@ -1539,6 +1561,8 @@ __global__ void k_evb_clear(Dev d, EvbDev e, int* cand_n, int S) {
 // ================================================================================================
 // layout of the packed per-step upload (bytes)
 #define ENUM_BLOCK_INTS (16 + MAXS * (2 + MAXC * 5))
+// result[8 ints] | e_ground | evec[MAXS] | h_full[2 MAXS] | err_flag[4] as doubles | en[E_NSLOT]
+#define SOLVER_BLOCK_DOUBLES (5 + 3 * MAXS + 4 + E_NSLOT)
 #define PACK_OFF_ITEMS 0
 #define PACK_OFF_REAL (PACK_OFF_ITEMS + (RPB_MAX_ITEMS + 1) * (int)sizeof(EvbItem))
 #define PACK_OFF_SLOT_OF (PACK_OFF_REAL + (RPB_MAX_ITEMS + 1) * 4)
@@ -1583,10 +1607,14 @@ int evb_alloc(rpb_ctx* c) {
     e.n_states = blk; e.n_hops = blk + 16; e.parent = blk + 16 + MAXS; e.proton_log = blk + 16 + 2 * MAXS;
   }
   AL(e.snap, MAXS * NLEV); AL(e.n_items, 1); AL(e.item_energy, RPB_MAX_ITEMS + 1);
-  AL(e.n_real, 1); AL(e.corr_f, (size_t)MAXS * CM * MA * 3); AL(e.corr_atom, MAXS * CM * MA); AL(e.h_full, 2 * MAXS);
+  AL(e.n_real, 1); AL(e.corr_f, (size_t)MAXS * CM * MA * 3); AL(e.corr_atom, MAXS * CM * MA);
   AL(e.dF, (size_t)MAXS * 3 * N); AL(e.Foff, (size_t)MAXS * 3 * N);
-  AL(e.vex, MAXS); AL(e.e_recip, MAXS); AL(e.h_diag, 3 * MAXS); AL(e.f_mix, 3 * N); AL(e.evec, MAXS); AL(e.coef2, 3 * MAXS);
-  AL(e.e_ground, 1); AL(e.result, 8); AL(e.theta_mix, K3); AL(e.jac_v, MAXS * MAXS); AL(e.jac_sig, 2 + MAXS * MAXC * 5); AL(e.tree_mu, 2);
+  AL(e.vex, MAXS); AL(e.e_recip, MAXS); AL(e.h_diag, 3 * MAXS); AL(e.f_mix, 3 * N); AL(e.coef2, 3 * MAXS);
+  {  // solver results travel to the host every step: one contiguous block, one copy (SOLVER_BLOCK_DOUBLES)
+    double* blk;
+    AL(blk, SOLVER_BLOCK_DOUBLES);
+    e.result = (int*)blk; e.e_ground = blk + 4; e.evec = blk + 5; e.h_full = blk + 5 + MAXS; e.status_copy = blk + 5 + 3 * MAXS;
+  } AL(e.theta_mix, K3); AL(e.jac_v, MAXS * MAXS); AL(e.jac_sig, 2 + MAXS * MAXC * 5); AL(e.tree_mu, 2);
   EvbScratch s;
   AL(s.geo, MAXS); AL(s.coeff_dev, MAXS);
   // per-step host -> device tables travel as ONE packed copy from pinned memory (see PackLayout)
@@ -1606,7 +1634,7 @@ int evb_alloc(rpb_ctx* c) {
     cufftHandle pf, pi;
     if ((rc = pme_get_plans(c, b, &pf, &pi))) return rc;
   }
-  CKE(cudaMallocHost(&c->eh.pinned, (16 + MAXS * (2 + MAXC * 5)) * sizeof(int) + 4 * MAXS * sizeof(double)));
+  CKE(cudaMallocHost(&c->eh.pinned, ENUM_BLOCK_INTS * sizeof(int) + (SOLVER_BLOCK_DOUBLES + 8) * sizeof(double)));
   CKE(cudaMemset(e.n_states, 0, ENUM_BLOCK_INTS * sizeof(int)));
   CKE(cudaMemset(e.jac_sig, 0xff, (2 + MAXS * MAXC * 5) * sizeof(int)));
   CKE(cudaMemset(e.tree_mu, 0, 2 * sizeof(double)));
@@ -1667,14 +1695,19 @@ long HostClock::n = 0;
 
 int evb_enumerate_async(rpb_ctx* c) {
   Dev& d = c->d; EvbDev& e = c->e; EvbHost& h = c->eh;
+  k_evb_clear<<<148 * 2, 256, 0, c->stream>>>(d, e, g_scratch[c].cand_n, 0, -1);   // accumulators of the build (reads the PREVIOUS S)
   {
     ScopedTimer t(c, T_EVB_ENUM);
     k_evb_enumerate<<<1, ENUM_TPB, 0, c->stream>>>(d, e);
-    c->n_launch++;
+    c->n_launch += 2;
   }
   CKE(cudaMemcpyAsync(h.pinned, e.n_states, ENUM_BLOCK_INTS * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CKE(cudaMemcpyAsync(c->h_flags, d.err_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CKE(cudaEventRecord(c->ev_enum, c->stream));
+  // the diabat images need nothing from the host: built for however many diabats the enumeration found (grid sized
+  // for evb_max_states, surplus warps exit)
+  { ScopedTimer t(c, T_EVB_SNAP); k_evb_snapshots<<<(MAXS + SNAP_WPB - 1) / SNAP_WPB, 32 * SNAP_WPB, 0, c->stream>>>(d, e, -1); }
+  c->n_launch += 1;
   return 0;
 }
 
@@ -1739,19 +1772,22 @@ int evb_build(rpb_ctx* c) {
   for (int s = 1; s < S; s++)
     if (state_owned(s, d.rank, d.world)) { state_list[n_own++] = s; slot_of_state[s] = n_own; slot_state[n_own] = s; }
   if (n_own + 1 > c->grid_capacity) { c->err = "grid capacity exceeded"; return RPB_ERR_DIABATS; }
-  CKE(cudaMemcpyAsync(sc.pack_dev, sc.pack_host, PACK_BYTES, cudaMemcpyHostToDevice, c->stream));
-  k_evb_clear<<<148 * 4, 256, 0, c->stream>>>(d, e, sc.cand_n, S);   // every accumulator of the build, one launch
-  c->n_launch += 1;
-  { ScopedTimer t(c, T_EVB_SNAP); k_evb_snapshots<<<(S + SNAP_WPB - 1) / SNAP_WPB, 32 * SNAP_WPB, 0, c->stream>>>(d, e, -1); }
-  c->n_launch += 1;
-  // Three independent branches from here (joined before the Hamiltonian is assembled):
-  //   main   : candidate lists -> real-space / repulsion / bonded deltas of every (diabat, last hop, topology)
-  //   aux[0] : off-diagonal couplings (geometry factor, Vex with all atoms)
-  //   aux[1] : reciprocal space -- delta grids, ONE batched D2Z -> (x CB, E_rec) -> Z2D over the principal grid
-  //            (slot 0, spread on this stream by calculate_total_force_energy) and every owned diabat, chain-atom
-  //            force corrections
-  stream_depend(c, 4, c->main_stream, c->aux[0]);
-  stream_depend(c, 5, c->main_stream, c->aux[1]);
+  // The host part is done; from here three branches run concurrently (joined before the Hamiltonian is assembled):
+  //   main   : [pair forces of the principal diabat, already queued] -> candidate lists -> real-space / repulsion /
+  //            bonded deltas of every (diabat, last hop, topology)
+  //   aux[0] : [enumeration, images, bonded terms, already queued] -> per-step tables upload -> off-diagonal couplings
+  //            (geometry factor, Vex with all atoms)
+  //   aux[1] : [principal grid spread, already queued] -> delta grids, ONE batched D2Z -> (x CB, E_rec) -> Z2D over the
+  //            principal grid (slot 0) and every owned diabat, chain-atom force corrections
+  {
+    StreamScope ss(c, c->aux[0]);
+    const int cleared = std::min(MAXS, h.n_states_prev + CLEAR_MARGIN);
+    if (S > cleared) { k_evb_clear<<<148 * 2, 256, 0, c->stream>>>(d, e, sc.cand_n, cleared, S); c->n_launch++; }
+    CKE(cudaMemcpyAsync(sc.pack_dev, sc.pack_host, PACK_BYTES, cudaMemcpyHostToDevice, c->stream));
+  }
+  h.n_states_prev = S;
+  stream_depend(c, 4, c->aux[0], c->main_stream);
+  stream_depend(c, 5, c->aux[0], c->aux[1]);
   {
     StreamScope ss(c, c->aux[1]);
     if (n_own > 0) {
@@ -1797,15 +1833,14 @@ int evb_build(rpb_ctx* c) {
   }
   stream_depend(c, 6, c->aux[0], c->main_stream);
   stream_depend(c, 7, c->aux[1], c->main_stream);
-  {
+  if (d.world > 1 || c->evb_solver != 0) {
     ScopedTimer t(c, T_EVB_ASSEMBLE);
     k_evb_assemble<<<(MAXS + 31) / 32, 32, 0, c->stream>>>(d, e, sc.geo, sc.last_item, sc.slot_of_state);
     c->n_launch += 1;
-  }
+  } else h.assemble_pending = true;   // single rank, tree solver: assembled in the solver's prologue
   // keep the principal-diabat force (incl. EVB repulsion, without reciprocal part) in dF slot 0: d.force is
   // overwritten with the adiabatic force at commit time
-  k_copy<<<(unsigned)((n3 + 255) / 256), 256, 0, c->stream>>>(e.dF, d.force, n3);
-  c->n_launch++;
+  if (d.world > 1) { k_copy<<<(unsigned)((n3 + 255) / 256), 256, 0, c->stream>>>(e.dF, d.force, n3); c->n_launch++; }   // single rank: saved by k_evb_mix_forces
   h.built = true;
   HostClock::acc[2] += HostClock::now() - hc0;
   return 0;
@@ -1828,7 +1863,9 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
   {
     ScopedTimer t(c, T_EVB_DIAG);
     if (c->evb_solver == 0) {
-      k_evb_tree_solver<<<1, TREE_TPB, 0, c->stream>>>(d, e, coeff_dev);
+      const bool fuse = (d.world == 1 && !coeff_override_host && h.assemble_pending);
+      k_evb_tree_solver<<<1, TREE_TPB, 0, c->stream>>>(d, e, coeff_dev, fuse ? sc.geo : nullptr, sc.last_item, sc.slot_of_state);
+      h.assemble_pending = false;
       c->n_launch++;
     } else {
     const int np = S + (S & 1);
@@ -1840,25 +1877,27 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
     c->n_launch++;
     }
   }
-  double* pd = (double*)(h.pinned + 16 + MAXS * (2 + MAXC * 5));
+  double* pd = (double*)(h.pinned + ENUM_BLOCK_INTS + (ENUM_BLOCK_INTS & 1));   // solver read-back block (8-byte aligned)
+  const int* pres = (const int*)pd;
   if (!coeff_override_host) {
   // read back what the host needs for the commit decision and the accessors right behind the solver: the host waits
   // for THIS event only, while the mixing kernels queued below are still running
-  CKE(cudaMemcpyAsync(h.pinned + 1, e.result, 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CKE(cudaMemcpyAsync(pd, e.e_ground, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CKE(cudaMemcpyAsync(pd + 1, e.evec, MAXS * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CKE(cudaMemcpyAsync(pd + 1 + MAXS, e.h_full, 2 * MAXS * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CKE(cudaMemcpyAsync(c->h_flags, d.err_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CKE(cudaMemcpyAsync(c->h_en, d.en, E_NSLOT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CKE(cudaMemcpyAsync(pd, e.result, SOLVER_BLOCK_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CKE(cudaEventRecord(c->ev_enum, c->stream));
   }
   {
     int include_principal = (d.rank == 0) ? 1 : 0;
     // slot 0 (principal theta) only contributes on rank 0: mask it on the other ranks through slot_state
-    { ScopedTimer t(c, T_EVB_THETAMIX); k_evb_theta_mix<<<(unsigned)((K3 / 2 + 255) / 256), 256, 0, c->stream>>>(d, e, sc.slot_state, n_own + 1); }
-    { ScopedTimer t(c, T_EVB_MIXF); k_evb_mix_forces<<<(unsigned)((n3 + 255) / 256), 256, 0, c->stream>>>(d, e, sc.state_list, n_own, include_principal);
-      if (n_own > 0) { k_evb_add_corr<<<(n_own * CM * MA + 127) / 128, 128, 0, c->stream>>>(d, e, sc.state_list, n_own); c->n_launch++; } }
-    { ScopedTimer t(c, T_EVB_GATHERMIX); k_evb_gather_mix<<<(N * 32 + 255) / 256, 256, 0, c->stream>>>(d, e); }
+    // theta_mix (grids) runs on aux[1] next to the force mixing (per-atom arrays) on the main stream; the gather of
+    // the mixed grid then adds into the mixed force
+    stream_depend(c, 0, c->main_stream, c->aux[1]);
+    { StreamScope ss(c, c->aux[1]); ScopedTimer t(c, T_EVB_THETAMIX); k_evb_theta_mix<<<(unsigned)((K3 / 2 + 255) / 256), 256, 0, c->stream>>>(d, e, sc.slot_state, n_own + 1); }
+    const int in_place = (d.world == 1 && !coeff_override_host) ? 1 : 0;
+    double* out = in_place ? d.force : e.f_mix;
+    { ScopedTimer t(c, T_EVB_MIXF); k_evb_mix_forces<<<(unsigned)((n3 + 255) / 256), 256, 0, c->stream>>>(d, e, sc.state_list, n_own, include_principal, in_place);
+      if (n_own > 0) { k_evb_add_corr<<<(n_own * CM * MA + 127) / 128, 128, 0, c->stream>>>(d, e, sc.state_list, n_own, out); c->n_launch++; } }
+    stream_depend(c, 1, c->aux[1], c->main_stream);
+    { ScopedTimer t(c, T_EVB_GATHERMIX); k_evb_gather_mix<<<(N * 32 + 255) / 256, 256, 0, c->stream>>>(d, e, out); }
     c->n_launch += 3;
   }
   if (coeff_override_host) {
@@ -1869,18 +1908,20 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
   double hm1 = HostClock::now();
   CKE(cudaEventSynchronize(c->ev_enum));
   HostClock::acc[3] += hm1 - hm0; HostClock::acc[4] += HostClock::now() - hm1;
+  for (int k = 0; k < 4; k++) c->h_flags[k] = (int)pd[5 + 3 * MAXS + k];
+  for (int k = 0; k < E_NSLOT; k++) c->h_en[k] = pd[5 + 3 * MAXS + 4 + k];
   if (c->h_flags[1]) { c->err = "please increase size of verlet neighbor list"; return RPB_ERR_VERLET; }
   if (c->h_flags[3]) { c->err = "couldn't find index in subroutine 'get_index_atom_set' (code " + std::to_string(c->h_flags[3]) + ")"; return RPB_ERR_STATE; }
-  if (h.pinned[3]) { c->err = "too many iterations in jacobi"; return RPB_ERR_STATE; }
+  if (pres[2]) { c->err = "too many iterations in jacobi"; return RPB_ERR_STATE; }
   static const bool dbg_jacobi = getenv("RPB_DEBUG_JACOBI") != nullptr;
-  if (dbg_jacobi) fprintf(stderr, "[evb solver %s] S=%d %s=%d\n", c->evb_solver ? "jacobi" : "tree", S, c->evb_solver ? "sweeps" : "evaluations", h.pinned[5]);
-  h.principal_diabat = h.pinned[1]; h.new_hydronium = h.pinned[2];
-  h.adiabatic_potential = pd[0];
-  memcpy(h.evec, pd + 1, MAXS * sizeof(double));
+  if (dbg_jacobi) fprintf(stderr, "[evb solver %s] S=%d %s=%d\n", c->evb_solver ? "jacobi" : "tree", S, c->evb_solver ? "sweeps" : "evaluations", pres[4]);
+  h.principal_diabat = pres[0]; h.new_hydronium = pres[1];
+  h.adiabatic_potential = pd[4];
+  memcpy(h.evec, pd + 5, MAXS * sizeof(double));
   for (int i = 0; i < MAXS; i++) for (int j = 0; j < MAXS; j++) h.hamiltonian[i][j] = 0.0;
   for (int s = 0; s < S; s++) {
-    h.hamiltonian[s][s] = pd[1 + MAXS + s];
-    if (s > 0) h.hamiltonian[h.parent[s]][s] = pd[1 + 2 * MAXS + s];
+    h.hamiltonian[s][s] = pd[5 + MAXS + s];
+    if (s > 0) h.hamiltonian[h.parent[s]][s] = pd[5 + 2 * MAXS + s];
   }
   return 0;
 }
@@ -1903,8 +1944,7 @@ int evb_commit(rpb_ctx* c) {
   Dev& d = c->d; EvbDev& e = c->e; EvbHost& h = c->eh;
   EvbScratch& sc = g_scratch[c];
   const int N = d.N, M = d.M;
-  k_copy<<<(3 * N + 255) / 256, 256, 0, c->stream>>>(d.force, e.f_mix, (size_t)3 * N);
-  c->n_launch++;
+  if (d.world > 1) { k_copy<<<(3 * N + 255) / 256, 256, 0, c->stream>>>(d.force, e.f_mix, (size_t)3 * N); c->n_launch++; }   // single rank: mixed in place
   // energies as the reference leaves them: potential = adiabatic energy, components = principal diabat's
   {
     rpb_energies& en = c->last_en;

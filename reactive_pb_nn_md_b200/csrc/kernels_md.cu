@@ -20,16 +20,21 @@ __global__ void k_zero(double* p, size_t n) {
 }
 
 // v += dt/2/m * F * conv ; x += v*dt          (md_integration.f90:478,484)
-__global__ void k_integrate_first(Dev d) {
+// The thread that consumed F_i also clears it (and thread 0 the energy slots and the momentum scratch of the second
+// half-kick), so the force evaluation that follows needs no zeroing launches.
+__global__ void k_integrate_first(Dev d, double* psum) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { for (int k = 0; k < E_NSLOT; k++) d.en[k] = 0.0; for (int k = 0; k < 4; k++) psum[k] = 0.0; }
   if (i >= d.N) return;
+  const double f0 = d.force[3 * i], f1 = d.force[3 * i + 1], f2 = d.force[3 * i + 2];
+  d.force[3 * i] = 0.0; d.force[3 * i + 1] = 0.0; d.force[3 * i + 2] = 0.0;
   if (d.freeze[d.type[i]] == 1) return;
   double4 p = d.xq[i];
   double m = d.mass[i];
   double h = d.dt / 2.0 / m;
-  double v0 = d.vel[3 * i] + h * d.force[3 * i] * d.conv_kin;
-  double v1 = d.vel[3 * i + 1] + h * d.force[3 * i + 1] * d.conv_kin;
-  double v2 = d.vel[3 * i + 2] + h * d.force[3 * i + 2] * d.conv_kin;
+  double v0 = d.vel[3 * i] + h * f0 * d.conv_kin;
+  double v1 = d.vel[3 * i + 1] + h * f1 * d.conv_kin;
+  double v2 = d.vel[3 * i + 2] + h * f2 * d.conv_kin;
   d.vel[3 * i] = v0; d.vel[3 * i + 1] = v1; d.vel[3 * i + 2] = v2;
   p.x = p.x + v0 * d.dt; p.y = p.y + v1 * d.dt; p.z = p.z + v2 * d.dt;
   d.xq[i] = p;
@@ -318,9 +323,10 @@ void launch_zero_forces(rpb_ctx* c) {
 
 void launch_integrate_first(rpb_ctx* c) {
   ScopedTimer t(c, T_INTEGRATE);
-  k_integrate_first<<<nblk(c->d.N), TPB, 0, c->stream>>>(c->d);
+  k_integrate_first<<<nblk(c->d.N), TPB, 0, c->stream>>>(c->d, c->d.maxd + 2);
   k_com_shift<<<nblk(c->d.M), TPB, 0, c->stream>>>(c->d, 1);
   c->n_launch += 2;
+  c->forces_zeroed = true;
 }
 
 void launch_update_com_shift(rpb_ctx* c, bool shift) {
@@ -331,10 +337,9 @@ void launch_update_com_shift(rpb_ctx* c, bool shift) {
 void launch_integrate_second(rpb_ctx* c) {
   ScopedTimer t(c, T_INTEGRATE);
   double* psum = c->d.maxd + 2;  // 4 doubles of scratch after the two displacement maxima
-  k_zero<<<1, 32, 0, c->stream>>>(psum, 4);
-  k_integrate_second<<<nblk(c->d.N), TPB, 0, c->stream>>>(c->d, psum);
+  k_integrate_second<<<nblk(c->d.N), TPB, 0, c->stream>>>(c->d, psum);      // psum was cleared by k_integrate_first
   k_remove_com_momentum<<<nblk(c->d.N), TPB, 0, c->stream>>>(c->d, psum);
-  c->n_launch += 3;
+  c->n_launch += 2;
 }
 
 void launch_kinetic_energy(rpb_ctx* c) {

@@ -18,7 +18,6 @@
 #include "rpb_bonded.cuh"
 
 #define PAIR_TPB 128
-#define PAIR_B 4        // neighbours in flight per lane
 
 // cold path of the pair kernel: a SAPT row with non-zero coefficients (pairwise_real_space_sapt :651-690; the example
 // force field has none).  Out of line and fed with scalars so that it costs the hot loop no registers.
@@ -38,7 +37,8 @@ __device__ __noinline__ void sapt_pair(const double* __restrict__ tt_t, const do
   fs += fac / dr2;
 }
 
-__global__ void __launch_bounds__(PAIR_TPB, 3) k_pair_verlet(Dev d) {
+template <int PAIR_B, int TPB_, int MINB>
+__global__ void __launch_bounds__(TPB_, MINB) k_pair_verlet(Dev d) {
   extern __shared__ double sh_par[];           // [nT*nT][6] vdw parameters
   __shared__ int sh_vt[RPB_MAXT * RPB_MAXT];   // atype_vdw_type; 2 = SAPT row with all-zero coefficients (contributes exactly 0)
   __shared__ double sh_red[32];
@@ -159,12 +159,26 @@ __global__ void k_molecule_terms(Dev d) {
   e = block_sum(E.e_dih, sh_red);  if (threadIdx.x == 0) atomicAdd(&d.en[E_DIH], e);
 }
 
+template <int B, int T, int M>
+static void launch_pair_variant(rpb_ctx* c) {
+  const int wpb = T / 32, blocks = (c->d.N + wpb - 1) / wpb;
+  const size_t shmem = (size_t)c->d.nT * c->d.nT * 6 * sizeof(double);
+  k_pair_verlet<B, T, M><<<blocks, T, shmem, c->stream>>>(c->d);
+}
+
 void launch_pair_verlet(rpb_ctx* c) {
   ScopedTimer t(c, T_PAIR);
-  const int warps_per_block = PAIR_TPB / 32;
-  const int blocks = (c->d.N + warps_per_block - 1) / warps_per_block;
-  const size_t shmem = (size_t)c->d.nT * c->d.nT * 6 * sizeof(double);
-  k_pair_verlet<<<blocks, PAIR_TPB, shmem, c->stream>>>(c->d);
+  static const int variant = getenv("RPB_PAIR_VARIANT") ? atoi(getenv("RPB_PAIR_VARIANT")) : 0;
+  switch (variant) {
+    case 1: launch_pair_variant<2, 256, 3>(c); break;
+    case 2: launch_pair_variant<2, 256, 4>(c); break;
+    case 3: launch_pair_variant<3, 256, 2>(c); break;
+    case 4: launch_pair_variant<3, 128, 5>(c); break;
+    case 5: launch_pair_variant<4, 256, 2>(c); break;
+    case 6: launch_pair_variant<2, 128, 6>(c); break;
+    case 7: launch_pair_variant<4, 128, 3>(c); break;
+    default: launch_pair_variant<3, 256, 2>(c); break;   // best of the sweep on B200 (C3): 89 us
+  }
   c->n_launch += 1;
 }
 

@@ -4,6 +4,8 @@
 // ms_evb_calculate_total_force_energy (ms_evb.f90:181-235), md_integrate_atomic (md_integration.f90:438-541).
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "rpb_host.h"
 
@@ -61,24 +63,34 @@ static void energies_from_slots(rpb_ctx* c) {
 // bonded / intramolecular terms on aux[0], and the PME reciprocal branch (scaled coordinates, spreading, FFT) on
 // aux[1].  In MS-EVB mode aux[1] is NOT joined here: evb_build keeps using it for the batched diabat grids.
 int calculate_total_force_energy(rpb_ctx* c, bool evb_principal) {
-  launch_zero_forces(c);
+  if (!c->forces_zeroed) launch_zero_forces(c);
+  c->forces_zeroed = false;
   stream_depend(c, 0, c->main_stream, c->aux[0]);
   stream_depend(c, 1, c->main_stream, c->aux[1]);
-  { StreamScope sc(c, c->aux[0]); launch_molecule_terms(c); }
+  // the long main-stream kernels are issued first: the host needs ~3 us per launch, and the GPU should not idle while
+  // the side branches are being queued
+  launch_verlet_update(c);
   int rc = 0;
+  if (evb_principal) {
+    // MS-EVB: the diabat enumeration (and the diabat images, which need nothing from the host) need positions and
+    // centres of mass only; they run on a side stream so that the host learns the number of diabats -- which sizes the
+    // later launches -- while the GPU is busy with the pair forces.  Both short side branches are queued AHEAD of the
+    // pair kernel so that their CTAs get SMs before that grid floods the GPU.
+    StreamScope sc(c, c->aux[0]);
+    rc = evb_enumerate_async(c);
+  }
+  if (rc) return rc;
   {
     StreamScope sc(c, c->aux[1]);
     launch_spread_principal(c);
     if (!evb_principal) rc = launch_convolve(c, 0, 1, c->d.en + E_RECIP, true);
   }
   if (rc) return rc;
-  // MS-EVB: the diabat enumeration needs positions and centres of mass only; it goes first on the main stream so that
-  // the host learns the number of diabats (which sizes the later launches) while the GPU is busy with the pair forces
-  if (evb_principal && (rc = evb_enumerate_async(c))) return rc;
-  launch_verlet_update(c);
   launch_pair_verlet(c);
+  if (evb_principal) launch_molecule_terms(c);      // main stream has slack behind the pair kernel in MS-EVB mode
+  else { StreamScope sc(c, c->aux[0]); launch_molecule_terms(c); }
+  if (evb_principal) return 0;     // evb_build keeps both side streams busy and joins them before the Hamiltonian
   stream_depend(c, 2, c->aux[0], c->main_stream);
-  if (evb_principal) return 0;
   stream_depend(c, 3, c->aux[1], c->main_stream);
   launch_gather(c, c->d.theta, c->d.force_recip, true);
   return 0;
@@ -129,9 +141,15 @@ int rpb_create(rpb_ctx** out, const rpb_config* cfg) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { c->err = "no CUDA device: librpbmd.so has no CPU fallback"; return RPB_ERR_CUDA; }
   CK(cudaSetDevice(cfg->device));
-  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  c->main_stream = c->stream;
-  for (int k = 0; k < 2; k++) CK(cudaStreamCreateWithFlags(&c->aux[k], cudaStreamNonBlocking));
+  {
+    // the side streams carry short kernels that must not starve behind the grid of the pair kernel on the main stream:
+    // they get the higher priority, so their blocks are scheduled first whenever an SM frees resources
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_lo));
+    c->main_stream = c->stream;
+    for (int k = 0; k < 2; k++) CK(cudaStreamCreateWithPriority(&c->aux[k], cudaStreamNonBlocking, prio_hi));
+  }
   for (int k = 0; k < 8; k++) CK(cudaEventCreateWithFlags(&c->ev_sync[k], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_enum, cudaEventDisableTiming));
   CK(cudaMallocHost(&c->h_en, E_NSLOT * sizeof(double)));
@@ -603,6 +621,20 @@ int rpb_get_launch_counts(rpb_ctx* c, long long* own, long long* fft) {
 static void timers_resolve(rpb_ctx* c) {
   if (c->ev_used == 0) return;
   cudaStreamSynchronize(c->stream);
+  if (getenv("RPB_DEBUG_TIMELINE")) {   // offsets of every recorded interval from the start of the last step (all streams)
+    int last_step = -1;
+    for (int k = 0; k < c->ev_used; k++) if (c->ev_id[k] == T_STEP) last_step = k;
+    if (last_step >= 0) {
+      fprintf(stderr, "[timeline, us from step start]");
+      for (int k = last_step; k < c->ev_used; k++) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, c->ev_pool[2 * last_step], c->ev_pool[2 * k]);
+        cudaEventElapsedTime(&b, c->ev_pool[2 * last_step], c->ev_pool[2 * k + 1]);
+        fprintf(stderr, " %s:%.0f-%.0f", k_timer_names[c->ev_id[k]], a * 1e3, b * 1e3);
+      }
+      fprintf(stderr, "\n");
+    }
+  }
   for (int k = 0; k < c->ev_used; k++) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, c->ev_pool[2 * k], c->ev_pool[2 * k + 1]) == cudaSuccess) { c->t_ms[c->ev_id[k]] += ms; c->t_calls[c->ev_id[k]]++; }

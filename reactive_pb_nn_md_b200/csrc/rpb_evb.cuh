@@ -61,6 +61,7 @@ struct EvbDev {
   double* evec;               // ground-state eigenvector [MAXS]
   double* coef2;              // [3*MAXS] c_s^2 | 2 c_parent c_s | sum of c_t^2 over the DFS subtree of s
   double* e_ground;           // adiabatic potential
+  double* status_copy;        // [4 + E_NSLOT] error flags and energy slots, copied by the solver into its read-back block
   int* result;                // [0] principal diabat (0-based) [1] new hydronium molecule (0-based) [2] jacobi status
   double* coupling_geo;       // [MAXS][16] A, Vconst, dA[3][3], atoms...
   double* theta_mix;          // K^3
@@ -71,6 +72,7 @@ struct EvbDev {
 struct EvbHost {
   int* pinned = nullptr;      // read-back area: [0]=S, [1]=n_items, [2..] n_hops, proton_log, parent, result
   int n_states = 0, n_items = 0;
+  int n_states_prev = 0;      // S of the previous build: bounds what the early clear kernel covered
   int n_hops[RPB_MAXS];
   int proton_log[RPB_MAXS][RPB_MAXC][5];
   int parent[RPB_MAXS];
@@ -79,4 +81,5 @@ struct EvbHost {
   double hamiltonian[RPB_MAXS][RPB_MAXS];
   double evec[RPB_MAXS];
   bool built = false;
+  bool assemble_pending = false;   // evb_build left the Hamiltonian assembly to the solver kernel
 };

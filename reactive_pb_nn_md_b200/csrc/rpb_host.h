@@ -15,6 +15,7 @@ enum {
 struct rpb_ctx {
   rpb_config cfg;
   std::string err;
+  bool forces_zeroed = false;   // k_integrate_first cleared d.force / d.en: the next force evaluation skips its zeroing launches
   bool have_tables = false, have_ff = false, have_mt = false, have_evb = false, have_state = false, initialized = false;
   cudaStream_t stream = nullptr;        // stream the launchers use (normally the main stream; see StreamScope)
   cudaStream_t main_stream = nullptr;   // the library's main stream: host synchronisation and timing happen here
