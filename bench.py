@@ -13,6 +13,13 @@ One "step" = md_integrate_atomic: half-kick/drift, COM+wrap, MS-EVB force (princ
 diabats' matrix elements with batched PME, Jacobi, Hellmann-Feynman mixing), half-kick, COM momentum removal.
 Timing: CUDA events on the library's stream around every step, L2 flushed (256 MiB write) between steps outside
 the timed intervals, barrier + synchronize on both sides, max over ranks.
+
+The headline loop runs the library as shipped (three concurrent streams).  The per-kernel table (`kernels`, `roofline`)
+comes from a second context created with RPB_SERIAL_STREAMS=1 -- every branch on one stream -- so that each kernel's
+CUDA-event time is its own and not inflated by whatever overlapped it; ALGORITHMIC bytes / flops per launch follow
+DESIGN.md section 4.  `roofline` is the dominant HBM-bound PME kernel (the metric BASELINE.json quotes:
+"PME spread/gather GB/s vs HBM"); `roofline_fp64` is the real-space pair kernel against the measured fp64 FMA peak.
+`traffic` (DRAM bytes per launch) is read from profiles/r01_dram_traffic.json (ncu --set full of the same command).
 """
 import argparse
 import json
@@ -129,7 +136,10 @@ def algorithmic_model(name, N, K, S, n_own, pairs_listed, pairs_cut):
     m = {
         "pme_spread": ("hbm", 32 * N + 8 * K3),
         "pme_gather": ("hbm", 8 * K3 + 32 * N + 24 * N),
-        "pme_convolve": ("hbm", 2 * 16 * (K // 2 + 1) * K * K * 1 + 8 * (K // 2 + 1) * K * K),
+        # batched over the principal grid + every owned diabat: read + write the half spectrum, CB once (shared)
+        "pme_convolve": ("hbm", 2 * 16 * (K // 2 + 1) * K * K * (n_own + 1) + 8 * (K // 2 + 1) * K * K),
+        # cuFFT (library): one batched D2Z or Z2D exec = real grids on one side, half spectra on the other
+        "pme_fft": ("hbm", (8 * K3 + 16 * (K // 2 + 1) * K * K) * (n_own + 1)),
         "evb_grid_broadcast": ("hbm", 8 * K3 + 8 * K3 * n_own),
         "evb_theta_mix": ("hbm", 8 * K3 * (n_own + 1) + 8 * K3),
         "evb_mix_forces": ("hbm", 24 * N * (2 * n_own + 1) + 24 * N),
@@ -202,18 +212,31 @@ def run_ours(args):
     clocks = sampler.finish() if rank == 0 else None
     sps = args.steps / (ms_total * 1e-3)
 
-    # ---- per-kernel pass (events recorded inside the library on its own stream; separate from the headline loop)
-    sim.timers_enable(True)
-    sim.timers(reset=True)
+    # ---- per-kernel pass: a second context with every branch on ONE stream (clean per-kernel event times), started from
+    #      the state the headline loop reached
+    n_states = sim.evb()["n_states"] if evb else 1
+    st_now = sim.download_state()
+    os.environ["RPB_SERIAL_STREAMS"] = "1"
+    sim2 = engine.Simulation(s, params_for(args.workload), library=lib, device=local_rank, rank=rank if evb else 0,
+                             world_size=world if evb else 1, process_group=pg)
+    del os.environ["RPB_SERIAL_STREAMS"]
+    sim2.upload_state(st_now["xyz"], st_now["velocity"], st_now)
+    sim2._check(sim2.dll.rpb_initialize(sim2.ctx))
+    (sim2.ms_evb_calculate_total_force_energy if evb else sim2.calculate_total_force_energy)()
+    step2 = lambda n=1: sim2.md_integrate_atomic(n, ms_evb=evb)
+    for _ in range(3):
+        step2()
+    sim2.timers_enable(True)
+    sim2.timers(reset=True)
     n_prof = min(args.steps, 20)
     for k in range(n_prof):
         flush.fill_(float(k)); torch.cuda.synchronize()
-        step()
-    tm = sim.timers()
-    sim.timers_enable(False)
-    n_states = sim.evb()["n_states"] if evb else 1
+        step2()
+    tm = sim2.timers()
+    sim2.timers_enable(False)
+    n_states = sim2.evb()["n_states"] if evb else 1
     n_own = len([x for x in range(1, n_states) if (x - 1) % world == rank]) if evb else 0
-    vp, nl, _ = sim.neighbor_list()
+    vp, nl, _ = sim2.neighbor_list()
     pairs_listed = len(nl)
     model = algorithmic_model(args.workload, s.n_atoms, wl["pme_grid"], n_states, n_own, pairs_listed, int(0.58 * pairs_listed))
     peaks = {}
@@ -240,14 +263,23 @@ def run_ours(args):
                 ach = work / (per_launch * 1e-3) / 1e12
                 ent.update({"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak, "algorithmic_flops": work})
         kernels[name] = ent
-    single = {k: v for k, v in kernels.items() if "bound" in v}
-    dom = max(single, key=lambda k: single[k]["ms_per_step"]) if single else None
-    roofline = None
-    if dom:
-        r = single[dom]
-        roofline = {"kernel": dom, "bound": r["bound"], "achieved": r["achieved"], "peak": r["peak"], "unit": r["unit"],
-                    "frac": r["frac"], "traffic": None,
-                    "peak_source": hbm_src if r["bound"] == "hbm" else "fp64 FMA micro-benchmark run inside this bench (8 DFMA chains/thread)"}
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json"))).get(args.workload, {})
+    except Exception:
+        pass
+
+    def roof(name):
+        r = kernels[name]
+        return {"kernel": name, "bound": r["bound"], "achieved": r["achieved"], "peak": r["peak"], "unit": r["unit"],
+                "frac": r["frac"], "traffic": traffic.get(name),
+                "algorithmic": r.get("algorithmic_bytes", r.get("algorithmic_flops")),
+                "us_per_launch": 1e3 * r["ms_per_step"] / max(r["launches_per_step"], 1e-9),
+                "peak_source": hbm_src if r["bound"] == "hbm" else "fp64 FMA micro-benchmark run inside this bench (8 DFMA chains/thread)"}
+    hbm_k = {k: v for k, v in kernels.items() if v.get("bound") == "hbm"}
+    dom = max(hbm_k, key=lambda k: hbm_k[k]["ms_per_step"]) if hbm_k else None
+    roofline = roof(dom) if dom else None
+    roofline_fp64 = roof("pair_real_space") if "pair_real_space" in kernels and "bound" in kernels["pair_real_space"] else None
 
     # ---- end-to-end through the reference-facing call with HOST buffers: upload x,v -> step -> download x,v,F + energies
     e2e = None
@@ -298,7 +330,8 @@ def run_ours(args):
                        "n_states": n_states, "delta_t_ps": DT_PS, "parallelism": "diabatic-state sharding x%d" % world,
                        "l2": "flushed between timed steps (256 MiB write)", "timing": "cuda events per step on the library stream, max over ranks"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(own1 - own0), "cufft_execs": int(fft1 - fft0),
-            "roofline": roofline, "kernels": kernels, "fp64_peak_tflops_measured": fp64_peak,
+            "roofline": roofline, "roofline_fp64": roofline_fp64, "kernels": kernels,
+            "kernels_note": "per-kernel CUDA-event times from a serial-stream context (RPB_SERIAL_STREAMS=1); the headline value runs three concurrent streams", "fp64_peak_tflops_measured": fp64_peak,
             "cpu_baseline": cpu_baseline, "wall_s_timed_region": wall,
         }
         print(json.dumps(line), flush=True)

@@ -1629,8 +1629,10 @@ int evb_alloc(rpb_ctx* c) {
   AL(s.xq2, N); AL(s.vel2, 3 * N); AL(s.force2, 3 * N); AL(s.mass2, N); AL(s.type2, N); AL(s.moa2, N);
 #undef AL
   g_scratch[c] = s;
-  // every FFT batch size this context can meet (no plan is built inside a step)
-  for (int b = 1; b <= c->grid_capacity; b++) {
+  // cuFFT path only: every FFT batch size this context can meet (no plan is built inside a step)
+  const int own_fft = fft_conv_supported(c);
+  if (own_fft < 0) return own_fft;
+  for (int b = 1; b <= c->grid_capacity && !own_fft; b++) {
     cufftHandle pf, pi;
     if ((rc = pme_get_plans(c, b, &pf, &pi))) return rc;
   }
@@ -1956,6 +1958,7 @@ int evb_commit(rpb_ctx* c) {
   }
   if (h.new_hydronium == c->hydronium_mol) return 0;
   // ---- proton hop accepted: evb_change_diabat_data_structure_topology (ms_evb.f90:806-834)
+  c->state_cache_valid = false;
   const int pdiab = h.principal_diabat;
   if (d.world > 1 && !state_owned(pdiab, d.rank, d.world)) {
     // every rank needs the final snapshot of the new principal diabat; non-owned diabats were not built in evb_build

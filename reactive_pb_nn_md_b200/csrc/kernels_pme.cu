@@ -124,6 +124,10 @@ void launch_spread_principal(rpb_ctx* c) {
 
 int launch_convolve(rpb_ctx* c, int first_grid, int n_grids, double* e_recip_dev, bool inverse) {
   if (n_grids <= 0) return 0;
+  {   // hand-written fused path (kernels_fft.cu); cuFFT below only for grid sizes with factors other than 2 and 3
+    const int r = fft_conv_batched(c, first_grid, n_grids, e_recip_dev, inverse);
+    if (r != 0) return r < 0 ? r : 0;
+  }
   cufftHandle pf, pi;
   int rc = pme_get_plans(c, n_grids, &pf, &pi);
   if (rc) return rc;

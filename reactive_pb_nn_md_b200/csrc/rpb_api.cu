@@ -148,7 +148,12 @@ int rpb_create(rpb_ctx** out, const rpb_config* cfg) {
     CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_lo));
     c->main_stream = c->stream;
-    for (int k = 0; k < 2; k++) CK(cudaStreamCreateWithPriority(&c->aux[k], cudaStreamNonBlocking, prio_hi));
+    // RPB_SERIAL_STREAMS=1: every branch on the main stream (clean per-kernel CUDA-event times for the roofline table)
+    c->serial_streams = getenv("RPB_SERIAL_STREAMS") != nullptr;
+    for (int k = 0; k < 2; k++) {
+      if (c->serial_streams) c->aux[k] = c->stream;
+      else CK(cudaStreamCreateWithPriority(&c->aux[k], cudaStreamNonBlocking, prio_hi));
+    }
   }
   for (int k = 0; k < 8; k++) CK(cudaEventCreateWithFlags(&c->ev_sync[k], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_enum, cudaEventDisableTiming));
@@ -229,17 +234,19 @@ void rpb_destroy(rpb_ctx* c) {
   if (!c) return;
   if (c->stream) cudaStreamSynchronize(c->stream);
   evb_free(c);
+  fft_conv_free(c);
   for (auto& kv : c->plan_fwd) cufftDestroy(kv.second);
   for (auto& kv : c->plan_inv) cufftDestroy(kv.second);
   for (void* p : c->allocs) cudaFree(p);
   if (c->h_en) cudaFreeHost(c->h_en);
   if (c->h_flags) cudaFreeHost(c->h_flags);
+  if (c->staging) cudaFreeHost(c->staging);
   if (c->eh.pinned) cudaFreeHost(c->eh.pinned);
   if (c->stream) {
     for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
     for (int k = 0; k < 8; k++) if (c->ev_sync[k]) cudaEventDestroy(c->ev_sync[k]);
     if (c->ev_enum) cudaEventDestroy(c->ev_enum);
-    for (int k = 0; k < 2; k++) if (c->aux[k]) { cudaStreamSynchronize(c->aux[k]); cudaStreamDestroy(c->aux[k]); }
+    for (int k = 0; k < 2; k++) if (c->aux[k] && !c->serial_streams) { cudaStreamSynchronize(c->aux[k]); cudaStreamDestroy(c->aux[k]); }
     cudaStreamDestroy(c->stream);
   }
   delete c;
@@ -443,34 +450,74 @@ int rpb_set_evb(rpb_ctx* c, const int* da_i, const double* da_p, const int* pa_i
   return 0;
 }
 
+// Host <-> device state transfers go through one pinned staging area (allocated once) with asynchronous copies on the
+// main stream; per-atom / per-molecule tables that did not change since the last upload are not sent again.
+struct Staging {
+  double4* xq; double* vel; double* force; double* mass; int* type; int* moa; int* mol;   // mol: first | n_atom | type
+};
+static int staging_get(rpb_ctx* c, Staging& st) {
+  const size_t N = c->d.N, M = c->d.M;
+  const size_t bytes = N * sizeof(double4) + (3 * N + 3 * N + N) * sizeof(double) + (2 * N + 3 * M) * sizeof(int);
+  if (!c->staging) {
+    CK(cudaMallocHost(&c->staging, bytes));
+    memset(c->staging, 0xff, bytes);
+  }
+  char* p = (char*)c->staging;
+  st.xq = (double4*)p; p += N * sizeof(double4);
+  st.vel = (double*)p; p += 3 * N * sizeof(double);
+  st.force = (double*)p; p += 3 * N * sizeof(double);
+  st.mass = (double*)p; p += N * sizeof(double);
+  st.type = (int*)p; p += N * sizeof(int);
+  st.moa = (int*)p; p += N * sizeof(int);
+  st.mol = (int*)p;
+  return 0;
+}
+
 int rpb_upload_state(rpb_ctx* c, const double* xyz, const double* velocity, const double* mass, const double* charge,
                      const int* atom_type_index, const int* mol_first_atom, const int* mol_n_atom, const int* mol_type,
                      int hydronium_mol) {
   const int N = c->d.N, M = c->d.M;
-  std::vector<double4> xq(N);
-  std::vector<int> ty(N), moa(N);
-  for (int i = 0; i < N; i++) { xq[i] = make_double4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], charge[i]); ty[i] = atom_type_index[i] - 1; }
+  Staging st;
+  int rc = staging_get(c, st);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(c->stream));          // the staging area may still feed an earlier copy
+  const bool all = !c->have_state || !c->state_cache_valid;   // a committed proton hop permuted the device tables
+  bool type_changed = all, mass_changed = all, mol_changed = all;
+  for (int i = 0; i < N; i++) {
+    st.xq[i] = make_double4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], charge[i]);
+    const int t = atom_type_index[i] - 1;
+    if (st.type[i] != t) { st.type[i] = t; type_changed = true; }
+    if (st.mass[i] != mass[i]) { st.mass[i] = mass[i]; mass_changed = true; }
+  }
   c->mol_first.resize(M); c->mol_natom.resize(M); c->mol_type.resize(M);
   int expect = 0;
   for (int m = 0; m < M; m++) {
-    c->mol_first[m] = mol_first_atom[m] - 1; c->mol_natom[m] = mol_n_atom[m]; c->mol_type[m] = mol_type[m] - 1;
-    if (c->mol_first[m] != expect) { c->err = "molecules must be contiguous ascending atom ranges"; return RPB_ERR_ARG; }
-    for (int a = 0; a < mol_n_atom[m]; a++) moa[expect + a] = m;
-    expect += mol_n_atom[m];
+    const int f = mol_first_atom[m] - 1, n = mol_n_atom[m], t = mol_type[m] - 1;
+    if (f != expect) { c->err = "molecules must be contiguous ascending atom ranges"; return RPB_ERR_ARG; }
+    if (st.mol[m] != f || st.mol[M + m] != n || st.mol[2 * M + m] != t) { st.mol[m] = f; st.mol[M + m] = n; st.mol[2 * M + m] = t; mol_changed = true; }
+    c->mol_first[m] = f; c->mol_natom[m] = n; c->mol_type[m] = t;
+    if (mol_changed) for (int a = 0; a < n; a++) st.moa[expect + a] = m;
+    expect += n;
   }
   if (expect != N) { c->err = "molecule table does not cover all atoms"; return RPB_ERR_ARG; }
+  memcpy(st.vel, velocity, 3 * (size_t)N * sizeof(double));
+  if (c->hydronium_mol != hydronium_mol - 1) mol_changed = true;
   c->hydronium_mol = hydronium_mol - 1;
-  CK(cudaStreamSynchronize(c->stream));
-  CK(cudaMemcpy(c->d.xq, xq.data(), N * sizeof(double4), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(c->d.vel, velocity, 3 * N * sizeof(double), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(c->d.mass, mass, N * sizeof(double), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(c->d.type, ty.data(), N * sizeof(int), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(c->d.mol_of_atom, moa.data(), N * sizeof(int), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(c->d.mol_first, c->mol_first.data(), M * sizeof(int), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(c->d.mol_natom, c->mol_natom.data(), M * sizeof(int), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(c->d.mol_type, c->mol_type.data(), M * sizeof(int), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(c->d.hydronium, &c->hydronium_mol, sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpyAsync(c->d.xq, st.xq, N * sizeof(double4), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d.vel, st.vel, 3 * (size_t)N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (mass_changed) CK(cudaMemcpyAsync(c->d.mass, st.mass, N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (type_changed) CK(cudaMemcpyAsync(c->d.type, st.type, N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  if (mol_changed) {
+    CK(cudaMemcpyAsync(c->d.mol_of_atom, st.moa, N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d.mol_first, st.mol, M * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d.mol_natom, st.mol + M, M * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d.mol_type, st.mol + 2 * M, M * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    int* hp = c->h_flags + 4;                     // pinned scratch for the scalar
+    *hp = c->hydronium_mol;
+    CK(cudaMemcpyAsync(c->d.hydronium, hp, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  }
   c->have_state = true;
+  c->state_cache_valid = true;
   return 0;
 }
 
@@ -530,22 +577,26 @@ int rpb_get_energies(rpb_ctx* c, rpb_energies* e) {
 int rpb_download_state(rpb_ctx* c, double* xyz, double* velocity, double* force, double* mass, double* charge,
                        int* atom_type_index, int* mol_first_atom, int* mol_n_atom, int* mol_type, int* hydronium_mol) {
   const int N = c->d.N, M = c->d.M;
+  Staging st;
+  int rc = staging_get(c, st);
+  if (rc) return rc;
+  // a separate pinned block would be needed to keep the upload cache valid: downloads use the tail halves only where they
+  // do not alias cached tables (xq, vel, force are re-sent on every upload anyway)
+  if (xyz || charge) CK(cudaMemcpyAsync(st.xq, c->d.xq, N * sizeof(double4), cudaMemcpyDeviceToHost, c->stream));
+  if (velocity) CK(cudaMemcpyAsync(st.vel, c->d.vel, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (force) CK(cudaMemcpyAsync(st.force, c->d.force, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (mass) CK(cudaMemcpyAsync(st.mass, c->d.mass, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (atom_type_index) CK(cudaMemcpyAsync(st.type, c->d.type, N * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  if (xyz || charge) {
-    std::vector<double4> xq(N);
-    CK(cudaMemcpy(xq.data(), c->d.xq, N * sizeof(double4), cudaMemcpyDeviceToHost));
+  if (xyz || charge)
     for (int i = 0; i < N; i++) {
-      if (xyz) { xyz[3 * i] = xq[i].x; xyz[3 * i + 1] = xq[i].y; xyz[3 * i + 2] = xq[i].z; }
-      if (charge) charge[i] = xq[i].w;
+      if (xyz) { xyz[3 * i] = st.xq[i].x; xyz[3 * i + 1] = st.xq[i].y; xyz[3 * i + 2] = st.xq[i].z; }
+      if (charge) charge[i] = st.xq[i].w;
     }
-  }
-  if (velocity) CK(cudaMemcpy(velocity, c->d.vel, 3 * N * sizeof(double), cudaMemcpyDeviceToHost));
-  if (force) CK(cudaMemcpy(force, c->d.force, 3 * N * sizeof(double), cudaMemcpyDeviceToHost));
-  if (mass) CK(cudaMemcpy(mass, c->d.mass, N * sizeof(double), cudaMemcpyDeviceToHost));
-  if (atom_type_index) {
-    CK(cudaMemcpy(atom_type_index, c->d.type, N * sizeof(int), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < N; i++) atom_type_index[i] += 1;
-  }
+  if (velocity) memcpy(velocity, st.vel, 3 * (size_t)N * sizeof(double));
+  if (force) memcpy(force, st.force, 3 * (size_t)N * sizeof(double));
+  if (mass) memcpy(mass, st.mass, N * sizeof(double));
+  if (atom_type_index) for (int i = 0; i < N; i++) atom_type_index[i] = st.type[i] + 1;
   for (int m = 0; m < M; m++) {
     if (mol_first_atom) mol_first_atom[m] = c->mol_first[m] + 1;
     if (mol_n_atom) mol_n_atom[m] = c->mol_natom[m];

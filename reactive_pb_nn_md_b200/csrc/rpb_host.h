@@ -46,6 +46,9 @@ struct rpb_ctx {
   // pinned scratch
   double* h_en = nullptr;      // [E_NSLOT]
   int* h_flags = nullptr;      // [8]
+  void* staging = nullptr;     // pinned staging area of rpb_upload_state / rpb_download_state (also caches the last uploaded tables)
+  bool serial_streams = false;
+  bool state_cache_valid = false;   // the staging area mirrors the per-atom / per-molecule tables on the device
   // measurement
   long long n_launch = 0, n_fft = 0;
   bool timers_on = false;
@@ -114,6 +117,10 @@ void launch_scaled_coords(rpb_ctx*);
 void launch_spread_principal(rpb_ctx*);     // pme.f90:184-264
 int launch_convolve(rpb_ctx*, int first_grid, int n_grids, double* e_recip_dev, bool inverse);  // pme.f90:73-129
 void launch_gather(rpb_ctx*, const double* theta, double* out_force, bool add_to_force);       // pme.f90:346-498
+// ---- kernels_fft.cu
+int fft_conv_supported(rpb_ctx*);   // 1: hand-written batched FFT convolution handles this grid size, 0: cuFFT path
+int fft_conv_batched(rpb_ctx*, int first_grid, int n_grids, double* e_recip_dev, bool inverse);
+void fft_conv_free(rpb_ctx*);
 // ---- kernels_evb.cu
 int evb_alloc(rpb_ctx*);
 void evb_free(rpb_ctx*);

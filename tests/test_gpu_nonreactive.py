@@ -77,4 +77,28 @@ def test_short_trajectory(oracle_lib, cuda_lib):
 def test_launch_counter(pair):
     sg, _ = pair
     own, fft = sg.launch_counts()
-    assert own > 0 and fft > 0
+    assert own > 0 and fft == 0      # 32^3 grid: the hand-written FFT convolution runs, cuFFT is not called
+
+
+@pytest.mark.parametrize("K", [36, 40, 48, 64])
+def test_reciprocal_space_all_grid_sizes(oracle_lib, cuda_lib, K, monkeypatch):
+    """The hand-written batched FFT convolution (grid sizes 2^a 3^b: 36, 48, 64), the cuFFT fallback (40 = 2^3 5) and
+    the cuFFT cross-check of the hand-written path all give the oracle's theta grid, E_rec and reciprocal forces."""
+    s = water_system(10)
+    p = small_params(pme_grid=K)
+    so = engine.Simulation(s, p, library=oracle_lib)
+    so.calculate_total_force_energy()
+    Qo, tho, fro = so.pme()
+    sims = []
+    monkeypatch.delenv("RPB_FFT", raising=False)
+    sims.append(engine.Simulation(s, p, library=cuda_lib))
+    monkeypatch.setenv("RPB_FFT", "cufft")
+    sims.append(engine.Simulation(s, p, library=cuda_lib))
+    monkeypatch.delenv("RPB_FFT", raising=False)
+    for sg in sims:
+        sg.calculate_total_force_energy()
+        Qg, thg, frg = sg.pme()
+        assert rel_rms(thg, tho) < 1e-12
+        assert rel_rms(frg, fro) < F_RTOL
+        assert abs(sg.energies()["E_recip"] - so.energies()["E_recip"]) <= 1e-11 * abs(so.energies()["E_recip"])
+    assert rel_rms(sims[0].pme()[1], sims[1].pme()[1]) < 1e-13
