@@ -328,6 +328,8 @@ def run_ours(args):
             "ns_per_day": sps * DT_PS * 86.4,
             "config": {"workload": args.workload, "description": wl["desc"], "n_atoms": s.n_atoms, "pme_grid": wl["pme_grid"],
                        "n_states": n_states, "delta_t_ps": DT_PS, "parallelism": "diabatic-state sharding x%d" % world,
+                       "exchange": {"none": "single GPU", "peer": "peer-memory all-reduce kernels over NVLink (in-library, rank-ordered sums)",
+                                    "collective": "torch.distributed all-reduce (NCCL) between the phase calls"}[sim.exchange],
                        "l2": "flushed between timed steps (256 MiB write)", "timing": "cuda events per step on the library stream, max over ranks"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(own1 - own0), "cufft_execs": int(fft1 - fft0),
             "roofline": roofline, "roofline_fp64": roofline_fp64, "kernels": kernels,

@@ -180,6 +180,20 @@ int rpb_evb_phase_commit(rpb_ctx*);
 int rpb_evb_exchange_h(rpb_ctx*, void** ptr, int* n_doubles);
 int rpb_evb_exchange_f(rpb_ctx*, void** ptr, int* n_doubles);
 
+/* Peer-memory exchange (CUDA library; NVLink / NVSwitch): with it rpb_step / rpb_force_energy run the whole sharded
+ * MS-EVB step inside the library -- the two all-reduces become one kernel each that pulls the peers' partials over
+ * peer memory and adds them in rank order (bit-identical on every rank), no host round trip, no library collective.
+ *   one process per GPU:  rpb_peer_export -> exchange the RPB_PEER_HANDLE_BYTES-byte handles of all ranks (rank order)
+ *                         by any means (MPI_Allgather, torch.distributed.all_gather) -> rpb_peer_import
+ *   one process, several contexts:  rpb_peer_attach_local(contexts in rank order)
+ * The oracle returns RPB_ERR_UNSUPPORTED. */
+#define RPB_PEER_HANDLE_BYTES 64
+#define RPB_MAX_RANKS 16
+int rpb_peer_export(rpb_ctx*, void* handle_out /*RPB_PEER_HANDLE_BYTES*/);
+int rpb_peer_import(rpb_ctx*, const void* handles /*world_size x RPB_PEER_HANDLE_BYTES*/, int world_size);
+int rpb_peer_attach_local(rpb_ctx** ranks, int world_size);
+int rpb_peer_enabled(rpb_ctx*);
+
 /* ---- results ---- */
 int rpb_get_energies(rpb_ctx*, rpb_energies* out);   /* KE from calculate_kinetic_energy total_energy_forces.f90:106 */
 int rpb_download_state(rpb_ctx*, double* xyz, double* velocity, double* force,

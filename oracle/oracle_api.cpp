@@ -165,6 +165,12 @@ int rpb_evb_phase_commit(rpb_ctx* c) { return evb_phase_commit(*c); }
 int rpb_evb_exchange_h(rpb_ctx* c, void** ptr, int* n) { *ptr = c->xh.data(); *n = (int)c->xh.size(); return 0; }
 int rpb_evb_exchange_f(rpb_ctx* c, void** ptr, int* n) { *ptr = c->xf.data(); *n = (int)c->xf.size(); return 0; }
 
+// peer-memory exchange is a device feature of the CUDA library
+int rpb_peer_export(rpb_ctx* c, void*) { c->err = "peer-memory exchange: CUDA library only"; return RPB_ERR_UNSUPPORTED; }
+int rpb_peer_import(rpb_ctx* c, const void*, int) { c->err = "peer-memory exchange: CUDA library only"; return RPB_ERR_UNSUPPORTED; }
+int rpb_peer_attach_local(rpb_ctx**, int) { return RPB_ERR_UNSUPPORTED; }
+int rpb_peer_enabled(rpb_ctx*) { return 0; }
+
 int rpb_step(rpb_ctx* c, int n_steps, int ms_evb) {
   for (int s = 0; s < n_steps; s++) {
     md_step_begin(*c);

@@ -15,6 +15,7 @@ MAX_N_MOLE_TYPE = 10      # src/glob_v.f90:34
 MAX_INTERACTION_TYPE = 15  # src/glob_v.f90:72
 EVB_MAX_STATES = 80       # src/glob_v.f90:60
 EVB_MAX_CHAIN = 3         # src/glob_v.f90:65
+PEER_HANDLE_BYTES = 64    # RPB_PEER_HANDLE_BYTES, include/rpbmd.h
 EVB_MAX_NEIGHBORS = 10    # src/glob_v.f90:56
 MAX_MOLE_ATOMS = 8
 
@@ -76,6 +77,10 @@ _PROTOS = {
     "rpb_evb_phase_commit": (C.c_int, [_vp]),
     "rpb_evb_exchange_h": (C.c_int, [_vp, C.POINTER(_vp), _ip]),
     "rpb_evb_exchange_f": (C.c_int, [_vp, C.POINTER(_vp), _ip]),
+    "rpb_peer_export": (C.c_int, [_vp, _vp]),
+    "rpb_peer_import": (C.c_int, [_vp, _vp, C.c_int]),
+    "rpb_peer_attach_local": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "rpb_peer_enabled": (C.c_int, [_vp]),
     "rpb_get_energies": (C.c_int, [_vp, C.POINTER(RpbEnergies)]),
     "rpb_download_state": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _ip, _ip, _ip]),
     "rpb_get_r_com": (C.c_int, [_vp, _dp]),

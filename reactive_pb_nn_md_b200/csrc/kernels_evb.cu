@@ -1012,15 +1012,22 @@ __device__ void assemble_state(const Dev& d, EvbDev& e, const CouplingGeo* geo, 
   int S = *e.n_states;
   if (s >= MAXS) return;
   e.h_diag[s] = 0.0; e.h_diag[MAXS + s] = 0.0; e.h_diag[2 * MAXS + s] = 0.0;
-  if (s >= S || !state_owned(s, d.rank, d.world)) return;
   if (s == 0) {
-    // principal energy: calculate_total_force_energy + repulsion + reference (ms_evb.f90:411-436)
-    double E_elec = d.en[E_ELEC] + d.en[E_RECIP] + d.ewald_self;
-    double H11 = E_elec + d.en[E_VDW] + d.en[E_BOND] + d.en[E_ANGLE] + d.en[E_DIH];
-    H11 = H11 + e.item_energy[0];     // item 0 = the principal diabat's EVB repulsion + reference energy
+    // principal energy: calculate_total_force_energy + repulsion + reference (ms_evb.f90:411-436).  Sharded runs: every
+    // rank holds the pair energies of its slice of atoms; the bonded terms, E_rec, the Ewald self term and the EVB
+    // repulsion / reference energy are counted on rank 0 only.  The energy slots travel behind the Hamiltonian elements.
+    double* en_x = e.h_diag + 3 * MAXS;
+    for (int k = 0; k < E_NSLOT; k++) en_x[k] = (d.rank == 0 || k == E_ELEC || k == E_VDW) ? d.en[k] : 0.0;
+    double H11 = d.en[E_ELEC] + d.en[E_VDW];
+    if (d.rank == 0) {
+      double E_elec = d.en[E_ELEC] + d.en[E_RECIP] + d.ewald_self;
+      H11 = E_elec + d.en[E_VDW] + d.en[E_BOND] + d.en[E_ANGLE] + d.en[E_DIH];
+      H11 = H11 + e.item_energy[0];     // item 0 = the principal diabat's EVB repulsion + reference energy
+    }
     e.h_diag[0] = H11;
     return;
   }
+  if (s >= S || !state_owned(s, d.rank, d.world)) return;
   // energy delta of the last hop: acceptor-topology item minus donor-topology item (ms_evb.f90:1546)
   const int ii = last_item[s];      // acceptor-topology item of the last hop; the donor-topology item precedes it
   double dE = e.item_energy[ii] - e.item_energy[ii - 1];
@@ -1046,7 +1053,7 @@ __global__ void k_evb_assemble(Dev d, EvbDev e, const CouplingGeo* geo, const in
 __device__ void hellmann_feynman_weights(const Dev& d, EvbDev& e, int S, int tid, int nth) {
   // error flags and energy slots ride along in the solver's read-back block
   if (tid < 4) e.status_copy[tid] = (double)d.err_flag[tid];
-  if (tid < E_NSLOT) e.status_copy[4 + tid] = d.en[tid];
+  if (tid < E_NSLOT) e.status_copy[4 + tid] = (d.world > 1) ? e.h_diag[3 * MAXS + tid] : d.en[tid];
   for (int i = tid; i < MAXS; i += nth) {
     double ci = i < S ? e.evec[i] : 0.0;
     e.coef2[i] = ci * ci;
@@ -1609,7 +1616,7 @@ int evb_alloc(rpb_ctx* c) {
   AL(e.snap, MAXS * NLEV); AL(e.n_items, 1); AL(e.item_energy, RPB_MAX_ITEMS + 1);
   AL(e.n_real, 1); AL(e.corr_f, (size_t)MAXS * CM * MA * 3); AL(e.corr_atom, MAXS * CM * MA);
   AL(e.dF, (size_t)MAXS * 3 * N); AL(e.Foff, (size_t)MAXS * 3 * N);
-  AL(e.vex, MAXS); AL(e.e_recip, MAXS); AL(e.h_diag, 3 * MAXS); AL(e.f_mix, 3 * N); AL(e.coef2, 3 * MAXS);
+  AL(e.vex, MAXS); AL(e.e_recip, MAXS); AL(e.h_diag, 3 * MAXS + E_NSLOT); AL(e.f_mix, 3 * N); AL(e.coef2, 3 * MAXS);
   {  // solver results travel to the host every step: one contiguous block, one copy (SOLVER_BLOCK_DOUBLES)
     double* blk;
     AL(blk, SOLVER_BLOCK_DOUBLES);
@@ -1654,7 +1661,8 @@ void evb_free(rpb_ctx* c) {
 static void host_items(rpb_ctx* c, std::vector<EvbItem>& items) {
   EvbHost& h = c->eh;
   items.clear();
-  EvbItem p; p.state = 0; p.level = 0; p.donor_slot = -1; p.acceptor_slot = -1; p.sign = 1.0; p.real = 1; p.pad = 0;
+  EvbItem p; p.state = 0; p.level = 0; p.donor_slot = -1; p.acceptor_slot = -1; p.sign = 1.0; p.pad = 0;
+  p.real = (c->d.rank == 0) ? 1 : 0;   // sharded runs: the principal diabat's repulsion / reference energy is counted once
   items.push_back(p);   // principal diabat: EVB repulsion + reference energy (ms_evb.f90:418-426)
   for (int s = 1; s < h.n_states; s++) {
     if (!state_owned(s, c->d.rank, c->d.world)) continue;
@@ -1727,6 +1735,7 @@ int evb_build(rpb_ctx* c) {
     CKE(cudaEventSynchronize(c->ev_enum));           // only the enumeration: the pair forces etc. are still running
     HostClock::acc[0] += hc1 - hc0; hc0 = HostClock::now(); HostClock::acc[1] += hc0 - hc1;
     if (c->h_flags[2]) { c->err = "Found more diabat states than the current setting of evb_max_states"; return RPB_ERR_DIABATS; }
+    if (c->h_flags[3] >= 30) { c->err = "peer-memory exchange: rank " + std::to_string(c->h_flags[3] - 30) + " did not arrive"; return RPB_ERR_CUDA; }
     if (c->h_flags[3]) { c->err = "error in subroutine find_bonded_atom_hydrogen"; return RPB_ERR_STATE; }
     h.n_states = pin[0];
     memcpy(h.n_hops, pin + 16, MAXS * sizeof(int));
@@ -1888,7 +1897,7 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
   CKE(cudaEventRecord(c->ev_enum, c->stream));
   }
   {
-    int include_principal = (d.rank == 0) ? 1 : 0;
+    int include_principal = 1;            // every rank holds its share of the principal-diabat force (pair forces are sharded by atoms)
     // slot 0 (principal theta) only contributes on rank 0: mask it on the other ranks through slot_state
     // theta_mix (grids) runs on aux[1] next to the force mixing (per-atom arrays) on the main stream; the gather of
     // the mixed grid then adds into the mixed force
@@ -1913,6 +1922,7 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
   for (int k = 0; k < 4; k++) c->h_flags[k] = (int)pd[5 + 3 * MAXS + k];
   for (int k = 0; k < E_NSLOT; k++) c->h_en[k] = pd[5 + 3 * MAXS + 4 + k];
   if (c->h_flags[1]) { c->err = "please increase size of verlet neighbor list"; return RPB_ERR_VERLET; }
+  if (c->h_flags[3] >= 30) { c->err = "peer-memory exchange: rank " + std::to_string(c->h_flags[3] - 30) + " did not arrive"; return RPB_ERR_CUDA; }
   if (c->h_flags[3]) { c->err = "couldn't find index in subroutine 'get_index_atom_set' (code " + std::to_string(c->h_flags[3]) + ")"; return RPB_ERR_STATE; }
   if (pres[2]) { c->err = "too many iterations in jacobi"; return RPB_ERR_STATE; }
   static const bool dbg_jacobi = getenv("RPB_DEBUG_JACOBI") != nullptr;
@@ -1946,7 +1956,8 @@ int evb_commit(rpb_ctx* c) {
   Dev& d = c->d; EvbDev& e = c->e; EvbHost& h = c->eh;
   EvbScratch& sc = g_scratch[c];
   const int N = d.N, M = d.M;
-  if (d.world > 1) { k_copy<<<(3 * N + 255) / 256, 256, 0, c->stream>>>(d.force, e.f_mix, (size_t)3 * N); c->n_launch++; }   // single rank: mixed in place
+  if (d.world > 1 && !c->peer.f_reduced_in_place) { k_copy<<<(3 * N + 255) / 256, 256, 0, c->stream>>>(d.force, e.f_mix, (size_t)3 * N); c->n_launch++; }   // single rank: mixed in place; peer exchange: reduced into d.force
+  c->peer.f_reduced_in_place = false;
   // energies as the reference leaves them: potential = adiabatic energy, components = principal diabat's
   {
     rpb_energies& en = c->last_en;

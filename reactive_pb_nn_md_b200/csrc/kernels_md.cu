@@ -20,11 +20,10 @@ __global__ void k_zero(double* p, size_t n) {
 }
 
 // v += dt/2/m * F * conv ; x += v*dt          (md_integration.f90:478,484)
-// The thread that consumed F_i also clears it (and thread 0 the energy slots and the momentum scratch of the second
-// half-kick), so the force evaluation that follows needs no zeroing launches.
-__global__ void k_integrate_first(Dev d, double* psum) {
+// The thread that consumed F_i also clears it (and thread 0 the energy slots), so the force evaluation that follows needs no zeroing launches.
+__global__ void k_integrate_first(Dev d) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { for (int k = 0; k < E_NSLOT; k++) d.en[k] = 0.0; for (int k = 0; k < 4; k++) psum[k] = 0.0; }
+  if (i == 0) { for (int k = 0; k < E_NSLOT; k++) d.en[k] = 0.0; }
   if (i >= d.N) return;
   const double f0 = d.force[3 * i], f1 = d.force[3 * i + 1], f2 = d.force[3 * i + 2];
   d.force[3 * i] = 0.0; d.force[3 * i + 1] = 0.0; d.force[3 * i + 2] = 0.0;
@@ -91,16 +90,25 @@ __global__ void k_integrate_second(Dev d, double* psum /*[4]: px,py,pz,count*/) 
     p0 = m * v0; p1 = m * v1; p2 = m * v2; cnt = 1.0;
   }
   p0 = block_sum(p0, sh); p1 = block_sum(p1, sh); p2 = block_sum(p2, sh); cnt = block_sum(cnt, sh);
-  if (threadIdx.x == 0) { atomicAdd(&psum[0], p0); atomicAdd(&psum[1], p1); atomicAdd(&psum[2], p2); atomicAdd(&psum[3], cnt); }
+  // per-block partial sums, combined in a FIXED order by k_remove_com_momentum: the total momentum must come out bit-identical
+  // on every rank of a state-sharded run (replicated integration), which a floating-point atomicAdd does not guarantee
+  if (threadIdx.x == 0) { double* o = psum + 4 * blockIdx.x; o[0] = p0; o[1] = p1; o[2] = p2; o[3] = cnt; }
 }
 
-__global__ void k_remove_com_momentum(Dev d, const double* psum) {
+__global__ void k_remove_com_momentum(Dev d, const double* psum, int n_partial) {
+  __shared__ double sh[32];
+  __shared__ double tot[4];
+  double a[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int b = threadIdx.x; b < n_partial; b += blockDim.x)
+    for (int k = 0; k < 4; k++) a[k] += psum[4 * b + k];
+  for (int k = 0; k < 4; k++) { double v = block_sum(a[k], sh); if (threadIdx.x == 0) tot[k] = v; }
+  __syncthreads();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= d.N || d.freeze[d.type[i]] == 1) return;
-  double n = psum[3], m = d.mass[i];
-  d.vel[3 * i] = d.vel[3 * i] - (psum[0] / n) / m;
-  d.vel[3 * i + 1] = d.vel[3 * i + 1] - (psum[1] / n) / m;
-  d.vel[3 * i + 2] = d.vel[3 * i + 2] - (psum[2] / n) / m;
+  double n = tot[3], m = d.mass[i];
+  d.vel[3 * i] = d.vel[3 * i] - (tot[0] / n) / m;
+  d.vel[3 * i + 1] = d.vel[3 * i + 1] - (tot[1] / n) / m;
+  d.vel[3 * i + 2] = d.vel[3 * i + 2] - (tot[2] / n) / m;
 }
 
 __global__ void k_kinetic(Dev d) {
@@ -323,7 +331,7 @@ void launch_zero_forces(rpb_ctx* c) {
 
 void launch_integrate_first(rpb_ctx* c) {
   ScopedTimer t(c, T_INTEGRATE);
-  k_integrate_first<<<nblk(c->d.N), TPB, 0, c->stream>>>(c->d, c->d.maxd + 2);
+  k_integrate_first<<<nblk(c->d.N), TPB, 0, c->stream>>>(c->d);
   k_com_shift<<<nblk(c->d.M), TPB, 0, c->stream>>>(c->d, 1);
   c->n_launch += 2;
   c->forces_zeroed = true;
@@ -336,9 +344,10 @@ void launch_update_com_shift(rpb_ctx* c, bool shift) {
 
 void launch_integrate_second(rpb_ctx* c) {
   ScopedTimer t(c, T_INTEGRATE);
-  double* psum = c->d.maxd + 2;  // 4 doubles of scratch after the two displacement maxima
-  k_integrate_second<<<nblk(c->d.N), TPB, 0, c->stream>>>(c->d, psum);      // psum was cleared by k_integrate_first
-  k_remove_com_momentum<<<nblk(c->d.N), TPB, 0, c->stream>>>(c->d, psum);
+  const int nb = nblk(c->d.N);
+  double* psum = c->d.maxd + 8 + 2 * ((c->d.N + 255) / 256 + 1);   // [nb][4] per-block momentum partials behind the displacement scratch
+  k_integrate_second<<<nb, TPB, 0, c->stream>>>(c->d, psum);
+  k_remove_com_momentum<<<nb, TPB, 0, c->stream>>>(c->d, psum, nb);
   c->n_launch += 2;
 }
 

@@ -38,7 +38,7 @@ __device__ __noinline__ void sapt_pair(const double* __restrict__ tt_t, const do
 }
 
 template <int PAIR_B, int TPB_, int MINB>
-__global__ void __launch_bounds__(TPB_, MINB) k_pair_verlet(Dev d) {
+__global__ void __launch_bounds__(TPB_, MINB) k_pair_verlet(Dev d, int i_begin, int i_end) {
   extern __shared__ double sh_par[];           // [nT*nT][6] vdw parameters
   __shared__ int sh_vt[RPB_MAXT * RPB_MAXT];   // atype_vdw_type; 2 = SAPT row with all-zero coefficients (contributes exactly 0)
   __shared__ double sh_red[32];
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_verlet(Dev d) {
   const double bx = d.box[0], by = d.box[1], bz = d.box[2];
   const int* __restrict__ L = d.full_list;
   double e_el = 0.0, e_vdw = 0.0;
-  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < d.N; i += nwarp_total) {
+  for (int i = i_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < i_end; i += nwarp_total) {
     const int vs = d.full_point[i], vf = d.full_point[i + 1];
     const double4 pi = d.xq[i];
     const int ti = d.type[i] * d.nT;
@@ -160,24 +160,28 @@ __global__ void k_molecule_terms(Dev d) {
 }
 
 template <int B, int T, int M>
-static void launch_pair_variant(rpb_ctx* c) {
-  const int wpb = T / 32, blocks = (c->d.N + wpb - 1) / wpb;
+static void launch_pair_variant(rpb_ctx* c, bool shard) {
+  // state-sharded runs also shard the principal diabat's pair forces: rank r takes the atoms [N r / R, N (r+1) / R); the
+  // partial forces and energies ride the two all-reduces the sharded step has anyway
+  const int R = shard ? c->d.world : 1, r = shard ? c->d.rank : 0, N = c->d.N;
+  const int i0 = (int)((long long)N * r / R), i1 = (int)((long long)N * (r + 1) / R);
+  const int wpb = T / 32, blocks = std::max(1, (i1 - i0 + wpb - 1) / wpb);
   const size_t shmem = (size_t)c->d.nT * c->d.nT * 6 * sizeof(double);
-  k_pair_verlet<B, T, M><<<blocks, T, shmem, c->stream>>>(c->d);
+  k_pair_verlet<B, T, M><<<blocks, T, shmem, c->stream>>>(c->d, i0, i1);
 }
 
-void launch_pair_verlet(rpb_ctx* c) {
+void launch_pair_verlet(rpb_ctx* c, bool shard) {
   ScopedTimer t(c, T_PAIR);
   static const int variant = getenv("RPB_PAIR_VARIANT") ? atoi(getenv("RPB_PAIR_VARIANT")) : 0;
   switch (variant) {
-    case 1: launch_pair_variant<2, 256, 3>(c); break;
-    case 2: launch_pair_variant<2, 256, 4>(c); break;
-    case 3: launch_pair_variant<3, 256, 2>(c); break;
-    case 4: launch_pair_variant<3, 128, 5>(c); break;
-    case 5: launch_pair_variant<4, 256, 2>(c); break;
-    case 6: launch_pair_variant<2, 128, 6>(c); break;
-    case 7: launch_pair_variant<4, 128, 3>(c); break;
-    default: launch_pair_variant<3, 256, 2>(c); break;   // best of the sweep on B200 (C3): 89 us
+    case 1: launch_pair_variant<2, 256, 3>(c, shard); break;
+    case 2: launch_pair_variant<2, 256, 4>(c, shard); break;
+    case 3: launch_pair_variant<3, 256, 2>(c, shard); break;
+    case 4: launch_pair_variant<3, 128, 5>(c, shard); break;
+    case 5: launch_pair_variant<4, 256, 2>(c, shard); break;
+    case 6: launch_pair_variant<2, 128, 6>(c, shard); break;
+    case 7: launch_pair_variant<4, 128, 3>(c, shard); break;
+    default: launch_pair_variant<3, 256, 2>(c, shard); break;   // best of the sweep on B200 (C3): 89 us
   }
   c->n_launch += 1;
 }

@@ -42,6 +42,7 @@ static int fetch_status(rpb_ctx* c) {
   CK(cudaStreamSynchronize(c->stream));
   if (c->h_flags[1]) { c->err = "please increase size of verlet neighbor list"; return RPB_ERR_VERLET; }
   if (c->h_flags[2]) { c->err = "Found more diabat states than the current setting of evb_max_states"; return RPB_ERR_DIABATS; }
+  if (c->h_flags[3] >= 30) { c->err = "peer-memory exchange: rank " + std::to_string(c->h_flags[3] - 30) + " did not arrive"; return RPB_ERR_CUDA; }
   if (c->h_flags[3]) { c->err = "couldn't find index in subroutine 'get_index_atom_set'"; return RPB_ERR_STATE; }
   if (c->h_flags[0]) { c->err = "force on atom " + std::to_string(c->h_flags[0]) + " is too big"; return RPB_ERR_FORCE; }
   return 0;
@@ -86,8 +87,8 @@ int calculate_total_force_energy(rpb_ctx* c, bool evb_principal) {
     if (!evb_principal) rc = launch_convolve(c, 0, 1, c->d.en + E_RECIP, true);
   }
   if (rc) return rc;
-  launch_pair_verlet(c);
-  if (evb_principal) launch_molecule_terms(c);      // main stream has slack behind the pair kernel in MS-EVB mode
+  launch_pair_verlet(c, evb_principal);   // the sharded MS-EVB step all-reduces the forces; the non-reactive call is never sharded
+  if (evb_principal) { if (c->d.rank == 0) launch_molecule_terms(c); }   // main stream has slack behind the pair kernel in MS-EVB mode; sharded: counted once
   else { StreamScope sc(c, c->aux[0]); launch_molecule_terms(c); }
   if (evb_principal) return 0;     // evb_build keeps both side streams busy and joins them before the Hamiltonian
   stream_depend(c, 2, c->aux[0], c->main_stream);
@@ -100,8 +101,12 @@ static int force_energy(rpb_ctx* c, int ms_evb, bool sync) {
   int rc;
   if (ms_evb) {
     if (!c->have_evb) { c->err = "rpb_set_evb not called"; return RPB_ERR_STATE; }
+    const bool sharded = c->d.world > 1;   // peer-memory exchange (kernels_peer.cu); checked by the callers
+    if (sharded) peer_begin(c, PEER_H);
     rc = evb_build(c); if (rc) return rc;
+    if (sharded) { rc = peer_allreduce(c, PEER_H); if (rc) return rc; peer_begin(c, PEER_F); }
     rc = evb_mix(c, nullptr, nullptr); if (rc) return rc;
+    if (sharded) { rc = peer_allreduce(c, PEER_F); if (rc) return rc; }
     rc = evb_commit(c); if (rc) return rc;
     return 0;
   }
@@ -211,7 +216,7 @@ int rpb_create(rpb_ctx** out, const rpb_config* cfg) {
   AL(d.vrow_tmp, (size_t)N * 1024); AL(d.vsort_xq, N); AL(d.vsort_mol, N); AL(d.vsort_entry, N); AL(d.vstore, 3 * N); AL(d.vdisp, 3 * N);
   AL(d.flag_verlet, 1); AL(d.rebuild_now, 1); AL(d.err_flag, 4); AL(d.vdone, 1);
   AL(d.cell_count, 2 * (ncell + 1)); AL(d.cell_start, ncell + 1); AL(d.cell_atoms, N); AL(d.atom_cell, N); AL(d.row_count, N + 1); AL(d.row_count_full, N + 1);
-  AL(d.maxd, 8 + 2 * ((N + 255) / 256 + 1));
+  AL(d.maxd, 8 + 2 * ((N + 255) / 256 + 1) + 4 * ((N + 127) / 128 + 1));
   AL(d.uscale, 3 * N); AL(d.force_recip, 3 * N); AL(d.en, E_NSLOT);
   c->grid_capacity = 1;
   if (cfg->evb_max_states > 0) c->grid_capacity = cfg->evb_max_states;
@@ -233,6 +238,7 @@ int rpb_create(rpb_ctx** out, const rpb_config* cfg) {
 void rpb_destroy(rpb_ctx* c) {
   if (!c) return;
   if (c->stream) cudaStreamSynchronize(c->stream);
+  peer_free(c);
   evb_free(c);
   fft_conv_free(c);
   for (auto& kv : c->plan_fwd) cufftDestroy(kv.second);
@@ -533,7 +539,7 @@ int rpb_initialize(rpb_ctx* c) {
 
 int rpb_force_energy(rpb_ctx* c, int ms_evb) {
   if (!c->initialized) { c->err = "rpb_initialize not called"; return RPB_ERR_STATE; }
-  if (ms_evb && c->d.world > 1) { c->err = "world_size>1: use the phase calls"; return RPB_ERR_STATE; }
+  if (ms_evb && c->d.world > 1 && !c->peer.on) { c->err = "world_size>1: set up the peer-memory exchange (rpb_peer_*) or use the phase calls"; return RPB_ERR_STATE; }
   return force_energy(c, ms_evb, true);
 }
 
@@ -543,15 +549,16 @@ int rpb_step_end(rpb_ctx* c) {
   int rc = fetch_status(c);
   return rc;
 }
-int rpb_evb_phase_build(rpb_ctx* c) { return evb_build(c); }
-int rpb_evb_phase_mix(rpb_ctx* c) { return evb_mix(c, nullptr, nullptr); }
+// the phase calls always use the library's own exchange buffers (the caller runs the collectives), never the peer arena
+int rpb_evb_phase_build(rpb_ctx* c) { if (c->peer.h_local) c->e.h_diag = c->peer.h_local; return evb_build(c); }
+int rpb_evb_phase_mix(rpb_ctx* c) { if (c->peer.f_local) c->e.f_mix = c->peer.f_local; c->peer.f_reduced_in_place = false; return evb_mix(c, nullptr, nullptr); }
 int rpb_evb_phase_commit(rpb_ctx* c) { return evb_commit(c); }
-int rpb_evb_exchange_h(rpb_ctx* c, void** ptr, int* n) { *ptr = c->e.h_diag; *n = 3 * RPB_MAXS; return 0; }
+int rpb_evb_exchange_h(rpb_ctx* c, void** ptr, int* n) { *ptr = c->e.h_diag; *n = 3 * RPB_MAXS + E_NSLOT; return 0; }
 int rpb_evb_exchange_f(rpb_ctx* c, void** ptr, int* n) { *ptr = c->e.f_mix; *n = 3 * c->d.N; return 0; }
 
 int rpb_step(rpb_ctx* c, int n_steps, int ms_evb) {
   if (!c->initialized) { c->err = "rpb_initialize not called"; return RPB_ERR_STATE; }
-  if (ms_evb && c->d.world > 1) { c->err = "world_size>1: use the phase calls"; return RPB_ERR_STATE; }
+  if (ms_evb && c->d.world > 1 && !c->peer.on) { c->err = "world_size>1: set up the peer-memory exchange (rpb_peer_*) or use the phase calls"; return RPB_ERR_STATE; }
   for (int s = 0; s < n_steps; s++) {
     ScopedTimer t(c, T_STEP);
     launch_integrate_first(c);

@@ -12,6 +12,22 @@ enum {
   T_EVB_GATHERMIX, T_EVB_SNAP, T_EVB_COUPLING_GEO, T_EVB_ASSEMBLE, T_STEP, T_NTIMER
 };
 
+// Peer-memory exchange of the state-sharded step (kernels_peer.cu)
+enum { PEER_H = 0, PEER_F = 1 };
+struct PeerExchange {
+  bool on = false;
+  int world = 1;
+  double* arena = nullptr;                 // this rank's arena (flags + 2 parities of each partial)
+  double* peer[RPB_MAX_RANKS] = {};        // every rank's arena as mapped here (peer[rank] == arena)
+  bool opened[RPB_MAX_RANKS] = {};         // mapped with cudaIpcOpenMemHandle (closed in peer_free)
+  double* h_total = nullptr;               // all-reduced Hamiltonian block
+  double* h_local = nullptr; double* f_local = nullptr;   // the library's own (non-arena) exchange buffers
+  long long seq[2] = {0, 0};               // collectives issued per kind
+  bool f_reduced_in_place = false;         // the force all-reduce of this step wrote d.force directly (evb_commit skips its copy)
+  size_t off_flags = 0, off[2] = {0, 0}, arena_doubles = 0;
+  int n[2] = {0, 0}, n_act[2] = {0, 0};    // stride / length in doubles of one partial
+};
+
 struct rpb_ctx {
   rpb_config cfg;
   std::string err;
@@ -58,6 +74,7 @@ struct rpb_ctx {
   double t_ms[T_NTIMER];
   long long t_calls[T_NTIMER];
   rpb_energies last_en;
+  PeerExchange peer;
 };
 
 template <typename T>
@@ -108,7 +125,7 @@ void launch_zero_forces(rpb_ctx*);
 void launch_kinetic_energy(rpb_ctx*);
 int measure_fp64_peak(rpb_ctx*, double* tflops);
 // ---- kernels_pair.cu
-void launch_pair_verlet(rpb_ctx*);          // pair_int_real_space.f90:135-371
+void launch_pair_verlet(rpb_ctx*, bool shard_by_rank);   // pair_int_real_space.f90:135-371; shard: rank r takes atoms [N r/R, N (r+1)/R)
 void launch_molecule_terms(rpb_ctx*);       // pair_int_real_space.f90:386-588 + intra_bonded_interactions.f90:17-552
 // ---- kernels_pme.cu
 int pme_round_batch(int batch);
@@ -121,6 +138,10 @@ void launch_gather(rpb_ctx*, const double* theta, double* out_force, bool add_to
 int fft_conv_supported(rpb_ctx*);   // 1: hand-written batched FFT convolution handles this grid size, 0: cuFFT path
 int fft_conv_batched(rpb_ctx*, int first_grid, int n_grids, double* e_recip_dev, bool inverse);
 void fft_conv_free(rpb_ctx*);
+// ---- kernels_peer.cu
+void peer_begin(rpb_ctx*, int kind);      // producers of partial `kind` write into this step's parity of the arena
+int peer_allreduce(rpb_ctx*, int kind);   // one kernel: signal, wait, pull + add in rank order
+void peer_free(rpb_ctx*);
 // ---- kernels_evb.cu
 int evb_alloc(rpb_ctx*);
 void evb_free(rpb_ctx*);

@@ -8,16 +8,20 @@ Method names follow the reference routines they stand for:
 Errors the reference reports with `stop "..."` surface as RpbError.
 
 Diabatic-state sharding: with a torch.distributed process group the two
-collectives of the sharded MS-EVB step (Hamiltonian elements, Hellmann-Feynman partial forces)
-run here, directly on the library's exchange buffers (device memory for the CUDA library over
-NCCL; host memory for gloo in the CPU tests).
+exchange steps of the sharded MS-EVB step (Hamiltonian elements, Hellmann-Feynman partial forces)
+are set up here.  CUDA library: the ranks' exchange arenas are mapped into each other over CUDA IPC
+once, after which the whole step -- including the two all-reduces, one peer-memory kernel each --
+runs inside rpb_step (exchange == "peer").  Otherwise (RPB_EXCHANGE=collective, no peer access, or
+the CPU oracle under gloo) the collectives run here on the library's exchange buffers.
 """
 import ctypes as C
+import os
+import sys
 
 import numpy as np
 
 from . import tables
-from ._binding import (EVB_MAX_CHAIN, EVB_MAX_STATES, Library, RpbConfig, RpbEnergies, RpbError, dptr, iptr,
+from ._binding import (EVB_MAX_CHAIN, EVB_MAX_STATES, PEER_HANDLE_BYTES, Library, RpbConfig, RpbEnergies, RpbError, dptr, iptr,
                        load_cuda)
 from .forcefield import flatten_molecule_types
 
@@ -116,6 +120,47 @@ class Simulation:
         self.upload_state(system.xyz, system.velocity)
         self._check(self.dll.rpb_initialize(self.ctx))
         self._xh = self._xf = None
+        self._ext_stream = None
+        self.exchange = "none" if world_size == 1 else "collective"
+        if (world_size > 1 and ff.has_evb and self.lib.backend.startswith("cuda") and process_group is not None
+                and os.environ.get("RPB_EXCHANGE", "peer") == "peer"):
+            self._setup_peer_exchange()
+
+    # -- peer-memory exchange (NVLink / NVSwitch) --------------------------------------------
+    def _setup_peer_exchange(self):
+        """One process per GPU: all-gather the 64-byte IPC handles of the ranks' exchange arenas over the process group
+        and map the peers' arenas.  From then on md_integrate_atomic / ms_evb_calculate_total_force_energy run inside
+        the library (rpb_step / rpb_force_energy); torch.distributed is no longer on the step's path.  If the arenas
+        cannot be mapped (no peer access between the devices), every rank keeps the collective path."""
+        import torch
+        import torch.distributed as dist
+        hb = C.create_string_buffer(PEER_HANDLE_BYTES)
+        self._check(self.dll.rpb_peer_export(self.ctx, hb))
+        # the handles travel on whatever the process group moves: device tensors for NCCL, host tensors otherwise
+        dev = torch.device("cuda", self.cfg.device) if dist.get_backend(self.pg) == "nccl" else torch.device("cpu")
+        mine = torch.frombuffer(bytearray(hb.raw), dtype=torch.uint8).to(dev)
+        every = [torch.empty_like(mine) for _ in range(self.world_size)]
+        dist.all_gather(every, mine, group=self.pg)
+        blob = b"".join(t.cpu().numpy().tobytes() for t in every)
+        rc = self.dll.rpb_peer_import(self.ctx, C.c_char_p(blob), self.world_size)
+        ok = torch.tensor([1 if rc == 0 else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.pg)
+        if int(ok.item()) == 1:
+            self.exchange = "peer"
+        else:
+            msg = self.dll.rpb_last_error(self.ctx)
+            sys.stderr.write("[rpbmd] peer-memory exchange unavailable (%s); using torch.distributed all-reduce\n"
+                             % (msg.decode() if msg else "a peer failed"))
+
+    @staticmethod
+    def attach_local(sims):
+        """Several ranks inside ONE process, each context on its OWN device (contexts in rank order): map the arenas
+        directly.  (Ranks sharing a device inside one process would deadlock: a kernel waiting for its peer keeps the
+        peer's cooperative neighbour-list kernel from ever becoming co-resident.)"""
+        arr = (C.c_void_p * len(sims))(*[s.ctx for s in sims])
+        sims[0]._check(sims[0].dll.rpb_peer_attach_local(arr, len(sims)))
+        for s in sims:
+            s.exchange = "peer"
 
     # -- plumbing ---------------------------------------------------------------------------
     def _check(self, rc):
@@ -152,7 +197,7 @@ class Simulation:
         self._check(self.dll.rpb_force_energy(self.ctx, 0))
 
     def ms_evb_calculate_total_force_energy(self):
-        if self.world_size == 1:
+        if self.world_size == 1 or self.exchange == "peer":
             self._check(self.dll.rpb_force_energy(self.ctx, 1))
             return
         self._check(self.dll.rpb_evb_phase_build(self.ctx))
@@ -162,7 +207,7 @@ class Simulation:
         self._check(self.dll.rpb_evb_phase_commit(self.ctx))
 
     def md_integrate_atomic(self, n_steps=1, ms_evb=False):
-        if self.world_size == 1:
+        if self.world_size == 1 or self.exchange == "peer" or not ms_evb:
             self._check(self.dll.rpb_step(self.ctx, int(n_steps), int(bool(ms_evb))))
             return
         for _ in range(n_steps):
@@ -187,10 +232,14 @@ class Simulation:
         import torch.distributed as dist
         t = self._exchange_tensor(which)
         if t.is_cuda:
+            # Stream-ordered: with the library's main stream as torch's current stream, NCCL's collective waits for the
+            # kernels that filled the buffer and the library's next kernels wait for the collective -- no host sync.
             import torch
-            torch.cuda.synchronize()          # library stream -> NCCL stream
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
-            torch.cuda.synchronize()          # NCCL stream -> library stream
+            if self._ext_stream is None:
+                self._ext_stream = torch.cuda.ExternalStream(self.dll.rpb_get_stream(self.ctx),
+                                                             device=torch.device("cuda", self.cfg.device))
+            with torch.cuda.stream(self._ext_stream):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
         else:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
 

@@ -1,6 +1,7 @@
 """CUDA MS-EVB path on the hand-built clusters (hop commit, chain cut, Eigen cation), the state-sharded path
 emulated on one GPU, and size-independent properties at BASELINE's full sizes."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -67,27 +68,122 @@ def test_eigen_and_wire_clusters(oracle_lib, cuda_lib, ff):
     assert rel_rms(sg.forces(), so.forces()) < F_RTOL
 
 
-def test_state_sharding_emulated_on_one_gpu(cuda_lib, oracle_lib):
-    """two contexts (rank 0/1 of 2) on the same device; the two all-reduces are done by hand on the exchange buffers"""
+def _emulated_allreduce(ranks, which):
     import torch
-    s = water_system(10, hydronium=True)
-    p = small_params()
-    ref = engine.Simulation(s, p, library=oracle_lib); ref.ms_evb_calculate_total_force_energy()
-    ranks = [engine.Simulation(s, p, library=cuda_lib, rank=r, world_size=2) for r in range(2)]
+    torch.cuda.synchronize()
+    bufs = [sim._exchange_tensor(which) for sim in ranks]
+    total = bufs[0].clone()
+    for b in bufs[1:]:
+        total += b
+    for b in bufs:
+        b.copy_(total)
+    torch.cuda.synchronize()
+
+
+def _emulated_force(ranks):
     for which, phase in (("h", "rpb_evb_phase_build"), ("f", "rpb_evb_phase_mix")):
         for sim in ranks:
             sim._check(getattr(sim.dll, phase)(sim.ctx))
-        torch.cuda.synchronize()
-        bufs = [sim._exchange_tensor(which) for sim in ranks]
-        total = bufs[0] + bufs[1]
-        for b in bufs:
-            b.copy_(total)
-        torch.cuda.synchronize()
+        _emulated_allreduce(ranks, which)
     for sim in ranks:
         sim._check(sim.dll.rpb_evb_phase_commit(sim.ctx))
+
+
+@pytest.mark.parametrize("world", [2, 3, 8, 16])
+def test_state_sharding_emulated_on_one_gpu(cuda_lib, oracle_lib, world):
+    """`world` contexts (rank r of world) on the same device; the two all-reduces are done by hand on the exchange
+    buffers.  world=16 exceeds the number of non-principal diabats of this box, so some ranks own no diabat at all;
+    every rank still holds its slice of the principal diabat's pair forces."""
+    s = water_system(10, hydronium=True)
+    p = small_params()
+    ref = engine.Simulation(s, p, library=oracle_lib); ref.ms_evb_calculate_total_force_energy()
+    ranks = [engine.Simulation(s, p, library=cuda_lib, rank=r, world_size=world) for r in range(world)]
+    _emulated_force(ranks)
+    er = ref.energies()
+    for sim in ranks:
         assert sim.evb()["n_states"] == ref.evb()["n_states"]
+        assert np.array_equal(sim.evb()["proton_log"], ref.evb()["proton_log"])
         assert abs(sim.evb()["adiabatic_potential"] - ref.evb()["adiabatic_potential"]) <= E_RTOL * abs(ref.evb()["adiabatic_potential"])
+        assert np.abs(sim.evb()["hamiltonian"] - ref.evb()["hamiltonian"]).max() <= E_RTOL * np.abs(np.diag(ref.evb()["hamiltonian"])).max()
         assert rel_rms(sim.forces(), ref.forces()) < F_RTOL
+        assert abs(sim.energies()["potential_energy"] - er["potential_energy"]) <= E_RTOL * abs(er["potential_energy"])
+    # a short trajectory through the split step (rpb_step_begin / phases / rpb_step_end) stays on the oracle's
+    ref.md_integrate_atomic(4, ms_evb=True)
+    for _ in range(4):
+        for sim in ranks:
+            sim._check(sim.dll.rpb_step_begin(sim.ctx))
+        _emulated_force(ranks)
+        for sim in ranks:
+            sim._check(sim.dll.rpb_step_end(sim.ctx))
+    xr = ref.download_state()
+    for sim in ranks:
+        st = sim.download_state()
+        assert st["hydronium_mol"] == xr["hydronium_mol"]
+        assert np.abs(st["xyz"] - xr["xyz"]).max() < 1e-9
+        assert rel_rms(st["force"], xr["force"]) < F_RTOL
+
+
+def _peer_worker(rank, world, port, outdir, n_steps):
+    """one process per rank, as in production; with fewer devices than ranks the processes share device 0 (CUDA IPC
+    works within a device too; the driver time-slices the waiting kernels)"""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import torch
+    import torch.distributed as dist
+    from reactive_pb_nn_md_b200 import engine as eng
+    from reactive_pb_nn_md_b200._binding import load_cuda
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dev = rank if torch.cuda.device_count() >= world else 0
+    torch.cuda.set_device(dev)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    s = water_system(10, hydronium=True)
+    sim = eng.Simulation(s, small_params(), library=load_cuda(), device=dev, rank=rank, world_size=world,
+                         process_group=dist.group.WORLD)
+    assert sim.exchange == "peer" and sim.dll.rpb_peer_enabled(sim.ctx) == 1
+    sim.ms_evb_calculate_total_force_energy()
+    f0, ev0, e0 = sim.forces(), sim.evb(), sim.energies()
+    sim.md_integrate_atomic(n_steps, ms_evb=True)
+    st = sim.download_state()
+    np.savez(os.path.join(outdir, "rank%d.npz" % rank), f0=f0, S=ev0["n_states"], log=ev0["proton_log"],
+             H=ev0["hamiltonian"], ad=ev0["adiabatic_potential"], pe=e0["potential_energy"], xyz=st["xyz"],
+             vel=st["velocity"], force=st["force"], hyd=st["hydronium_mol"])
+    dist.barrier()
+    sim.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_memory_exchange_between_processes(oracle_lib, world):
+    """The sharded step with the peer-memory all-reduce kernels (kernels_peer.cu), one process per rank: IPC handles
+    travel over the process group, rpb_step runs the whole step inside the library, results match the oracle and every
+    rank ends with the bit-identical replicated state."""
+    import tempfile
+    import torch.multiprocessing as mp
+    n_steps = 8
+    s = water_system(10, hydronium=True)
+    ref = engine.Simulation(s, small_params(), library=oracle_lib)
+    ref.ms_evb_calculate_total_force_energy()
+    er, evr, fr = ref.energies(), ref.evb(), ref.forces()
+    ref.md_integrate_atomic(n_steps, ms_evb=True)
+    xr = ref.download_state()
+    with tempfile.TemporaryDirectory() as d:
+        port = 29700 + (os.getpid() % 2000)
+        mp.spawn(_peer_worker, args=(world, port, d, n_steps), nprocs=world, join=True)
+        z = [np.load(os.path.join(d, "rank%d.npz" % r)) for r in range(world)]
+        for q in z:
+            assert int(q["S"]) == evr["n_states"] and np.array_equal(q["log"], evr["proton_log"])
+            assert abs(float(q["ad"]) - evr["adiabatic_potential"]) <= E_RTOL * abs(evr["adiabatic_potential"])
+            assert np.abs(q["H"] - evr["hamiltonian"]).max() <= E_RTOL * np.abs(np.diag(evr["hamiltonian"])).max()
+            assert abs(float(q["pe"]) - er["potential_energy"]) <= E_RTOL * abs(er["potential_energy"])
+            assert rel_rms(q["f0"], fr) < F_RTOL
+            assert int(q["hyd"]) == xr["hydronium_mol"]
+            assert np.abs(q["xyz"] - xr["xyz"]).max() < 1e-9
+            assert rel_rms(q["force"], xr["force"]) < F_RTOL
+            for k in ("xyz", "vel", "force"):
+                assert np.array_equal(q[k], z[0][k]), k                    # replicated state: bit-identical
 
 
 def test_full_size_c2_properties(cuda_lib):
