@@ -39,6 +39,8 @@ WORKLOADS = {
     "c2": dict(desc="3375 flexible H2O, non-reactive (BASELINE configs[1])", pme_grid=48, ms_evb=False),
     "c3": dict(desc="H3O+ + 2999 H2O, MS-EVB (BASELINE configs[2])", pme_grid=48, ms_evb=True),
     "c4": dict(desc="H3O+ + 9999 H2O, MS-EVB, 64^3 PME (BASELINE configs[3], single excess proton)", pme_grid=64, ms_evb=True),
+    "c5": dict(desc="independent H3O+ + 2999 H2O MS-EVB replicas, seeds 0..R-1 per GPU (BASELINE configs[4]); replicas only, no communication",
+               pme_grid=48, ms_evb=True),
 }
 
 
@@ -128,6 +130,74 @@ def run_reference(args):
         "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def run_ensemble(args):
+    """--workload c5: R independent replicas per GPU ("replicas only": weak scaling, no collective on the data path).
+    value = replica-steps/s summed over all replicas of all ranks."""
+    import torch
+    from reactive_pb_nn_md_b200 import engine, system
+    from reactive_pb_nn_md_b200._binding import load_cuda
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    lib = load_cuda()
+    R = args.replicas
+    sims = []
+    for r in range(R):
+        s = system.config_c3(seed=20171017 + rank * R + r)
+        sim = engine.Simulation(s, params_for("c5"), library=lib, device=local_rank)
+        sim.ms_evb_calculate_total_force_energy()
+        sims.append(sim)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier(); torch.cuda.synchronize()
+
+    engine.Simulation.ensemble_step(sims, max(args.warmup, 3), ms_evb=True)
+    l0 = sum(s.launch_counts()[0] for s in sims)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start(); time.sleep(0.3)
+    flush.fill_(1.0)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    engine.Simulation.ensemble_step(sims, args.steps, ms_evb=True)      # returns when every replica's last step has completed
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    l1 = sum(s.launch_counts()[0] for s in sims)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clocks = sampler.finish() if rank == 0 else None
+    # one replica alone, same device, for the concurrency gain
+    t0 = time.perf_counter(); sims[0].md_integrate_atomic(args.steps, ms_evb=True); torch.cuda.synchronize(); single = args.steps / (time.perf_counter() - t0)
+    if rank == 0:
+        total = world * R * args.steps / (ms * 1e-3)
+        print(json.dumps({
+            "metric": "ms_evb_steps_per_s", "value": total, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "ns_per_day": total * DT_PS * 86.4,
+            "config": {"workload": "c5", "description": WORKLOADS["c5"]["desc"], "replicas_per_gpu": R, "n_atoms": sims[0].system.n_atoms,
+                       "pme_grid": 48, "n_states": [s.evb()["n_states"] for s in sims], "delta_t_ps": DT_PS,
+                       "parallelism": "%d independent replicas per GPU x %d GPUs, one host thread per replica (rpb_ensemble_step)" % (R, world),
+                       "l2": "working set of %d replicas exceeds L2" % R, "timing": "cuda events around the K ensemble steps, max over ranks"},
+            "clocks": clocks, "gpu_launches": int(l1 - l0), "single_replica_steps_per_s_same_device": single,
+            "concurrency_gain": (R * args.steps / (ms * 1e-3)) / single, "e2e": None, "roofline": None, "cpu_baseline": None}), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 def algorithmic_model(name, N, K, S, n_own, pairs_listed, pairs_cut):
@@ -351,9 +421,14 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicas", type=int, default=16, help="replicas per GPU of --workload c5")
     args = ap.parse_args()
     if args.impl == "reference":
+        if args.workload == "c5":
+            args.workload = "c3"        # one replica of the ensemble on the CPU
         run_reference(args)
+    elif args.workload == "c5":
+        run_ensemble(args)
     else:
         run_ours(args)
 

@@ -163,6 +163,10 @@ int rpb_force_energy(rpb_ctx*, int ms_evb);
 /* == md_integrate_atomic, NVE branch (md_integration.f90:438-541), n_steps times, on device. */
 int rpb_step(rpb_ctx*, int n_steps, int ms_evb);
 
+/* Independent replicas on one device ("replicas only", BASELINE config 5): rpb_step on every context, one host thread
+ * per context so that the replicas' launches overlap on the device.  Returns the first non-zero status. */
+int rpb_ensemble_step(rpb_ctx** replicas, int n_replicas, int n_steps, int ms_evb);
+
 /* Sharded variant of the MS-EVB force call (world_size>1): the caller runs the two
  * collectives between the phases:
  *   rpb_evb_phase_build   principal diabat, enumeration, owned states' matrix elements

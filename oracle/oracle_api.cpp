@@ -165,6 +165,13 @@ int rpb_evb_phase_commit(rpb_ctx* c) { return evb_phase_commit(*c); }
 int rpb_evb_exchange_h(rpb_ctx* c, void** ptr, int* n) { *ptr = c->xh.data(); *n = (int)c->xh.size(); return 0; }
 int rpb_evb_exchange_f(rpb_ctx* c, void** ptr, int* n) { *ptr = c->xf.data(); *n = (int)c->xf.size(); return 0; }
 
+int rpb_step(rpb_ctx* c, int n_steps, int ms_evb);
+int rpb_ensemble_step(rpb_ctx** replicas, int n_replicas, int n_steps, int ms_evb) {   // serial on the CPU
+  if (!replicas || n_replicas < 1) return RPB_ERR_ARG;
+  for (int r = 0; r < n_replicas; r++) { int rc = rpb_step(replicas[r], n_steps, ms_evb); if (rc) return rc; }
+  return 0;
+}
+
 // peer-memory exchange is a device feature of the CUDA library
 int rpb_peer_export(rpb_ctx* c, void*) { c->err = "peer-memory exchange: CUDA library only"; return RPB_ERR_UNSUPPORTED; }
 int rpb_peer_import(rpb_ctx* c, const void*, int) { c->err = "peer-memory exchange: CUDA library only"; return RPB_ERR_UNSUPPORTED; }

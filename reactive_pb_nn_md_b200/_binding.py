@@ -70,6 +70,7 @@ _PROTOS = {
     "rpb_initialize": (C.c_int, [_vp]),
     "rpb_force_energy": (C.c_int, [_vp, C.c_int]),
     "rpb_step": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "rpb_ensemble_step": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int]),
     "rpb_step_begin": (C.c_int, [_vp]),
     "rpb_step_end": (C.c_int, [_vp]),
     "rpb_evb_phase_build": (C.c_int, [_vp]),

@@ -321,14 +321,14 @@ __device__ __forceinline__ void warp_copy_struct(T* dst, const T* src, int lane)
 // and store every level's snapshot cooperatively; lane 0 replays the hops on the shared copy.
 // only_state >= 0: build that diabat regardless of ownership (hop commit needs the new principal's images on every rank)
 #define SNAP_WPB 4
-__global__ void __launch_bounds__(32 * SNAP_WPB) k_evb_snapshots(Dev d, EvbDev e, int only_state) {
+__global__ void __launch_bounds__(32 * SNAP_WPB) k_evb_snapshots(Dev d, EvbDev e, int only_state, int all_states) {
   static_assert(CM * MA == 32, "one lane per (chain molecule, atom)");
   __shared__ Snapshot Wsh[SNAP_WPB];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int s = blockIdx.x * SNAP_WPB + w;
   const int S = *e.n_states;
   if (only_state >= 0) { if (s != 0) return; s = only_state; }
-  else if (s >= S || !(s == 0 || state_owned(s, d.rank, d.world))) return;
+  else if (s >= S || !(s == 0 || all_states || state_owned(s, d.rank, d.world))) return;
   Snapshot& W = Wsh[w];
   const int* L = &e.proton_log[s * MAXC * 5];
   const int nh = e.n_hops[s];
@@ -1032,7 +1032,7 @@ __device__ void assemble_state(const Dev& d, EvbDev& e, const CouplingGeo* geo, 
   const int ii = last_item[s];      // acceptor-topology item of the last hop; the donor-topology item precedes it
   double dE = e.item_energy[ii] - e.item_energy[ii - 1];
   e.h_diag[s] = dE;
-  e.h_diag[2 * MAXS + s] = e.e_recip[slot_of_state[s]] - e.e_recip[0];
+  e.h_diag[2 * MAXS + s] = slot_of_state ? e.e_recip[slot_of_state[s]] - e.e_recip[0] : e.rcp_dE[s];   // null: delta algebra
   const CouplingGeo& G = geo[s];
   double pref = G.Vconst + e.vex[s];
   e.h_diag[MAXS + s] = pref * G.A;
@@ -1505,6 +1505,243 @@ __global__ void k_evb_gather_mix(Dev d, EvbDev e, double* __restrict__ out) {
   }
 }
 
+
+// ================================================================================================
+// Reciprocal space of the diabats WITHOUT per-diabat grids ("delta algebra").
+//
+// The reference copies the principal Q grid per diabat, re-spreads the donor/acceptor molecules, and runs one full
+// 3-D FFT convolution per diabat (ms_evb.f90:1445-1556, 1962-2248).  A diabat differs from the principal one only in
+// the CHARGES of the atoms of its chain molecules -- the positions, hence the B-spline footprints w_a(x), are the
+// principal ones.  With dq_a(s) = q_a(s) - q_a(1), g = IDFT(CB) the real-space Green function of the convolution and
+//     P_a  = <w_a, theta_1>          G_a  = <grad w_a, theta_1>          (one 216-point gather per chain atom)
+//     M_ab = <w_a, g * w_b>          N_ab = <grad w_a, g * w_b>          (pairs of chain atoms that share a diabat)
+// linearity of the convolution gives, exactly:
+//     E_rec(s) - E_rec(1) = sum_a dq_a P_a + 1/2 sum_ab dq_a dq_b M_ab                     -> H_ss  (ms_evb.f90:2083)
+//     sum_s c_s^2 theta_s = theta_1 + g * sum_a D_a w_a,   D_a = sum_s c_s^2 dq_a(s)        -> ONE more convolution of
+//         the grid carrying the Hellmann-Feynman averaged charges, gathered once for all atoms (ms_evb.f90:292-309),
+//     chain atom a:  F_a += -K kk sum_{s contains a} c_s^2 dq_a(s) [ G_a + sum_b dq_b(s) N_ab ]   (ms_evb.f90:2171-2228)
+// M_ab needs no grid at all: w is a product of 1-D splines, so <w_a, g * w_b> = sum over the 11^3 displacements t of
+// g(n_a - n_b - t) cx(t_x) cy(t_y) cz(t_z) with the 1-D cross-correlations c(t) = sum_{k-k'=t} w_a[k] w_b[k'].
+// Two convolutions per step instead of S+1, no per-diabat grid traffic; differences from the per-diabat transforms are
+// rounding only (~1e-13 relative, checked against the grid path, RPB_EVB_RECIP=grids, in tests/).
+// ================================================================================================
+#define RA_MOLS (MAXS + 1)            // distinct chain molecules of a step
+#define RA_SLOTS (RA_MOLS * MA)       // chain-atom slots: (chain molecule, atom offset inside the molecule)
+#define RA_MAXPAIR (8 * MAXS + 8)     // ordered pairs of chain molecules that share a diabat
+#define RA_ENT (CM * MA)              // chain atoms of one diabat
+
+struct RecipDev {
+  const int* mol;          // [n_mol] distinct chain molecules (host, from the hop logs)
+  const int* molpair;      // [n_pair] i * RA_MOLS + j
+  int* mol_slot;           // [M] molecule -> index in mol[]
+  double* P; double* G;    // [RA_SLOTS], [RA_SLOTS][3]   (conv included)
+  double* Mx; double* Nx;  // [RA_SLOTS][RA_SLOTS], [3][RA_SLOTS][RA_SLOTS]
+  double* D;               // [RA_SLOTS] Hellmann-Feynman averaged charge deltas
+  int* st_n; int* st_slot; double* st_dq;   // per diabat: chain atoms with their charge deltas  [MAXS], [MAXS][RA_ENT]
+  const double* gtab;      // K^3 Green function g = IDFT(CB)
+};
+
+// spline weights (lanes 0..17) and derivative factors of the atom with scaled coordinates u, as gather_atom_warp
+__device__ __forceinline__ void spline_pair_lane(const Dev& d, const double u[3], int np[3], int lane, double& b6, double& dm) {
+  np[0] = (int)floor(u[0]); np[1] = (int)floor(u[1]); np[2] = (int)floor(u[2]);
+  b6 = 0.0; dm = 0.0;
+  if (lane < 18) {
+    int dim = lane / 6, k = lane - 6 * dim;
+    double arg1 = u[dim] - (double)(np[dim] - k);
+    double arg2 = arg1 - 1.0;
+    int g1n = (int)ceil(arg1 / 6.0 * d.spline_grid);
+    b6 = __ldg(&d.B6[g1n - 1]);
+    if (arg1 < 5.0) { int g = (int)ceil(arg1 / 5.0 * d.spline_grid); dm = __ldg(&d.B5[g - 1]); }
+    if (0.0 < arg2) { int g = (int)ceil(arg2 / 5.0 * d.spline_grid); dm = dm - __ldg(&d.B5[g - 1]); }
+  }
+}
+
+// warp per chain-atom slot: P_a, G_a from theta_1; also publishes the molecule -> slot map and clears D
+__global__ void k_evb_rcp_atoms(Dev d, RecipDev r, int n_mol) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_mol * MA) return;
+  const int im = w / MA, a = w % MA, mol = r.mol[im];
+  if (a == 0 && lane == 0) r.mol_slot[mol] = im;
+  if (a >= d.mol_natom[mol]) return;
+  const int atom = d.mol_first[mol] + a;
+  const double u[3] = {d.uscale[3 * atom], d.uscale[3 * atom + 1], d.uscale[3 * atom + 2]};
+  int np[3];
+  double b6, dm;
+  spline_pair_lane(d, u, np, lane, b6, dm);
+  const int K = d.K;
+  double p = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
+#pragma unroll 1
+  for (int it = 0; it < 7; it++) {
+    int pt = it * 32 + lane;
+    int pp = pt < 216 ? pt : 215;
+    int k1 = pp % 6, k2 = (pp / 6) % 6, k3 = pp / 36;
+    double w1 = __shfl_sync(0xffffffffu, b6, k1), w2 = __shfl_sync(0xffffffffu, b6, 6 + k2), w3 = __shfl_sync(0xffffffffu, b6, 12 + k3);
+    double d1 = __shfl_sync(0xffffffffu, dm, k1), d2 = __shfl_sync(0xffffffffu, dm, 6 + k2), d3 = __shfl_sync(0xffffffffu, dm, 12 + k3);
+    if (pt < 216) {
+      int n1 = np[0] - k1; if (n1 < 0) n1 += K;
+      int n2 = np[1] - k2; if (n2 < 0) n2 += K;
+      int n3 = np[2] - k3; if (n3 < 0) n3 += K;
+      double th = __ldg(&d.theta[(size_t)n1 + (size_t)K * n2 + (size_t)K * K * n3]) * d.conv;
+      p = fma(w1 * w2 * w3, th, p);
+      g0 = fma(d1 * w2 * w3, th, g0); g1 = fma(d2 * w1 * w3, th, g1); g2 = fma(d3 * w1 * w2, th, g2);
+    }
+  }
+  p = warp_sum(p); g0 = warp_sum(g0); g1 = warp_sum(g1); g2 = warp_sum(g2);
+  if (lane == 0) { r.P[w] = p; r.G[3 * w] = g0; r.G[3 * w + 1] = g1; r.G[3 * w + 2] = g2; }
+}
+
+// warp per (ordered pair of chain molecules, atom a of the first, atom b of the second): M_ab, N_ab
+__global__ void __launch_bounds__(128) k_evb_rcp_pairs(Dev d, RecipDev r, int n_pair) {
+  __shared__ double sh_c[4][2][3][11];      // per warp: cross-correlations cw (0) / cd (1) per dimension, t = -5..5
+  __shared__ double sh_w[4][3][18];         // per warp: w_a, dw_a, w_b
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * 4 + wib;
+  const bool live = w < n_pair * MA * MA;
+  int sa = 0, sb = 0, dn[3] = {0, 0, 0};
+  bool act = false;
+  if (live) {
+    const int ip = w / (MA * MA), a = (w / MA) % MA, b = w % MA;
+    const int mi = r.molpair[ip] / RA_MOLS, mj = r.molpair[ip] % RA_MOLS;
+    const int moli = r.mol[mi], molj = r.mol[mj];
+    act = a < d.mol_natom[moli] && b < d.mol_natom[molj];
+    if (act) {
+      sa = mi * MA + a; sb = mj * MA + b;
+      const int ia = d.mol_first[moli] + a, ib = d.mol_first[molj] + b;
+      const double ua[3] = {d.uscale[3 * ia], d.uscale[3 * ia + 1], d.uscale[3 * ia + 2]};
+      const double ub[3] = {d.uscale[3 * ib], d.uscale[3 * ib + 1], d.uscale[3 * ib + 2]};
+      int na[3], nb[3];
+      double wa, da, wb, db;   // (db unused: the gradient acts on the first atom)
+      spline_pair_lane(d, ua, na, lane, wa, da);
+      spline_pair_lane(d, ub, nb, lane, wb, db);
+      for (int c = 0; c < 3; c++) dn[c] = na[c] - nb[c];
+      if (lane < 18) { sh_w[wib][0][lane] = wa; sh_w[wib][1][lane] = da; sh_w[wib][2][lane] = wb; }
+    }
+  }
+  __syncwarp();
+  if (!act) return;
+  // c(t) = sum_{k - k' = t} f_a[k] w_b[k'],  lane -> (dimension, t): 33 values, two rounds
+  for (int v = lane; v < 33; v += 32) {
+    const int dim = v / 11, t = v % 11 - 5;
+    double cw = 0.0, cd = 0.0;
+    for (int k = 0; k < 6; k++) {
+      const int kp = k - t;
+      if (kp >= 0 && kp < 6) { cw = fma(sh_w[wib][0][6 * dim + k], sh_w[wib][2][6 * dim + kp], cw); cd = fma(sh_w[wib][1][6 * dim + k], sh_w[wib][2][6 * dim + kp], cd); }
+    }
+    sh_c[wib][0][dim][t + 5] = cw; sh_c[wib][1][dim][t + 5] = cd;
+  }
+  __syncwarp();
+  const int K = d.K;
+  double m = 0.0, n0 = 0.0, n1 = 0.0, n2 = 0.0;
+  for (int pt = lane; pt < 1331; pt += 32) {
+    const int tx = pt % 11, ty = (pt / 11) % 11, tz = pt / 121;
+    int gx = (dn[0] - (tx - 5)) % K; if (gx < 0) gx += K;
+    int gy = (dn[1] - (ty - 5)) % K; if (gy < 0) gy += K;
+    int gz = (dn[2] - (tz - 5)) % K; if (gz < 0) gz += K;
+    const double g = __ldg(&r.gtab[(size_t)gx + (size_t)K * gy + (size_t)K * K * gz]);
+    const double cx = sh_c[wib][0][0][tx], cy = sh_c[wib][0][1][ty], cz = sh_c[wib][0][2][tz];
+    const double ex = sh_c[wib][1][0][tx], ey = sh_c[wib][1][1][ty], ez = sh_c[wib][1][2][tz];
+    const double gyz = g * cy * cz;
+    m = fma(gyz, cx, m);
+    n0 = fma(gyz, ex, n0);
+    n1 = fma(g * cx * cz, ey, n1);
+    n2 = fma(g * cx * cy, ez, n2);
+  }
+  m = warp_sum(m); n0 = warp_sum(n0); n1 = warp_sum(n1); n2 = warp_sum(n2);
+  if (lane == 0) {
+    const size_t o = (size_t)sa * RA_SLOTS + sb, plane = (size_t)RA_SLOTS * RA_SLOTS;
+    r.Mx[o] = m * d.conv; r.Nx[o] = n0 * d.conv; r.Nx[plane + o] = n1 * d.conv; r.Nx[2 * plane + o] = n2 * d.conv;
+  }
+}
+
+// warp per diabat s >= 1: chain atoms of the FINAL topology with their charge deltas, and E_rec(s) - E_rec(1)
+__global__ void k_evb_rcp_energy(Dev d, EvbDev e, RecipDev r) {
+  __shared__ int sh_slot[4][RA_ENT];
+  __shared__ double sh_dq[4][RA_ENT];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * 4 + wib;
+  const int S = *e.n_states;
+  if (s >= S) return;
+  if (s == 0) { if (lane == 0) r.st_n[0] = 0; return; }
+  static_assert(RA_ENT == 32, "one lane per (chain molecule, atom) of the snapshot");
+  const Snapshot& Sn = e.snap[s * NLEV + e.n_hops[s]];
+  const int k = lane / MA, a = lane % MA;
+  int slot = -1;
+  double dq = 0.0;
+  if (k < Sn.n_mol && a < Sn.m[k].n_atom) {
+    const int atom = Sn.m[k].atom[a];
+    const int mol = d.mol_of_atom[atom];
+    slot = r.mol_slot[mol] * MA + (atom - d.mol_first[mol]);
+    dq = Sn.m[k].q[a] - d.xq[atom].w;
+  }
+  // compact the entries with a charge delta
+  const unsigned keep = __ballot_sync(0xffffffffu, slot >= 0 && dq != 0.0);
+  const int n = __popc(keep), pos = __popc(keep & ((1u << lane) - 1u));
+  if (slot >= 0 && dq != 0.0) { sh_slot[wib][pos] = slot; sh_dq[wib][pos] = dq; r.st_slot[s * RA_ENT + pos] = slot; r.st_dq[s * RA_ENT + pos] = dq; }
+  if (lane == 0) r.st_n[s] = n;
+  __syncwarp();
+  double acc = 0.0;
+  if (lane < n) {
+    const int sa = sh_slot[wib][lane];
+    double inner = 0.0;
+    for (int j = 0; j < n; j++) inner = fma(sh_dq[wib][j], r.Mx[(size_t)sa * RA_SLOTS + sh_slot[wib][j]], inner);
+    acc = sh_dq[wib][lane] * (r.P[sa] + 0.5 * inner);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) e.rcp_dE[s] = acc;
+}
+
+// after the solver: thread per (diabat, chain-atom entry): D_a += c_s^2 dq_a(s), and the chain atom's own force term
+// mode bit 0: accumulate D; bit 1: add the chain atom's force term to out
+__global__ void k_evb_rcp_mix(Dev d, EvbDev e, RecipDev r, double* __restrict__ out, int mode) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = t / RA_ENT, k = t % RA_ENT;
+  if (s >= *e.n_states || k >= r.st_n[s]) return;
+  const double w = e.coef2[s];
+  const int sa = r.st_slot[s * RA_ENT + k];
+  const double dqa = r.st_dq[s * RA_ENT + k];
+  if (mode & 1) atomicAdd(&r.D[sa], w * dqa);
+  if (!(mode & 2)) return;
+  const size_t plane = (size_t)RA_SLOTS * RA_SLOTS;
+  double f0 = r.G[3 * sa], f1 = r.G[3 * sa + 1], f2 = r.G[3 * sa + 2];
+  const int n = r.st_n[s];
+  for (int j = 0; j < n; j++) {
+    const size_t o = (size_t)sa * RA_SLOTS + r.st_slot[s * RA_ENT + j];
+    const double dqb = r.st_dq[s * RA_ENT + j];
+    f0 = fma(dqb, r.Nx[o], f0); f1 = fma(dqb, r.Nx[plane + o], f1); f2 = fma(dqb, r.Nx[2 * plane + o], f2);
+  }
+  const int mol = r.mol[sa / MA], atom = d.mol_first[mol] + sa % MA;
+  const double Kd = (double)d.K, c = w * dqa;
+  atomicAdd(&out[3 * atom], -(Kd * d.kk[0]) * (c * f0));
+  atomicAdd(&out[3 * atom + 1], -(Kd * d.kk[1]) * (c * f1));
+  atomicAdd(&out[3 * atom + 2], -(Kd * d.kk[2]) * (c * f2));
+}
+
+// Q_mix = Q_1 + sum_a D_a w_a : the copy is made early (k_copy), this adds the averaged charge deltas (warp per slot)
+__global__ void k_evb_rcp_patch(Dev d, RecipDev r, double* __restrict__ Qmix, int n_mol) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_mol * MA) return;
+  const int mol = r.mol[w / MA], a = w % MA;
+  if (a >= d.mol_natom[mol]) return;
+  const double D = r.D[w];
+  if (D == 0.0) return;
+  const int atom = d.mol_first[mol] + a;
+  const double u[3] = {d.uscale[3 * atom], d.uscale[3 * atom + 1], d.uscale[3 * atom + 2]};
+  spread_atom_warp(d, Qmix, u, D, 1.0, lane);
+}
+
+// gather of the mixed grid for the atoms [i0, i1)
+__global__ void k_evb_gather_range(Dev d, const double* __restrict__ theta, double* __restrict__ out, int i0, int i1) {
+  int w = i0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (w >= i1) return;
+  double u[3] = {d.uscale[3 * w], d.uscale[3 * w + 1], d.uscale[3 * w + 2]};
+  double F[3];
+  gather_atom_warp(d, theta, u, d.xq[w].w, lane, F);
+  if (lane < 3) {
+    double v = lane == 0 ? F[0] : (lane == 1 ? F[1] : F[2]);
+    out[3 * w + lane] += v;
+  }
+}
+
 __global__ void k_copy(double* dst, const double* src, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i];
@@ -1577,7 +1814,9 @@ __global__ void k_evb_clear(Dev d, EvbDev e, int* cand_n, int s_begin, int s_end
 #define PACK_OFF_STATE_LIST (PACK_OFF_SLOT_STATE + MAXS * 4)
 #define PACK_OFF_UNIQ (PACK_OFF_STATE_LIST + MAXS * 4)
 #define PACK_OFF_LAST (PACK_OFF_UNIQ + CAND_SLOTS * 4)
-#define PACK_BYTES (PACK_OFF_LAST + MAXS * 4)
+#define PACK_OFF_RMOL (PACK_OFF_LAST + MAXS * 4)
+#define PACK_OFF_RPAIR (PACK_OFF_RMOL + RA_MOLS * 4)
+#define PACK_BYTES (PACK_OFF_RPAIR + RA_MAXPAIR * 4)
 
 struct EvbScratch {   // device scratch owned by the context (allocated in evb_alloc)
   char* pack_dev; char* pack_host;
@@ -1589,6 +1828,8 @@ struct EvbScratch {   // device scratch owned by the context (allocated in evb_a
   int* perm; int* new_first;
   int* chain_slot; int* cand; int* cand_n; int* uniq_atom; int* last_item;
   double4* xq2; double* vel2; double* force2; double* mass2; int* type2; int* moa2;
+  RecipDev rd; double* gtab; int n_rmol, n_rpair;   // reciprocal-space delta algebra (default) ...
+  bool recip_grids;                                 // ... or one grid + FFT convolution per diabat (RPB_EVB_RECIP=grids, cross-check)
 };
 static std::map<rpb_ctx*, EvbScratch> g_scratch;
 
@@ -1634,6 +1875,18 @@ int evb_alloc(rpb_ctx* c) {
   AL(s.perm, N); AL(s.new_first, CM);
   AL(s.chain_slot, N); AL(s.cand, (size_t)CAND_SLOTS * CAND_CAP); AL(s.cand_n, CAND_SLOTS + 2);
   AL(s.xq2, N); AL(s.vel2, 3 * N); AL(s.force2, 3 * N); AL(s.mass2, N); AL(s.type2, N); AL(s.moa2, N);
+  {
+    RecipDev& r = s.rd;
+    r.mol = (const int*)(s.pack_dev + PACK_OFF_RMOL); r.molpair = (const int*)(s.pack_dev + PACK_OFF_RPAIR);
+    AL(r.mol_slot, c->d.M); AL(r.P, RA_SLOTS); AL(r.G, 3 * RA_SLOTS); AL(r.Mx, (size_t)RA_SLOTS * RA_SLOTS); AL(r.Nx, (size_t)3 * RA_SLOTS * RA_SLOTS);
+    AL(r.D, RA_SLOTS); AL(r.st_n, MAXS); AL(r.st_slot, MAXS * RA_ENT); AL(r.st_dq, MAXS * RA_ENT);
+    AL(s.gtab, K3); r.gtab = s.gtab;
+    AL(e.rcp_dE, MAXS);
+    CKE(cudaMemset(e.rcp_dE, 0, MAXS * sizeof(double)));
+    s.n_rmol = s.n_rpair = 0;
+    const char* rv = getenv("RPB_EVB_RECIP");
+    s.recip_grids = rv && std::string(rv) == "grids";
+  }
 #undef AL
   g_scratch[c] = s;
   // cuFFT path only: every FFT batch size this context can meet (no plan is built inside a step)
@@ -1642,6 +1895,15 @@ int evb_alloc(rpb_ctx* c) {
   for (int b = 1; b <= c->grid_capacity && !own_fft; b++) {
     cufftHandle pf, pi;
     if ((rc = pme_get_plans(c, b, &pf, &pi))) return rc;
+  }
+  {   // Green function of the reciprocal-space convolution, g = IDFT(CB): the convolution of a unit charge at the origin
+    if (!c->have_tables) { c->err = "rpb_set_tables must precede rpb_set_evb"; return RPB_ERR_STATE; }
+    const double one = 1.0;
+    CKE(cudaMemsetAsync(c->d.Q + K3, 0, K3 * sizeof(double), c->stream));
+    CKE(cudaMemcpyAsync(c->d.Q + K3, &one, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = launch_convolve(c, 1, 1, e.e_recip, true))) return rc;
+    CKE(cudaMemcpyAsync(s.gtab, c->d.theta + K3, K3 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    CKE(cudaStreamSynchronize(c->stream));
   }
   CKE(cudaMallocHost(&c->eh.pinned, ENUM_BLOCK_INTS * sizeof(int) + (SOLVER_BLOCK_DOUBLES + 8) * sizeof(double)));
   CKE(cudaMemset(e.n_states, 0, ENUM_BLOCK_INTS * sizeof(int)));
@@ -1716,7 +1978,7 @@ int evb_enumerate_async(rpb_ctx* c) {
   CKE(cudaEventRecord(c->ev_enum, c->stream));
   // the diabat images need nothing from the host: built for however many diabats the enumeration found (grid sized
   // for evb_max_states, surplus warps exit)
-  { ScopedTimer t(c, T_EVB_SNAP); k_evb_snapshots<<<(MAXS + SNAP_WPB - 1) / SNAP_WPB, 32 * SNAP_WPB, 0, c->stream>>>(d, e, -1); }
+  { ScopedTimer t(c, T_EVB_SNAP); k_evb_snapshots<<<(MAXS + SNAP_WPB - 1) / SNAP_WPB, 32 * SNAP_WPB, 0, c->stream>>>(d, e, -1, g_scratch[c].recip_grids ? 0 : 1); }   // delta algebra: every rank needs the charges of every diabat
   c->n_launch += 1;
   return 0;
 }
@@ -1727,8 +1989,21 @@ int evb_build(rpb_ctx* c) {
   const int N = d.N;
   const size_t K3 = (size_t)d.K * d.K * d.K, n3 = (size_t)3 * N;
   double hc0 = HostClock::now();
-  int rc = calculate_total_force_energy(c, true);   // principal diabat (+ enumeration); its FFT convolution joins the batch below
+  int rc = calculate_total_force_energy(c, true);   // principal diabat (+ enumeration)
   if (rc) return rc;
+  const bool algebra = !sc.recip_grids;
+  if (algebra) {
+    // delta algebra: the principal grid is the only one convolved before the solver -- queued right behind the
+    // spreading, while the host is still waiting for the enumeration; its copy in slot 1 later receives the
+    // Hellmann-Feynman averaged charge deltas (evb_mix)
+    StreamScope ss(c, c->aux[1]);
+    k_copy<<<(unsigned)((K3 + 255) / 256), 256, 0, c->stream>>>(d.Q + K3, d.Q, K3);
+    c->n_launch += 1;
+    rc = launch_convolve(c, 0, 1, e.e_recip, true);
+    if (rc) return rc;
+    k_copy<<<1, 32, 0, c->stream>>>(d.en + E_RECIP, e.e_recip, 1);   // E_rec of the principal diabat (pme.f90:127)
+    c->n_launch += 1;
+  }
   double hc1 = HostClock::now();
   {
     int* pin = h.pinned;
@@ -1774,6 +2049,36 @@ int evb_build(rpb_ctx* c) {
         uniq_atom[n_uniq++] = c->mol_first[m] + a;
       }
   }
+  if (algebra) {
+    // distinct chain molecules over ALL diabats (every rank evaluates the cheap reciprocal-space algebra of every diabat)
+    // and the ordered pairs of them that share a diabat
+    int* rmol = (int*)(sc.pack_host + PACK_OFF_RMOL);
+    int* rpair = (int*)(sc.pack_host + PACK_OFF_RPAIR);
+    int nm = 0, np = 0;
+    static thread_local std::vector<unsigned char> seen;
+    seen.assign((size_t)RA_MOLS * RA_MOLS, 0);
+    auto mol_index = [&](int m) { for (int k = 0; k < nm; k++) if (rmol[k] == m) return k; rmol[nm] = m; return nm++; };
+    mol_index(c->hydronium_mol);
+    for (int s = 1; s < S; s++) {
+      int idx[CM], ni = 0;
+      idx[ni++] = 0;
+      for (int k = 0; k < h.n_hops[s]; k++) {
+        const int mi = mol_index(h.proton_log[s][k][3]);
+        bool dup = false;
+        for (int q = 0; q < ni; q++) dup |= (idx[q] == mi);
+        if (!dup) idx[ni++] = mi;
+      }
+      for (int a = 0; a < ni; a++)
+        for (int b = 0; b < ni; b++) {
+          const int key = idx[a] * RA_MOLS + idx[b];
+          if (!seen[key]) {
+            if (np >= RA_MAXPAIR) { c->err = "more chain-molecule pairs than RA_MAXPAIR"; return RPB_ERR_DIABATS; }
+            seen[key] = 1; rpair[np++] = key;
+          }
+        }
+    }
+    sc.n_rmol = nm; sc.n_rpair = np;
+  }
   int* slot_of_state = (int*)(sc.pack_host + PACK_OFF_SLOT_OF);
   int* slot_state = (int*)(sc.pack_host + PACK_OFF_SLOT_STATE);
   int* state_list = (int*)(sc.pack_host + PACK_OFF_STATE_LIST);
@@ -1797,16 +2102,33 @@ int evb_build(rpb_ctx* c) {
     CKE(cudaMemcpyAsync(sc.pack_dev, sc.pack_host, PACK_BYTES, cudaMemcpyHostToDevice, c->stream));
   }
   h.n_states_prev = S;
+  if (n_own > 0 && !algebra) {
+    // the copies of the principal grid need only the NUMBER of owned diabats: queued behind the spreading right away,
+    // they run while the diabat images and the per-step tables are still on their way
+    StreamScope ss(c, c->aux[1]);
+    ScopedTimer t(c, T_EVB_BCAST);
+    k_evb_broadcast_grid<<<(unsigned)((K3 / 2 + 255) / 256), 256, 0, c->stream>>>(d.Q, d.Q + K3, K3, n_own);
+    c->n_launch += 1;
+  }
   stream_depend(c, 4, c->aux[0], c->main_stream);
   stream_depend(c, 5, c->aux[0], c->aux[1]);
-  {
+  if (algebra) {
+    StreamScope ss(c, c->aux[1]);
+    if (S > 1) {
+      ScopedTimer t(c, T_EVB_CORR);
+      const int pw = sc.n_rpair * MA * MA;
+      k_evb_rcp_pairs<<<(pw + 3) / 4, 128, 0, c->stream>>>(d, sc.rd, sc.n_rpair);
+      k_evb_rcp_atoms<<<(sc.n_rmol * MA * 32 + 255) / 256, 256, 0, c->stream>>>(d, sc.rd, sc.n_rmol);
+      k_evb_rcp_energy<<<(S + 3) / 4, 128, 0, c->stream>>>(d, e, sc.rd);
+      c->n_launch += 3;
+    }
+  } else {
     StreamScope ss(c, c->aux[1]);
     if (n_own > 0) {
-      { ScopedTimer t(c, T_EVB_BCAST); k_evb_broadcast_grid<<<(unsigned)((K3 / 2 + 255) / 256), 256, 0, c->stream>>>(d.Q, d.Q + K3, K3, n_own); }
       int warps = h.n_items * 2 * MA;
       ScopedTimer t(c, T_EVB_PATCH);
       k_evb_item_pme<<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(d, e, h.n_items, sc.slot_of_state, 0);
-      c->n_launch += 2;
+      c->n_launch += 1;
     }
     rc = launch_convolve(c, 0, n_own + 1, e.e_recip, true);
     if (rc) return rc;
@@ -1846,7 +2168,7 @@ int evb_build(rpb_ctx* c) {
   stream_depend(c, 7, c->aux[1], c->main_stream);
   if (d.world > 1 || c->evb_solver != 0) {
     ScopedTimer t(c, T_EVB_ASSEMBLE);
-    k_evb_assemble<<<(MAXS + 31) / 32, 32, 0, c->stream>>>(d, e, sc.geo, sc.last_item, sc.slot_of_state);
+    k_evb_assemble<<<(MAXS + 31) / 32, 32, 0, c->stream>>>(d, e, sc.geo, sc.last_item, algebra ? nullptr : sc.slot_of_state);
     c->n_launch += 1;
   } else h.assemble_pending = true;   // single rank, tree solver: assembled in the solver's prologue
   // keep the principal-diabat force (incl. EVB repulsion, without reciprocal part) in dF slot 0: d.force is
@@ -1875,7 +2197,7 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
     ScopedTimer t(c, T_EVB_DIAG);
     if (c->evb_solver == 0) {
       const bool fuse = (d.world == 1 && !coeff_override_host && h.assemble_pending);
-      k_evb_tree_solver<<<1, TREE_TPB, 0, c->stream>>>(d, e, coeff_dev, fuse ? sc.geo : nullptr, sc.last_item, sc.slot_of_state);
+      k_evb_tree_solver<<<1, TREE_TPB, 0, c->stream>>>(d, e, coeff_dev, fuse ? sc.geo : nullptr, sc.last_item, sc.recip_grids ? sc.slot_of_state : nullptr);
       h.assemble_pending = false;
       c->n_launch++;
     } else {
@@ -1901,15 +2223,40 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
     // slot 0 (principal theta) only contributes on rank 0: mask it on the other ranks through slot_state
     // theta_mix (grids) runs on aux[1] next to the force mixing (per-atom arrays) on the main stream; the gather of
     // the mixed grid then adds into the mixed force
-    stream_depend(c, 0, c->main_stream, c->aux[1]);
-    { StreamScope ss(c, c->aux[1]); ScopedTimer t(c, T_EVB_THETAMIX); k_evb_theta_mix<<<(unsigned)((K3 / 2 + 255) / 256), 256, 0, c->stream>>>(d, e, sc.slot_state, n_own + 1); }
+    const bool algebra = !sc.recip_grids;
     const int in_place = (d.world == 1 && !coeff_override_host) ? 1 : 0;
     double* out = in_place ? d.force : e.f_mix;
+    stream_depend(c, 0, c->main_stream, c->aux[1]);
+    if (algebra) {
+      // aux[1]: averaged charge deltas -> patch the copy of the principal grid -> ONE convolution; main: force mixing and the
+      // chain atoms' own reciprocal terms; then the mixed grid is gathered once (sharded runs: this rank's slice of atoms)
+      {
+        StreamScope ss(c, c->aux[1]);
+        if (coeff_override_host) { k_copy<<<(unsigned)((K3 + 255) / 256), 256, 0, c->stream>>>(d.Q + K3, d.Q, K3); c->n_launch++; }   // debug re-mix: fresh copy
+        if (S > 1) {
+          ScopedTimer t(c, T_EVB_PATCH);
+          CKE(cudaMemsetAsync(sc.rd.D, 0, RA_SLOTS * sizeof(double), c->stream));
+          k_evb_rcp_mix<<<(S * RA_ENT + 127) / 128, 128, 0, c->stream>>>(d, e, sc.rd, out, 1);
+          k_evb_rcp_patch<<<(sc.n_rmol * MA * 32 + 255) / 256, 256, 0, c->stream>>>(d, sc.rd, d.Q + K3, sc.n_rmol);
+          c->n_launch += 2;
+        }
+        int rc2 = launch_convolve(c, 1, 1, e.e_recip, true);
+        if (rc2) return rc2;
+      }
+      { ScopedTimer t(c, T_EVB_MIXF); k_evb_mix_forces<<<(unsigned)((n3 + 255) / 256), 256, 0, c->stream>>>(d, e, sc.state_list, n_own, include_principal, in_place);
+        if (S > 1 && d.rank == 0) { k_evb_rcp_mix<<<(S * RA_ENT + 127) / 128, 128, 0, c->stream>>>(d, e, sc.rd, out, 2); c->n_launch++; } }
+      stream_depend(c, 1, c->aux[1], c->main_stream);
+      const int i0 = (int)((long long)N * d.rank / d.world), i1 = (int)((long long)N * (d.rank + 1) / d.world);
+      { ScopedTimer t(c, T_EVB_GATHERMIX); k_evb_gather_range<<<((i1 - i0) * 32 + 255) / 256, 256, 0, c->stream>>>(d, d.theta + K3, out, i0, i1); }
+      c->n_launch += 2;
+    } else {
+    { StreamScope ss(c, c->aux[1]); ScopedTimer t(c, T_EVB_THETAMIX); k_evb_theta_mix<<<(unsigned)((K3 / 2 + 255) / 256), 256, 0, c->stream>>>(d, e, sc.slot_state, n_own + 1); }
     { ScopedTimer t(c, T_EVB_MIXF); k_evb_mix_forces<<<(unsigned)((n3 + 255) / 256), 256, 0, c->stream>>>(d, e, sc.state_list, n_own, include_principal, in_place);
       if (n_own > 0) { k_evb_add_corr<<<(n_own * CM * MA + 127) / 128, 128, 0, c->stream>>>(d, e, sc.state_list, n_own, out); c->n_launch++; } }
     stream_depend(c, 1, c->aux[1], c->main_stream);
     { ScopedTimer t(c, T_EVB_GATHERMIX); k_evb_gather_mix<<<(N * 32 + 255) / 256, 256, 0, c->stream>>>(d, e, out); }
     c->n_launch += 3;
+    }
   }
   if (coeff_override_host) {
     CKE(cudaStreamSynchronize(c->stream));
@@ -1973,7 +2320,7 @@ int evb_commit(rpb_ctx* c) {
   const int pdiab = h.principal_diabat;
   if (d.world > 1 && !state_owned(pdiab, d.rank, d.world)) {
     // every rank needs the final snapshot of the new principal diabat; non-owned diabats were not built in evb_build
-    k_evb_snapshots<<<1, 32, 0, c->stream>>>(d, e, pdiab);
+    k_evb_snapshots<<<1, 32, 0, c->stream>>>(d, e, pdiab, 0);
     c->n_launch++;
   }
   std::vector<int> perm(N), first = c->mol_first, natom = c->mol_natom;

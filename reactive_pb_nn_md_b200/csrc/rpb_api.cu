@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include "rpb_host.h"
 
 static const char* k_timer_names[T_NTIMER] = {
@@ -569,6 +570,25 @@ int rpb_step(rpb_ctx* c, int n_steps, int ms_evb) {
   int rc = fetch_status(c);
   if (rc) return rc;
   if (!ms_evb) energies_from_slots(c);
+  return 0;
+}
+
+// Independent replicas (BASELINE config 5, "replicas only": no communication): every context is driven by its own host
+// thread, so the replicas' kernels -- most of them latency-bound single-CTA or small-grid launches -- overlap on the
+// device through the contexts' own streams.  Returns the first non-zero status.
+int rpb_ensemble_step(rpb_ctx** replicas, int n_replicas, int n_steps, int ms_evb) {
+  if (!replicas || n_replicas < 1) return RPB_ERR_ARG;
+  std::vector<int> rc(n_replicas, 0);
+  std::vector<std::thread> th;
+  th.reserve(n_replicas);
+  for (int r = 0; r < n_replicas; r++)
+    th.emplace_back([&, r]() {
+      rpb_ctx* c = replicas[r];
+      if (cudaSetDevice(c->cfg.device) != cudaSuccess) { c->err = "cudaSetDevice failed"; rc[r] = RPB_ERR_CUDA; return; }   // the current device is per host thread
+      rc[r] = rpb_step(c, n_steps, ms_evb);
+    });
+  for (auto& t : th) t.join();
+  for (int r = 0; r < n_replicas; r++) if (rc[r]) return rc[r];
   return 0;
 }
 

@@ -55,6 +55,7 @@ struct EvbDev {
   double* Foff;               // [MAXS][3N] off-diagonal coupling forces
   double* vex;                // [MAXS]
   double* e_recip;            // [MAXS] E_rec of each diabat grid
+  double* rcp_dE;             // [MAXS] E_rec(s) - E_rec(1) from the delta algebra (kernels_evb.cu); unused on the per-diabat grid path
   double* h_diag;             // exchange buffer [3*MAXS]: (H_11, dE_s of the last hop) | H_parent(s),s | E_rec(s)-E_rec(1)
   double* h_full;             // [2*MAXS] assembled H_ss | H_parent(s),s (after the exchange)
   double* f_mix;              // exchange buffer [3N]

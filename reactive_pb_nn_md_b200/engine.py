@@ -162,6 +162,19 @@ class Simulation:
         for s in sims:
             s.exchange = "peer"
 
+    @staticmethod
+    def ensemble_step(sims, n_steps=1, ms_evb=False):
+        """md_integrate_atomic on independent replicas sharing one device (BASELINE config 5): one host thread per
+        replica inside the library, so their kernels overlap."""
+        arr = (C.c_void_p * len(sims))(*[s.ctx for s in sims])
+        rc = sims[0].dll.rpb_ensemble_step(arr, len(sims), int(n_steps), int(bool(ms_evb)))
+        if rc != 0:
+            for s in sims:
+                msg = s.dll.rpb_last_error(s.ctx)
+                if msg:
+                    raise RpbError(rc, msg.decode())
+            raise RpbError(rc, "")
+
     # -- plumbing ---------------------------------------------------------------------------
     def _check(self, rc):
         if rc != 0:

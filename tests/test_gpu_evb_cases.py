@@ -186,6 +186,24 @@ def test_peer_memory_exchange_between_processes(oracle_lib, world):
                 assert np.array_equal(q[k], z[0][k]), k                    # replicated state: bit-identical
 
 
+def test_replica_ensemble_matches_individual_runs(cuda_lib):
+    """rpb_ensemble_step (BASELINE config 5, replicas only): replicas driven concurrently by one host thread each end
+    where the same replicas end when stepped one after the other."""
+    n_steps = 10
+    seeds = (1, 2, 3, 4)
+    ens = [engine.Simulation(water_system(10, hydronium=True, seed=sd), small_params(), library=cuda_lib) for sd in seeds]
+    one = [engine.Simulation(water_system(10, hydronium=True, seed=sd), small_params(), library=cuda_lib) for sd in seeds]
+    for sim in ens + one:
+        sim.ms_evb_calculate_total_force_energy()
+    engine.Simulation.ensemble_step(ens, n_steps, ms_evb=True)
+    for a, b in zip(ens, one):
+        b.md_integrate_atomic(n_steps, ms_evb=True)
+        sa, sb = a.download_state(), b.download_state()
+        assert sa["hydronium_mol"] == sb["hydronium_mol"] and a.evb()["n_states"] == b.evb()["n_states"]
+        assert np.abs(sa["xyz"] - sb["xyz"]).max() < 1e-9
+        assert rel_rms(sa["force"], sb["force"]) < F_RTOL
+
+
 def test_full_size_c2_properties(cuda_lib):
     """BASELINE config 2 (10 125 atoms): properties that need no oracle run -- Newton's third law for the real-space
     part, energy conservation, momentum removal, on-device rebuild reproducibility"""
@@ -220,6 +238,38 @@ def test_full_size_c3_properties(cuda_lib):
     assert np.count_nonzero(np.triu(H, 1)) == S - 1                   # tree: one coupling per non-principal diabat
     # linearity of the Hellmann-Feynman mix in c_i c_j: F(c) for the ground state equals the stored adiabatic force
     assert rel_rms(sim.debug_mix_forces(ev["eigenvector"]), sim.forces()) < 1e-12
+
+
+def test_recip_delta_algebra_matches_per_diabat_grids(cuda_lib, oracle_lib, monkeypatch):
+    """Default reciprocal-space treatment of the diabats (charge-delta algebra on the principal grid: two convolutions
+    per step) against the reference's structure -- one patched grid and one FFT convolution per diabat
+    (RPB_EVB_RECIP=grids, ms_evb.f90:1962-2248) -- and against the oracle: Hamiltonian, forces, trajectory."""
+    s = water_system(10, hydronium=True)
+    p = small_params()
+    monkeypatch.delenv("RPB_EVB_RECIP", raising=False)
+    sa = engine.Simulation(s, p, library=cuda_lib)
+    monkeypatch.setenv("RPB_EVB_RECIP", "grids")
+    sg = engine.Simulation(s, p, library=cuda_lib)
+    monkeypatch.delenv("RPB_EVB_RECIP", raising=False)
+    so = engine.Simulation(s, p, library=oracle_lib)
+    for sim in (sa, sg, so):
+        sim.ms_evb_calculate_total_force_energy()
+    ea, eg, eo = sa.evb(), sg.evb(), so.evb()
+    assert ea["n_states"] == eg["n_states"] == eo["n_states"] > 4
+    scale = np.abs(np.diag(eo["hamiltonian"])).max()
+    assert np.abs(ea["hamiltonian"] - eg["hamiltonian"]).max() <= 1e-12 * scale
+    assert np.abs(ea["hamiltonian"] - eo["hamiltonian"]).max() <= E_RTOL * scale
+    assert rel_rms(sa.forces(), sg.forces()) < 1e-11
+    assert rel_rms(sa.forces(), so.forces()) < F_RTOL
+    # every diabat's own force (c = e_s): the chain atoms' reciprocal terms are exercised state by state
+    for k in range(ea["n_states"]):
+        c = np.zeros(ea["n_states"]); c[k] = 1.0
+        assert rel_rms(sa.debug_mix_forces(c), sg.debug_mix_forces(c)) < 1e-11, k
+    for sim in (sa, sg, so):
+        sim.md_integrate_atomic(10, ms_evb=True)
+    xa, xg, xo = (sim.download_state() for sim in (sa, sg, so))
+    assert xa["hydronium_mol"] == xg["hydronium_mol"] == xo["hydronium_mol"]
+    assert np.abs(xa["xyz"] - xg["xyz"]).max() < 1e-10 and np.abs(xa["xyz"] - xo["xyz"]).max() < 1e-9
 
 
 def test_tree_solver_matches_block_jacobi(cuda_lib, oracle_lib, monkeypatch):
