@@ -206,10 +206,11 @@ def algorithmic_model(name, N, K, S, n_own, pairs_listed, pairs_cut):
     m = {
         "pme_spread": ("hbm", 32 * N + 8 * K3),
         "pme_gather": ("hbm", 8 * K3 + 32 * N + 24 * N),
-        # batched over the principal grid + every owned diabat: read + write the half spectrum, CB once (shared)
-        "pme_convolve": ("hbm", 2 * 16 * (K // 2 + 1) * K * K * (n_own + 1) + 8 * (K // 2 + 1) * K * K),
-        # cuFFT (library): one batched D2Z or Z2D exec = real grids on one side, half spectra on the other
-        "pme_fft": ("hbm", (8 * K3 + 16 * (K // 2 + 1) * K * K) * (n_own + 1)),
+        # ONE grid per launch (delta algebra: the principal grid before the solver, the Hellmann-Feynman averaged grid
+        # after it): z-DFT x CB x inverse z-DFT in place on the half spectrum, CB read once
+        "pme_convolve": ("hbm", 2 * 16 * (K // 2 + 1) * K * K + 8 * (K // 2 + 1) * K * K),
+        # forward: real slab in, half spectrum out; inverse: the reverse
+        "pme_fft": ("hbm", 8 * K3 + 16 * (K // 2 + 1) * K * K),
         "evb_grid_broadcast": ("hbm", 8 * K3 + 8 * K3 * n_own),
         "evb_theta_mix": ("hbm", 8 * K3 * (n_own + 1) + 8 * K3),
         "evb_mix_forces": ("hbm", 24 * N * (2 * n_own + 1) + 24 * N),

@@ -1538,6 +1538,7 @@ struct RecipDev {
   double* Mx; double* Nx;  // [RA_SLOTS][RA_SLOTS], [3][RA_SLOTS][RA_SLOTS]
   double* D;               // [RA_SLOTS] Hellmann-Feynman averaged charge deltas
   int* st_n; int* st_slot; double* st_dq;   // per diabat: chain atoms with their charge deltas  [MAXS], [MAXS][RA_ENT]
+  int* sl_n; int* sl_state; double* sl_dq;  // the same table by chain-atom slot: diabats that change its charge  [RA_SLOTS], [RA_SLOTS][MAXS]
   const double* gtab;      // K^3 Green function g = IDFT(CB)
 };
 
@@ -1562,6 +1563,7 @@ __global__ void k_evb_rcp_atoms(Dev d, RecipDev r, int n_mol) {
   if (w >= n_mol * MA) return;
   const int im = w / MA, a = w % MA, mol = r.mol[im];
   if (a == 0 && lane == 0) r.mol_slot[mol] = im;
+  if (lane == 0) r.sl_n[w] = 0;
   if (a >= d.mol_natom[mol]) return;
   const int atom = d.mol_first[mol] + a;
   const double u[3] = {d.uscale[3 * atom], d.uscale[3 * atom + 1], d.uscale[3 * atom + 2]};
@@ -1594,6 +1596,7 @@ __global__ void k_evb_rcp_atoms(Dev d, RecipDev r, int n_mol) {
 __global__ void __launch_bounds__(128) k_evb_rcp_pairs(Dev d, RecipDev r, int n_pair) {
   __shared__ double sh_c[4][2][3][11];      // per warp: cross-correlations cw (0) / cd (1) per dimension, t = -5..5
   __shared__ double sh_w[4][3][18];         // per warp: w_a, dw_a, w_b
+  __shared__ int sh_i[4][3][11];            // per warp: wrapped, stride-scaled grid offset of displacement t per dimension
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w = blockIdx.x * 4 + wib;
   const bool live = w < n_pair * MA * MA;
@@ -1631,20 +1634,40 @@ __global__ void __launch_bounds__(128) k_evb_rcp_pairs(Dev d, RecipDev r, int n_
   }
   __syncwarp();
   const int K = d.K;
+  // wrapped grid offsets of the 11 displacements per dimension (no integer division in the hot loop)
+  for (int v = lane; v < 33; v += 32) {
+    const int dim = v / 11, t = v % 11 - 5;
+    int gi = (dn[dim] - t) % K; if (gi < 0) gi += K;
+    sh_i[wib][dim][t + 5] = gi * (dim == 0 ? 1 : (dim == 1 ? K : K * K));
+  }
+  __syncwarp();
   double m = 0.0, n0 = 0.0, n1 = 0.0, n2 = 0.0;
-  for (int pt = lane; pt < 1331; pt += 32) {
-    const int tx = pt % 11, ty = (pt / 11) % 11, tz = pt / 121;
-    int gx = (dn[0] - (tx - 5)) % K; if (gx < 0) gx += K;
-    int gy = (dn[1] - (ty - 5)) % K; if (gy < 0) gy += K;
-    int gz = (dn[2] - (tz - 5)) % K; if (gz < 0) gz += K;
-    const double g = __ldg(&r.gtab[(size_t)gx + (size_t)K * gy + (size_t)K * K * gz]);
-    const double cx = sh_c[wib][0][0][tx], cy = sh_c[wib][0][1][ty], cz = sh_c[wib][0][2][tz];
-    const double ex = sh_c[wib][1][0][tx], ey = sh_c[wib][1][1][ty], ez = sh_c[wib][1][2][tz];
-    const double gyz = g * cy * cz;
-    m = fma(gyz, cx, m);
-    n0 = fma(gyz, ex, n0);
-    n1 = fma(g * cx * cz, ey, n1);
-    n2 = fma(g * cx * cy, ez, n2);
+  // 1331 displacements, 6 batches of 7 per lane: the 7 Green-function values of a batch are in flight together
+  // (a plain loop exposes one L2 round trip per value)
+#pragma unroll 1
+  for (int base = 0; base < 1331; base += 32 * 7) {
+    double gv[7];
+#pragma unroll
+    for (int q = 0; q < 7; q++) {
+      const int pt = base + 32 * q + lane;
+      gv[q] = 0.0;
+      if (pt < 1331) { const int tx = pt % 11, ty = (pt / 11) % 11, tz = pt / 121; gv[q] = __ldg(&r.gtab[sh_i[wib][0][tx] + sh_i[wib][1][ty] + sh_i[wib][2][tz]]); }
+    }
+#pragma unroll
+    for (int q = 0; q < 7; q++) {
+      const int pt = base + 32 * q + lane;
+      if (pt < 1331) {
+        const int tx = pt % 11, ty = (pt / 11) % 11, tz = pt / 121;
+        const double g = gv[q];
+        const double cx = sh_c[wib][0][0][tx], cy = sh_c[wib][0][1][ty], cz = sh_c[wib][0][2][tz];
+        const double ex = sh_c[wib][1][0][tx], ey = sh_c[wib][1][1][ty], ez = sh_c[wib][1][2][tz];
+        const double gyz = g * cy * cz;
+        m = fma(gyz, cx, m);
+        n0 = fma(gyz, ex, n0);
+        n1 = fma(g * cx * cz, ey, n1);
+        n2 = fma(g * cx * cy, ez, n2);
+      }
+    }
   }
   m = warp_sum(m); n0 = warp_sum(n0); n1 = warp_sum(n1); n2 = warp_sum(n2);
   if (lane == 0) {
@@ -1676,31 +1699,38 @@ __global__ void k_evb_rcp_energy(Dev d, EvbDev e, RecipDev r) {
   // compact the entries with a charge delta
   const unsigned keep = __ballot_sync(0xffffffffu, slot >= 0 && dq != 0.0);
   const int n = __popc(keep), pos = __popc(keep & ((1u << lane) - 1u));
-  if (slot >= 0 && dq != 0.0) { sh_slot[wib][pos] = slot; sh_dq[wib][pos] = dq; r.st_slot[s * RA_ENT + pos] = slot; r.st_dq[s * RA_ENT + pos] = dq; }
+  if (slot >= 0 && dq != 0.0) {
+    sh_slot[wib][pos] = slot; sh_dq[wib][pos] = dq; r.st_slot[s * RA_ENT + pos] = slot; r.st_dq[s * RA_ENT + pos] = dq;
+    const int k2 = atomicAdd(&r.sl_n[slot], 1);          // < MAXS: one entry per diabat at most
+    r.sl_state[slot * MAXS + k2] = s; r.sl_dq[slot * MAXS + k2] = dq;
+  }
   if (lane == 0) r.st_n[s] = n;
   __syncwarp();
   double acc = 0.0;
-  if (lane < n) {
-    const int sa = sh_slot[wib][lane];
-    double inner = 0.0;
-    for (int j = 0; j < n; j++) inner = fma(sh_dq[wib][j], r.Mx[(size_t)sa * RA_SLOTS + sh_slot[wib][j]], inner);
-    acc = sh_dq[wib][lane] * (r.P[sa] + 0.5 * inner);
+  if (lane < n) acc = sh_dq[wib][lane] * r.P[sh_slot[wib][lane]];
+  for (int q0 = 0; q0 < n * n; q0 += 128) {          // pairs (a, b) dealt to the lanes, four independent loads in flight
+    double mv[4], ww[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int q = q0 + 32 * u + lane;
+      mv[u] = 0.0; ww[u] = 0.0;
+      if (q < n * n) { const int a2 = q / n, b2 = q - a2 * n; ww[u] = 0.5 * sh_dq[wib][a2] * sh_dq[wib][b2]; mv[u] = r.Mx[(size_t)sh_slot[wib][a2] * RA_SLOTS + sh_slot[wib][b2]]; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) acc = fma(ww[u], mv[u], acc);
   }
   acc = warp_sum(acc);
   if (lane == 0) e.rcp_dE[s] = acc;
 }
 
-// after the solver: thread per (diabat, chain-atom entry): D_a += c_s^2 dq_a(s), and the chain atom's own force term
-// mode bit 0: accumulate D; bit 1: add the chain atom's force term to out
-__global__ void k_evb_rcp_mix(Dev d, EvbDev e, RecipDev r, double* __restrict__ out, int mode) {
+// after the solver: thread per (diabat, chain-atom entry): the chain atom's own reciprocal force term
+__global__ void k_evb_rcp_mix(Dev d, EvbDev e, RecipDev r, double* __restrict__ out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int s = t / RA_ENT, k = t % RA_ENT;
   if (s >= *e.n_states || k >= r.st_n[s]) return;
   const double w = e.coef2[s];
   const int sa = r.st_slot[s * RA_ENT + k];
   const double dqa = r.st_dq[s * RA_ENT + k];
-  if (mode & 1) atomicAdd(&r.D[sa], w * dqa);
-  if (!(mode & 2)) return;
   const size_t plane = (size_t)RA_SLOTS * RA_SLOTS;
   double f0 = r.G[3 * sa], f1 = r.G[3 * sa + 1], f2 = r.G[3 * sa + 2];
   const int n = r.st_n[s];
@@ -1716,13 +1746,17 @@ __global__ void k_evb_rcp_mix(Dev d, EvbDev e, RecipDev r, double* __restrict__ 
   atomicAdd(&out[3 * atom + 2], -(Kd * d.kk[2]) * (c * f2));
 }
 
-// Q_mix = Q_1 + sum_a D_a w_a : the copy is made early (k_copy), this adds the averaged charge deltas (warp per slot)
-__global__ void k_evb_rcp_patch(Dev d, RecipDev r, double* __restrict__ Qmix, int n_mol) {
+// Q_mix = Q_1 + sum_a D_a w_a,  D_a = sum_s c_s^2 dq_a(s): the copy of Q_1 is made early (k_copy); one warp per chain-atom
+// slot collects its averaged charge delta from the diabats' tables and spreads it
+__global__ void k_evb_rcp_patch(Dev d, EvbDev e, RecipDev r, double* __restrict__ Qmix, int n_mol) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= n_mol * MA) return;
   const int mol = r.mol[w / MA], a = w % MA;
   if (a >= d.mol_natom[mol]) return;
-  const double D = r.D[w];
+  const int n = r.sl_n[w];
+  double D = 0.0;
+  for (int k = lane; k < n; k += 32) D = fma(e.coef2[r.sl_state[w * MAXS + k]], r.sl_dq[w * MAXS + k], D);
+  D = __shfl_sync(0xffffffffu, warp_sum(D), 0);   // warp_sum leaves the total in lane 0
   if (D == 0.0) return;
   const int atom = d.mol_first[mol] + a;
   const double u[3] = {d.uscale[3 * atom], d.uscale[3 * atom + 1], d.uscale[3 * atom + 2]};
@@ -1782,11 +1816,9 @@ __global__ void k_evb_commit_patch(Dev d, EvbDev e, int state, int level, const 
 
 // zero (or -1) every accumulator evb_build adds into: item energies, Vex, candidate counters, chain-atom corrections,
 // and the per-diabat force deltas / coupling forces of the S diabats in flight
-#define CLEAR_MARGIN 8
-// s_end < 0: launched BEFORE the enumeration of the step, it clears the diabats [0, previous S + CLEAR_MARGIN) -- the
-// host repeats the rule and issues a second launch for [that bound, S) in the rare step that gains more diabats
+// s_end < 0: launched right behind the enumeration of the step, it clears the diabats [0, S) that enumeration found
 __global__ void k_evb_clear(Dev d, EvbDev e, int* cand_n, int s_begin, int s_end) {
-  if (s_end < 0) s_end = min(MAXS, *e.n_states + CLEAR_MARGIN);
+  if (s_end < 0) s_end = min(MAXS, *e.n_states);
   const int S = s_end - s_begin;
   e.dF += (size_t)s_begin * 3 * d.N; e.Foff += (size_t)s_begin * 3 * d.N;
   e.corr_f += (size_t)s_begin * CM * MA * 3; e.corr_atom += (size_t)s_begin * CM * MA;
@@ -1880,6 +1912,7 @@ int evb_alloc(rpb_ctx* c) {
     r.mol = (const int*)(s.pack_dev + PACK_OFF_RMOL); r.molpair = (const int*)(s.pack_dev + PACK_OFF_RPAIR);
     AL(r.mol_slot, c->d.M); AL(r.P, RA_SLOTS); AL(r.G, 3 * RA_SLOTS); AL(r.Mx, (size_t)RA_SLOTS * RA_SLOTS); AL(r.Nx, (size_t)3 * RA_SLOTS * RA_SLOTS);
     AL(r.D, RA_SLOTS); AL(r.st_n, MAXS); AL(r.st_slot, MAXS * RA_ENT); AL(r.st_dq, MAXS * RA_ENT);
+    AL(r.sl_n, RA_SLOTS); AL(r.sl_state, RA_SLOTS * MAXS); AL(r.sl_dq, RA_SLOTS * MAXS);
     AL(s.gtab, K3); r.gtab = s.gtab;
     AL(e.rcp_dE, MAXS);
     CKE(cudaMemset(e.rcp_dE, 0, MAXS * sizeof(double)));
@@ -1965,13 +1998,13 @@ struct HostClock {
 double HostClock::acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 long HostClock::n = 0;
 
-int evb_enumerate_async(rpb_ctx* c) {
+int evb_enumerate_async(rpb_ctx* c, int part) {
   Dev& d = c->d; EvbDev& e = c->e; EvbHost& h = c->eh;
-  k_evb_clear<<<148 * 2, 256, 0, c->stream>>>(d, e, g_scratch[c].cand_n, 0, -1);   // accumulators of the build (reads the PREVIOUS S)
-  {
+  if (part == 0) {   // the kernel alone: the caller queues the pair kernel on the main stream before the rest
     ScopedTimer t(c, T_EVB_ENUM);
     k_evb_enumerate<<<1, ENUM_TPB, 0, c->stream>>>(d, e);
-    c->n_launch += 2;
+    c->n_launch += 1;
+    return 0;
   }
   CKE(cudaMemcpyAsync(h.pinned, e.n_states, ENUM_BLOCK_INTS * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CKE(cudaMemcpyAsync(c->h_flags, d.err_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -1979,7 +2012,10 @@ int evb_enumerate_async(rpb_ctx* c) {
   // the diabat images need nothing from the host: built for however many diabats the enumeration found (grid sized
   // for evb_max_states, surplus warps exit)
   { ScopedTimer t(c, T_EVB_SNAP); k_evb_snapshots<<<(MAXS + SNAP_WPB - 1) / SNAP_WPB, 32 * SNAP_WPB, 0, c->stream>>>(d, e, -1, g_scratch[c].recip_grids ? 0 : 1); }   // delta algebra: every rank needs the charges of every diabat
-  c->n_launch += 1;
+  // accumulators of the build, for the S this enumeration found: behind the enumeration (which is on the step's critical
+  // path) and the images, ahead of everything that accumulates
+  k_evb_clear<<<148 * 2, 256, 0, c->stream>>>(d, e, g_scratch[c].cand_n, 0, -1);
+  c->n_launch += 2;
   return 0;
 }
 
@@ -2097,8 +2133,6 @@ int evb_build(rpb_ctx* c) {
   //            principal grid (slot 0) and every owned diabat, chain-atom force corrections
   {
     StreamScope ss(c, c->aux[0]);
-    const int cleared = std::min(MAXS, h.n_states_prev + CLEAR_MARGIN);
-    if (S > cleared) { k_evb_clear<<<148 * 2, 256, 0, c->stream>>>(d, e, sc.cand_n, cleared, S); c->n_launch++; }
     CKE(cudaMemcpyAsync(sc.pack_dev, sc.pack_host, PACK_BYTES, cudaMemcpyHostToDevice, c->stream));
   }
   h.n_states_prev = S;
@@ -2142,6 +2176,7 @@ int evb_build(rpb_ctx* c) {
     }
   }
   {
+    // aux[0] (behind images, clears and the per-step tables): off-diagonal couplings
     StreamScope ss(c, c->aux[0]);
     {
       ScopedTimer t(c, T_EVB_COUPLING_GEO);
@@ -2156,6 +2191,7 @@ int evb_build(rpb_ctx* c) {
     }
   }
   {
+    // main (behind the pair forces): candidate lists -> real-space / repulsion / bonded deltas
     {
       ScopedTimer t(c, T_EVB_CAND);
       dim3 g((N + 255) / 256, n_uniq);
@@ -2166,6 +2202,7 @@ int evb_build(rpb_ctx* c) {
   }
   stream_depend(c, 6, c->aux[0], c->main_stream);
   stream_depend(c, 7, c->aux[1], c->main_stream);
+  if (d.rank == 0) stream_depend(c, 9, c->aux[2], c->main_stream);   // bonded terms of the principal diabat
   if (d.world > 1 || c->evb_solver != 0) {
     ScopedTimer t(c, T_EVB_ASSEMBLE);
     k_evb_assemble<<<(MAXS + 31) / 32, 32, 0, c->stream>>>(d, e, sc.geo, sc.last_item, algebra ? nullptr : sc.slot_of_state);
@@ -2235,16 +2272,14 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
         if (coeff_override_host) { k_copy<<<(unsigned)((K3 + 255) / 256), 256, 0, c->stream>>>(d.Q + K3, d.Q, K3); c->n_launch++; }   // debug re-mix: fresh copy
         if (S > 1) {
           ScopedTimer t(c, T_EVB_PATCH);
-          CKE(cudaMemsetAsync(sc.rd.D, 0, RA_SLOTS * sizeof(double), c->stream));
-          k_evb_rcp_mix<<<(S * RA_ENT + 127) / 128, 128, 0, c->stream>>>(d, e, sc.rd, out, 1);
-          k_evb_rcp_patch<<<(sc.n_rmol * MA * 32 + 255) / 256, 256, 0, c->stream>>>(d, sc.rd, d.Q + K3, sc.n_rmol);
-          c->n_launch += 2;
+          k_evb_rcp_patch<<<(sc.n_rmol * MA * 32 + 255) / 256, 256, 0, c->stream>>>(d, e, sc.rd, d.Q + K3, sc.n_rmol);
+          c->n_launch += 1;
         }
         int rc2 = launch_convolve(c, 1, 1, e.e_recip, true);
         if (rc2) return rc2;
       }
       { ScopedTimer t(c, T_EVB_MIXF); k_evb_mix_forces<<<(unsigned)((n3 + 255) / 256), 256, 0, c->stream>>>(d, e, sc.state_list, n_own, include_principal, in_place);
-        if (S > 1 && d.rank == 0) { k_evb_rcp_mix<<<(S * RA_ENT + 127) / 128, 128, 0, c->stream>>>(d, e, sc.rd, out, 2); c->n_launch++; } }
+        if (S > 1 && d.rank == 0) { k_evb_rcp_mix<<<(S * RA_ENT + 127) / 128, 128, 0, c->stream>>>(d, e, sc.rd, out); c->n_launch++; } }
       stream_depend(c, 1, c->aux[1], c->main_stream);
       const int i0 = (int)((long long)N * d.rank / d.world), i1 = (int)((long long)N * (d.rank + 1) / d.world);
       { ScopedTimer t(c, T_EVB_GATHERMIX); k_evb_gather_range<<<((i1 - i0) * 32 + 255) / 256, 256, 0, c->stream>>>(d, d.theta + K3, out, i0, i1); }

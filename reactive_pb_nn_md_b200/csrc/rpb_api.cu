@@ -74,23 +74,34 @@ int calculate_total_force_energy(rpb_ctx* c, bool evb_principal) {
   launch_verlet_update(c);
   int rc = 0;
   if (evb_principal) {
-    // MS-EVB: the diabat enumeration (and the diabat images, which need nothing from the host) need positions and
-    // centres of mass only; they run on a side stream so that the host learns the number of diabats -- which sizes the
-    // later launches -- while the GPU is busy with the pair forces.  Both short side branches are queued AHEAD of the
-    // pair kernel so that their CTAs get SMs before that grid floods the GPU.
-    StreamScope sc(c, c->aux[0]);
-    rc = evb_enumerate_async(c);
+    // MS-EVB.  Two chains bound the time to the Hamiltonian: [pair forces -> candidate lists -> per-diabat real-space
+    // deltas] on the main stream and [enumeration -> host -> per-step tables] on aux[0].  The host needs ~3 us per launch,
+    // so the two long kernels are issued first, everything else behind them:
+    //   aux[0]: enumeration + images (positions and centres of mass only; the host learns the number of diabats -- which
+    //           sizes the later launches -- while the GPU is busy with the pair forces)
+    //   main  : pair forces (sharded by atoms in a state-sharded run)
+    //   aux[1]: spreading of the principal grid            aux[2]: bonded terms (24 small CTAs; rank 0 only)
+    // evb_build keeps the side streams busy and joins them before the Hamiltonian.
+    { StreamScope sc(c, c->aux[0]); evb_enumerate_async(c, 0); }
+    if (c->d.rank == 0) stream_depend(c, 8, c->main_stream, c->aux[2]);   // fork ahead of the pair kernel
+    launch_pair_verlet(c, true);
+    {
+      StreamScope sc(c, c->aux[0]);
+      rc = evb_enumerate_async(c, 1);
+      if (rc) return rc;
+    }
+    { StreamScope sc(c, c->aux[1]); launch_spread_principal(c); }
+    if (c->d.rank == 0) { StreamScope sc(c, c->aux[2]); launch_molecule_terms(c); }
+    return 0;
   }
-  if (rc) return rc;
   {
     StreamScope sc(c, c->aux[1]);
     launch_spread_principal(c);
-    if (!evb_principal) rc = launch_convolve(c, 0, 1, c->d.en + E_RECIP, true);
+    rc = launch_convolve(c, 0, 1, c->d.en + E_RECIP, true);
   }
   if (rc) return rc;
-  launch_pair_verlet(c, evb_principal);   // the sharded MS-EVB step all-reduces the forces; the non-reactive call is never sharded
-  if (evb_principal) { if (c->d.rank == 0) launch_molecule_terms(c); }   // main stream has slack behind the pair kernel in MS-EVB mode; sharded: counted once
-  else { StreamScope sc(c, c->aux[0]); launch_molecule_terms(c); }
+  launch_pair_verlet(c, false);   // the non-reactive call is never sharded
+  { StreamScope sc(c, c->aux[0]); launch_molecule_terms(c); }
   if (evb_principal) return 0;     // evb_build keeps both side streams busy and joins them before the Hamiltonian
   stream_depend(c, 2, c->aux[0], c->main_stream);
   stream_depend(c, 3, c->aux[1], c->main_stream);
@@ -156,12 +167,12 @@ int rpb_create(rpb_ctx** out, const rpb_config* cfg) {
     c->main_stream = c->stream;
     // RPB_SERIAL_STREAMS=1: every branch on the main stream (clean per-kernel CUDA-event times for the roofline table)
     c->serial_streams = getenv("RPB_SERIAL_STREAMS") != nullptr;
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < 3; k++) {
       if (c->serial_streams) c->aux[k] = c->stream;
       else CK(cudaStreamCreateWithPriority(&c->aux[k], cudaStreamNonBlocking, prio_hi));
     }
   }
-  for (int k = 0; k < 8; k++) CK(cudaEventCreateWithFlags(&c->ev_sync[k], cudaEventDisableTiming));
+  for (int k = 0; k < 12; k++) CK(cudaEventCreateWithFlags(&c->ev_sync[k], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_enum, cudaEventDisableTiming));
   CK(cudaMallocHost(&c->h_en, E_NSLOT * sizeof(double)));
   CK(cudaMallocHost(&c->h_flags, 8 * sizeof(int)));
@@ -251,9 +262,9 @@ void rpb_destroy(rpb_ctx* c) {
   if (c->eh.pinned) cudaFreeHost(c->eh.pinned);
   if (c->stream) {
     for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
-    for (int k = 0; k < 8; k++) if (c->ev_sync[k]) cudaEventDestroy(c->ev_sync[k]);
+    for (int k = 0; k < 12; k++) if (c->ev_sync[k]) cudaEventDestroy(c->ev_sync[k]);
     if (c->ev_enum) cudaEventDestroy(c->ev_enum);
-    for (int k = 0; k < 2; k++) if (c->aux[k] && !c->serial_streams) { cudaStreamSynchronize(c->aux[k]); cudaStreamDestroy(c->aux[k]); }
+    for (int k = 0; k < 3; k++) if (c->aux[k] && !c->serial_streams) { cudaStreamSynchronize(c->aux[k]); cudaStreamDestroy(c->aux[k]); }
     cudaStreamDestroy(c->stream);
   }
   delete c;
