@@ -357,26 +357,23 @@ def run_ours(args):
     cpu_baseline = None
     if world == 1:
         st = sim.download_state()
-        xyz = torch.from_numpy(st["xyz"]).pin_memory().numpy()
-        vel = torch.from_numpy(st["velocity"]).pin_memory().numpy()
         n_e2e = min(args.steps, 50)
         N = s.n_atoms
         h2d = 2 * 3 * N * 8 + 2 * N * 8 + N * 4 + 3 * s.n_mole * 4
         d2h = 3 * 3 * N * 8 + 8 * 8
         for _ in range(3):
-            sim.upload_state(xyz, vel, st); step(); st = sim.download_state(); xyz[:] = st["xyz"]; vel[:] = st["velocity"]; sim.energies()
+            sim.upload_state(st["xyz"], st["velocity"], st); step(); st = sim.download_state(out=st); sim.energies()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(n_e2e):
-            sim.upload_state(xyz, vel, st)          # host buffers -> device (positions, velocities, topology)
+            sim.upload_state(st["xyz"], st["velocity"], st)   # host buffers -> device (positions, velocities, topology)
             step()
-            st = sim.download_state()               # device -> host: x, v, F, topology after possible hops
-            xyz[:] = st["xyz"]; vel[:] = st["velocity"]
+            st = sim.download_state(out=st)         # device -> host into the same host arrays: x, v, F, topology after possible hops
             sim.energies()
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
         e2e = {"value": n_e2e / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "call": "rpb_upload_state + rpb_step(1) + rpb_download_state + rpb_get_energies (host buffers)"}
+               "call": "rpb_upload_state + rpb_step(1) + rpb_download_state + rpb_get_energies; caller-owned host arrays, staged through the library's pinned buffer"}
         # ---- CPU baseline: bounded sample of the same workload on the host cores (oracle = port of the reference algorithm)
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

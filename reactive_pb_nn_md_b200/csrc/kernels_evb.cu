@@ -959,7 +959,11 @@ __global__ void __launch_bounds__(32 * GEO_WPB) k_evb_coupling_geo(Dev d, EvbDev
   warp_copy_struct(&geo[s], &G, lane);
 }
 
-// grid = (n_owned states list, ceil(N/256)): Vex between the Zundel sites and the background atoms
+// grid = (n_owned states list, ceil(N / (256 * VEX_APT))): Vex between the Zundel sites and the background atoms
+// (evb_diabatic_coupling_electrostatics, ms_evb.f90:1324-1397: no cutoff, minimum image by molecule).  Every thread
+// keeps VEX_APT atoms in registers, so that the per-site warp reductions of the site forces are paid once per
+// VEX_APT * 32 atoms; q/r and q/r^3 come from ONE rsqrt instead of a sqrt and two divisions (relative differences ~1e-16).
+#define VEX_APT 4
 __global__ void __launch_bounds__(256) k_evb_coupling_vex(Dev d, EvbDev e, const CouplingGeo* geo, const int* state_list) {
   __shared__ double red[32];
   __shared__ double facc[8][2 * MA][3];
@@ -969,33 +973,51 @@ __global__ void __launch_bounds__(256) k_evb_coupling_vex(Dev d, EvbDev e, const
   for (int k = threadIdx.x; k < 8 * 2 * MA * 3; k += blockDim.x) (&facc[0][0][0])[k] = 0.0;
   __syncthreads();
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  int j = blockIdx.y * blockDim.x + threadIdx.x;
-  bool active = j < d.N;
-  if (active) for (int k = 0; k < G.n_chain; k++) active &= (G.chain_atoms[k] != j);
-  double vex = 0.0, fj[3] = {0, 0, 0};
-  double xj[3] = {0, 0, 0}, qj = 0.0, sh[3] = {0, 0, 0};
-  if (active) {
-    double4 p = d.xq[j];
-    xj[0] = p.x; xj[1] = p.y; xj[2] = p.z; qj = p.w;
-    int jm = d.mol_of_atom[j];
-    for (int k = 0; k < 3; k++) sh[k] = floor(d.inv_box[k] * (d.r_com[3 * jm + k] - G.rz[k]) + 0.5) * d.box[k];
-  }
-  for (int n = 0; n < G.n_site; n++) {
-    double dV[3] = {0, 0, 0};
-    if (active) {
-      double r[3];
-      for (int k = 0; k < 3; k++) r[k] = -(xj[k] - G.site_x[n][k] - sh[k]);
-      double rm = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
-      double qq = G.site_q[n] * qj;
-      vex += qq / rm * d.conv;
-      double g = -qq / (rm * rm * rm) * d.conv;
-      for (int k = 0; k < 3; k++) { dV[k] = g * r[k]; fj[k] -= dV[k]; }
+  bool active[VEX_APT];
+  int jj[VEX_APT];
+  double xj[VEX_APT][3], qj[VEX_APT], fj[VEX_APT][3];
+#pragma unroll
+  for (int q = 0; q < VEX_APT; q++) {
+    const int j = (blockIdx.y * VEX_APT + q) * blockDim.x + threadIdx.x;
+    jj[q] = j;
+    active[q] = j < d.N;
+    if (active[q]) for (int k = 0; k < G.n_chain; k++) active[q] &= (G.chain_atoms[k] != j);
+    xj[q][0] = xj[q][1] = xj[q][2] = 0.0; qj[q] = 0.0; fj[q][0] = fj[q][1] = fj[q][2] = 0.0;
+    if (active[q]) {
+      const double4 p = d.xq[j];
+      const int jm = d.mol_of_atom[j];
+      // the molecule's minimum-image shift is folded into the stored position
+      xj[q][0] = p.x - floor(d.inv_box[0] * (d.r_com[3 * jm] - G.rz[0]) + 0.5) * d.box[0];
+      xj[q][1] = p.y - floor(d.inv_box[1] * (d.r_com[3 * jm + 1] - G.rz[1]) + 0.5) * d.box[1];
+      xj[q][2] = p.z - floor(d.inv_box[2] * (d.r_com[3 * jm + 2] - G.rz[2]) + 0.5) * d.box[2];
+      qj[q] = p.w;
     }
-    double s0 = warp_sum(dV[0]), s1 = warp_sum(dV[1]), s2 = warp_sum(dV[2]);
+  }
+  double vex = 0.0;
+  for (int n = 0; n < G.n_site; n++) {
+    const double sx = G.site_x[n][0], sy = G.site_x[n][1], sz = G.site_x[n][2], sq = G.site_q[n] * d.conv;
+    double dV0 = 0.0, dV1 = 0.0, dV2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < VEX_APT; q++) {
+      if (active[q]) {
+        const double r0 = sx - xj[q][0], r1 = sy - xj[q][1], r2 = sz - xj[q][2];
+        const double inv = rsqrt(r0 * r0 + r1 * r1 + r2 * r2);
+        const double qq = sq * qj[q];
+        const double v = qq * inv;
+        vex += v;
+        const double g = -v * (inv * inv);
+        const double t0 = g * r0, t1 = g * r1, t2 = g * r2;
+        dV0 += t0; dV1 += t1; dV2 += t2;
+        fj[q][0] -= t0; fj[q][1] -= t1; fj[q][2] -= t2;
+      }
+    }
+    const double s0 = warp_sum(dV0), s1 = warp_sum(dV1), s2 = warp_sum(dV2);
     if (lane == 0) { facc[w][n][0] += s0; facc[w][n][1] += s1; facc[w][n][2] += s2; }
   }
   double* Fo = e.Foff + (size_t)s * 3 * d.N;
-  if (active) { Fo[3 * j] = -G.A * fj[0]; Fo[3 * j + 1] = -G.A * fj[1]; Fo[3 * j + 2] = -G.A * fj[2]; }  // only this thread writes atom j
+#pragma unroll
+  for (int q = 0; q < VEX_APT; q++)   // only this thread writes atom j
+    if (active[q]) { const int j = jj[q]; Fo[3 * j] = -G.A * fj[q][0]; Fo[3 * j + 1] = -G.A * fj[q][1]; Fo[3 * j + 2] = -G.A * fj[q][2]; }
   vex = block_sum(vex, red);
   if (threadIdx.x == 0) atomicAdd(&e.vex[s], vex);
   __syncthreads();
@@ -1816,9 +1838,7 @@ __global__ void k_evb_commit_patch(Dev d, EvbDev e, int state, int level, const 
 
 // zero (or -1) every accumulator evb_build adds into: item energies, Vex, candidate counters, chain-atom corrections,
 // and the per-diabat force deltas / coupling forces of the S diabats in flight
-// s_end < 0: launched right behind the enumeration of the step, it clears the diabats [0, S) that enumeration found
 __global__ void k_evb_clear(Dev d, EvbDev e, int* cand_n, int s_begin, int s_end) {
-  if (s_end < 0) s_end = min(MAXS, *e.n_states);
   const int S = s_end - s_begin;
   e.dF += (size_t)s_begin * 3 * d.N; e.Foff += (size_t)s_begin * 3 * d.N;
   e.corr_f += (size_t)s_begin * CM * MA * 3; e.corr_atom += (size_t)s_begin * CM * MA;
@@ -2006,17 +2026,27 @@ int evb_enumerate_async(rpb_ctx* c, int part) {
     c->n_launch += 1;
     return 0;
   }
-  CKE(cudaMemcpyAsync(h.pinned, e.n_states, ENUM_BLOCK_INTS * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CKE(cudaMemcpyAsync(c->h_flags, d.err_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CKE(cudaEventRecord(c->ev_enum, c->stream));
+  // read-back on its own stream: the images below must not queue behind two device-to-host copies
+  CKE(cudaEventRecord(c->ev_sync[10], c->stream));
+  CKE(cudaStreamWaitEvent(c->aux[3], c->ev_sync[10], 0));
+  CKE(cudaMemcpyAsync(h.pinned, e.n_states, ENUM_BLOCK_INTS * sizeof(int), cudaMemcpyDeviceToHost, c->aux[3]));
+  CKE(cudaMemcpyAsync(c->h_flags, d.err_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->aux[3]));
+  CKE(cudaEventRecord(c->ev_enum, c->aux[3]));
   // the diabat images need nothing from the host: built for however many diabats the enumeration found (grid sized
   // for evb_max_states, surplus warps exit)
   { ScopedTimer t(c, T_EVB_SNAP); k_evb_snapshots<<<(MAXS + SNAP_WPB - 1) / SNAP_WPB, 32 * SNAP_WPB, 0, c->stream>>>(d, e, -1, g_scratch[c].recip_grids ? 0 : 1); }   // delta algebra: every rank needs the charges of every diabat
-  // accumulators of the build, for the S this enumeration found: behind the enumeration (which is on the step's critical
-  // path) and the images, ahead of everything that accumulates
-  k_evb_clear<<<148 * 2, 256, 0, c->stream>>>(d, e, g_scratch[c].cand_n, 0, -1);
-  c->n_launch += 2;
+  c->n_launch += 1;
   return 0;
+}
+
+// Accumulators of the build (per-diabat force deltas, coupling forces, item energies, Vex, candidate counters) for the
+// diabats [0, previous S + CLEAR_MARGIN): the number of diabats changes slowly, and evb_build clears the rest in the rare
+// step that gains more.  The bound comes from the host (the enumeration kernel is rewriting the device copy of S).
+#define CLEAR_MARGIN 8
+void evb_clear_early(rpb_ctx* c) {
+  const int cleared = std::min(MAXS, c->eh.n_states_prev + CLEAR_MARGIN);
+  k_evb_clear<<<148 * 2, 256, 0, c->stream>>>(c->d, c->e, g_scratch[c].cand_n, 0, cleared);
+  c->n_launch += 1;
 }
 
 int evb_build(rpb_ctx* c) {
@@ -2133,6 +2163,9 @@ int evb_build(rpb_ctx* c) {
   //            principal grid (slot 0) and every owned diabat, chain-atom force corrections
   {
     StreamScope ss(c, c->aux[0]);
+    CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[11], 0));      // the early clears (aux[1])
+    const int cleared = std::min(MAXS, h.n_states_prev + CLEAR_MARGIN);
+    if (S > cleared) { k_evb_clear<<<148 * 2, 256, 0, c->stream>>>(d, e, sc.cand_n, cleared, S); c->n_launch++; }
     CKE(cudaMemcpyAsync(sc.pack_dev, sc.pack_host, PACK_BYTES, cudaMemcpyHostToDevice, c->stream));
   }
   h.n_states_prev = S;
@@ -2146,13 +2179,36 @@ int evb_build(rpb_ctx* c) {
   }
   stream_depend(c, 4, c->aux[0], c->main_stream);
   stream_depend(c, 5, c->aux[0], c->aux[1]);
+  stream_depend(c, 12, c->aux[0], c->aux[4]);
+  // issued first: the per-diabat real-space deltas are the longest branch between the tables and the Hamiltonian
+  {
+    // aux[4] (NOT behind the pair forces: needs the tables, images and clears only): candidate lists -> real-space /
+    // repulsion / bonded deltas
+    StreamScope ss(c, c->aux[4]);
+    {
+      ScopedTimer t(c, T_EVB_CAND);
+      dim3 g((N + 255) / 256, n_uniq);
+      k_evb_candidates<<<g, 256, 0, c->stream>>>(d, sc.uniq_atom, c->evb_rcand * c->evb_rcand, sc.chain_slot, sc.cand, sc.cand_n);
+    }
+    { ScopedTimer t(c, T_EVB_ITEMS_BG); k_evb_items<<<dim3(n_real, ITEM_SPLIT), ITEM_TPB, 0, c->stream>>>(d, e, sc.chain_slot, sc.cand, sc.cand_n, c->evb_rcand, c->evb_rep_reach); }
+    c->n_launch += 2;
+  }
   if (algebra) {
-    StreamScope ss(c, c->aux[1]);
     if (S > 1) {
+      {   // the pair matrix needs the tables and the scaled coordinates only, not theta_1: on aux[2] (idle since the bonded
+          // terms), next to the principal convolution instead of behind it
+        StreamScope ss(c, c->aux[2]);
+        stream_depend(c, 14, c->aux[0], c->aux[2]);
+        CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[15], 0));
+        ScopedTimer t(c, T_EVB_CORR);
+        const int pw = sc.n_rpair * MA * MA;
+        k_evb_rcp_pairs<<<(pw + 3) / 4, 128, 0, c->stream>>>(d, sc.rd, sc.n_rpair);
+        CKE(cudaEventRecord(c->ev_sync[16], c->stream));
+      }
+      StreamScope ss(c, c->aux[1]);
       ScopedTimer t(c, T_EVB_CORR);
-      const int pw = sc.n_rpair * MA * MA;
-      k_evb_rcp_pairs<<<(pw + 3) / 4, 128, 0, c->stream>>>(d, sc.rd, sc.n_rpair);
       k_evb_rcp_atoms<<<(sc.n_rmol * MA * 32 + 255) / 256, 256, 0, c->stream>>>(d, sc.rd, sc.n_rmol);
+      CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[16], 0));
       k_evb_rcp_energy<<<(S + 3) / 4, 128, 0, c->stream>>>(d, e, sc.rd);
       c->n_launch += 3;
     }
@@ -2185,24 +2241,15 @@ int evb_build(rpb_ctx* c) {
     }
     if (n_own > 0) {
       ScopedTimer t(c, T_EVB_COUPLING);
-      dim3 g(n_own, (N + 255) / 256);
+      dim3 g(n_own, (N + 256 * VEX_APT - 1) / (256 * VEX_APT));
       k_evb_coupling_vex<<<g, 256, 0, c->stream>>>(d, e, sc.geo, sc.state_list);
       c->n_launch += 1;
     }
   }
-  {
-    // main (behind the pair forces): candidate lists -> real-space / repulsion / bonded deltas
-    {
-      ScopedTimer t(c, T_EVB_CAND);
-      dim3 g((N + 255) / 256, n_uniq);
-      k_evb_candidates<<<g, 256, 0, c->stream>>>(d, sc.uniq_atom, c->evb_rcand * c->evb_rcand, sc.chain_slot, sc.cand, sc.cand_n);
-    }
-    { ScopedTimer t(c, T_EVB_ITEMS_BG); k_evb_items<<<dim3(n_real, ITEM_SPLIT), ITEM_TPB, 0, c->stream>>>(d, e, sc.chain_slot, sc.cand, sc.cand_n, c->evb_rcand, c->evb_rep_reach); }
-    c->n_launch += 2;
-  }
   stream_depend(c, 6, c->aux[0], c->main_stream);
   stream_depend(c, 7, c->aux[1], c->main_stream);
   if (d.rank == 0) stream_depend(c, 9, c->aux[2], c->main_stream);   // bonded terms of the principal diabat
+  stream_depend(c, 13, c->aux[4], c->main_stream);
   if (d.world > 1 || c->evb_solver != 0) {
     ScopedTimer t(c, T_EVB_ASSEMBLE);
     k_evb_assemble<<<(MAXS + 31) / 32, 32, 0, c->stream>>>(d, e, sc.geo, sc.last_item, algebra ? nullptr : sc.slot_of_state);

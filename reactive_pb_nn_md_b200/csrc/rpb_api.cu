@@ -80,7 +80,8 @@ int calculate_total_force_energy(rpb_ctx* c, bool evb_principal) {
     //   aux[0]: enumeration + images (positions and centres of mass only; the host learns the number of diabats -- which
     //           sizes the later launches -- while the GPU is busy with the pair forces)
     //   main  : pair forces (sharded by atoms in a state-sharded run)
-    //   aux[1]: spreading of the principal grid            aux[2]: bonded terms (24 small CTAs; rank 0 only)
+    //   aux[1]: accumulator clears, spreading of the principal grid      aux[2]: bonded terms (24 small CTAs; rank 0 only)
+    //   aux[3]: the enumeration's read-back (so that the images on aux[0] do not queue behind two D2H copies)
     // evb_build keeps the side streams busy and joins them before the Hamiltonian.
     { StreamScope sc(c, c->aux[0]); evb_enumerate_async(c, 0); }
     if (c->d.rank == 0) stream_depend(c, 8, c->main_stream, c->aux[2]);   // fork ahead of the pair kernel
@@ -90,7 +91,14 @@ int calculate_total_force_energy(rpb_ctx* c, bool evb_principal) {
       rc = evb_enumerate_async(c, 1);
       if (rc) return rc;
     }
-    { StreamScope sc(c, c->aux[1]); launch_spread_principal(c); }
+    {
+      // aux[1] has slack before its first consumer: the accumulators of the build are cleared here, off both chains
+      StreamScope sc(c, c->aux[1]);
+      evb_clear_early(c);
+      cudaEventRecord(c->ev_sync[11], c->stream);
+      launch_spread_principal(c);
+      cudaEventRecord(c->ev_sync[15], c->stream);   // scaled coordinates ready (pair matrix of the chain atoms, aux[2])
+    }
     if (c->d.rank == 0) { StreamScope sc(c, c->aux[2]); launch_molecule_terms(c); }
     return 0;
   }
@@ -167,12 +175,12 @@ int rpb_create(rpb_ctx** out, const rpb_config* cfg) {
     c->main_stream = c->stream;
     // RPB_SERIAL_STREAMS=1: every branch on the main stream (clean per-kernel CUDA-event times for the roofline table)
     c->serial_streams = getenv("RPB_SERIAL_STREAMS") != nullptr;
-    for (int k = 0; k < 3; k++) {
+    for (int k = 0; k < 5; k++) {
       if (c->serial_streams) c->aux[k] = c->stream;
       else CK(cudaStreamCreateWithPriority(&c->aux[k], cudaStreamNonBlocking, prio_hi));
     }
   }
-  for (int k = 0; k < 12; k++) CK(cudaEventCreateWithFlags(&c->ev_sync[k], cudaEventDisableTiming));
+  for (int k = 0; k < 20; k++) CK(cudaEventCreateWithFlags(&c->ev_sync[k], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_enum, cudaEventDisableTiming));
   CK(cudaMallocHost(&c->h_en, E_NSLOT * sizeof(double)));
   CK(cudaMallocHost(&c->h_flags, 8 * sizeof(int)));
@@ -262,9 +270,9 @@ void rpb_destroy(rpb_ctx* c) {
   if (c->eh.pinned) cudaFreeHost(c->eh.pinned);
   if (c->stream) {
     for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
-    for (int k = 0; k < 12; k++) if (c->ev_sync[k]) cudaEventDestroy(c->ev_sync[k]);
+    for (int k = 0; k < 20; k++) if (c->ev_sync[k]) cudaEventDestroy(c->ev_sync[k]);
     if (c->ev_enum) cudaEventDestroy(c->ev_enum);
-    for (int k = 0; k < 3; k++) if (c->aux[k] && !c->serial_streams) { cudaStreamSynchronize(c->aux[k]); cudaStreamDestroy(c->aux[k]); }
+    for (int k = 0; k < 5; k++) if (c->aux[k] && !c->serial_streams) { cudaStreamSynchronize(c->aux[k]); cudaStreamDestroy(c->aux[k]); }
     cudaStreamDestroy(c->stream);
   }
   delete c;

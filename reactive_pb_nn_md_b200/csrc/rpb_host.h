@@ -35,8 +35,8 @@ struct rpb_ctx {
   bool have_tables = false, have_ff = false, have_mt = false, have_evb = false, have_state = false, initialized = false;
   cudaStream_t stream = nullptr;        // stream the launchers use (normally the main stream; see StreamScope)
   cudaStream_t main_stream = nullptr;   // the library's main stream: host synchronisation and timing happen here
-  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // side streams for the independent branches of a force evaluation (aux[2]: bonded terms of the MS-EVB principal diabat)
-  cudaEvent_t ev_sync[12] = {};   // fork / join points
+  cudaStream_t aux[5] = {};   // side streams for the independent branches of a force evaluation; MS-EVB: [2] bonded terms of the principal diabat, [3] read-backs, [4] per-diabat real-space deltas
+  cudaEvent_t ev_sync[20] = {};   // fork / join points
   cudaEvent_t ev_enum = nullptr;        // enumeration results have reached pinned host memory
   Dev d;                       // device pointer table (host copy, passed by value to kernels)
   std::vector<void*> allocs;   // everything cudaMalloc'ed (freed in rpb_destroy)
@@ -145,7 +145,8 @@ void peer_free(rpb_ctx*);
 // ---- kernels_evb.cu
 int evb_alloc(rpb_ctx*);
 void evb_free(rpb_ctx*);
-int evb_enumerate_async(rpb_ctx*, int part);   // launched early in the principal evaluation (part 0: the kernel, part 1: read-back, images, clears); evb_build waits for its read-back
+int evb_enumerate_async(rpb_ctx*, int part);   // launched early in the principal evaluation (part 0: the kernel, part 1: read-back on aux[3], images); evb_build waits for its read-back
+void evb_clear_early(rpb_ctx*);      // accumulators of the build for the previous S + margin (launch on a stream with slack)
 int evb_build(rpb_ctx*);
 int evb_mix(rpb_ctx*, const double* coeff_override_host, double* force_out_host);
 int evb_commit(rpb_ctx*);

@@ -265,11 +265,14 @@ class Simulation:
     def calculate_kinetic_energy(self):
         return self.energies()["kinetic_energy"]
 
-    def download_state(self):
+    def download_state(self, out=None):
+        """atom_data / molecule_data <- library.  `out`: a dict returned by an earlier call, whose arrays are reused
+        (a caller that owns its arrays, like the Fortran driver, never allocates per step)."""
         N, M = self.system.n_atoms, self.system.n_mole
-        out = dict(xyz=np.zeros((N, 3)), velocity=np.zeros((N, 3)), force=np.zeros((N, 3)), mass=np.zeros(N),
-                   charge=np.zeros(N), atom_type=np.zeros(N, np.int32), mol_first_atom=np.zeros(M, np.int32),
-                   mol_n_atom=np.zeros(M, np.int32), mol_type=np.zeros(M, np.int32))
+        if out is None:
+            out = dict(xyz=np.zeros((N, 3)), velocity=np.zeros((N, 3)), force=np.zeros((N, 3)), mass=np.zeros(N),
+                       charge=np.zeros(N), atom_type=np.zeros(N, np.int32), mol_first_atom=np.zeros(M, np.int32),
+                       mol_n_atom=np.zeros(M, np.int32), mol_type=np.zeros(M, np.int32))
         h = C.c_int()
         self._check(self.dll.rpb_download_state(
             self.ctx, dptr(out["xyz"]), dptr(out["velocity"]), dptr(out["force"]), dptr(out["mass"]),

@@ -116,3 +116,28 @@ def test_synthetic_configs_shapes():
     assert np.array_equal(s.xyz, np.round(s.xyz, 2))           # .gro precision
     p = (s.mass[:, None] * s.velocity).sum(axis=0)
     assert np.abs(p).max() < 1e-9
+
+
+def test_ensemble_step_and_peer_entry_points_on_the_oracle(oracle_lib):
+    """rpb_ensemble_step (replicas only) steps every context; the peer-memory exchange is a device feature that the
+    oracle refuses with RPB_ERR_UNSUPPORTED (the engine then keeps the collective path)."""
+    import ctypes as C
+    import pytest
+    from reactive_pb_nn_md_b200 import engine
+    from reactive_pb_nn_md_b200._binding import RpbError
+    from tests.util import small_params, water_system
+    s = water_system(10, hydronium=True)
+    p = small_params(pme_grid=32, n_threads=2)
+    ens = [engine.Simulation(s, p, library=oracle_lib) for _ in range(2)]
+    one = engine.Simulation(s, p, library=oracle_lib)
+    for sim in ens + [one]:
+        sim.ms_evb_calculate_total_force_energy()
+    engine.Simulation.ensemble_step(ens, 2, ms_evb=True)
+    one.md_integrate_atomic(2, ms_evb=True)
+    for sim in ens:
+        assert np.abs(sim.download_state()["xyz"] - one.download_state()["xyz"]).max() < 1e-10     # OpenMP reduction order
+    assert one.dll.rpb_peer_enabled(one.ctx) == 0
+    buf = C.create_string_buffer(64)
+    assert one.dll.rpb_peer_export(one.ctx, buf) == -7
+    with pytest.raises(RpbError):
+        one._check(one.dll.rpb_peer_import(one.ctx, buf, 1))
