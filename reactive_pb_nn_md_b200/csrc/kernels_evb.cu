@@ -853,12 +853,12 @@ __device__ void coupling_function(double& A, double& Vc, double dA[3][3], int ft
 // one warp per owned diabat s>=1: geometric factor and Zundel sites (lane 0, on a shared-memory copy of the final-level
 // snapshot), then the Vex terms of the OTHER chain molecules with (atom, site) pairs dealt to the lanes
 #define GEO_WPB 4
-__global__ void __launch_bounds__(32 * GEO_WPB) k_evb_coupling_geo(Dev d, EvbDev e, CouplingGeo* geo) {
+__global__ void __launch_bounds__(32 * GEO_WPB) k_evb_coupling_geo(Dev d, EvbDev e, CouplingGeo* geo, int s_begin, int s_end) {
   __shared__ Snapshot Ssh[GEO_WPB];
   __shared__ CouplingGeo Gsh[GEO_WPB];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int s = blockIdx.x * GEO_WPB + w;
-  const int S = *e.n_states;
+  const int s = s_begin + blockIdx.x * GEO_WPB + w;
+  const int S = min(*e.n_states, s_end);
   if (s >= S) return;
   if (s == 0 || !state_owned(s, d.rank, d.world)) { if (lane == 0) geo[s].valid = 0; return; }
   const EvbTables& E = *d.evb;
@@ -1847,9 +1847,12 @@ __global__ void k_evb_clear(Dev d, EvbDev e, int* cand_n, int s_begin, int s_end
   for (size_t k = tid; k < nbig; k += nth) { e.dF[k] = 0.0; e.Foff[k] = 0.0; }
   for (size_t k = tid; k < (size_t)S * CM * MA * 3; k += nth) e.corr_f[k] = 0.0;
   for (size_t k = tid; k < (size_t)S * CM * MA; k += nth) e.corr_atom[k] = -1;
-  for (size_t k = tid; k < RPB_MAX_ITEMS + 1; k += nth) e.item_energy[k] = 0.0;
-  for (size_t k = tid; k < MAXS; k += nth) e.vex[k] = 0.0;
-  for (size_t k = tid; k < CAND_SLOTS; k += nth) cand_n[k] = 0;
+  if (s_begin == 0) {   // the step-wide accumulators belong to the first (early) launch only: the coupling geometry of the
+                        // diabats it covers may already have added its Vex terms when a second launch clears [s_begin, S)
+    for (size_t k = tid; k < RPB_MAX_ITEMS + 1; k += nth) e.item_energy[k] = 0.0;
+    for (size_t k = tid; k < MAXS; k += nth) e.vex[k] = 0.0;
+    for (size_t k = tid; k < CAND_SLOTS; k += nth) cand_n[k] = 0;
+  }
 }
 
 // ================================================================================================
@@ -2018,6 +2021,7 @@ struct HostClock {
 double HostClock::acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 long HostClock::n = 0;
 
+#define CLEAR_MARGIN 8
 int evb_enumerate_async(rpb_ctx* c, int part) {
   Dev& d = c->d; EvbDev& e = c->e; EvbHost& h = c->eh;
   if (part == 0) {   // the kernel alone: the caller queues the pair kernel on the main stream before the rest
@@ -2036,13 +2040,30 @@ int evb_enumerate_async(rpb_ctx* c, int part) {
   // for evb_max_states, surplus warps exit)
   { ScopedTimer t(c, T_EVB_SNAP); k_evb_snapshots<<<(MAXS + SNAP_WPB - 1) / SNAP_WPB, 32 * SNAP_WPB, 0, c->stream>>>(d, e, -1, g_scratch[c].recip_grids ? 0 : 1); }   // delta algebra: every rank needs the charges of every diabat
   c->n_launch += 1;
+  {
+    // geometry factors of the couplings need the images only (and the early clears: they add the Vex terms of the other
+    // chain molecules): launched for the diabats the early clears cover, before the host knows S; evb_build adds the rest
+    // in the rare step that gains more diabats than the margin
+    // On the read-back stream (idle once the enumeration has been copied): aux[0] must stay free for the per-step tables.
+    EvbScratch& sc = g_scratch[c];
+    const int cleared = std::min(MAXS, h.n_states_prev + CLEAR_MARGIN);
+    CKE(cudaEventRecord(c->ev_sync[18], c->stream));
+    StreamScope ss(c, c->aux[3]);
+    CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[18], 0));
+    CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[11], 0));
+    {
+      ScopedTimer t(c, T_EVB_COUPLING_GEO);
+      k_evb_coupling_geo<<<(cleared + GEO_WPB - 1) / GEO_WPB, 32 * GEO_WPB, 0, c->stream>>>(d, e, sc.geo, 0, cleared);
+    }
+    CKE(cudaEventRecord(c->ev_sync[19], c->stream));
+    c->n_launch += 1;
+  }
   return 0;
 }
 
 // Accumulators of the build (per-diabat force deltas, coupling forces, item energies, Vex, candidate counters) for the
 // diabats [0, previous S + CLEAR_MARGIN): the number of diabats changes slowly, and evb_build clears the rest in the rare
 // step that gains more.  The bound comes from the host (the enumeration kernel is rewriting the device copy of S).
-#define CLEAR_MARGIN 8
 void evb_clear_early(rpb_ctx* c) {
   const int cleared = std::min(MAXS, c->eh.n_states_prev + CLEAR_MARGIN);
   k_evb_clear<<<148 * 2, 256, 0, c->stream>>>(c->d, c->e, g_scratch[c].cand_n, 0, cleared);
@@ -2165,7 +2186,11 @@ int evb_build(rpb_ctx* c) {
     StreamScope ss(c, c->aux[0]);
     CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[11], 0));      // the early clears (aux[1])
     const int cleared = std::min(MAXS, h.n_states_prev + CLEAR_MARGIN);
-    if (S > cleared) { k_evb_clear<<<148 * 2, 256, 0, c->stream>>>(d, e, sc.cand_n, cleared, S); c->n_launch++; }
+    if (S > cleared) {
+      k_evb_clear<<<148 * 2, 256, 0, c->stream>>>(d, e, sc.cand_n, cleared, S);
+      k_evb_coupling_geo<<<(S - cleared + GEO_WPB - 1) / GEO_WPB, 32 * GEO_WPB, 0, c->stream>>>(d, e, sc.geo, cleared, S);
+      c->n_launch += 2;
+    }
     CKE(cudaMemcpyAsync(sc.pack_dev, sc.pack_host, PACK_BYTES, cudaMemcpyHostToDevice, c->stream));
   }
   h.n_states_prev = S;
@@ -2234,12 +2259,8 @@ int evb_build(rpb_ctx* c) {
   {
     // aux[0] (behind images, clears and the per-step tables): off-diagonal couplings
     StreamScope ss(c, c->aux[0]);
-    {
-      ScopedTimer t(c, T_EVB_COUPLING_GEO);
-      k_evb_coupling_geo<<<(S + GEO_WPB - 1) / GEO_WPB, 32 * GEO_WPB, 0, c->stream>>>(d, e, sc.geo);
-      c->n_launch += 1;
-    }
     if (n_own > 0) {
+      CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[19], 0));     // coupling geometry (aux[3])
       ScopedTimer t(c, T_EVB_COUPLING);
       dim3 g(n_own, (N + 256 * VEX_APT - 1) / (256 * VEX_APT));
       k_evb_coupling_vex<<<g, 256, 0, c->stream>>>(d, e, sc.geo, sc.state_list);
@@ -2299,8 +2320,10 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
   if (!coeff_override_host) {
   // read back what the host needs for the commit decision and the accessors right behind the solver: the host waits
   // for THIS event only, while the mixing kernels queued below are still running
-  CKE(cudaMemcpyAsync(pd, e.result, SOLVER_BLOCK_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CKE(cudaEventRecord(c->ev_enum, c->stream));
+  CKE(cudaEventRecord(c->ev_sync[17], c->stream));
+  CKE(cudaStreamWaitEvent(c->aux[3], c->ev_sync[17], 0));
+  CKE(cudaMemcpyAsync(pd, e.result, SOLVER_BLOCK_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, c->aux[3]));   // copy stream: the mixing kernels do not queue behind it
+  CKE(cudaEventRecord(c->ev_enum, c->aux[3]));
   }
   {
     int include_principal = 1;            // every rank holds its share of the principal-diabat force (pair forces are sharded by atoms)

@@ -87,17 +87,17 @@ int calculate_total_force_energy(rpb_ctx* c, bool evb_principal) {
     if (c->d.rank == 0) stream_depend(c, 8, c->main_stream, c->aux[2]);   // fork ahead of the pair kernel
     launch_pair_verlet(c, true);
     {
-      StreamScope sc(c, c->aux[0]);
-      rc = evb_enumerate_async(c, 1);
-      if (rc) return rc;
-    }
-    {
       // aux[1] has slack before its first consumer: the accumulators of the build are cleared here, off both chains
       StreamScope sc(c, c->aux[1]);
       evb_clear_early(c);
       cudaEventRecord(c->ev_sync[11], c->stream);
       launch_spread_principal(c);
       cudaEventRecord(c->ev_sync[15], c->stream);   // scaled coordinates ready (pair matrix of the chain atoms, aux[2])
+    }
+    {   // after the clears have been queued: the coupling geometry launched here waits for them (event 11)
+      StreamScope sc(c, c->aux[0]);
+      rc = evb_enumerate_async(c, 1);
+      if (rc) return rc;
     }
     if (c->d.rank == 0) { StreamScope sc(c, c->aux[2]); launch_molecule_terms(c); }
     return 0;
