@@ -1,9 +1,10 @@
 """ncu --set full report (.ncu-rep) -> per-kernel summary CSV (averaged over the captured launches) and the DRAM
 traffic JSON that bench.py attaches to its roofline objects.
-usage: extract_ncu_summary.py report.ncu-rep out_summary.csv out_traffic.json workload"""
+usage: extract_ncu_summary.py report.ncu-rep|raw_page.csv out_summary.csv out_traffic.json workload"""
 import csv, json, subprocess, sys, collections, io
 rep, out_csv, out_json, workload = sys.argv[1:5]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# a .csv argument is the raw page already exported on the GPU box (ncu -i report --page raw --csv)
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr = rows[0]
 cols = {"duration_us": "gpu__time_duration.sum", "dram_read_B": "dram__bytes_read.sum", "dram_write_B": "dram__bytes_write.sum",
