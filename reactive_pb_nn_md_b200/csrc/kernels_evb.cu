@@ -235,7 +235,7 @@ __device__ void load_principal_image(const Dev& d, int mol, MolImage& im) {
   int f = d.mol_first[mol];
   for (int a = 0; a < im.n_atom; a++) {
     double4 p = d.xq[f + a];
-    im.atom[a] = f + a; im.type[a] = d.type[f + a]; im.q[a] = p.w; im.mass[a] = d.mass[f + a];
+    im.atom[a] = f + a; im.ratom[a] = f + a; im.type[a] = d.type[f + a]; im.q[a] = p.w; im.mass[a] = d.mass[f + a];
     im.x[a][0] = p.x; im.x[a][1] = p.y; im.x[a][2] = p.z;
   }
   for (int k = 0; k < 3; k++) im.r_com[k] = d.r_com[3 * mol + k];
@@ -265,11 +265,11 @@ __device__ void image_proton_transfer(const Dev& d, MolImage& D, MolImage& A, in
   const EvbTables& E = *d.evb;
   // shift_array_data_donor_acceptor_transfer: the proton leaves the donor and is appended to the acceptor
   int last = A.n_atom;
-  A.atom[last] = D.atom[i_atom_donor]; A.type[last] = D.type[i_atom_donor]; A.q[last] = D.q[i_atom_donor];
+  A.atom[last] = D.atom[i_atom_donor]; A.ratom[last] = D.ratom[i_atom_donor]; A.type[last] = D.type[i_atom_donor]; A.q[last] = D.q[i_atom_donor];
   A.mass[last] = D.mass[i_atom_donor];
   for (int k = 0; k < 3; k++) A.x[last][k] = D.x[i_atom_donor][k];
   for (int a = i_atom_donor; a < D.n_atom - 1; a++) {
-    D.atom[a] = D.atom[a + 1]; D.type[a] = D.type[a + 1]; D.q[a] = D.q[a + 1]; D.mass[a] = D.mass[a + 1];
+    D.atom[a] = D.atom[a + 1]; D.ratom[a] = D.ratom[a + 1]; D.type[a] = D.type[a + 1]; D.q[a] = D.q[a + 1]; D.mass[a] = D.mass[a + 1];
     for (int k = 0; k < 3; k++) D.x[a][k] = D.x[a + 1][k];
   }
   D.n_atom -= 1; A.n_atom += 1;
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(32 * SNAP_WPB) k_evb_snapshots(Dev d, EvbDev e
       if (a == 0) { im.n_atom = n; im.mtype = d.mol_type[mol]; for (int c = 0; c < 3; c++) im.r_com[c] = d.r_com[3 * mol + c]; }
       if (a < n) {
         double4 p = d.xq[f + a];
-        im.atom[a] = f + a; im.type[a] = d.type[f + a]; im.q[a] = p.w; im.mass[a] = d.mass[f + a];
+        im.atom[a] = f + a; im.ratom[a] = f + a; im.type[a] = d.type[f + a]; im.q[a] = p.w; im.mass[a] = d.mass[f + a];
         im.x[a][0] = p.x; im.x[a][1] = p.y; im.x[a][2] = p.z;
       }
     }
@@ -1785,6 +1785,51 @@ __global__ void k_evb_rcp_patch(Dev d, EvbDev e, RecipDev r, double* __restrict_
   spread_atom_warp(d, Qmix, u, D, 1.0, lane);
 }
 
+// Reference quirk (ms_evb.f90:2523-2656): every force array of diabat s -- its diagonal force, its reciprocal-space
+// force, its coupling force -- is mapped back to the principal atom order by undoing the proton TRANSFERS only; the
+// re-ordering of a protonated acceptor to its molecule-type template (reorder_molecule_data_structures, :941-1006, e.g. a
+// sulfonate protonated on an oxygen that is not its last) is not undone, so the diabat's force on such an atom g is
+// credited to the atom t that sits at g's position in the principal order.  Everything here is computed on the true
+// atoms; this kernel moves the mixed contribution X_s(g) = c_s^2 F_s(g) + 2 c_p c_s Foff_s(g) from g to t, one warp
+// per diabat, one lane per (chain molecule, atom) of its final topology.  (Water / hydronium never re-order.)
+__global__ void k_evb_reorder_quirk(Dev d, EvbDev e, RecipDev r, double* __restrict__ out, int recip_algebra) {
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * 4 + wib;
+  if (s < 1 || s >= *e.n_states) return;
+  const Snapshot& Sn = e.snap[s * NLEV + e.n_hops[s]];
+  const int k = lane / MA, a = lane % MA;
+  if (k >= Sn.n_mol || a >= Sn.m[k].n_atom) return;
+  const int g = Sn.m[k].atom[a], t = Sn.m[k].ratom[a];
+  if (g == t) return;
+  const size_t n3 = (size_t)3 * d.N;
+  const double w = e.coef2[s], wc = e.coef2[MAXS + s];
+  double X[3] = {0.0, 0.0, 0.0};
+  // diagonal force of diabat s on g: principal-diabat force (this rank's share) + the hop deltas along the chain (owned ones)
+  for (int c = 0; c < 3; c++) X[c] = w * e.dF[3 * g + c];
+  for (int q = s; q > 0; q = e.parent[q])
+    if (state_owned(q, d.rank, d.world))
+      for (int c = 0; c < 3; c++) X[c] = fma(w, e.dF[(size_t)q * n3 + 3 * g + c], X[c]);
+  if (state_owned(s, d.rank, d.world))
+    for (int c = 0; c < 3; c++) X[c] = fma(wc, e.Foff[(size_t)s * n3 + 3 * g + c], X[c]);
+  if (recip_algebra && d.rank == 0) {
+    // reciprocal-space force of diabat s on g: -K kk q_g(s) [ G_g + sum_b dq_b(s) N_gb ]
+    const int mol = d.mol_of_atom[g];
+    const int sg = r.mol_slot[mol] * MA + (g - d.mol_first[mol]);
+    const size_t plane = (size_t)RA_SLOTS * RA_SLOTS;
+    double f0 = r.G[3 * sg], f1 = r.G[3 * sg + 1], f2 = r.G[3 * sg + 2];
+    const int n = r.st_n[s];
+    for (int j = 0; j < n; j++) {
+      const size_t o = (size_t)sg * RA_SLOTS + r.st_slot[s * RA_ENT + j];
+      const double dqb = r.st_dq[s * RA_ENT + j];
+      f0 = fma(dqb, r.Nx[o], f0); f1 = fma(dqb, r.Nx[plane + o], f1); f2 = fma(dqb, r.Nx[2 * plane + o], f2);
+    }
+    const double Kd = (double)d.K, qs = w * Sn.m[k].q[a];
+    X[0] += -(Kd * d.kk[0]) * (qs * f0); X[1] += -(Kd * d.kk[1]) * (qs * f1); X[2] += -(Kd * d.kk[2]) * (qs * f2);
+  }
+  for (int c = 0; c < 3; c++) { atomicAdd(&out[3 * g + c], -X[c]); atomicAdd(&out[3 * t + c], X[c]); }
+}
+
+
 // gather of the mixed grid for the atoms [i0, i1)
 __global__ void k_evb_gather_range(Dev d, const double* __restrict__ theta, double* __restrict__ out, int i0, int i1) {
   int w = i0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
@@ -2349,7 +2394,8 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
         if (rc2) return rc2;
       }
       { ScopedTimer t(c, T_EVB_MIXF); k_evb_mix_forces<<<(unsigned)((n3 + 255) / 256), 256, 0, c->stream>>>(d, e, sc.state_list, n_own, include_principal, in_place);
-        if (S > 1 && d.rank == 0) { k_evb_rcp_mix<<<(S * RA_ENT + 127) / 128, 128, 0, c->stream>>>(d, e, sc.rd, out); c->n_launch++; } }
+        if (S > 1 && d.rank == 0) { k_evb_rcp_mix<<<(S * RA_ENT + 127) / 128, 128, 0, c->stream>>>(d, e, sc.rd, out); c->n_launch++; }
+        if (S > 1 && c->evb_may_reorder) { k_evb_reorder_quirk<<<(S + 3) / 4, 128, 0, c->stream>>>(d, e, sc.rd, out, 1); c->n_launch++; } }
       stream_depend(c, 1, c->aux[1], c->main_stream);
       const int i0 = (int)((long long)N * d.rank / d.world), i1 = (int)((long long)N * (d.rank + 1) / d.world);
       { ScopedTimer t(c, T_EVB_GATHERMIX); k_evb_gather_range<<<((i1 - i0) * 32 + 255) / 256, 256, 0, c->stream>>>(d, d.theta + K3, out, i0, i1); }

@@ -14,6 +14,9 @@ struct MolImage {
   int n_atom;
   int mtype;                  // molecule type at this level
   int atom[RPB_MA];           // principal (global) atom index of each image atom, in diabat order
+  int ratom[RPB_MA];          // principal index the REFERENCE attributes this position's force to: its back-mapping
+                              // (map_diabat_force_to_principle_recursive, ms_evb.f90:2608-2656) undoes the proton transfers
+                              // but not reorder_molecule_data_structures -- tracks the transfers, ignores the re-ordering
   int type[RPB_MA];
   double q[RPB_MA];
   double mass[RPB_MA];

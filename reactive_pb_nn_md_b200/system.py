@@ -117,6 +117,79 @@ def build_water_box(n_side, with_hydronium=False, n_molecules=None, seed=2017101
     return sysm
 
 
+def build_acid_box(n_side=10, seed=20171017, density=0.03334, temperature=300.0, jitter=0.05, ff=None, ion_pair=False):
+    """BASELINE config 1 -- the reference's own example system: one CH3SO3H (united-atom methyl, 6 sites) in water, the
+    acid at the centre of the lattice with its O-H pointing at the +x lattice neighbour (so that proton-transfer
+    diabats so3h + h2o -> so3 + h3o exist), the lattice sites within 3.3 A of its heavy atoms left out to make room.  Molecule types
+    in the order of the example topology: so3h, so3, h3o, h2o.  ion_pair: the same geometry written as the contact ion pair
+    CH3SO3- + H3O+ (molecules so3, h3o, waters; the H3O+ donates to the sulfonate oxygen): the acid diabat is the ground
+    state, so the first evaluation commits the hop h3o + so3 -> h2o + so3h and re-orders the acceptor to its template."""
+    rng = np.random.default_rng(seed)
+    if ff is None:
+        ff = example_forcefield(molecule_type_order=("so3h", "so3", "h3o", "h2o"))
+    n_sites = n_side ** 3
+    L = round((n_sites / density) ** (1.0 / 3.0), 2)
+    a0 = L / n_side
+    sites = np.array([(i, j, k) for i in range(n_side) for j in range(n_side) for k in range(n_side)], float)
+    centre = np.array([n_side // 2] * 3, float)
+    # acid geometry: tetrahedral S, O_ah along +x, C / O_a / O_a on the cone at 109.47 degrees
+    eye = np.eye(3)
+    sS = (centre + 0.5) * a0 + np.array([-1.2, 0.0, 0.0])
+    cone = lambda phi: np.array([-1.0 / 3.0, 2.0 * np.sqrt(2.0) / 3.0 * np.cos(phi), 2.0 * np.sqrt(2.0) / 3.0 * np.sin(phi)])
+    C = sS + 1.77 * cone(np.radians(90.0))
+    Oa1 = sS + 1.45 * cone(np.radians(210.0))
+    Oa2 = sS + 1.45 * cone(np.radians(330.0))
+    Oah = sS + 1.60 * eye[0]
+    Ha = Oah + 0.97 * np.array([np.cos(np.radians(40.0)), 0.0, np.sin(np.radians(40.0))])   # S-O-H = 140 degrees: dihedral C-S-O-H defined
+    acceptor = centre + np.array([1.0, 0.0, 0.0])
+    acid = np.array([C, sS, Oa1, Oa2, Oah, Ha])
+    pos = (sites + 0.5) * a0
+    dmin = np.sqrt(((pos[:, None, :] - acid[None, :5, :]) ** 2).sum(axis=2)).min(axis=1)
+    keep = (dmin > 3.3) | (sites == centre).all(axis=1) | (sites == acceptor).all(axis=1)
+    sites = sites[keep]
+    ic = int(np.where((sites == centre).all(axis=1))[0][0])
+    order = np.concatenate(([ic], np.delete(np.arange(len(sites)), ic)))
+    eye = np.eye(3)
+    names, coords = [], []
+    for n, idx in enumerate(order):
+        o = (sites[idx] + 0.5) * a0 + rng.normal(0.0, jitter, 3)
+        if n == 0 and ion_pair:
+            names.append("so3")
+            coords += [C, sS, Oah, Oa1, Oa2]                    # the oxygen that will be protonated is NOT last: exercises the re-ordering
+        elif n == 0:
+            names.append("so3h")
+            coords += list(acid)                                # atom order of [ moleculetype ] so3h
+        elif (sites[idx] == acceptor).all() and ion_pair:
+            o = (sites[idx] + 0.5) * a0
+            names.append("h3o")
+            coords.append(o)
+            coords += [o + h for h in _h3o_geometry([-eye[0], eye[1], eye[2]])]
+        elif (sites[idx] == acceptor).all():
+            # the acceptor: lone pair towards the acid, both O-H pointing away from it
+            h1, h2 = _water_geometry(rng, eye[0], eye[1])
+            names.append("h2o")
+            coords += [o, o + h1, o + h2]
+        else:
+            ax = rng.choice(3, 2, replace=False)
+            a = eye[ax[0]] * rng.choice([-1.0, 1.0]); b = eye[ax[1]] * rng.choice([-1.0, 1.0])
+            h1, h2 = _water_geometry(rng, a, b)
+            names.append("h2o")
+            coords += [o, o + h1, o + h2]
+    xyz = np.round(np.array(coords), 2)
+    sysm = System(ff, L, names, xyz)
+    sigma = np.sqrt(tables.BOLTZMANN * temperature / sysm.mass * tables.CONV_KJMOL)
+    v = rng.normal(size=(sysm.n_atoms, 3)) * sigma[:, None]
+    p = (sysm.mass[:, None] * v).sum(axis=0)
+    v -= p / sysm.mass.sum()
+    sysm.velocity = np.ascontiguousarray(v)
+    return sysm
+
+
+def config_c1(**kw):
+    """BASELINE config 1: CH3SO3H + 993 H2O (the reference's example input), MS-EVB, 2985 atoms, L~31.1 A."""
+    return build_acid_box(10, **kw)
+
+
 def config_c2(n_side=15, **kw):
     """BASELINE config 2: non-reactive flexible water box, 3375 H2O = 10125 atoms, L~46.6 A."""
     return build_water_box(n_side, with_hydronium=False, **kw)

@@ -186,6 +186,67 @@ def test_peer_memory_exchange_between_processes(oracle_lib, world):
                 assert np.array_equal(q[k], z[0][k]), k                    # replicated state: bit-identical
 
 
+def _compare_full_state(sg, so):
+    a, b = sg.download_state(), so.download_state()
+    for k in ("atom_type", "mol_first_atom", "mol_n_atom", "mol_type"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["hydronium_mol"] == b["hydronium_mol"]
+    assert np.abs(a["charge"] - b["charge"]).max() == 0.0 and np.abs(a["mass"] - b["mass"]).max() == 0.0
+    assert np.abs(a["xyz"] - b["xyz"]).max() < 1e-9 and np.abs(a["velocity"] - b["velocity"]).max() < 1e-8
+    assert rel_rms(a["force"], b["force"]) < F_RTOL
+
+
+@pytest.mark.parametrize("ion_pair", [False, True])
+def test_reference_example_system_acid_in_water(cuda_lib, oracle_lib, ion_pair):
+    """BASELINE config 1, the reference's own example input (CH3SO3H in water: 6-site acid with G96 bonds, cosine
+    angles, proper + improper dihedrals, three basic oxygens on the conjugate base, coupling type of the acid pair).
+    ion_pair=False: the acid as principal diabat; every diabat's own force is compared (c = e_s).
+    ion_pair=True: the same geometry written as CH3SO3- + H3O+: the first evaluation commits the hop onto the
+    sulfonate, which protonates an oxygen that is not last in the molecule -> reorder_molecule_data_structures."""
+    s = system.build_acid_box(10, ion_pair=ion_pair)
+    p = small_params()
+    so = engine.Simulation(s, p, library=oracle_lib)
+    sg = engine.Simulation(s, p, library=cuda_lib)
+    vo, lo, _ = so.neighbor_list(); vg, lg, _ = sg.neighbor_list()
+    assert np.array_equal(vo, vg) and np.array_equal(lo, lg)
+    so.ms_evb_calculate_total_force_energy(); sg.ms_evb_calculate_total_force_energy()
+    eg, eo = sg.evb(), so.evb()
+    assert eg["n_states"] == eo["n_states"] >= 7 and np.array_equal(eg["proton_log"], eo["proton_log"])
+    assert np.array_equal(eg["coupling_matrix"], eo["coupling_matrix"])
+    scale = np.abs(np.diag(eo["hamiltonian"])).max()
+    assert np.abs(eg["hamiltonian"] - eo["hamiltonian"]).max() <= E_RTOL * max(scale, abs(so.energies()["E_elec"]))
+    assert abs(eg["adiabatic_potential"] - eo["adiabatic_potential"]) <= E_RTOL * max(abs(eo["adiabatic_potential"]), abs(so.energies()["E_elec"]))
+    assert eg["principal_diabat"] == eo["principal_diabat"] == (2 if ion_pair else 1)
+    assert eg["new_hydronium_mol"] == eo["new_hydronium_mol"]
+    assert_en = ("E_elec", "E_vdw", "E_bond", "E_angle", "E_dihedral", "E_recip")
+    for k in assert_en:
+        assert abs(sg.energies()[k] - so.energies()[k]) <= E_RTOL * max(abs(so.energies()[k]), abs(so.energies()["E_elec"])), k
+    if not ion_pair:
+        assert rel_rms(sg.forces(), so.forces()) < F_RTOL
+        for k in range(eo["n_states"]):
+            c = np.zeros(eo["n_states"]); c[k] = 1.0
+            assert rel_rms(sg.debug_mix_forces(c), so.debug_mix_forces(c)) < F_RTOL, k
+    _compare_full_state(sg, so)                                  # after a committed hop: permuted / retyped arrays identical
+    vo, lo, _ = so.neighbor_list(); vg, lg, _ = sg.neighbor_list()
+    assert np.array_equal(vo, vg) and np.array_equal(lo, lg)     # the commit rebuilds the list (ms_evb.f90:223-225)
+    so.md_integrate_atomic(12, ms_evb=True); sg.md_integrate_atomic(12, ms_evb=True)
+    _compare_full_state(sg, so)
+    assert sg.evb()["n_states"] == so.evb()["n_states"]
+
+
+def test_state_sharding_emulated_acid_ion_pair(cuda_lib, oracle_lib):
+    """three emulated ranks on the contact ion pair CH3SO3- + H3O+: the hop commit onto the sulfonate (re-ordered acceptor,
+    reference force back-mapping quirk) with the diabats' pieces spread over the ranks"""
+    s = system.build_acid_box(10, ion_pair=True)
+    p = small_params()
+    ref = engine.Simulation(s, p, library=oracle_lib); ref.ms_evb_calculate_total_force_energy()
+    ranks = [engine.Simulation(s, p, library=cuda_lib, rank=r, world_size=3) for r in range(3)]
+    _emulated_force(ranks)
+    for sim in ranks:
+        assert sim.evb()["principal_diabat"] == ref.evb()["principal_diabat"] == 2
+        _compare_full_state(sim, ref)
+
+
 def test_replica_ensemble_matches_individual_runs(cuda_lib):
     """rpb_ensemble_step (BASELINE config 5, replicas only): replicas driven concurrently by one host thread each end
     where the same replicas end when stepped one after the other."""
