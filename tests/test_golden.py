@@ -65,3 +65,34 @@ def test_cuda_matches_golden_nonreactive(cuda_lib):
 @pytest.mark.gpu
 def test_cuda_matches_golden_msevb(cuda_lib):
     check_msevb(engine.Simulation(water_system(10, hydronium=True), small_params(), library=cuda_lib), E_RTOL, F_RTOL)
+
+
+def check_acid_ion_pair(sim, etol, ftol):
+    """BASELINE config 1 written as CH3SO3- + H3O+: enumeration, Hamiltonian, the committed hop (re-ordered sulfonate)
+    and the force array AFTER the commit -- which carries the reference's back-mapping quirk (ms_evb.f90:2608-2656)"""
+    g = np.load(os.path.join(GOLD, "acid_ion_pair_msevb.npz"))
+    sim.ms_evb_calculate_total_force_energy()
+    ev, st, e = sim.evb(), sim.download_state(), sim.energies()
+    assert ev["n_states"] == int(g["n_states"]) and np.array_equal(ev["proton_log"], g["proton_log"])
+    assert ev["principal_diabat"] == int(g["principal_diabat"]) == 2 and ev["new_hydronium_mol"] == int(g["new_hydronium_mol"]) == 1
+    scale = max(np.abs(np.diag(g["hamiltonian"])).max(), abs(float(g["energies"][0])))
+    assert np.abs(ev["hamiltonian"] - g["hamiltonian"]).max() <= etol * scale
+    assert abs(ev["adiabatic_potential"] - float(g["adiabatic_potential"])) <= etol * scale
+    for k, name in enumerate(("E_elec", "E_vdw", "E_bond", "E_angle", "E_dihedral", "E_recip")):
+        assert abs(e[name] - float(g["energies"][k])) <= etol * scale, name
+    assert np.array_equal(st["atom_type"][:12], g["atom_type_head"]) and np.array_equal(st["mol_type"][:4], g["mol_type_head"])
+    assert np.array_equal(st["mol_n_atom"][:4], g["mol_n_atom_head"])
+    assert np.abs(st["xyz"][:12] - g["xyz_head"]).max() < 1e-12
+    assert np.abs(st["force"][:24] - g["force_head"]).max() <= ftol * np.abs(g["force_head"]).max()
+    assert abs((st["force"] ** 2).sum() - g["force_sq_sum"]) <= 2 * ftol * g["force_sq_sum"]
+
+
+def test_oracle_matches_golden_acid_ion_pair(oracle_lib):
+    from reactive_pb_nn_md_b200 import system
+    check_acid_ion_pair(engine.Simulation(system.build_acid_box(10, ion_pair=True), small_params(), library=oracle_lib), 1e-12, 1e-11)
+
+
+@pytest.mark.gpu
+def test_cuda_matches_golden_acid_ion_pair(cuda_lib):
+    from reactive_pb_nn_md_b200 import system
+    check_acid_ion_pair(engine.Simulation(system.build_acid_box(10, ion_pair=True), small_params(), library=cuda_lib), E_RTOL, F_RTOL)

@@ -35,4 +35,16 @@ np.savez_compressed(os.path.join(out, "h3o_water999_msevb.npz"), n_states=ev["n_
                     coupling_matrix=ev["coupling_matrix"], hamiltonian=ev["hamiltonian"], eigenvector=ev["eigenvector"],
                     adiabatic_potential=ev["adiabatic_potential"], principal_diabat=ev["principal_diabat"],
                     force_head=f[:96], force_sq_sum=(f ** 2).sum())
+# BASELINE config 1 as the contact ion pair CH3SO3- + H3O+: the first evaluation commits the hop onto the sulfonate
+from reactive_pb_nn_md_b200 import system  # noqa: E402
+s = system.build_acid_box(10, ion_pair=True)
+sim = engine.Simulation(s, small_params(), library=lib)
+sim.ms_evb_calculate_total_force_energy()
+ev = sim.evb(); st = sim.download_state(); e = sim.energies()
+np.savez_compressed(os.path.join(out, "acid_ion_pair_msevb.npz"), n_states=ev["n_states"], proton_log=ev["proton_log"],
+                    hamiltonian=ev["hamiltonian"], eigenvector=ev["eigenvector"], adiabatic_potential=ev["adiabatic_potential"],
+                    principal_diabat=ev["principal_diabat"], new_hydronium_mol=ev["new_hydronium_mol"],
+                    energies=np.array([e[k] for k in ("E_elec", "E_vdw", "E_bond", "E_angle", "E_dihedral", "E_recip")]),
+                    force_head=st["force"][:24], force_sq_sum=(st["force"] ** 2).sum(), atom_type_head=st["atom_type"][:12],
+                    mol_type_head=st["mol_type"][:4], mol_n_atom_head=st["mol_n_atom"][:4], xyz_head=st["xyz"][:12])
 print("golden vectors written to", out)
