@@ -54,9 +54,14 @@ __host__ __device__ inline bool state_owned(int s, int rank, int world) {
 #define ENUM_NEAR 40           // molecules inside the first-solvation cutoff of one molecule (~17 in water at 5 A)
 #define ENUM_HITS 12           // acceptor atoms inside the reactive-pair distance of one proton (10 are kept)
 #define ENUM_COMPACT 2048
+#define ENUM_SMEM_BYTES (ENUM_COMPACT * (3 * sizeof(double) + 3 * sizeof(int)))
 struct EnumFrame { int mol, v, diabat, count, ip, cursor; int log[MAXC][5]; };
 
 __global__ void __launch_bounds__(ENUM_TPB) k_evb_enumerate(Dev d, EvbDev e) {
+  extern __shared__ double compact_com[];        // dynamic: [ENUM_COMPACT][3] centres of mass of the compacted molecules, then their
+  int* compact_first = reinterpret_cast<int*>(compact_com + 3 * ENUM_COMPACT);   // first atom, molecule type and atom count
+  int* compact_type = compact_first + ENUM_COMPACT;
+  int* compact_nat = compact_type + ENUM_COMPACT;
   __shared__ int compact[ENUM_COMPACT];
   __shared__ int vis_mol[ENUM_MAXMOL];
   __shared__ unsigned char prot_n[ENUM_MAXMOL], prot[ENUM_MAXMOL][ENUM_MAXP], heavy[ENUM_MAXMOL][ENUM_MAXP];
@@ -66,6 +71,7 @@ __global__ void __launch_bounds__(ENUM_TPB) k_evb_enumerate(Dev d, EvbDev e) {
   __shared__ int nb[ENUM_MAXMOL][ENUM_MAXP][ENUM_HITS];          // acceptor molecule * 16 + acceptor atom
   __shared__ unsigned char nb_v[ENUM_MAXMOL][ENUM_MAXP][RPB_EVB_MAX_NEIGHBORS];
   __shared__ int s_ncomp, s_nvis, s_fail;
+  __shared__ double vis_com[ENUM_MAXMOL][3];
   __shared__ EnumFrame fr[MAXC + 1];
   const int tid = threadIdx.x, nth = blockDim.x;
   const int hyd = *d.hydronium;
@@ -85,7 +91,11 @@ __global__ void __launch_bounds__(ENUM_TPB) k_evb_enumerate(Dev d, EvbDev e) {
              a2 = min_image(d.r_com[3 * jm + 2] - c2, d.box[2]);
       if (a0 * a0 + a1 * a1 + a2 * a2 < R2) {
         int slot = atomicAdd(&s_ncomp, 1);
-        if (slot < ENUM_COMPACT) compact[slot] = jm;
+        if (slot < ENUM_COMPACT) {
+          compact[slot] = jm;
+          compact_com[3 * slot] = d.r_com[3 * jm]; compact_com[3 * slot + 1] = d.r_com[3 * jm + 1]; compact_com[3 * slot + 2] = d.r_com[3 * jm + 2];
+          compact_first[slot] = d.mol_first[jm]; compact_type[slot] = d.mol_type[jm]; compact_nat[slot] = d.mol_natom[jm];
+        }
       }
     }
   }
@@ -115,20 +125,23 @@ __global__ void __launch_bounds__(ENUM_TPB) k_evb_enumerate(Dev d, EvbDev e) {
       prot_n[vv] = (unsigned char)np;
     }
     // a) centre-of-mass test of find_evb_reactive_neighbors (:724-733), flattened over (molecule, compact entry)
+    for (int vv = lvl_begin + tid; vv < lvl_end; vv += nth)
+      for (int k = 0; k < 3; k++) vis_com[vv][k] = d.r_com[3 * vis_mol[vv] + k];
+    __syncthreads();
     for (int idx = tid; idx < nlvl * ncomp; idx += nth) {
-      const int vv = lvl_begin + idx / ncomp, jm = compact[idx % ncomp], im = vis_mol[vv];
+      const int vv = lvl_begin + idx / ncomp, cs = idx % ncomp, jm = compact[cs], im = vis_mol[vv];
       if (jm == im) continue;
       double dc2 = 0.0;
 #pragma unroll
-      for (int k = 0; k < 3; k++) {
-        double dr = d.r_com[3 * jm + k] - d.r_com[3 * im + k];
+      for (int k = 0; k < 3; k++) {      // same operands, same order as before: the values now come from shared memory
+        double dr = compact_com[3 * cs + k] - vis_com[vv][k];
         double shift = floor(d.inv_box[k] * dr + 0.5) * d.box[k];
-        double dc = d.r_com[3 * jm + k] - d.r_com[3 * im + k] - shift;
+        double dc = compact_com[3 * cs + k] - vis_com[vv][k] - shift;
         dc2 = k == 0 ? dc * dc : dc2 + dc * dc;
       }
       if (dc2 < d.cut_solv2) {
         int slot = atomicAdd(&near_n[vv], 1);
-        if (slot < ENUM_NEAR) near_mol[vv][slot] = jm; else s_fail = 3;
+        if (slot < ENUM_NEAR) near_mol[vv][slot] = cs; else s_fail = 3;      // compact slot of the near molecule
       }
     }
     __syncthreads();
@@ -136,16 +149,16 @@ __global__ void __launch_bounds__(ENUM_TPB) k_evb_enumerate(Dev d, EvbDev e) {
     for (int idx = tid; idx < nlvl * ENUM_MAXP * ENUM_NEAR; idx += nth) {
       const int vv = lvl_begin + idx / (ENUM_MAXP * ENUM_NEAR), ip = (idx / ENUM_NEAR) % ENUM_MAXP, kn = idx % ENUM_NEAR;
       if (ip >= prot_n[vv] || kn >= min(near_n[vv], ENUM_NEAR)) continue;
-      const int im = vis_mol[vv], jm = near_mol[vv][kn];
+      const int im = vis_mol[vv], cs = near_mol[vv][kn], jm = compact[cs];
       double4 ph = d.xq[d.mol_first[im] + prot[vv][ip]];
       double shift[3];
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        double dr = d.r_com[3 * jm + k] - d.r_com[3 * im + k];
+        double dr = compact_com[3 * cs + k] - vis_com[vv][k];
         shift[k] = floor(d.inv_box[k] * dr + 0.5) * d.box[k];
       }
-      const MolTypeDev& TJ = d.mt[d.mol_type[jm]];
-      const int fj = d.mol_first[jm], nj = d.mol_natom[jm];
+      const MolTypeDev& TJ = d.mt[compact_type[cs]];
+      const int fj = compact_first[cs], nj = compact_nat[cs];
       for (int ja = 0; ja < nj; ja++) {
         if (TJ.reactive_basic[ja] != 1) continue;
         double4 pj = d.xq[fj + ja];
@@ -2010,6 +2023,7 @@ int evb_alloc(rpb_ctx* c) {
   CKE(cudaMemset(e.n_states, 0, ENUM_BLOCK_INTS * sizeof(int)));
   CKE(cudaMemset(e.jac_sig, 0xff, (2 + MAXS * MAXC * 5) * sizeof(int)));
   CKE(cudaMemset(e.tree_mu, 0, 2 * sizeof(double)));
+  CKE(cudaFuncSetAttribute(k_evb_enumerate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENUM_SMEM_BYTES));
   { const char* sv = getenv("RPB_EVB_SOLVER"); c->evb_solver = (sv && std::string(sv) == "jacobi") ? 1 : 0; }
   return 0;
 }
@@ -2071,7 +2085,7 @@ int evb_enumerate_async(rpb_ctx* c, int part) {
   Dev& d = c->d; EvbDev& e = c->e; EvbHost& h = c->eh;
   if (part == 0) {   // the kernel alone: the caller queues the pair kernel on the main stream before the rest
     ScopedTimer t(c, T_EVB_ENUM);
-    k_evb_enumerate<<<1, ENUM_TPB, 0, c->stream>>>(d, e);
+    k_evb_enumerate<<<1, ENUM_TPB, ENUM_SMEM_BYTES, c->stream>>>(d, e);
     c->n_launch += 1;
     return 0;
   }
