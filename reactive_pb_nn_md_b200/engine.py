@@ -59,7 +59,8 @@ class _DevArray:
 
 
 class Simulation:
-    def __init__(self, system, params, library=None, device=0, rank=0, world_size=1, process_group=None):
+    def __init__(self, system, params, library=None, device=0, rank=0, world_size=1, process_group=None,
+                 evb_max_states=EVB_MAX_STATES, verlet_capacity=0):
         self.lib = library if library is not None else load_cuda()
         assert isinstance(self.lib, Library)
         self.dll = self.lib.dll
@@ -73,10 +74,10 @@ class Simulation:
         cfg.pme_grid, cfg.spline_order = params.pme_grid, params.spline_order
         cfg.spline_grid, cfg.erfc_grid, cfg.tt_grid = tables.SPLINE_GRID, tables.ERFC_GRID, tables.TT_GRID
         cfg.na_nslist, cfg.nb_nslist, cfg.nc_nslist = params.na_nslist, params.nb_nslist, params.nc_nslist
-        cfg.verlet_capacity = 0
+        cfg.verlet_capacity = int(verlet_capacity)      # 0: the reference's size formula (general_routines.f90:1231-1239)
         cfg.device, cfg.rank, cfg.world_size = device, rank, world_size
         cfg.n_threads = params.n_threads
-        cfg.evb_max_chain, cfg.evb_max_states = EVB_MAX_CHAIN, EVB_MAX_STATES
+        cfg.evb_max_chain, cfg.evb_max_states = EVB_MAX_CHAIN, int(evb_max_states)    # glob_v.f90:60,65
         for i, v in enumerate(system.box.flatten(order="F")):
             cfg.box[i] = v
         cfg.alpha_sqrt, cfg.real_space_cutoff = params.alpha_sqrt, params.real_space_cutoff
