@@ -102,18 +102,19 @@ int calculate_total_force_energy(rpb_ctx* c, bool evb_principal) {
     if (c->d.rank == 0) { StreamScope sc(c, c->aux[2]); launch_molecule_terms(c); }
     return 0;
   }
+  launch_pair_verlet(c, false);   // issued first (the longest kernel); the non-reactive call is never sharded
   {
+    // the whole reciprocal branch -- spreading, convolution AND the force gather (atomic adds into d.force, like the
+    // pair kernel's) -- runs next to the pair kernel
     StreamScope sc(c, c->aux[1]);
     launch_spread_principal(c);
     rc = launch_convolve(c, 0, 1, c->d.en + E_RECIP, true);
+    if (rc) return rc;
+    launch_gather(c, c->d.theta, c->d.force_recip, true);
   }
-  if (rc) return rc;
-  launch_pair_verlet(c, false);   // the non-reactive call is never sharded
   { StreamScope sc(c, c->aux[0]); launch_molecule_terms(c); }
-  if (evb_principal) return 0;     // evb_build keeps both side streams busy and joins them before the Hamiltonian
   stream_depend(c, 2, c->aux[0], c->main_stream);
   stream_depend(c, 3, c->aux[1], c->main_stream);
-  launch_gather(c, c->d.theta, c->d.force_recip, true);
   return 0;
 }
 
