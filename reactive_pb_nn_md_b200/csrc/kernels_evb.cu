@@ -1043,9 +1043,10 @@ __global__ void __launch_bounds__(256) k_evb_coupling_vex(Dev d, EvbDev e, const
 }
 
 // one thread per owned diabat: H_ss, H_parent,s and the geometric part of the coupling force
-__device__ void assemble_state(const Dev& d, EvbDev& e, const CouplingGeo* geo, const int* __restrict__ last_item, const int* slot_of_state, int s) {
+__device__ void assemble_state(const Dev& d, EvbDev& e, const CouplingGeo* geo, const int* __restrict__ last_item, const int* slot_of_state, int s, bool defer_principal = false) {
   int S = *e.n_states;
   if (s >= MAXS) return;
+  if (s == 0 && defer_principal) return;      // H_11 is assembled by k_evb_finalize_principal once the pair forces are done
   e.h_diag[s] = 0.0; e.h_diag[MAXS + s] = 0.0; e.h_diag[2 * MAXS + s] = 0.0;
   if (s == 0) {
     // principal energy: calculate_total_force_energy + repulsion + reference (ms_evb.f90:411-436).  Sharded runs: every
@@ -1085,10 +1086,10 @@ __global__ void k_evb_assemble(Dev d, EvbDev e, const CouplingGeo* geo, const in
 // Hellmann-Feynman weights from the ground-state vector e.evec (whole CTA; caller has synchronised):
 // c_s^2 (diagonal), 2 c_parent c_s (coupling) (ms_evb.f90:298-303), and the subtree sums used by the hop-tree
 // de-duplication of the real-space deltas.
-__device__ void hellmann_feynman_weights(const Dev& d, EvbDev& e, int S, int tid, int nth) {
+__device__ void hellmann_feynman_weights(const Dev& d, EvbDev& e, int S, int tid, int nth, bool with_status = true) {
   // error flags and energy slots ride along in the solver's read-back block
-  if (tid < 4) e.status_copy[tid] = (double)d.err_flag[tid];
-  if (tid < E_NSLOT) e.status_copy[4 + tid] = (d.world > 1) ? e.h_diag[3 * MAXS + tid] : d.en[tid];
+  if (with_status && tid < 4) e.status_copy[tid] = (double)d.err_flag[tid];
+  if (with_status && tid < E_NSLOT) e.status_copy[4 + tid] = (d.world > 1) ? e.h_diag[3 * MAXS + tid] : d.en[tid];
   for (int i = tid; i < MAXS; i += nth) {
     double ci = i < S ? e.evec[i] : 0.0;
     e.coef2[i] = ci * ci;
@@ -1155,15 +1156,19 @@ __device__ __forceinline__ bool tree_pivots(TreeShared& T, int S, int maxlev, in
 }
 
 // geo != nullptr (single rank): the Hamiltonian elements are assembled here first (one launch less on the critical path)
+// defer_principal: the ground state only needs the diabats' energies RELATIVE to H_11, so the solver can run while the
+// principal diabat's pair forces are still being computed; H_11 itself, the absolute energies and the status / energy
+// slots of the read-back block are then filled in by k_evb_finalize_principal.
 __global__ void __launch_bounds__(TREE_TPB) k_evb_tree_solver(Dev d, EvbDev e, const double* coeff_override, const CouplingGeo* geo,
-                                                                const int* __restrict__ last_item, const int* slot_of_state) {
+                                                                const int* __restrict__ last_item, const int* slot_of_state, int defer_principal) {
   __shared__ TreeShared T;
   const int S = *e.n_states;
   const int tid = threadIdx.x, nth = blockDim.x, i = tid;
   if (geo) {
-    assemble_state(d, e, geo, last_item, slot_of_state, tid);
+    assemble_state(d, e, geo, last_item, slot_of_state, tid, defer_principal != 0);
     __syncthreads();     // h_diag is read back below by the same CTA
   }
+  const double h11 = defer_principal ? 0.0 : e.h_diag[0];
   if (coeff_override) {
     for (int k = tid; k < S; k += nth) e.evec[k] = coeff_override[k];
     __syncthreads();
@@ -1174,7 +1179,7 @@ __global__ void __launch_bounds__(TREE_TPB) k_evb_tree_solver(Dev d, EvbDev e, c
     // H_ss = H_11 + sum of the hop deltas along the chain (root first) + (E_rec(s) - E_rec(1))   ms_evb.f90:1546, 2083
     int chain[MAXC + 1], nc = 0;
     for (int t = i; t > 0 && nc <= MAXC; t = e.parent[t]) chain[nc++] = t;
-    double Hs = e.h_diag[0], dl = 0.0;
+    double Hs = h11, dl = 0.0;
     for (int k = nc - 1; k >= 0; k--) { Hs = Hs + e.h_diag[chain[k]]; dl = dl + e.h_diag[chain[k]]; }
     Hs = Hs + e.h_diag[2 * MAXS + i]; dl = dl + e.h_diag[2 * MAXS + i];
     e.h_full[i] = Hs; e.h_full[MAXS + i] = (i > 0) ? e.h_diag[MAXS + i] : 0.0;
@@ -1271,7 +1276,7 @@ __global__ void __launch_bounds__(TREE_TPB) k_evb_tree_solver(Dev d, EvbDev e, c
   }
   if (i < S) e.evec[i] = T.y[i];
   if (tid == 0) {
-    *e.e_ground = e.h_diag[0] + mu;
+    *e.e_ground = h11 + mu;
     int pd = 0;
     double coef = fabs(T.y[0]);
     for (int k = 0; k < S; k++) if (coef < fabs(T.y[k])) { coef = fabs(T.y[k]); pd = k; }
@@ -1284,7 +1289,21 @@ __global__ void __launch_bounds__(TREE_TPB) k_evb_tree_solver(Dev d, EvbDev e, c
     e.tree_mu[0] = mu; e.tree_mu[1] = (status == 0) ? 1.0 : 0.0;
   }
   __syncthreads();
-  hellmann_feynman_weights(d, e, S, tid, nth);
+  hellmann_feynman_weights(d, e, S, tid, nth, defer_principal == 0);
+}
+
+// H_11 = energy of the principal diabat (calculate_total_force_energy + EVB repulsion + reference energy, ms_evb.f90:411-436)
+// once its pair forces and bonded terms are complete; absolute H_ss, the adiabatic energy and the status / energy slots of
+// the read-back block.  One CTA of MAXS threads, behind k_evb_tree_solver(defer_principal = 1).
+__global__ void k_evb_finalize_principal(Dev d, EvbDev e) {
+  const int tid = threadIdx.x, S = *e.n_states;
+  const double E_elec = d.en[E_ELEC] + d.en[E_RECIP] + d.ewald_self;
+  double H11 = E_elec + d.en[E_VDW] + d.en[E_BOND] + d.en[E_ANGLE] + d.en[E_DIH];
+  H11 = H11 + e.item_energy[0];
+  if (tid < S) e.h_full[tid] = H11 + e.h_full[tid];
+  if (tid == 0) { e.h_diag[0] = H11; *e.e_ground = H11 + *e.e_ground; }
+  if (tid < 4) e.status_copy[tid] = (double)d.err_flag[tid];
+  if (tid < E_NSLOT) e.status_copy[4 + tid] = d.en[tid];
 }
 
 // ================================================================================================
@@ -2326,10 +2345,21 @@ int evb_build(rpb_ctx* c) {
       c->n_launch += 1;
     }
   }
-  stream_depend(c, 6, c->aux[0], c->main_stream);
-  stream_depend(c, 7, c->aux[1], c->main_stream);
+  // Single rank, tree solver, delta algebra: the ground state needs only energies RELATIVE to H_11, so the solver (and the
+  // averaged-grid convolution behind it) must not wait for the principal diabat's pair forces -- the longest kernel of the
+  // step on large boxes.  The branches join on aux[0], where evb_mix runs the solver; the main stream (pair forces) is
+  // joined only by k_evb_finalize_principal and the force mixing.
+  h.overlap_solver = (d.world == 1 && c->evb_solver == 0 && algebra);
+  if (h.overlap_solver) {
+    stream_depend(c, 7, c->aux[1], c->aux[0]);
+    stream_depend(c, 13, c->aux[4], c->aux[0]);
+    CKE(cudaStreamWaitEvent(c->aux[0], c->ev_sync[19], 0));          // coupling geometry (aux[3])
+  } else {
+    stream_depend(c, 6, c->aux[0], c->main_stream);
+    stream_depend(c, 7, c->aux[1], c->main_stream);
+    stream_depend(c, 13, c->aux[4], c->main_stream);
+  }
   if (d.rank == 0) stream_depend(c, 9, c->aux[2], c->main_stream);   // bonded terms of the principal diabat
-  stream_depend(c, 13, c->aux[4], c->main_stream);
   if (d.world > 1 || c->evb_solver != 0) {
     ScopedTimer t(c, T_EVB_ASSEMBLE);
     k_evb_assemble<<<(MAXS + 31) / 32, 32, 0, c->stream>>>(d, e, sc.geo, sc.last_item, algebra ? nullptr : sc.slot_of_state);
@@ -2357,13 +2387,25 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
     CKE(cudaMemcpyAsync(sc.coeff_dev, coeff_override_host, S * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     coeff_dev = sc.coeff_dev;
   }
-  {
+  const bool fuse = (c->evb_solver == 0 && d.world == 1 && !coeff_override_host && h.assemble_pending);
+  const bool overlap = fuse && h.overlap_solver;
+  if (overlap) {
+    {
+      StreamScope ss(c, c->aux[0]);
+      ScopedTimer t(c, T_EVB_DIAG);
+      k_evb_tree_solver<<<1, TREE_TPB, 0, c->stream>>>(d, e, nullptr, sc.geo, sc.last_item, nullptr, 1);
+      CKE(cudaEventRecord(c->ev_sync[6], c->stream));               // "ground state known"
+    }
+    CKE(cudaStreamWaitEvent(c->main_stream, c->ev_sync[6], 0));     // main: [pair forces, bonded terms] + solver
+    k_evb_finalize_principal<<<1, MAXS, 0, c->main_stream>>>(d, e);
+    c->n_launch += 2;
+    h.assemble_pending = false;
+  } else {
     ScopedTimer t(c, T_EVB_DIAG);
     if (c->evb_solver == 0) {
-      const bool fuse = (d.world == 1 && !coeff_override_host && h.assemble_pending);
-      k_evb_tree_solver<<<1, TREE_TPB, 0, c->stream>>>(d, e, coeff_dev, fuse ? sc.geo : nullptr, sc.last_item, sc.recip_grids ? sc.slot_of_state : nullptr);
-      h.assemble_pending = false;
+      k_evb_tree_solver<<<1, TREE_TPB, 0, c->stream>>>(d, e, coeff_dev, fuse ? sc.geo : nullptr, sc.last_item, sc.recip_grids ? sc.slot_of_state : nullptr, 0);
       c->n_launch++;
+      h.assemble_pending = false;
     } else {
     const int np = S + (S & 1);
     size_t shmem = ((size_t)3 * np * np + 2 * np) * sizeof(double);
@@ -2392,7 +2434,8 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
     const bool algebra = !sc.recip_grids;
     const int in_place = (d.world == 1 && !coeff_override_host) ? 1 : 0;
     double* out = in_place ? d.force : e.f_mix;
-    stream_depend(c, 0, c->main_stream, c->aux[1]);
+    if (overlap) CKE(cudaStreamWaitEvent(c->aux[1], c->ev_sync[6], 0));   // the averaged grid needs the ground state, not the pair forces
+    else stream_depend(c, 0, c->main_stream, c->aux[1]);
     if (algebra) {
       // aux[1]: averaged charge deltas -> patch the copy of the principal grid -> ONE convolution; main: force mixing and the
       // chain atoms' own reciprocal terms; then the mixed grid is gathered once (sharded runs: this rank's slice of atoms)

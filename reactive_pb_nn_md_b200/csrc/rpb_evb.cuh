@@ -86,4 +86,5 @@ struct EvbHost {
   double evec[RPB_MAXS];
   bool built = false;
   bool assemble_pending = false;   // evb_build left the Hamiltonian assembly to the solver kernel
+  bool overlap_solver = false;     // the branches of evb_build were joined on aux[0] (not on the main stream): evb_mix runs the solver there
 };
