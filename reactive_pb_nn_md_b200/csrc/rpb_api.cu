@@ -633,8 +633,11 @@ int rpb_download_state(rpb_ctx* c, double* xyz, double* velocity, double* force,
   if (xyz || charge) CK(cudaMemcpyAsync(st.xq, c->d.xq, N * sizeof(double4), cudaMemcpyDeviceToHost, c->stream));
   if (velocity) CK(cudaMemcpyAsync(st.vel, c->d.vel, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   if (force) CK(cudaMemcpyAsync(st.force, c->d.force, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  if (mass) CK(cudaMemcpyAsync(st.mass, c->d.mass, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  if (atom_type_index) CK(cudaMemcpyAsync(st.type, c->d.type, N * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  // masses and atom types only change when a proton hop is committed: while the staging area still mirrors the device
+  // tables (state_cache_valid, see rpb_upload_state) they are served from it without a copy
+  const bool cached = c->state_cache_valid;
+  if (mass && !cached) CK(cudaMemcpyAsync(st.mass, c->d.mass, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (atom_type_index && !cached) CK(cudaMemcpyAsync(st.type, c->d.type, N * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   if (xyz || charge)
     for (int i = 0; i < N; i++) {
