@@ -362,7 +362,7 @@ def run_ours(args):
     if roofline and roofline["bound"] == "fp64":
         roofline["bound_note"] = ("FP64-pipe-bound kernel (neither 'hbm' nor 'tensor'): achieved = reference operation count "
                                   "(24 per listed + 56 per in-cutoff pair, each pair once) / launch time; ncu fp64 pipe utilisation "
-                                  "in profiles/r01_v4_ncu_full_summary.csv")
+                                  "in profiles/r01_v5_ncu_full_summary.csv")
 
     # ---- end-to-end through the reference-facing call with HOST buffers: upload x,v -> step -> download x,v,F + energies
     e2e = None
