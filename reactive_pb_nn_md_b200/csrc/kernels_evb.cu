@@ -2243,6 +2243,8 @@ int evb_build(rpb_ctx* c) {
         }
     }
     sc.n_rmol = nm; sc.n_rpair = np;
+    c->evb_may_reorder = false;
+    for (int k = 0; k < nm; k++) if (c->mt_multi_basic[c->mol_type[rmol[k]]]) c->evb_may_reorder = true;
   }
   int* slot_of_state = (int*)(sc.pack_host + PACK_OFF_SLOT_OF);
   int* slot_state = (int*)(sc.pack_host + PACK_OFF_SLOT_STATE);
@@ -2396,8 +2398,13 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
       k_evb_tree_solver<<<1, TREE_TPB, 0, c->stream>>>(d, e, nullptr, sc.geo, sc.last_item, nullptr, 1);
       CKE(cudaEventRecord(c->ev_sync[6], c->stream));               // "ground state known"
     }
-    CKE(cudaStreamWaitEvent(c->main_stream, c->ev_sync[6], 0));     // main: [pair forces, bonded terms] + solver
-    k_evb_finalize_principal<<<1, MAXS, 0, c->main_stream>>>(d, e);
+    // H_11, absolute energies and the read-back block: on the read-back stream, behind the solver and behind what the main
+    // stream holds so far (pair forces; bonded terms were joined by evb_build) -- not in the chain of the force mixing
+    CKE(cudaEventRecord(c->ev_sync[0], c->main_stream));
+    CKE(cudaStreamWaitEvent(c->aux[3], c->ev_sync[6], 0));
+    CKE(cudaStreamWaitEvent(c->aux[3], c->ev_sync[0], 0));
+    k_evb_finalize_principal<<<1, MAXS, 0, c->aux[3]>>>(d, e);
+    CKE(cudaStreamWaitEvent(c->main_stream, c->ev_sync[6], 0));     // main: [pair forces, bonded terms] + ground state -> mixing
     c->n_launch += 2;
     h.assemble_pending = false;
   } else {
@@ -2421,8 +2428,10 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
   if (!coeff_override_host) {
   // read back what the host needs for the commit decision and the accessors right behind the solver: the host waits
   // for THIS event only, while the mixing kernels queued below are still running
-  CKE(cudaEventRecord(c->ev_sync[17], c->stream));
-  CKE(cudaStreamWaitEvent(c->aux[3], c->ev_sync[17], 0));
+  if (!overlap) {
+    CKE(cudaEventRecord(c->ev_sync[17], c->stream));
+    CKE(cudaStreamWaitEvent(c->aux[3], c->ev_sync[17], 0));
+  }
   CKE(cudaMemcpyAsync(pd, e.result, SOLVER_BLOCK_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, c->aux[3]));   // copy stream: the mixing kernels do not queue behind it
   CKE(cudaEventRecord(c->ev_enum, c->aux[3]));
   }

@@ -367,7 +367,7 @@ int rpb_set_molecule_types(rpb_ctx* c, const int* n_atom, const int* atom_type, 
       m.reactive_basic[a] = evb_reactive_basic_atoms ? evb_reactive_basic_atoms[t * MA + a] : 0;
       for (int b = 0; b < MA; b++) m.pair_excl[a][b] = pair_exclusions[t * MA * MA + a + MA * b];
     }
-    { int nb = 0; for (int a = 0; a < MA; a++) nb += (m.reactive_basic[a] == 1); if (nb > 1) c->evb_may_reorder = true; }
+    { int nb = 0; for (int a = 0; a < MA; a++) nb += (m.reactive_basic[a] == 1); c->mt_multi_basic.resize(c->d.nMT, 0); c->mt_multi_basic[t] = nb > 1; }
     m.n_bond = n_bond[t]; m.n_angle = n_angle[t]; m.n_dih = n_dihedral[t];
     for (int b = 0; b < m.n_bond; b++) {
       int i = bonds[2 * (ob + b)] - 1, j = bonds[2 * (ob + b) + 1] - 1;

@@ -57,8 +57,9 @@ struct rpb_ctx {
   EvbHost eh;                  // pinned host read-back area + per-step host state
   int grid_capacity = 0;       // number of K^3 grids usable in d.Q / d.theta (4 spare ones follow for the rounded FFT batch)
   int evb_solver = 0;          // 0: tree-structured ground-state solver (default)  1: block Jacobi (RPB_EVB_SOLVER=jacobi)
-  bool evb_may_reorder = false; // some molecule type has more than one atom of a type that can be protonated: a protonated acceptor may be
-                               // re-ordered to its template (reference quirk handled by k_evb_reorder_quirk)
+  std::vector<char> mt_multi_basic;   // per molecule type: more than one atom that can be protonated
+  bool evb_may_reorder = false; // this step, some chain molecule has such a type: a protonated acceptor may be re-ordered to its
+                               // template (reference quirk handled by k_evb_reorder_quirk)
   double evb_rcand = 0.0;      // candidate-list radius of the diabat real-space deltas
   double evb_rep_reach = 0.0;  // largest cutoff of the EVB proton-acceptor repulsion
   // pinned scratch
