@@ -10,13 +10,24 @@ import bench
 from reactive_pb_nn_md_b200 import engine
 from reactive_pb_nn_md_b200._binding import Library
 
-libs = [Library(os.path.abspath(p)) for p in sys.argv[1:3]]
+# an argument "NAME=VALUE:path" sets that environment variable while the context of that build is created
+specs = []
+for a in sys.argv[1:3]:
+    env, path = (a.split(":", 1) if "=" in a.split(":", 1)[0] else ("", a))
+    specs.append((env, path))
+libs = [Library(os.path.abspath(p)) for _, p in specs]
 wl = sys.argv[3] if len(sys.argv) > 3 else "c3"
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 100
 rounds = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 evb = bench.WORKLOADS[wl]["ms_evb"]
 s = bench.build_system(wl)
-sims = [engine.Simulation(s, bench.params_for(wl), library=l) for l in libs]
+sims = []
+for (env, _), l in zip(specs, libs):
+    if env:
+        k, v = env.split("=", 1); os.environ[k] = v
+    sims.append(engine.Simulation(s, bench.params_for(wl), library=l))
+    if env:
+        del os.environ[k]
 for sim in sims:
     (sim.ms_evb_calculate_total_force_energy if evb else sim.calculate_total_force_energy)()
     sim.md_integrate_atomic(20, ms_evb=evb)
