@@ -2088,7 +2088,7 @@ static void host_items(rpb_ctx* c, std::vector<EvbItem>& items) {
 struct HostClock {
   static bool on() { static const bool v = getenv("RPB_DEBUG_HOST") != nullptr; return v; }
   static double now() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-  static double acc[8]; static long n;
+  static thread_local double acc[8]; static thread_local long n;   // per host thread: rpb_ensemble_step drives one context per thread
   static void report() {
     if (!on() || ++n % 20) return;
     fprintf(stderr, "[host us/step] principal-launch %.0f | wait-enumerate %.0f | build-launch %.0f | mix-launch %.0f | wait-mix %.0f | commit %.0f\n",
@@ -2096,8 +2096,8 @@ struct HostClock {
     for (int k = 0; k < 8; k++) acc[k] = 0;
   }
 };
-double HostClock::acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-long HostClock::n = 0;
+thread_local double HostClock::acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+thread_local long HostClock::n = 0;
 
 #define CLEAR_MARGIN 8
 int evb_enumerate_async(rpb_ctx* c, int part) {

@@ -434,7 +434,7 @@ static void verlet_common(rpb_ctx* c, int force_rebuild) {
   int ncell = d.ncx * d.ncy * d.ncz;
   double* blk_top2 = d.maxd + 8;
   int nb = nblk(d.N);
-  static int coop_blocks = 0;
+  static int coop_blocks = 0;     // same for every context of the process: one process drives one kind of device
   if (!coop_blocks) {
     int per_sm = 0, sms = 0, dev = 0;
     cudaGetDevice(&dev);
