@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_verlet(Dev d, int i_begin, 
     // pending load, so every lane works on PAIR_B neighbours at once -- PAIR_B list entries, then PAIR_B 32-byte
     // coordinate gathers, then PAIR_B 32-byte table gathers are issued back to back (one exposed latency per batch and
     // stage instead of one per neighbour), and the list entries of the next batch are fetched a full batch ahead.
-    // (Measured on B200, C3: 107 us one neighbour at a time -> 59 us with PAIR_B = 4; staging the gathers through
+    // (Measured on B200, C3, first version: 107 us one neighbour at a time -> 59 us with PAIR_B = 4; staging the gathers through
     // shared memory with cp.async was slower, 142 us -- twice the L1 wavefronts for 16-byte copies.)
     int jn[PAIR_B];
 #pragma unroll
@@ -181,7 +181,13 @@ void launch_pair_verlet(rpb_ctx* c, bool shard) {
     case 5: launch_pair_variant<4, 256, 2>(c, shard); break;
     case 6: launch_pair_variant<2, 128, 6>(c, shard); break;
     case 7: launch_pair_variant<4, 128, 3>(c, shard); break;
-    default: launch_pair_variant<3, 256, 2>(c, shard); break;   // best of the sweep on B200 (C3): 89 us
+    case 8: launch_pair_variant<3, 128, 3>(c, shard); break;
+    case 9: launch_pair_variant<3, 192, 2>(c, shard); break;
+    case 10: launch_pair_variant<2, 256, 2>(c, shard); break;
+    case 11: launch_pair_variant<2, 192, 3>(c, shard); break;
+    default: launch_pair_variant<2, 256, 2>(c, shard); break;   // best of the sweep on B200: batches of 2 x 32 neighbours fit 128 registers without
+                                                                // spills (3 x 32 spills loaded coordinates to local memory in the hot loop: ncu source
+                                                                // page, profiles/README.md); C2 107 -> 97 us, C4 260 -> 234 us
   }
   c->n_launch += 1;
 }
