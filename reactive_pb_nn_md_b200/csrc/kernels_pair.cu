@@ -185,6 +185,8 @@ void launch_pair_verlet(rpb_ctx* c, bool shard) {
     case 9: launch_pair_variant<3, 192, 2>(c, shard); break;
     case 10: launch_pair_variant<2, 256, 2>(c, shard); break;
     case 11: launch_pair_variant<2, 192, 3>(c, shard); break;
+    case 12: launch_pair_variant<2, 128, 4>(c, shard); break;
+    case 13: launch_pair_variant<2, 512, 1>(c, shard); break;
     default: launch_pair_variant<2, 256, 2>(c, shard); break;   // best of the sweep on B200: batches of 2 x 32 neighbours fit 128 registers without
                                                                 // spills (3 x 32 spills loaded coordinates to local memory in the hot loop: ncu source
                                                                 // page, profiles/README.md); C2 107 -> 97 us, C4 260 -> 234 us
