@@ -37,8 +37,22 @@ __device__ __noinline__ void sapt_pair(const double* __restrict__ tt_t, const do
   fs += fac / dr2;
 }
 
-template <int PAIR_B, int TPB_, int MINB>
+// BF: branch-free evaluation -- out-of-cutoff (and padding) lanes run the same arithmetic on harmless operands (r^2 = 1, q_i q_j = 0,
+// table entry 1) instead of sitting out behind divergent branches; the in-cutoff lanes execute exactly the same operations.
+// 1/sqrt(x) for x in the range of squared pair distances (normal, far from the exponent limits): single-precision seed
+// and two Newton-Raphson steps in fp64 -- no special-case branches, ~2 ulp (the library routine: 1 ulp)
+__device__ __forceinline__ double rsqrt_pair(double x) {
+  double y = (double)rsqrtf((float)x);
+  const double h = 0.5 * x;
+  y = y * fma(-h * y, y, 1.5);
+  y = y * fma(-h * y, y, 1.5);
+  return y;
+}
+
+// MODE bit 0 (BF), bit 1: rsqrt_pair instead of the library rsqrt
+template <int PAIR_B, int TPB_, int MINB, int MODE = 0>
 __global__ void __launch_bounds__(TPB_, MINB) k_pair_verlet(Dev d, int i_begin, int i_end) {
+  constexpr bool BF = (MODE & 1) != 0, FR = (MODE & 2) != 0;
   extern __shared__ double sh_par[];           // [nT*nT][6] vdw parameters
   __shared__ int sh_vt[RPB_MAXT * RPB_MAXT];   // atype_vdw_type; 2 = SAPT row with all-zero coefficients (contributes exactly 0)
   __shared__ double sh_red[32];
@@ -90,11 +104,22 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_verlet(Dev d, int i_begin, 
         dz = fma(-bz, floor(fma(dz, ibz, 0.5)), dz);
         const double dr2 = fma(dz, dz, fma(dy, dy, dx * dx));
         in[k] = j[k] >= 0 && dr2 < d.rc2;
+        if (BF) {
+          const double d2 = in[k] ? dr2 : 1.0;
+          const double inv_r = FR ? rsqrt_pair(d2) : rsqrt(d2);
+          const double x1 = (d2 * inv_r) * d.inv_erfc_dx;
+          const double ci = ceil(x1);
+          tb[k] = ldg256(&d.es2_t[in[k] ? (int)ci : 1]);
+          sc2[k] = (x1 + 1.0) - ci;
+          sinv[k] = inv_r;
+          sdx[k] = dx; sdy[k] = dy; sdz[k] = dz; sqq[k] = in[k] ? pi.w * p[k].w : 0.0;
+          continue;
+        }
         tb[k] = make_double4(0.0, 0.0, 0.0, 0.0);
         sdx[k] = dx; sdy[k] = dy; sdz[k] = dz; sqq[k] = pi.w * p[k].w;
         sinv[k] = 1.0; sc2[k] = 0.0;
         if (in[k]) {
-          const double inv_r = rsqrt(dr2);
+          const double inv_r = FR ? rsqrt_pair(dr2) : rsqrt(dr2);
           // linear_interpolation_ewald_tables  pair_int_real_space.f90:740-759
           const double x1 = (dr2 * inv_r) * d.inv_erfc_dx;
           const double ci = ceil(x1);
@@ -105,14 +130,21 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_verlet(Dev d, int i_begin, 
       }
 #pragma unroll
       for (int k = 0; k < PAIR_B; k++) {   // energies and force of the in-cutoff pairs
-        if (!in[k]) continue;
-        const int pidx = ti + (j[k] >> 24);
+        if (!BF && !in[k]) continue;
+        const int pidx = BF ? (in[k] ? ti + (j[k] >> 24) : 0) : ti + (j[k] >> 24);
         const double inv_r = sinv[k], inv_r2 = inv_r * inv_r, c1 = 1.0 - sc2[k];
         const double qr = sqq[k] * inv_r;
         e_el = fma(qr, fma(sc2[k], tb[k].z, c1 * tb[k].x), e_el);
         double fs = (qr * inv_r2) * fma(sc2[k], tb[k].w, c1 * tb[k].y);
-        const int vt = sh_vt[pidx];
-        if (vt == 0) {                       // pairwise_real_space_LJ :621-645
+        const int vt = (BF && !in[k]) ? -1 : sh_vt[pidx];
+        if (BF) {                            // LJ with the coefficients masked to zero for every lane that has no LJ term
+          const bool lj = vt == 0;
+          const double c12 = lj ? sh_par[6 * pidx] : 0.0, c6 = lj ? sh_par[6 * pidx + 1] : 0.0;
+          const double r6 = inv_r2 * inv_r2 * inv_r2, c12r6 = c12 * r6;
+          e_vdw = fma(r6, c12r6 - c6, e_vdw);
+          fs = fma(inv_r2 * r6, 12.0 * c12r6 - 6.0 * c6, fs);
+          if (vt == 1) sapt_pair(d.tt, d.dtt, d.tt_max, d.tt_grid, 1.0 / inv_r2, &sh_par[6 * pidx], e_vdw, fs);
+        } else if (vt == 0) {                // pairwise_real_space_LJ :621-645
           const double c12 = sh_par[6 * pidx], c6 = sh_par[6 * pidx + 1];
           const double r6 = inv_r2 * inv_r2 * inv_r2, c12r6 = c12 * r6;
           e_vdw = fma(r6, c12r6 - c6, e_vdw);
@@ -159,7 +191,7 @@ __global__ void k_molecule_terms(Dev d) {
   e = block_sum(E.e_dih, sh_red);  if (threadIdx.x == 0) atomicAdd(&d.en[E_DIH], e);
 }
 
-template <int B, int T, int M>
+template <int B, int T, int M, int MODE = 0>
 static void launch_pair_variant(rpb_ctx* c, bool shard) {
   // state-sharded runs also shard the principal diabat's pair forces: rank r takes the atoms [N r / R, N (r+1) / R); the
   // partial forces and energies ride the two all-reduces the sharded step has anyway
@@ -167,7 +199,7 @@ static void launch_pair_variant(rpb_ctx* c, bool shard) {
   const int i0 = (int)((long long)N * r / R), i1 = (int)((long long)N * (r + 1) / R);
   const int wpb = T / 32, blocks = std::max(1, (i1 - i0 + wpb - 1) / wpb);
   const size_t shmem = (size_t)c->d.nT * c->d.nT * 6 * sizeof(double);
-  k_pair_verlet<B, T, M><<<blocks, T, shmem, c->stream>>>(c->d, i0, i1);
+  k_pair_verlet<B, T, M, MODE><<<blocks, T, shmem, c->stream>>>(c->d, i0, i1);
 }
 
 void launch_pair_verlet(rpb_ctx* c, bool shard) {
@@ -187,6 +219,11 @@ void launch_pair_verlet(rpb_ctx* c, bool shard) {
     case 11: launch_pair_variant<2, 192, 3>(c, shard); break;
     case 12: launch_pair_variant<2, 128, 4>(c, shard); break;
     case 13: launch_pair_variant<2, 512, 1>(c, shard); break;
+    case 14: launch_pair_variant<2, 256, 2, 1>(c, shard); break;
+    case 15: launch_pair_variant<3, 256, 2, 1>(c, shard); break;
+    case 16: launch_pair_variant<2, 256, 2, 2>(c, shard); break;
+    case 17: launch_pair_variant<2, 256, 2, 3>(c, shard); break;
+    case 18: launch_pair_variant<3, 256, 2, 3>(c, shard); break;
     default: launch_pair_variant<2, 256, 2>(c, shard); break;   // best of the sweep on B200: batches of 2 x 32 neighbours fit 128 registers without
                                                                 // spills (3 x 32 spills loaded coordinates to local memory in the hot loop: ncu source
                                                                 // page, profiles/README.md); C2 107 -> 97 us, C4 260 -> 234 us
