@@ -224,9 +224,9 @@ void launch_pair_verlet(rpb_ctx* c, bool shard) {
     case 16: launch_pair_variant<2, 256, 2, 2>(c, shard); break;
     case 17: launch_pair_variant<2, 256, 2, 3>(c, shard); break;
     case 18: launch_pair_variant<3, 256, 2, 3>(c, shard); break;
-    default: launch_pair_variant<2, 256, 2>(c, shard); break;   // best of the sweep on B200: batches of 2 x 32 neighbours fit 128 registers without
+    default: launch_pair_variant<2, 256, 2, 2>(c, shard); break;   // best of the sweep on B200: batches of 2 x 32 neighbours fit 128 registers without
                                                                 // spills (3 x 32 spills loaded coordinates to local memory in the hot loop: ncu source
-                                                                // page, profiles/README.md); C2 107 -> 97 us, C4 260 -> 234 us
+                                                                // page, profiles/README.md); C2 107 -> 97 us, C4 260 -> 234 us; with the branch-free rsqrt_pair 94 / 228 us
   }
   c->n_launch += 1;
 }
