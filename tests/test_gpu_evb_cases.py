@@ -247,6 +247,24 @@ def test_state_sharding_emulated_acid_ion_pair(cuda_lib, oracle_lib):
         _compare_full_state(sim, ref)
 
 
+def test_acid_trajectory_through_single_diabat_steps(cuda_lib, oracle_lib):
+    """the acid box loses its hydrogen bond within ~25 steps: the diabat count drops to 1 (no acceptor in range), a
+    degenerate MS-EVB step (nothing to couple, empty reciprocal-space algebra) that must still follow the oracle"""
+    s = system.build_acid_box(10)
+    p = small_params()
+    so = engine.Simulation(s, p, library=oracle_lib)
+    sg = engine.Simulation(s, p, library=cuda_lib)
+    so.ms_evb_calculate_total_force_energy(); sg.ms_evb_calculate_total_force_energy()
+    seen = set()
+    for _ in range(6):
+        so.md_integrate_atomic(6, ms_evb=True); sg.md_integrate_atomic(6, ms_evb=True)
+        assert sg.evb()["n_states"] == so.evb()["n_states"]
+        seen.add(so.evb()["n_states"])
+        assert abs(sg.evb()["adiabatic_potential"] - so.evb()["adiabatic_potential"]) <= 1e-9 * max(abs(so.evb()["adiabatic_potential"]), abs(so.energies()["E_elec"]))
+        assert np.abs(sg.download_state()["xyz"] - so.download_state()["xyz"]).max() < 1e-8
+    assert 1 in seen, seen
+
+
 def test_replica_ensemble_matches_individual_runs(cuda_lib):
     """rpb_ensemble_step (BASELINE config 5, replicas only): replicas driven concurrently by one host thread each end
     where the same replicas end when stepped one after the other."""
