@@ -207,6 +207,10 @@ int rpb_get_r_com(rpb_ctx*, double* r_com /*(3,M)*/);
 /* verlet_point(N+1), neighbor_list(n_pairs): 1-based values exactly as general_routines.f90:1517,1568. */
 int rpb_get_neighbor_list(rpb_ctx*, int* verlet_point, int* neighbor_list, int capacity, int* n_pairs,
                           int* flag_verlet_list);
+/* The pair list the force kernel itself consumes, expanded into (i, j) pairs, i < j, 1-based, sorted by (i, j): as a SET
+ * it must equal the half list above (the CUDA library keeps cluster-pair tiles with per-atom-pair masks and generates
+ * the reference-ordered list only for the accessor; the oracle returns its own list re-sorted).  n_tiles: list words. */
+int rpb_debug_tile_pairs(rpb_ctx*, int* pair_i, int* pair_j, long long capacity, long long* n_pairs, long long* n_tiles);
 /* PME parity accessors: Q_grid, theta_conv_Q (K,K,K) of diabat `state` (1 = principal), force_recip(3,N). */
 int rpb_get_pme(rpb_ctx*, int state, double* Q_grid, double* theta_conv_Q, double* force_recip);
 /* evb_hamiltonian(80,80) upper triangle, ground-state eigenvector c(S), evb_diabat_proton_log(80,3,5),

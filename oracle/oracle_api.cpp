@@ -233,6 +233,22 @@ int rpb_get_neighbor_list(rpb_ctx* c, int* verlet_point, int* neighbor_list, int
   return 0;
 }
 
+int rpb_debug_tile_pairs(rpb_ctx* c, int* pair_i, int* pair_j, long long capacity, long long* n_pairs, long long* n_tiles) {
+  const int N = c->sys.total_atoms;
+  const long long np = c->verlet_point[N] - 1;
+  if (n_pairs) *n_pairs = np;
+  if (n_tiles) *n_tiles = np;
+  if (pair_i && pair_j) {
+    if (capacity < np) { c->err = "pair buffer too small"; return RPB_ERR_ARG; }
+    std::vector<std::pair<int, int>> pr;
+    for (int i = 0; i < N; i++)
+      for (int k = c->verlet_point[i] - 1; k < c->verlet_point[i + 1] - 1; k++) pr.emplace_back(i + 1, c->neighbor_list[k]);
+    std::sort(pr.begin(), pr.end());
+    for (size_t k = 0; k < pr.size(); k++) { pair_i[k] = pr[k].first; pair_j[k] = pr[k].second; }
+  }
+  return 0;
+}
+
 int rpb_get_pme(rpb_ctx* c, int state, double* Q_grid, double* theta, double* force_recip) {
   const std::vector<double>* Q = &c->Q_grid; const std::vector<double>* T = &c->theta_conv_Q;
   if (state > 1) {

@@ -86,6 +86,7 @@ _PROTOS = {
     "rpb_download_state": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _ip, _ip, _ip]),
     "rpb_get_r_com": (C.c_int, [_vp, _dp]),
     "rpb_get_neighbor_list": (C.c_int, [_vp, _ip, _ip, C.c_int, _ip, _ip]),
+    "rpb_debug_tile_pairs": (C.c_int, [_vp, _ip, _ip, C.c_longlong, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "rpb_get_pme": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp]),
     "rpb_get_evb": (C.c_int, [_vp, _ip, _dp, _dp, _ip, _ip, _ip, _ip, _dp]),
     "rpb_debug_mix_forces": (C.c_int, [_vp, _dp, _dp]),

@@ -9,12 +9,16 @@
 //   evb_diabatic_coupling (+ geometric / function / electrostatics)      ms_evb.f90:1021-1403
 //   diagonalize_evb_hamiltonian + jacobi                                 ms_evb.f90:242-351, general_routines.f90:2013-2088
 //
-// Structure (all diabats of this rank in flight; SURVEY 7 "two-pass" reciprocal formulation):
-//   enumerate -> [host reads S + hop log: sizes the launches] -> snapshots -> item kernels (background + chain)
-//   -> batched delta grids Q_s = Q_1 -/+ patches -> ONE batched D2Z/Z2D over the owned diabats with the k-space
-//   energy fused into the CB pass -> per-diabat corrections for the few chain atoms -> coupling -> H elements.
-//   After the (optional) all-reduce of H: warp-level cyclic Jacobi -> theta_mix = sum c_s^2 theta_s (streaming)
-//   -> ONE gather for all atoms -> F = sum c_i c_j F_ij.
+// Structure (all diabats of this rank in flight; SURVEY 7 "two-pass" reciprocal formulation).  The HOST is not part of a
+// step: the enumeration kernel writes the diabat set AND the work lists every later kernel needs (EvbPlan: chain
+// molecules, chain-molecule pairs, owned diabats, chain atoms) to device memory; every kernel is launched with a grid
+// sized from a recent diabat count and loops over the device-side counts; the solver's hop decision is carried out by
+// device kernels that exit at once when no hop was selected.  One step is therefore a fixed launch sequence that
+// rpb_step replays as a CUDA graph.
+//   enumerate (+ plan) -> snapshots -> candidate lists -> item kernels (real-space / repulsion / bonded deltas of every
+//   diabat's last hop) | couplings (geometry, Vex) | reciprocal-space charge-delta algebra on the principal grid
+//   -> tree solver (ground state, hop decision) -> F = sum c_i c_j F_ij | averaged grid -> ONE convolution -> ONE gather
+//   -> hop commit (permutation + retyping + list rebuild) when the principal diabat changed.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -57,7 +61,7 @@ __host__ __device__ inline bool state_owned(int s, int rank, int world) {
 #define ENUM_SMEM_BYTES (ENUM_COMPACT * (3 * sizeof(double) + 3 * sizeof(int)))
 struct EnumFrame { int mol, v, diabat, count, ip, cursor; int log[MAXC][5]; };
 
-__global__ void __launch_bounds__(ENUM_TPB) k_evb_enumerate(Dev d, EvbDev e) {
+__global__ void __launch_bounds__(ENUM_TPB) k_evb_enumerate(Dev d, EvbDev e, int* __restrict__ cand_n) {
   extern __shared__ double compact_com[];        // dynamic: [ENUM_COMPACT][3] centres of mass of the compacted molecules, then their
   int* compact_first = reinterpret_cast<int*>(compact_com + 3 * ENUM_COMPACT);   // first atom, molecule type and atom count
   int* compact_type = compact_first + ENUM_COMPACT;
@@ -75,6 +79,10 @@ __global__ void __launch_bounds__(ENUM_TPB) k_evb_enumerate(Dev d, EvbDev e) {
   __shared__ EnumFrame fr[MAXC + 1];
   const int tid = threadIdx.x, nth = blockDim.x;
   const int hyd = *d.hydronium;
+  EvbPlan& plan = *e.plan;
+  __shared__ int s_S, s_ncmol, s_npair;
+  // the chain molecules of the previous step give their slots back
+  for (int k = tid; k < plan.n_cmol; k += nth) e.mol_slot[plan.cmol[k]] = -1;
   for (int i = tid; i < MAXS * MAXC * 5; i += nth) e.proton_log[i] = -1;
   for (int i = tid; i < MAXS; i += nth) { e.parent[i] = -1; e.n_hops[i] = 0; }
   for (int i = tid; i < ENUM_MAXMOL * ENUM_MAXP; i += nth) (&nb_n[0][0])[i] = 0;
@@ -237,7 +245,79 @@ __global__ void __launch_bounds__(ENUM_TPB) k_evb_enumerate(Dev d, EvbDev e) {
       else depth--;
     }
     *e.n_states = s_count;
+    s_S = s_count; s_ncmol = 1; s_npair = 0;
+    e.mol_slot[hyd] = 0;
   }
+  // ---- 4. this step's work lists (what the host used to derive from the read-back hop logs).  The enumeration's own
+  //         dynamic shared arrays are dead from here on: the pair-seen bit matrix, the ownership marks and the atom
+  //         offsets alias the compact list.
+  __syncthreads();
+  const int S = s_S;
+  unsigned int* seen = reinterpret_cast<unsigned int*>(compact_com);     // bit (i * RA_MOLS + j): pair already listed
+  constexpr int SEEN_WORDS = (RPB_RA_MOLS * RPB_RA_MOLS + 31) / 32;
+  int* own_mol = reinterpret_cast<int*>(seen + SEEN_WORDS);              // [RA_MOLS] chain molecule of a diabat this rank owns
+  int* uniq_base = own_mol + RPB_RA_MOLS;                                // [RA_MOLS + 1] first slot of the molecule's atoms in uniq_atom
+  for (int k = tid; k < SEEN_WORDS + 2 * RPB_RA_MOLS + 1; k += nth) seen[k] = 0u;
+  for (int k = tid; k < RPB_CAND_SLOTS; k += nth) cand_n[k] = 0;
+  // a) distinct chain molecules over all diabats: the first thread to claim a molecule gives it the next slot
+  if (tid >= 1 && tid < S) {
+    const int nh = e.n_hops[tid];
+    for (int h = 0; h < nh; h++) {
+      const int a = e.proton_log[(tid * MAXC + h) * 5 + 3];
+      if (atomicCAS(&e.mol_slot[a], -1, -2) == -1) {
+        const int slot = atomicAdd(&s_ncmol, 1);
+        if (slot < RPB_RA_MOLS) { plan.cmol[slot] = a; e.mol_slot[a] = slot; }
+        else { e.mol_slot[a] = 0; atomicMax(&d.err_flag[2], 1); }
+      }
+    }
+  }
+  if (tid == 0) plan.cmol[0] = hyd;
+  __syncthreads();
+  // b) ordered pairs of chain molecules that share a diabat; chain molecules of the diabats this rank owns
+  if (tid == 0) own_mol[0] = 1;
+  if (tid >= 1 && tid < S) {
+    int idx[CM], ni = 1;
+    idx[0] = 0;
+    const int nh = e.n_hops[tid];
+    for (int h = 0; h < nh; h++) {
+      const int mi = e.mol_slot[e.proton_log[(tid * MAXC + h) * 5 + 3]];
+      bool dup = false;
+      for (int q = 0; q < ni; q++) dup |= (idx[q] == mi);
+      if (!dup && ni < CM) idx[ni++] = mi;
+    }
+    const bool owned = state_owned(tid, d.rank, d.world);
+    for (int a = 0; a < ni; a++) {
+      if (owned) own_mol[idx[a]] = 1;
+      for (int b = 0; b < ni; b++) {
+        const int key = idx[a] * RPB_RA_MOLS + idx[b];
+        const unsigned int bit = 1u << (key & 31);
+        if (!(atomicOr(&seen[key >> 5], bit) & bit)) {
+          const int p = atomicAdd(&s_npair, 1);
+          if (p < RPB_RA_MAXPAIR) plan.molpair[p] = key; else atomicMax(&d.err_flag[2], 1);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // c) owned diabats (ascending) and the atoms of their chain molecules
+  const int ncm = min(s_ncmol, RPB_RA_MOLS);
+  if (tid == 0) {
+    int n_own = 0;
+    for (int s2 = 1; s2 < S; s2++) if (state_owned(s2, d.rank, d.world)) plan.state_list[n_own++] = s2;
+    int nu = 0;
+    for (int k = 0; k < ncm; k++) { uniq_base[k] = nu; if (own_mol[k]) nu += d.mol_natom[plan.cmol[k]]; }
+    uniq_base[ncm] = nu;
+    if (nu > RPB_CAND_SLOTS) { atomicMax(&d.err_flag[2], 1); nu = 0; }
+    plan.n_own = n_own; plan.n_uniq = nu; plan.n_cmol = ncm; plan.n_pair = min(s_npair, RPB_RA_MAXPAIR); plan.hop = 0;
+  }
+  __syncthreads();
+  if (uniq_base[ncm] <= RPB_CAND_SLOTS)
+    for (int t = tid; t < ncm * MA; t += nth) {
+      const int k = t / MA, a = t % MA;
+      if (!own_mol[k]) continue;
+      const int m = plan.cmol[k];
+      if (a < d.mol_natom[m]) plan.uniq_atom[uniq_base[k] + a] = d.mol_first[m] + a;
+    }
 }
 
 // ================================================================================================
@@ -405,7 +485,7 @@ struct ItemShared {
 };
 
 // executed by the whole CTA (tid 0 copies the images, threads t < RPB_MAXT resolve the parameter rows); caller syncs
-__device__ void fill_item_shared(const Dev& d, const Snapshot& S, const EvbItem& it, ItemShared& sh, int tid) {
+__device__ void fill_item_shared(const Dev& d, const Snapshot& S, const int donor_slot, const int acceptor_slot, ItemShared& sh, int tid) {
   const MolImage& H = S.m[S.hydronium];
   const EvbTables& E = *d.evb;
   if (tid == 0) {
@@ -413,13 +493,13 @@ __device__ void fill_item_shared(const Dev& d, const Snapshot& S, const EvbItem&
     for (int k = 0; k < S.n_mol; k++)
       for (int a = 0; a < S.m[k].n_atom; a++) sh.chain_atoms[sh.n_chain++] = S.m[k].atom[a];
     sh.nd = sh.na = 0;
-    if (it.donor_slot >= 0) {
-      const MolImage& D = S.m[it.donor_slot];
+    if (donor_slot >= 0) {
+      const MolImage& D = S.m[donor_slot];
       sh.nd = D.n_atom;
       for (int a = 0; a < D.n_atom; a++) { sh.d_atom[a] = D.atom[a]; sh.d_type[a] = D.type[a]; sh.d_q[a] = D.q[a]; for (int k = 0; k < 3; k++) sh.d_x[a][k] = D.x[a][k]; }
     }
-    if (it.acceptor_slot >= 0) {
-      const MolImage& A = S.m[it.acceptor_slot];
+    if (acceptor_slot >= 0) {
+      const MolImage& A = S.m[acceptor_slot];
       sh.na = A.n_atom;
       for (int a = 0; a < A.n_atom; a++) { sh.a_atom[a] = A.atom[a]; sh.a_type[a] = A.type[a]; sh.a_q[a] = A.q[a]; for (int k = 0; k < 3; k++) sh.a_x[a][k] = A.x[a][k]; }
     }
@@ -542,36 +622,40 @@ __device__ inline double repulsion_with_atom(const Dev& d, const ItemShared& sh,
 
 #define ITEM_TPB 256
 #define CAND_CAP 2048        // atoms inside the candidate radius of one chain atom (~420 at 10 A in water)
-#define CAND_SLOTS 1024      // distinct chain atoms over all diabats of a step
+#define CAND_SLOTS RPB_CAND_SLOTS
 
-// ---- candidate lists: for every distinct chain atom g (principal index; the host lists them from the hop log)
+// ---- candidate lists: for every distinct chain atom g (principal index; listed by the enumeration kernel, EvbPlan)
 // the atoms j whose minimum-image distance from g is below the candidate radius (real-space cutoff + margin, or the
 // EVB repulsion reach if that is larger), from the CURRENT positions -- so the set is exact, unlike a Verlet row
 // between rebuilds (the reference scans all N atoms per image atom, ms_evb.f90:1629-1841).  The item kernel applies
 // the reference's own cutoff test to the image position; this pass only removes the ~95 % of atoms that are far away,
 // once per chain atom instead of once per (diabat, topology, image atom).
-// grid = (ceil(N/256), n_unique)
-__global__ void __launch_bounds__(256) k_evb_candidates(Dev d, const int* __restrict__ uniq_atom, double r2cand,
+// grid = (ceil(N/256), a bound of the number of chain atoms; the slots beyond it are reached by the loop)
+__global__ void __launch_bounds__(256) k_evb_candidates(Dev d, EvbDev e, double r2cand,
                                                         int* __restrict__ chain_slot, int* __restrict__ cand, int* __restrict__ cand_n) {
-  const int slot = blockIdx.y, g = uniq_atom[slot];
   const int lane = threadIdx.x & 31;
-  if (blockIdx.x == 0 && threadIdx.x == 0) chain_slot[g] = slot;
-  const double4 pg = d.xq[g];
+  const int n_uniq = e.plan->n_uniq;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  bool hit = false;
-  if (j < d.N && j != g) {
-    double4 pj = d.xq[j];
-    double dx = min_image(pg.x - pj.x, d.box[0]), dy = min_image(pg.y - pj.y, d.box[1]), dz = min_image(pg.z - pj.z, d.box[2]);
-    hit = dx * dx + dy * dy + dz * dz < r2cand;
-  }
-  unsigned m = __ballot_sync(0xffffffffu, hit);
-  if (m) {
-    int leader = __ffs(m) - 1, base = 0;
-    if (lane == leader) base = atomicAdd(&cand_n[slot], __popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (hit) {
-      int p = base + __popc(m & ((1u << lane) - 1u));
-      if (p < CAND_CAP) cand[(size_t)slot * CAND_CAP + p] = j;
+  double4 pj = make_double4(0.0, 0.0, 0.0, 0.0);
+  if (j < d.N) pj = d.xq[j];
+  for (int slot = blockIdx.y; slot < n_uniq; slot += gridDim.y) {
+    const int g = e.plan->uniq_atom[slot];
+    if (blockIdx.x == 0 && threadIdx.x == 0) chain_slot[g] = slot;
+    const double4 pg = d.xq[g];
+    bool hit = false;
+    if (j < d.N && j != g) {
+      double dx = min_image(pg.x - pj.x, d.box[0]), dy = min_image(pg.y - pj.y, d.box[1]), dz = min_image(pg.z - pj.z, d.box[2]);
+      hit = dx * dx + dy * dy + dz * dz < r2cand;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m) {
+      int leader = __ffs(m) - 1, base = 0;
+      if (lane == leader) base = atomicAdd(&cand_n[slot], __popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (hit) {
+        int p = base + __popc(m & ((1u << lane) - 1u));
+        if (p < CAND_CAP) cand[(size_t)slot * CAND_CAP + p] = j;
+      }
     }
   }
 }
@@ -585,25 +669,44 @@ struct ItemBlock {
   double red[32];
 };
 
-// ITEM_SPLIT CTAs per (diabat, last hop, topology) item.
+// ITEM_SPLIT CTAs per (diabat, last hop, topology) item; item ids as in rpb_evb.cuh (0: principal diabat, 2s-1 / 2s: donor
+// / acceptor topology of the last hop of diabat s); the grid covers a bound of the item count, the loop the rest.
 //   every warp of every CTA : (image atom, 32-candidate chunk) tasks -- real-space pairs of the donor/acceptor image atoms
 //                             with the background atoms (ms_evb.f90:1629-1841); the chunks of the hydronium's heavy atom
 //                             also carry the EVB repulsion (ms_evb.f90:2259-2478)
 //   CTA 0 only, thread 0/32 : bonded + intramolecular terms of donor / acceptor   (ms_evb.f90:1472, 1849-1855)
 //   CTA 0 only, threads 64+ : pairs among the chain molecules                      (ms_evb.f90:1629-1841 restricted to chain atoms)
 //   CTA 0 only, warp 7      : repulsion of the hydronium image with chain atoms    (ms_evb.f90:2259-2478)
+struct ItemDesc { int state, level, donor_slot, acceptor_slot; double sign; };
+__device__ __forceinline__ bool item_describe(const Dev& d, const EvbDev& e, int item_id, int S, ItemDesc& it) {
+  if (item_id == 0) {     // sharded runs: the principal diabat's repulsion / reference energy is counted on rank 0
+    it.state = 0; it.level = 0; it.donor_slot = -1; it.acceptor_slot = -1; it.sign = 1.0;
+    return d.rank == 0;
+  }
+  const int s = (item_id + 1) >> 1, side = (item_id + 1) & 1;     // 2s-1 -> side 0 (donor topology), 2s -> side 1
+  if (s >= S || !state_owned(s, d.rank, d.world)) return false;
+  const int nh = e.n_hops[s];
+  it.state = s; it.level = nh - 1 + side; it.sign = side ? 1.0 : -1.0;
+  it.donor_slot = e.snap[s * NLEV + nh - 1].hydronium;            // the donor of hop h is the hydronium of level h
+  it.acceptor_slot = e.snap[s * NLEV + nh].hydronium;
+  return true;
+}
+
 __global__ void __launch_bounds__(ITEM_TPB) k_evb_items(Dev d, EvbDev e, const int* __restrict__ chain_slot,
                                                         const int* __restrict__ cand, const int* __restrict__ cand_n,
                                                         double rcand, double rep_reach) {
   __shared__ ItemBlock B;
   ItemShared& sh = B.sh;
-  const int item_id = e.real_list[blockIdx.x];
-  const EvbItem it = e.items[item_id];
+  const int n_items = 2 * (*e.n_states) - 1;
+  for (int item_id = blockIdx.x; item_id < n_items; item_id += gridDim.x) {
+  ItemDesc it;
+  if (!item_describe(d, e, item_id, *e.n_states, it)) continue;      // (uniform over the CTA)
+  __syncthreads();                                                    // the previous item of this CTA is done with B
   const Snapshot& S = e.snap[it.state * NLEV + it.level];
   const EvbTables& E = *d.evb;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int part = blockIdx.y, nparts = gridDim.y;
-  fill_item_shared(d, S, it, sh, tid);
+  fill_item_shared(d, S, it.donor_slot, it.acceptor_slot, sh, tid);
   for (int k = tid; k < CM * MA * 3; k += blockDim.x) (&B.fl[0][0])[k] = 0.0;
   __syncthreads();
   const int ds = it.donor_slot, as = it.acceptor_slot;
@@ -767,50 +870,6 @@ __global__ void __launch_bounds__(ITEM_TPB) k_evb_items(Dev d, EvbDev e, const i
     double v = B.fl[k][c];
     if (v != 0.0) atomicAdd(&outF[3 * sh.chain_atoms[k] + c], sign * v);
   }
-}
-
-// ================================================================================================
-// K2: batched delta grids.  Q_slot = Q_principal for every owned diabat (pure streaming copy), then
-// -/+ the B-spline patches of the donor / acceptor images (modify_Q_grid, |q| > 1e-6)
-// ================================================================================================
-__global__ void k_evb_broadcast_grid(const double* __restrict__ src, double* __restrict__ dst, size_t K3, int n_copies) {
-  size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 2;
-  if (i >= K3) return;
-  double2 v = *reinterpret_cast<const double2*>(src + i);
-  for (int g = 0; g < n_copies; g++) *reinterpret_cast<double2*>(dst + (size_t)g * K3 + i) = v;
-}
-
-// grid = n_items * 2*MA warps; mode 0: spread into Q_slot ; mode 1: reciprocal force correction from theta_slot
-__global__ void k_evb_item_pme(Dev d, EvbDev e, int n_items, const int* __restrict__ slot_of_state, int mode) {
-  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  int ii = w / (2 * MA), r = w % (2 * MA);
-  if (ii >= n_items) return;
-  const EvbItem it = e.items[ii];
-  if (it.donor_slot < 0) return;
-  const Snapshot& S = e.snap[it.state * NLEV + it.level];
-  const MolImage& I = S.m[r < MA ? it.donor_slot : it.acceptor_slot];
-  int a = r % MA;
-  if (a >= I.n_atom) return;
-  double q = I.q[a];
-  double u[3];
-  scaled_coords(d, I.x[a], u);
-  size_t K3 = (size_t)d.K * d.K * d.K;
-  int slot = slot_of_state[it.state];
-  if (mode == 0) {
-    if (!(fabs(q) > 1e-6)) return;    // modify_Q_grid pme.f90:296
-    spread_atom_warp(d, d.Q + K3 * slot, u, q, it.sign, lane);
-  } else {
-    double F[3];
-    gather_atom_warp(d, d.theta + K3 * slot, u, q, lane, F);
-    // slot of this atom in the diabat's chain-atom table (level-0 snapshot order)
-    const Snapshot& S0 = e.snap[it.state * NLEV];
-    int slot = -1, cnt = 0;
-    for (int k = 0; k < S0.n_mol; k++) for (int b = 0; b < S0.m[k].n_atom; b++) { if (S0.m[k].atom[b] == I.atom[a]) slot = cnt; cnt++; }
-    if (lane < 3 && slot >= 0) {
-      double v = lane == 0 ? F[0] : (lane == 1 ? F[1] : F[2]);
-      atomicAdd(&e.corr_f[((size_t)it.state * CM * MA + slot) * 3 + lane], it.sign * v);
-      if (lane == 0) e.corr_atom[it.state * CM * MA + slot] = I.atom[a];
-    }
   }
 }
 
@@ -866,14 +925,14 @@ __device__ void coupling_function(double& A, double& Vc, double dA[3][3], int ft
 // one warp per owned diabat s>=1: geometric factor and Zundel sites (lane 0, on a shared-memory copy of the final-level
 // snapshot), then the Vex terms of the OTHER chain molecules with (atom, site) pairs dealt to the lanes
 #define GEO_WPB 4
-__global__ void __launch_bounds__(32 * GEO_WPB) k_evb_coupling_geo(Dev d, EvbDev e, CouplingGeo* geo, int s_begin, int s_end) {
+__global__ void __launch_bounds__(32 * GEO_WPB) k_evb_coupling_geo(Dev d, EvbDev e, CouplingGeo* geo) {
   __shared__ Snapshot Ssh[GEO_WPB];
   __shared__ CouplingGeo Gsh[GEO_WPB];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int s = s_begin + blockIdx.x * GEO_WPB + w;
-  const int S = min(*e.n_states, s_end);
-  if (s >= S) return;
-  if (s == 0 || !state_owned(s, d.rank, d.world)) { if (lane == 0) geo[s].valid = 0; return; }
+  const int S = *e.n_states;
+  for (int s = blockIdx.x * GEO_WPB + w; s < S; s += gridDim.x * GEO_WPB) {     // (a warp keeps its own shared slot: no CTA barrier inside)
+  __syncwarp();
+  if (s == 0 || !state_owned(s, d.rank, d.world)) { if (lane == 0) geo[s].valid = 0; continue; }
   const EvbTables& E = *d.evb;
   const int nh = e.n_hops[s];
   Snapshot& Sn = Ssh[w];
@@ -970,19 +1029,23 @@ __global__ void __launch_bounds__(32 * GEO_WPB) k_evb_coupling_geo(Dev d, EvbDev
   }
   __syncwarp();
   warp_copy_struct(&geo[s], &G, lane);
+  }
 }
 
-// grid = (n_owned states list, ceil(N / (256 * VEX_APT))): Vex between the Zundel sites and the background atoms
+// grid = (bound of the owned diabats, ceil(N / (256 * VEX_APT))): Vex between the Zundel sites and the background atoms
 // (evb_diabatic_coupling_electrostatics, ms_evb.f90:1324-1397: no cutoff, minimum image by molecule).  Every thread
 // keeps VEX_APT atoms in registers, so that the per-site warp reductions of the site forces are paid once per
 // VEX_APT * 32 atoms; q/r and q/r^3 come from ONE rsqrt instead of a sqrt and two divisions (relative differences ~1e-16).
 #define VEX_APT 4
-__global__ void __launch_bounds__(256) k_evb_coupling_vex(Dev d, EvbDev e, const CouplingGeo* geo, const int* state_list) {
+__global__ void __launch_bounds__(256) k_evb_coupling_vex(Dev d, EvbDev e, const CouplingGeo* geo) {
   __shared__ double red[32];
   __shared__ double facc[8][2 * MA][3];
-  int s = state_list[blockIdx.x];
+  const int n_own = e.plan->n_own;
+  for (int io = blockIdx.x; io < n_own; io += gridDim.x) {
+  const int s = e.plan->state_list[io];
   const CouplingGeo& G = geo[s];
-  if (!G.valid) return;
+  if (!G.valid) continue;
+  __syncthreads();
   for (int k = threadIdx.x; k < 8 * 2 * MA * 3; k += blockDim.x) (&facc[0][0][0])[k] = 0.0;
   __syncthreads();
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1040,10 +1103,11 @@ __global__ void __launch_bounds__(256) k_evb_coupling_vex(Dev d, EvbDev e, const
     for (int ww = 0; ww < 8; ww++) t += facc[ww][n][c];
     atomicAdd(&Fo[3 * G.site_atom[n] + c], -G.A * t);
   }
+  }
 }
 
 // one thread per owned diabat: H_ss, H_parent,s and the geometric part of the coupling force
-__device__ void assemble_state(const Dev& d, EvbDev& e, const CouplingGeo* geo, const int* __restrict__ last_item, const int* slot_of_state, int s, bool defer_principal = false) {
+__device__ void assemble_state(const Dev& d, EvbDev& e, const CouplingGeo* geo, int s, bool defer_principal = false) {
   int S = *e.n_states;
   if (s >= MAXS) return;
   if (s == 0 && defer_principal) return;      // H_11 is assembled by k_evb_finalize_principal once the pair forces are done
@@ -1065,10 +1129,10 @@ __device__ void assemble_state(const Dev& d, EvbDev& e, const CouplingGeo* geo, 
   }
   if (s >= S || !state_owned(s, d.rank, d.world)) return;
   // energy delta of the last hop: acceptor-topology item minus donor-topology item (ms_evb.f90:1546)
-  const int ii = last_item[s];      // acceptor-topology item of the last hop; the donor-topology item precedes it
+  const int ii = 2 * s;             // acceptor-topology item of the last hop; the donor-topology item precedes it
   double dE = e.item_energy[ii] - e.item_energy[ii - 1];
   e.h_diag[s] = dE;
-  e.h_diag[2 * MAXS + s] = slot_of_state ? e.e_recip[slot_of_state[s]] - e.e_recip[0] : e.rcp_dE[s];   // null: delta algebra
+  e.h_diag[2 * MAXS + s] = e.rcp_dE[s];
   const CouplingGeo& G = geo[s];
   double pref = G.Vconst + e.vex[s];
   e.h_diag[MAXS + s] = pref * G.A;
@@ -1079,14 +1143,16 @@ __device__ void assemble_state(const Dev& d, EvbDev& e, const CouplingGeo* geo, 
     atomicAdd(&Fo[3 * G.atom_H + c], -pref * G.dA[2][c]);
   }
 }
-__global__ void k_evb_assemble(Dev d, EvbDev e, const CouplingGeo* geo, const int* __restrict__ last_item, const int* slot_of_state) {
-  assemble_state(d, e, geo, last_item, slot_of_state, blockIdx.x * blockDim.x + threadIdx.x);
+__global__ void k_evb_assemble(Dev d, EvbDev e, const CouplingGeo* geo) {
+  assemble_state(d, e, geo, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // Hellmann-Feynman weights from the ground-state vector e.evec (whole CTA; caller has synchronised):
 // c_s^2 (diagonal), 2 c_parent c_s (coupling) (ms_evb.f90:298-303), and the subtree sums used by the hop-tree
 // de-duplication of the real-space deltas.
 __device__ void hellmann_feynman_weights(const Dev& d, EvbDev& e, int S, int tid, int nth, bool with_status = true) {
+  // the hop decision for the commit kernels, and how many diabats' accumulators the next step clears ahead of its enumeration
+  if (tid == 0) { e.plan->hop = (e.result[1] != *d.hydronium) ? 1 : 0; e.plan->n_clear = min(MAXS, S + 8); }
   // error flags and energy slots ride along in the solver's read-back block
   if (with_status && tid < 4) e.status_copy[tid] = (double)d.err_flag[tid];
   if (with_status && tid < E_NSLOT) e.status_copy[4 + tid] = (d.world > 1) ? e.h_diag[3 * MAXS + tid] : d.en[tid];
@@ -1160,12 +1226,12 @@ __device__ __forceinline__ bool tree_pivots(TreeShared& T, int S, int maxlev, in
 // principal diabat's pair forces are still being computed; H_11 itself, the absolute energies and the status / energy
 // slots of the read-back block are then filled in by k_evb_finalize_principal.
 __global__ void __launch_bounds__(TREE_TPB) k_evb_tree_solver(Dev d, EvbDev e, const double* coeff_override, const CouplingGeo* geo,
-                                                                const int* __restrict__ last_item, const int* slot_of_state, int defer_principal) {
+                                                                int defer_principal) {
   __shared__ TreeShared T;
   const int S = *e.n_states;
   const int tid = threadIdx.x, nth = blockDim.x, i = tid;
   if (geo) {
-    assemble_state(d, e, geo, last_item, slot_of_state, tid, defer_principal != 0);
+    assemble_state(d, e, geo, tid, defer_principal != 0);
     __syncthreads();     // h_diag is read back below by the same CTA
   }
   const double h11 = defer_principal ? 0.0 : e.h_diag[0];
@@ -1502,29 +1568,15 @@ __global__ void __launch_bounds__(JAC_TPB) k_evb_jacobi(Dev d, EvbDev e, const d
 // ================================================================================================
 // K13: Hellmann-Feynman mixing
 // ================================================================================================
-// theta_mix = sum over owned grids of c_s^2 theta_slot   (streaming: reads n_slots*K^3, writes K^3)
-__global__ void k_evb_theta_mix(Dev d, EvbDev e, const int* __restrict__ slot_state, int n_slots) {
-  size_t K3 = (size_t)d.K * d.K * d.K;
-  size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 2;
-  if (i >= K3) return;
-  double ax = 0.0, ay = 0.0;
-  for (int g = 0; g < n_slots; g++) {
-    int s = slot_state[g];
-    if (s < 0) continue;
-    double w = e.coef2[s];
-    double2 t = *reinterpret_cast<const double2*>(d.theta + (size_t)g * K3 + i);
-    ax = fma(w, t.x, ax); ay = fma(w, t.y, ay);
-  }
-  *reinterpret_cast<double2*>(e.theta_mix + i) = make_double2(ax, ay);
-}
-
 // f_mix = [rank 0: principal force] + sum_s c_s^2 dF_s + 2 c_p c_s Foff_s   over owned diabats
 // in_place (single rank, ground-state mix): the principal-diabat force is still in d.force; it is saved to dF slot 0
 // (the per-state debug accessors need it later) and d.force receives the mixed force -- no copies before or after.
-__global__ void k_evb_mix_forces(Dev d, EvbDev e, const int* __restrict__ state_list, int n_list, int include_principal, int in_place) {
+__global__ void k_evb_mix_forces(Dev d, EvbDev e, int include_principal, int in_place) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   size_t n3 = (size_t)3 * d.N;
   if (i >= n3) return;
+  const int n_list = e.plan->n_own;
+  const int* __restrict__ state_list = e.plan->state_list;
   double f = 0.0;
   if (in_place) { f = d.force[i]; e.dF[i] = f; }
   else if (include_principal) f = e.dF[i];        // dF slot 0 holds the principal-diabat force (without F_rec)
@@ -1534,29 +1586,6 @@ __global__ void k_evb_mix_forces(Dev d, EvbDev e, const int* __restrict__ state_
     f = fma(e.coef2[MAXS + s], e.Foff[(size_t)s * n3 + i], f);
   }
   (in_place ? d.force : e.f_mix)[i] = f;
-}
-
-// + sum_s c_s^2 * (reciprocal-space corrections of the chain atoms of diabat s)   ms_evb.f90:2103-2248
-__global__ void k_evb_add_corr(Dev d, EvbDev e, const int* __restrict__ state_list, int n_list, double* __restrict__ out) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_list * CM * MA) return;
-  int s = state_list[t / (CM * MA)], slot = t % (CM * MA);
-  int atom = e.corr_atom[s * CM * MA + slot];
-  if (atom < 0) return;
-  double w = e.coef2[s];
-  for (int c = 0; c < 3; c++) atomicAdd(&out[3 * atom + c], w * e.corr_f[((size_t)s * CM * MA + slot) * 3 + c]);
-}
-
-__global__ void k_evb_gather_mix(Dev d, EvbDev e, double* __restrict__ out) {
-  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= d.N) return;
-  double u[3] = {d.uscale[3 * w], d.uscale[3 * w + 1], d.uscale[3 * w + 2]};
-  double F[3];
-  gather_atom_warp(d, e.theta_mix, u, d.xq[w].w, lane, F);
-  if (lane < 3) {
-    double v = lane == 0 ? F[0] : (lane == 1 ? F[1] : F[2]);
-    out[3 * w + lane] += v;
-  }
 }
 
 
@@ -1579,15 +1608,14 @@ __global__ void k_evb_gather_mix(Dev d, EvbDev e, double* __restrict__ out) {
 // Two convolutions per step instead of S+1, no per-diabat grid traffic; differences from the per-diabat transforms are
 // rounding only (~1e-13 relative, checked against the grid path, RPB_EVB_RECIP=grids, in tests/).
 // ================================================================================================
-#define RA_MOLS (MAXS + 1)            // distinct chain molecules of a step
+#define RA_MOLS RPB_RA_MOLS           // distinct chain molecules of a step
 #define RA_SLOTS (RA_MOLS * MA)       // chain-atom slots: (chain molecule, atom offset inside the molecule)
-#define RA_MAXPAIR (8 * MAXS + 8)     // ordered pairs of chain molecules that share a diabat
+#define RA_MAXPAIR RPB_RA_MAXPAIR     // ordered pairs of chain molecules that share a diabat
 #define RA_ENT (CM * MA)              // chain atoms of one diabat
 
 struct RecipDev {
-  const int* mol;          // [n_mol] distinct chain molecules (host, from the hop logs)
-  const int* molpair;      // [n_pair] i * RA_MOLS + j
-  int* mol_slot;           // [M] molecule -> index in mol[]
+  const EvbPlan* plan;     // cmol[n_cmol]: distinct chain molecules; molpair[n_pair]: i * RA_MOLS + j   (enumeration kernel)
+  const int* mol_slot;     // [M] molecule -> index in plan->cmol
   double* P; double* G;    // [RA_SLOTS], [RA_SLOTS][3]   (conv included)
   double* Mx; double* Nx;  // [RA_SLOTS][RA_SLOTS], [3][RA_SLOTS][RA_SLOTS]
   double* D;               // [RA_SLOTS] Hellmann-Feynman averaged charge deltas
@@ -1612,13 +1640,13 @@ __device__ __forceinline__ void spline_pair_lane(const Dev& d, const double u[3]
 }
 
 // warp per chain-atom slot: P_a, G_a from theta_1; also publishes the molecule -> slot map and clears D
-__global__ void k_evb_rcp_atoms(Dev d, RecipDev r, int n_mol) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= n_mol * MA) return;
-  const int im = w / MA, a = w % MA, mol = r.mol[im];
-  if (a == 0 && lane == 0) r.mol_slot[mol] = im;
+__global__ void k_evb_rcp_atoms(Dev d, RecipDev r) {
+  const int lane = threadIdx.x & 31;
+  const int n_mol = r.plan->n_cmol;
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_mol * MA; w += (gridDim.x * blockDim.x) >> 5) {
+  const int im = w / MA, a = w % MA, mol = r.plan->cmol[im];
   if (lane == 0) r.sl_n[w] = 0;
-  if (a >= d.mol_natom[mol]) return;
+  if (a >= d.mol_natom[mol]) continue;
   const int atom = d.mol_first[mol] + a;
   const double u[3] = {d.uscale[3 * atom], d.uscale[3 * atom + 1], d.uscale[3 * atom + 2]};
   int np[3];
@@ -1644,22 +1672,24 @@ __global__ void k_evb_rcp_atoms(Dev d, RecipDev r, int n_mol) {
   }
   p = warp_sum(p); g0 = warp_sum(g0); g1 = warp_sum(g1); g2 = warp_sum(g2);
   if (lane == 0) { r.P[w] = p; r.G[3 * w] = g0; r.G[3 * w + 1] = g1; r.G[3 * w + 2] = g2; }
+  }
 }
 
 // warp per (ordered pair of chain molecules, atom a of the first, atom b of the second): M_ab, N_ab
-__global__ void __launch_bounds__(128) k_evb_rcp_pairs(Dev d, RecipDev r, int n_pair) {
+__global__ void __launch_bounds__(128) k_evb_rcp_pairs(Dev d, RecipDev r) {
   __shared__ double sh_c[4][2][3][11];      // per warp: cross-correlations cw (0) / cd (1) per dimension, t = -5..5
   __shared__ double sh_w[4][3][18];         // per warp: w_a, dw_a, w_b
   __shared__ int sh_i[4][3][11];            // per warp: wrapped, stride-scaled grid offset of displacement t per dimension
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int w = blockIdx.x * 4 + wib;
-  const bool live = w < n_pair * MA * MA;
+  const int n_pair = r.plan->n_pair;
+  for (int w = blockIdx.x * 4 + wib; w < n_pair * MA * MA; w += gridDim.x * 4) {     // (warp-private shared slots: no CTA barrier inside)
+  __syncwarp();
   int sa = 0, sb = 0, dn[3] = {0, 0, 0};
   bool act = false;
-  if (live) {
+  {
     const int ip = w / (MA * MA), a = (w / MA) % MA, b = w % MA;
-    const int mi = r.molpair[ip] / RA_MOLS, mj = r.molpair[ip] % RA_MOLS;
-    const int moli = r.mol[mi], molj = r.mol[mj];
+    const int mi = r.plan->molpair[ip] / RA_MOLS, mj = r.plan->molpair[ip] % RA_MOLS;
+    const int moli = r.plan->cmol[mi], molj = r.plan->cmol[mj];
     act = a < d.mol_natom[moli] && b < d.mol_natom[molj];
     if (act) {
       sa = mi * MA + a; sb = mj * MA + b;
@@ -1675,7 +1705,7 @@ __global__ void __launch_bounds__(128) k_evb_rcp_pairs(Dev d, RecipDev r, int n_
     }
   }
   __syncwarp();
-  if (!act) return;
+  if (!act) continue;
   // c(t) = sum_{k - k' = t} f_a[k] w_b[k'],  lane -> (dimension, t): 33 values, two rounds
   for (int v = lane; v < 33; v += 32) {
     const int dim = v / 11, t = v % 11 - 5;
@@ -1728,6 +1758,7 @@ __global__ void __launch_bounds__(128) k_evb_rcp_pairs(Dev d, RecipDev r, int n_
     const size_t o = (size_t)sa * RA_SLOTS + sb, plane = (size_t)RA_SLOTS * RA_SLOTS;
     r.Mx[o] = m * d.conv; r.Nx[o] = n0 * d.conv; r.Nx[plane + o] = n1 * d.conv; r.Nx[2 * plane + o] = n2 * d.conv;
   }
+  }
 }
 
 // warp per diabat s >= 1: chain atoms of the FINAL topology with their charge deltas, and E_rec(s) - E_rec(1)
@@ -1735,10 +1766,10 @@ __global__ void k_evb_rcp_energy(Dev d, EvbDev e, RecipDev r) {
   __shared__ int sh_slot[4][RA_ENT];
   __shared__ double sh_dq[4][RA_ENT];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int s = blockIdx.x * 4 + wib;
   const int S = *e.n_states;
-  if (s >= S) return;
-  if (s == 0) { if (lane == 0) r.st_n[0] = 0; return; }
+  for (int s = blockIdx.x * 4 + wib; s < S; s += gridDim.x * 4) {
+  __syncwarp();
+  if (s == 0) { if (lane == 0) r.st_n[0] = 0; continue; }
   static_assert(RA_ENT == 32, "one lane per (chain molecule, atom) of the snapshot");
   const Snapshot& Sn = e.snap[s * NLEV + e.n_hops[s]];
   const int k = lane / MA, a = lane % MA;
@@ -1775,13 +1806,15 @@ __global__ void k_evb_rcp_energy(Dev d, EvbDev e, RecipDev r) {
   }
   acc = warp_sum(acc);
   if (lane == 0) e.rcp_dE[s] = acc;
+  }
 }
 
 // after the solver: thread per (diabat, chain-atom entry): the chain atom's own reciprocal force term
 __global__ void k_evb_rcp_mix(Dev d, EvbDev e, RecipDev r, double* __restrict__ out) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int S = *e.n_states;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < S * RA_ENT; t += gridDim.x * blockDim.x) {
   const int s = t / RA_ENT, k = t % RA_ENT;
-  if (s >= *e.n_states || k >= r.st_n[s]) return;
+  if (s < 1 || k >= r.st_n[s]) continue;
   const double w = e.coef2[s];
   const int sa = r.st_slot[s * RA_ENT + k];
   const double dqa = r.st_dq[s * RA_ENT + k];
@@ -1793,28 +1826,31 @@ __global__ void k_evb_rcp_mix(Dev d, EvbDev e, RecipDev r, double* __restrict__ 
     const double dqb = r.st_dq[s * RA_ENT + j];
     f0 = fma(dqb, r.Nx[o], f0); f1 = fma(dqb, r.Nx[plane + o], f1); f2 = fma(dqb, r.Nx[2 * plane + o], f2);
   }
-  const int mol = r.mol[sa / MA], atom = d.mol_first[mol] + sa % MA;
+  const int mol = r.plan->cmol[sa / MA], atom = d.mol_first[mol] + sa % MA;
   const double Kd = (double)d.K, c = w * dqa;
   atomicAdd(&out[3 * atom], -(Kd * d.kk[0]) * (c * f0));
   atomicAdd(&out[3 * atom + 1], -(Kd * d.kk[1]) * (c * f1));
   atomicAdd(&out[3 * atom + 2], -(Kd * d.kk[2]) * (c * f2));
+  }
 }
 
 // Q_mix = Q_1 + sum_a D_a w_a,  D_a = sum_s c_s^2 dq_a(s): the copy of Q_1 is made early (k_copy); one warp per chain-atom
 // slot collects its averaged charge delta from the diabats' tables and spreads it
-__global__ void k_evb_rcp_patch(Dev d, EvbDev e, RecipDev r, double* __restrict__ Qmix, int n_mol) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= n_mol * MA) return;
-  const int mol = r.mol[w / MA], a = w % MA;
-  if (a >= d.mol_natom[mol]) return;
+__global__ void k_evb_rcp_patch(Dev d, EvbDev e, RecipDev r, double* __restrict__ Qmix) {
+  const int lane = threadIdx.x & 31;
+  const int n_mol = (*e.n_states > 1) ? r.plan->n_cmol : 0;
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_mol * MA; w += (gridDim.x * blockDim.x) >> 5) {
+  const int mol = r.plan->cmol[w / MA], a = w % MA;
+  if (a >= d.mol_natom[mol]) continue;
   const int n = r.sl_n[w];
   double D = 0.0;
   for (int k = lane; k < n; k += 32) D = fma(e.coef2[r.sl_state[w * MAXS + k]], r.sl_dq[w * MAXS + k], D);
   D = __shfl_sync(0xffffffffu, warp_sum(D), 0);   // warp_sum leaves the total in lane 0
-  if (D == 0.0) return;
+  if (D == 0.0) continue;
   const int atom = d.mol_first[mol] + a;
   const double u[3] = {d.uscale[3 * atom], d.uscale[3 * atom + 1], d.uscale[3 * atom + 2]};
   spread_atom_warp(d, Qmix, u, D, 1.0, lane);
+  }
 }
 
 // Reference quirk (ms_evb.f90:2523-2656): every force array of diabat s -- its diagonal force, its reciprocal-space
@@ -1826,13 +1862,14 @@ __global__ void k_evb_rcp_patch(Dev d, EvbDev e, RecipDev r, double* __restrict_
 // per diabat, one lane per (chain molecule, atom) of its final topology.  (Water / hydronium never re-order.)
 __global__ void k_evb_reorder_quirk(Dev d, EvbDev e, RecipDev r, double* __restrict__ out, int recip_algebra) {
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int s = blockIdx.x * 4 + wib;
-  if (s < 1 || s >= *e.n_states) return;
+  const int S = *e.n_states;
+  for (int s = blockIdx.x * 4 + wib; s < S; s += gridDim.x * 4) {
+  if (s < 1) continue;
   const Snapshot& Sn = e.snap[s * NLEV + e.n_hops[s]];
   const int k = lane / MA, a = lane % MA;
-  if (k >= Sn.n_mol || a >= Sn.m[k].n_atom) return;
+  if (k >= Sn.n_mol || a >= Sn.m[k].n_atom) continue;
   const int g = Sn.m[k].atom[a], t = Sn.m[k].ratom[a];
-  if (g == t) return;
+  if (g == t) continue;
   const size_t n3 = (size_t)3 * d.N;
   const double w = e.coef2[s], wc = e.coef2[MAXS + s];
   double X[3] = {0.0, 0.0, 0.0};
@@ -1859,6 +1896,7 @@ __global__ void k_evb_reorder_quirk(Dev d, EvbDev e, RecipDev r, double* __restr
     X[0] += -(Kd * d.kk[0]) * (qs * f0); X[1] += -(Kd * d.kk[1]) * (qs * f1); X[2] += -(Kd * d.kk[2]) * (qs * f2);
   }
   for (int c = 0; c < 3; c++) { atomicAdd(&out[3 * g + c], -X[c]); atomicAdd(&out[3 * t + c], X[c]); }
+  }
 }
 
 
@@ -2295,7 +2333,7 @@ int evb_build(rpb_ctx* c) {
       dim3 g((N + 255) / 256, n_uniq);
       k_evb_candidates<<<g, 256, 0, c->stream>>>(d, sc.uniq_atom, c->evb_rcand * c->evb_rcand, sc.chain_slot, sc.cand, sc.cand_n);
     }
-    { ScopedTimer t(c, T_EVB_ITEMS_BG); k_evb_items<<<dim3(n_real, ITEM_SPLIT), ITEM_TPB, 0, c->stream>>>(d, e, sc.chain_slot, sc.cand, sc.cand_n, c->evb_rcand, c->evb_rep_reach); }
+    if (n_real > 0) { ScopedTimer t(c, T_EVB_ITEMS_BG); k_evb_items<<<dim3(n_real, ITEM_SPLIT), ITEM_TPB, 0, c->stream>>>(d, e, sc.chain_slot, sc.cand, sc.cand_n, c->evb_rcand, c->evb_rep_reach); }
     c->n_launch += 2;
   }
   if (algebra) {
@@ -2592,7 +2630,7 @@ int evb_commit(rpb_ctx* c) {
   for (int k = 0; k < snap.n_mol; k++) c->mol_type[snap.m[k].mol] = snap.m[k].mtype;
   c->hydronium_mol = h.new_hydronium;
   // construct_verlet_list + update_verlet_displacements(init)  (ms_evb.f90:223-225)
-  launch_verlet_force_rebuild(c);
+  { int rcv = launch_verlet_force_rebuild(c); if (rcv) return rcv; }
   CKE(cudaStreamSynchronize(c->stream));
   return 0;
 }

@@ -1,16 +1,11 @@
-// Integrator, centre-of-mass / wrap, Verlet displacement tracker and on-device neighbour-list
-// rebuild.  Replaces (reference file:line):
+// Integrator, centre of mass / wrap, momentum removal, kinetic energy.  Replaces (reference file:line):
 //   md_integrate_atomic (NVE)            src/md_integration.f90:469-532
 //   subtract_center_of_mass_momentum     src/md_integration.f90:125-177
 //   update_r_com / shift_molecules_into_box   src/general_routines.f90:420-440, 1145-1197
-//   update_verlet_displacements          src/general_routines.f90:1259-1337
-//   construct_verlet_list_grid           src/general_routines.f90:1408-1595
-// All O(N), HBM/latency bound; the rebuild decision stays on the device (no host read-back):
-// every rebuild kernel is launched each step and exits immediately unless *rebuild_now == 1.
+//   calculate_kinetic_energy             src/total_energy_forces.f90:106-121
+// All O(N), HBM/latency bound.  (Neighbour list: kernels_nlist.cu.)
 #include <algorithm>
-#include <cooperative_groups.h>
 #include "rpb_host.h"
-namespace cg = cooperative_groups;
 
 #define TPB 256
 
@@ -124,202 +119,6 @@ __global__ void k_kinetic(Dev d) {
 }
 
 
-// per-block two largest |accumulated displacement|; merged by k_verlet_end
-__global__ void k_verlet_disp(Dev d, double* blk_top2, int* done_counter) {
-  __shared__ double s1[TPB], s2[TPB];
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int rebuild = *d.rebuild_now;
-  double nrm = 0.0;
-  if (i < d.N) {
-    double4 p = d.xq[i];
-    double xn[3] = {p.x, p.y, p.z};
-    if (rebuild) {
-      for (int k = 0; k < 3; k++) { d.vstore[3 * i + k] = xn[k]; d.vdisp[3 * i + k] = 0.0; }
-    } else {
-      double acc[3];
-      for (int k = 0; k < 3; k++) {
-        double xo = d.vstore[3 * i + k];
-        double dr = xn[k] - xo;                       // pbc_shift(old,new)
-        double sh = floor(d.inv_box[k] * dr + 0.5) * d.box[k];
-        double dd = xn[k] - xo - sh;                  // pbc_dr
-        acc[k] = d.vdisp[3 * i + k] + dd;
-        d.vdisp[3 * i + k] = acc[k];
-        d.vstore[3 * i + k] = xn[k];
-      }
-      nrm = sqrt(acc[0] * acc[0] + acc[1] * acc[1] + acc[2] * acc[2]);
-    }
-  }
-  s1[threadIdx.x] = nrm; s2[threadIdx.x] = 0.0;
-  __syncthreads();
-  for (int o = TPB / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      double a1 = s1[threadIdx.x], a2 = s2[threadIdx.x], b1 = s1[threadIdx.x + o], b2 = s2[threadIdx.x + o];
-      double m1 = fmax(a1, b1);
-      double m2 = fmax(fmin(a1, b1), fmax(a2, b2));
-      s1[threadIdx.x] = m1; s2[threadIdx.x] = m2;
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) { blk_top2[2 * blockIdx.x] = s1[0]; blk_top2[2 * blockIdx.x + 1] = s2[0]; }
-  // the last block to arrive merges the per-block results (what used to be a separate one-block kernel)
-  __shared__ int is_last;
-  __threadfence();
-  if (threadIdx.x == 0) is_last = (atomicAdd(done_counter, 1) == (int)gridDim.x - 1);
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  const int nblk = gridDim.x;
-  double m1 = 0.0, m2 = 0.0;
-  for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
-    double b1 = blk_top2[2 * b], b2 = blk_top2[2 * b + 1];
-    double n1 = fmax(m1, b1), n2 = fmax(fmin(m1, b1), fmax(m2, b2));
-    m1 = n1; m2 = n2;
-  }
-  s1[threadIdx.x] = m1; s2[threadIdx.x] = m2;
-  __syncthreads();
-  for (int o = TPB / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      double a1 = s1[threadIdx.x], a2 = s2[threadIdx.x], b1 = s1[threadIdx.x + o], b2 = s2[threadIdx.x + o];
-      s1[threadIdx.x] = fmax(a1, b1);
-      s2[threadIdx.x] = fmax(fmin(a1, b1), fmax(a2, b2));
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    d.maxd[0] = s1[0]; d.maxd[1] = s2[0];
-    int rb = *d.rebuild_now;
-    if (rb == 1) *d.flag_verlet = 0;
-    else if (rb == 0) *d.flag_verlet = ((s1[0] + s2[0]) > d.verlet_skin) ? 1 : 0;
-    *done_counter = 0;
-  }
-}
-
-
-// ------------------------------------------------------------------------------------------------
-// Neighbour-list rebuild (cell list -> half Verlet list in the reference's row order)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int wrap_cell(int ig, int n) { return ig - (int)floor((double)(ig - 1) / (double)n) * n; }
-
-
-
-
-
-
-// One warp per atom.  The reference visits the cells ia, ib, ic nested (:1523-1531) and, inside a cell, ascending atom
-// index; cells are stored z-fastest here, so the innermost ic loop of one (ia, ib) column is ONE contiguous range of
-// the cell-sorted arrays (two when the column wraps around the box), which the warp sweeps 64 atoms at a time with
-// ballot-ordered appends -- same row order as the reference.
-//   * The sweep reads cell-SORTED copies of the coordinates / molecule ids / packed entries (vsort_*), so its loads are
-//     coalesced and independent of each other (no index -> coordinate dependency), two chunks in flight per lane.
-//   * Columns, and cells of a column, that cannot hold an atom inside r_v are skipped (distance from the atom to the
-//     nearest face of the cell); skipping empty-handed cells does not change the order of what is found.
-//   * ONE distance pass: hits go to a fixed-capacity scratch row; after the row lengths are scanned, a copy pass writes
-//     the two CSR lists -- the reference's half list (j > i, 1-based) is the j > i subsequence of the symmetric row.
-// The minimum-image shift uses the reciprocal box: it can differ from the reference's division only for |dr| ~ L/2,
-// where the pair is outside r_v <= L/2 with either shift; dr - L*k itself is evaluated as in the reference.
-#define ROWCAP 1024
-__device__ __forceinline__ void verlet_rows_atom(const Dev& d, const int i, const int lane) {
-  const double4 pi = d.xq[i];
-  const int mi = d.mol_of_atom[i];
-  const int c = d.atom_cell[i];
-  const int iz = c % d.ncz + 1, iy = (c / d.ncz) % d.ncy + 1, ix = c / (d.ncz * d.ncy) + 1;
-  int* __restrict__ out = d.vrow_tmp + (size_t)i * ROWCAP;
-  int n_half = 0, n_full = 0;
-  // position of the atom inside its own cell, in cell units, and the cell sizes: lower bounds of the distance to the
-  // cells around it (only valid while an offset of (di+1) cells is the minimum image, i.e. (di+1) w <= L/2)
-  const double wx = d.box[0] / d.ncx, wy = d.box[1] / d.ncy, wz = d.box[2] / d.ncz;
-  double fx = (d.inv_box[0] * pi.x) * d.ncx; fx -= floor(fx);
-  double fy = (d.inv_box[1] * pi.y) * d.ncy; fy -= floor(fy);
-  double fz = (d.inv_box[2] * pi.z) * d.ncz; fz -= floor(fz);
-  const bool prune_x = (d.dia + 1) * wx <= 0.5 * d.box[0], prune_y = (d.dib + 1) * wy <= 0.5 * d.box[1],
-             prune_z = (d.dic + 1) * wz <= 0.5 * d.box[2];
-  const double slack = 1e-6;     // cell units; the bounds only have to be conservative
-  for (int ia = -d.dia; ia <= d.dia; ia++) {
-    const int g1 = wrap_cell(ix + ia, d.ncx);
-    double gx = 0.0;
-    if (prune_x && ia != 0) gx = fmax(0.0, (ia > 0 ? (double)ia - fx : fx - (double)(ia + 1)) - slack) * wx;
-    for (int ib = -d.dib; ib <= d.dib; ib++) {
-      double gy = 0.0;
-      if (prune_y && ib != 0) gy = fmax(0.0, (ib > 0 ? (double)ib - fy : fy - (double)(ib + 1)) - slack) * wy;
-      const double rem = d.rv2 - (gx * gx + gy * gy);
-      if (rem < 0.0) continue;                         // the whole column is out of reach
-      int ic_lo = -d.dic, ic_hi = d.dic;
-      if (prune_z) {
-        const double zc = sqrt(rem) / wz + slack;      // reach along z in cell units
-        ic_hi = min(d.dic, (int)floor(fz + zc));
-        ic_lo = -min(d.dic, (int)floor(1.0 - fz + zc));
-      }
-      const int g2 = wrap_cell(iy + ib, d.ncy);
-      const int col = d.ncz * ((g2 - 1) + d.ncy * (g1 - 1));
-      // z segments of the column: [iz+ic_lo, iz+ic_hi] wrapped into 1..ncz, in the order the reference meets them
-      int seg0[2], seg1[2], nseg = 1;
-      {
-        const int zl = iz + ic_lo, zh = iz + ic_hi;
-        if (zh < 1) { seg0[0] = zl + d.ncz; seg1[0] = zh + d.ncz; }
-        else if (zl > d.ncz) { seg0[0] = zl - d.ncz; seg1[0] = zh - d.ncz; }
-        else if (zl < 1) { seg0[0] = zl + d.ncz; seg1[0] = d.ncz; seg0[1] = 1; seg1[1] = zh; nseg = 2; }
-        else if (zh > d.ncz) { seg0[0] = zl; seg1[0] = d.ncz; seg0[1] = 1; seg1[1] = zh - d.ncz; nseg = 2; }
-        else { seg0[0] = zl; seg1[0] = zh; }
-      }
-      for (int sg = 0; sg < nseg; sg++) {
-        const int s = d.cell_start[col + seg0[sg] - 1], e = d.cell_start[col + seg1[sg]];
-        for (int b = s; b < e; b += 64) {
-          const int a0 = b + lane, a1 = b + 32 + lane;
-          int pk0 = -1, pk1 = -1, m0 = mi, m1 = mi;
-          double4 p0 = pi, p1 = pi;
-          if (a0 < e) { pk0 = d.vsort_entry[a0]; m0 = d.vsort_mol[a0]; p0 = ldg256(&d.vsort_xq[a0]); }
-          if (a1 < e) { pk1 = d.vsort_entry[a1]; m1 = d.vsort_mol[a1]; p1 = ldg256(&d.vsort_xq[a1]); }
-          bool hit0 = false, hit1 = false;
-          if (m0 != mi) {
-            double r0 = pi.x - p0.x, r1 = pi.y - p0.y, r2 = pi.z - p0.z;
-            r0 = r0 - d.box[0] * floor(r0 * d.inv_box[0] + 0.5);
-            r1 = r1 - d.box[1] * floor(r1 * d.inv_box[1] + 0.5);
-            r2 = r2 - d.box[2] * floor(r2 * d.inv_box[2] + 0.5);
-            hit0 = (r0 * r0 + r1 * r1 + r2 * r2) < d.rv2;
-          }
-          if (m1 != mi) {
-            double r0 = pi.x - p1.x, r1 = pi.y - p1.y, r2 = pi.z - p1.z;
-            r0 = r0 - d.box[0] * floor(r0 * d.inv_box[0] + 0.5);
-            r1 = r1 - d.box[1] * floor(r1 * d.inv_box[1] + 0.5);
-            r2 = r2 - d.box[2] * floor(r2 * d.inv_box[2] + 0.5);
-            hit1 = (r0 * r0 + r1 * r1 + r2 * r2) < d.rv2;
-          }
-          const unsigned below = (1u << lane) - 1u;
-          const unsigned bf0 = __ballot_sync(0xffffffffu, hit0), bf1 = __ballot_sync(0xffffffffu, hit1);
-          const unsigned bh0 = __ballot_sync(0xffffffffu, hit0 && i < (pk0 & 0xffffff)), bh1 = __ballot_sync(0xffffffffu, hit1 && i < (pk1 & 0xffffff));
-          if (hit0) { const int pos = n_full + __popc(bf0 & below); if (pos < ROWCAP) out[pos] = pk0; }
-          n_full += __popc(bf0);
-          if (hit1) { const int pos = n_full + __popc(bf1 & below); if (pos < ROWCAP) out[pos] = pk1; }
-          n_full += __popc(bf1);
-          n_half += __popc(bh0) + __popc(bh1);
-        }
-      }
-    }
-  }
-  if (lane == 0) {
-    if (n_full > ROWCAP) atomicMax(&d.err_flag[1], 1);
-    d.row_count[i] = n_half; d.row_count_full[i] = min(n_full, ROWCAP);
-  }
-}
-
-// scratch row -> the two CSR lists
-__device__ __forceinline__ void verlet_copy_atom(const Dev& d, const int i, const int lane) {
-  const int* __restrict__ in = d.vrow_tmp + (size_t)i * ROWCAP;
-  const int n = d.row_count_full[i];
-  int out_h = d.verlet_point[i] - 1;
-  const int out_f = d.full_point[i];
-  for (int k0 = 0; k0 < n; k0 += 32) {
-    const int k = k0 + lane;
-    int pk = -1;
-    if (k < n) { pk = in[k]; d.full_list[out_f + k] = pk; }          // atom type rides in the top byte
-    const int j = pk & 0xffffff;
-    const bool half = (k < n) && i < j;
-    const unsigned bal = __ballot_sync(0xffffffffu, half);
-    if (half) d.neighbor_list[out_h + __popc(bal & ((1u << lane) - 1u))] = j + 1;
-    out_h += __popc(bal);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 static inline int nblk(int n, int t = TPB) { return (n + t - 1) / t; }
 
@@ -356,100 +155,6 @@ void launch_kinetic_energy(rpb_ctx* c) {
   k_kinetic<<<nblk(c->d.N), TPB, 0, c->stream>>>(c->d);
   c->n_launch += 2;
 }
-
-// exclusive scan by ONE block: out[i] = base + sum_{j<i} in[j], out[n] = base + total
-__device__ void block_scan_exclusive(const int* __restrict__ in, int* __restrict__ out, int n, int base, int cap, int* err_flag) {
-  __shared__ int part[TPB];
-  const int tid = threadIdx.x, chunk = (n + TPB - 1) / TPB;
-  const int s0 = min(tid * chunk, n), s1 = min(s0 + chunk, n);
-  int sum = 0;
-  for (int k = s0; k < s1; k++) sum += in[k];
-  part[tid] = sum;
-  __syncthreads();
-  if (tid == 0) { int run = 0; for (int k = 0; k < TPB; k++) { int v = part[k]; part[k] = run; run += v; } out[n] = run + base; if (err_flag && run > cap) atomicMax(err_flag, 1); }
-  __syncthreads();
-  int run = part[tid] + base;
-  for (int k = s0; k < s1; k++) { int v = in[k]; out[k] = run; run += v; }
-  __syncthreads();
-}
-
-// The whole neighbour-list rebuild as ONE cooperative kernel (grid-wide barriers between the phases): on the ~95 % of
-// steps without a rebuild it costs a single launch that exits at once, instead of ten gated launches.
-__global__ void __launch_bounds__(TPB) k_verlet_rebuild(Dev d, int force_rebuild, int ncell) {
-  cg::grid_group grid = cg::this_grid();
-  // forced (init / hop commit): flag_verlet_list untouched (flag_junk, ms_evb.f90:223-225)
-  const int rb = force_rebuild ? 2 : ((*d.flag_verlet == 1) ? 1 : 0);
-  if (blockIdx.x == 0 && threadIdx.x == 0) { *d.rebuild_now = rb; d.maxd[0] = 0.0; d.maxd[1] = 0.0; }
-  if (!rb) return;
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
-  const int gwarp = gtid >> 5, nwarps = gthreads >> 5, lane = threadIdx.x & 31;
-  int* cursor = d.cell_count + (ncell + 1);
-  for (int c = gtid; c < 2 * ncell + 2; c += gthreads) d.cell_count[c] = 0;
-  grid.sync();
-  for (int i = gtid; i < d.N; i += gthreads) {       // cell of every atom (general_routines.f90:1458-1493)
-    double4 p = d.xq[i];
-    int ix = (int)floor((d.inv_box[0] * p.x) * d.ncx) + 1;
-    int iy = (int)floor((d.inv_box[1] * p.y) * d.ncy) + 1;
-    int iz = (int)floor((d.inv_box[2] * p.z) * d.ncz) + 1;
-    ix = wrap_cell(ix, d.ncx); iy = wrap_cell(iy, d.ncy); iz = wrap_cell(iz, d.ncz);
-    int c = (iz - 1) + d.ncz * ((iy - 1) + d.ncy * (ix - 1));   // z fastest: a column of the cell walk is contiguous in cell_atoms
-    d.atom_cell[i] = c;
-    atomicAdd(&d.cell_count[c], 1);
-  }
-  grid.sync();
-  if (blockIdx.x == 0) block_scan_exclusive(d.cell_count, d.cell_start, ncell, 0, 0, nullptr);
-  grid.sync();
-  for (int i = gtid; i < d.N; i += gthreads) {
-    int c = d.atom_cell[i];
-    int pos = atomicAdd(&cursor[c], 1);
-    d.cell_atoms[d.cell_start[c] + pos] = i;
-  }
-  grid.sync();
-  for (int c = gtid; c < ncell; c += gthreads) {     // ascending atom index inside each cell == the reference's append-at-tail linked list (:1486-1493)
-    int s = d.cell_start[c], e = d.cell_start[c + 1];
-    for (int a = s + 1; a < e; a++) {
-      int v = d.cell_atoms[a], b = a - 1;
-      while (b >= s && d.cell_atoms[b] > v) { d.cell_atoms[b + 1] = d.cell_atoms[b]; b--; }
-      d.cell_atoms[b + 1] = v;
-    }
-  }
-  grid.sync();
-  for (int a = gtid; a < d.N; a += gthreads) {       // cell-sorted copies for the sweep
-    const int j = d.cell_atoms[a];
-    d.vsort_xq[a] = d.xq[j]; d.vsort_mol[a] = d.mol_of_atom[j]; d.vsort_entry[a] = j | (d.type[j] << 24);
-  }
-  grid.sync();
-  for (int i = gwarp; i < d.N; i += nwarps) verlet_rows_atom(d, i, lane);
-  grid.sync();
-  if (blockIdx.x == 0) block_scan_exclusive(d.row_count, d.verlet_point, d.N, 1, d.verlet_cap, d.err_flag + 1);
-  if (blockIdx.x == 1 || gridDim.x == 1) block_scan_exclusive(d.row_count_full, d.full_point, d.N, 0, 2 * d.verlet_cap, d.err_flag + 1);
-  grid.sync();
-  if (d.err_flag[1]) return;
-  for (int i = gwarp; i < d.N; i += nwarps) verlet_copy_atom(d, i, lane);
-}
-
-static void verlet_common(rpb_ctx* c, int force_rebuild) {
-  ScopedTimer t(c, T_VERLET);
-  Dev& d = c->d;
-  int ncell = d.ncx * d.ncy * d.ncz;
-  double* blk_top2 = d.maxd + 8;
-  int nb = nblk(d.N);
-  static int coop_blocks = 0;     // same for every context of the process: one process drives one kind of device
-  if (!coop_blocks) {
-    int per_sm = 0, sms = 0, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_verlet_rebuild, TPB, 0);
-    coop_blocks = std::max(2, std::min(per_sm, 4) * sms);
-  }
-  void* args[] = {(void*)&d, (void*)&force_rebuild, (void*)&ncell};
-  cudaLaunchCooperativeKernel((void*)k_verlet_rebuild, dim3(coop_blocks), dim3(TPB), args, 0, c->stream);
-  k_verlet_disp<<<nb, TPB, 0, c->stream>>>(d, blk_top2, d.vdone);
-  c->n_launch += 2;
-}
-
-void launch_verlet_update(rpb_ctx* c) { verlet_common(c, 0); }
-void launch_verlet_force_rebuild(rpb_ctx* c) { verlet_common(c, 1); }
 
 // ------------------------------------------------------------------------------------------------
 // fp64 FMA peak of this device (roofline denominator for the FP64-pipe-bound pair kernels): 8 independent

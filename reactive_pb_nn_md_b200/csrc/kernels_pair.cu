@@ -1,23 +1,25 @@
-// Real-space pair forces over the half Verlet list, and per-molecule bonded / intramolecular terms.
+// Real-space pair forces over the cluster-pair (tile) list, and per-molecule bonded / intramolecular terms.
 // Replaces:
 //   pairwise_real_space_verlet            src/pair_int_real_space.f90:135-371
 //   pairwise_real_space_{ewald,LJ,sapt}   src/pair_int_real_space.f90:621-759
 //   intra_molecular_pairwise_energy_force src/pair_int_real_space.f90:386-588
 //   intra_molecular_energy_force          src/intra_bonded_interactions.f90:17-552
 //
-// Pair kernel: one warp per i-atom over its row of the SYMMETRIC list (both directions of every listed pair, built
-// next to the reference-ordered half list at every rebuild): each pair is evaluated from both of its atoms, F_i is
-// reduced in registers + shuffles and stored once -- no atomics, so the forces are reproducible run to run -- and the
-// energies are halved.  Per listed pair: minimum image with a reciprocal box (the shift can only differ from the
-// reference's division for |dr| ~ L/2, far outside the cutoff) and the cutoff test.  Per in-cutoff pair: ONE rsqrt
+// Pair kernel (k_pair_tiles): PAIR_WPC warps per cluster I (<= 3 consecutive atoms of one molecule, held in registers);
+// every lane takes one tile (I, J) of I's row per iteration: ONE list word, one 96-byte gather of cluster J and one
+// 12-byte gather of its atom types serve up to nine atom pairs, whose listed subset is the tile's 9-bit mask
+// (kernels_nlist.cu: exactly the reference's listed pairs).  Both directions of a tile are stored, so F_I is reduced
+// in registers + shuffles + shared memory and stored by one thread per atom: no j-scatter, no atomics inside the kernel
+// (the three ADDs into d.force per atom are the only ones; bonded terms and the PME gather add there too).  Energies
+// are halved.  Per listed pair: minimum image with a reciprocal box (the shift can only differ from the reference's
+// division for |dr| ~ L/2, far outside the cutoff) and the cutoff test dr^2 < r_c^2.  Per in-cutoff pair: ONE rsqrt
 // replaces the sqrt and the six divisions of pair_int_real_space.f90:621-645,698-759 (relative differences ~1e-16,
-// the interpolated tables are continuous across bins), and the erfc / ewaldscale tables are read interleaved.
-// Bound by the FP64 pipe -- see DESIGN.md.
+// the interpolated tables are continuous across bins), and the erfc / ewaldscale tables are read interleaved
+// (one 32-byte load per pair).  Pairs outside the mask or the cutoff run the same Coulomb arithmetic on harmless
+// operands (r^2 = 1, q_i q_j = 0, table entry 1) instead of diverging.  FP64-pipe bound -- see DESIGN.md.
 #include <cstdlib>
 #include "rpb_host.h"
 #include "rpb_bonded.cuh"
-
-#define PAIR_TPB 128
 
 // cold path of the pair kernel: a SAPT row with non-zero coefficients (pairwise_real_space_sapt :651-690; the example
 // force field has none).  Out of line and fed with scalars so that it costs the hot loop no registers.
@@ -37,8 +39,6 @@ __device__ __noinline__ void sapt_pair(const double* __restrict__ tt_t, const do
   fs += fac / dr2;
 }
 
-// BF: branch-free evaluation -- out-of-cutoff (and padding) lanes run the same arithmetic on harmless operands (r^2 = 1, q_i q_j = 0,
-// table entry 1) instead of sitting out behind divergent branches; the in-cutoff lanes execute exactly the same operations.
 // 1/sqrt(x) for x in the range of squared pair distances (normal, far from the exponent limits): single-precision seed
 // and two Newton-Raphson steps in fp64 -- no special-case branches, ~2 ulp (the library routine: 1 ulp)
 __device__ __forceinline__ double rsqrt_pair(double x) {
@@ -49,13 +49,15 @@ __device__ __forceinline__ double rsqrt_pair(double x) {
   return y;
 }
 
-// MODE bit 0 (BF), bit 1: rsqrt_pair instead of the library rsqrt
-template <int PAIR_B, int TPB_, int MINB, int MODE = 0>
-__global__ void __launch_bounds__(TPB_, MINB) k_pair_verlet(Dev d, int i_begin, int i_end) {
-  constexpr bool BF = (MODE & 1) != 0, FR = (MODE & 2) != 0;
+// WPC warps per cluster, TPB_ threads per CTA (TPB_/32/WPC clusters per CTA); rank r of R takes the clusters [NC r / R, NC (r+1) / R)
+template <int WPC, int TPB_, int MINB>
+__global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int world) {
+  constexpr int CPB = TPB_ / 32 / WPC;         // clusters per CTA
+  static_assert(RPB_TILE_PARTS % WPC == 0, "a warp takes whole row parts");
   extern __shared__ double sh_par[];           // [nT*nT][6] vdw parameters
   __shared__ int sh_vt[RPB_MAXT * RPB_MAXT];   // atype_vdw_type; 2 = SAPT row with all-zero coefficients (contributes exactly 0)
   __shared__ double sh_red[32];
+  __shared__ double sh_f[CPB][WPC][9];
   for (int k = threadIdx.x; k < d.nT * d.nT * 6; k += blockDim.x) sh_par[k] = d.vdw_param[k];
   for (int k = threadIdx.x; k < d.nT * d.nT; k += blockDim.x) {
     int vt = d.vdw_type[k];
@@ -66,97 +68,104 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_verlet(Dev d, int i_begin, 
     sh_vt[k] = vt;
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int nwarp_total = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int cib = w / WPC, part = w % WPC;     // cluster of this warp inside the CTA, and which share of its row
+  const int NC = *d.n_clusters;                // on the device: a committed hop can change it
+  const int c_begin = (int)((long long)NC * rank / world), c_end = (int)((long long)NC * (rank + 1) / world);
+  const int I = c_begin + blockIdx.x * CPB + cib;
   const double ibx = d.inv_box[0], iby = d.inv_box[1], ibz = d.inv_box[2];
   const double bx = d.box[0], by = d.box[1], bz = d.box[2];
-  const int* __restrict__ L = d.full_list;
+  const int nT = d.nT;
   double e_el = 0.0, e_vdw = 0.0;
-  for (int i = i_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < i_end; i += nwarp_total) {
-    const int vs = d.full_point[i], vf = d.full_point[i + 1];
-    const double4 pi = d.xq[i];
-    const int ti = d.type[i] * d.nT;
-    double fx = 0.0, fy = 0.0, fz = 0.0;
-    // The loop is bound by memory latency, not arithmetic: a warp issues in order and stalls at the first USE of a
-    // pending load, so every lane works on PAIR_B neighbours at once -- PAIR_B list entries, then PAIR_B 32-byte
-    // coordinate gathers, then PAIR_B 32-byte table gathers are issued back to back (one exposed latency per batch and
-    // stage instead of one per neighbour), and the list entries of the next batch are fetched a full batch ahead.
-    // (Measured on B200, C3, first version: 107 us one neighbour at a time -> 59 us with PAIR_B = 4; staging the gathers through
-    // shared memory with cp.async was slower, 142 us -- twice the L1 wavefronts for 16-byte copies.)
-    int jn[PAIR_B];
+  double f[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+  int fi = 0, ni = 0;
+  if (I < c_end) {
+    const int info = d.cl_info[I];
+    fi = info & 0xffffff; ni = info >> 24;
+    double4 pi[3];
+    int ti[3];
 #pragma unroll
-    for (int k = 0; k < PAIR_B; k++) { const int v = vs + 32 * k + lane; jn[k] = v < vf ? L[v] : -1; }
-    for (int base = vs; base < vf; base += 32 * PAIR_B) {
-      int j[PAIR_B];
-      double4 p[PAIR_B];
+    for (int a = 0; a < 3; a++) { const int ia = fi + (a < ni ? a : 0); pi[a] = d.xq[ia]; ti[a] = d.type[ia] * nT; }
+    // this warp's share of the cluster's RPB_TILE_PARTS row parts (contiguous in the list)
+    const int vs = d.tile_point[RPB_TILE_PARTS * I + part * (RPB_TILE_PARTS / WPC)], vf = d.tile_point[RPB_TILE_PARTS * I + (part + 1) * (RPB_TILE_PARTS / WPC)];
+    const unsigned* __restrict__ L = d.tile_list;
+    // the list word of the next iteration is fetched one iteration ahead; the three coordinate gathers and the type
+    // gathers of a tile are issued back to back, then the (up to) nine table gathers in batches of three
+    unsigned en = 0u;
+    { const int v = vs + lane; if (v < vf) en = L[v]; }
+    for (int base = vs; base < vf; base += 32) {
+      const unsigned ent = en;
+      const int vn = base + 32 + lane;
+      en = vn < vf ? L[vn] : 0u;
+      const unsigned mask = ent >> 23;             // 0 for the padding lanes of the last iteration
+      const int fj = ent & 0x7fffff;
+      double4 pj[3];
+      int tj[3];
 #pragma unroll
-      for (int k = 0; k < PAIR_B; k++) { j[k] = jn[k]; p[k] = make_double4(0.0, 0.0, 0.0, 0.0); if (j[k] >= 0) p[k] = ldg256(&d.xq[j[k] & 0xffffff]); }
+      for (int b = 0; b < 3; b++) { pj[b] = ldg256(&d.xq[fj + b]); tj[b] = __ldg(&d.type[fj + b]); }
 #pragma unroll
-      for (int k = 0; k < PAIR_B; k++) { const int v = base + 32 * (PAIR_B + k) + lane; jn[k] = v < vf ? L[v] : -1; }
-      double sdx[PAIR_B], sdy[PAIR_B], sdz[PAIR_B], sinv[PAIR_B], sc2[PAIR_B], sqq[PAIR_B];
-      double4 tb[PAIR_B];       // {erfc[i-1], scale[i-1], erfc[i], scale[i]}
-      bool in[PAIR_B];
+      for (int b = 0; b < 3; b++) {
+        double sdx[3], sdy[3], sdz[3], sinv[3], sc2[3], sqq[3];
+        double4 tb[3];
+        bool live[3];
 #pragma unroll
-      for (int k = 0; k < PAIR_B; k++) {   // minimum image, cutoff, table index, table load
-        double dx = pi.x - p[k].x, dy = pi.y - p[k].y, dz = pi.z - p[k].z;
-        dx = fma(-bx, floor(fma(dx, ibx, 0.5)), dx);
-        dy = fma(-by, floor(fma(dy, iby, 0.5)), dy);
-        dz = fma(-bz, floor(fma(dz, ibz, 0.5)), dz);
-        const double dr2 = fma(dz, dz, fma(dy, dy, dx * dx));
-        in[k] = j[k] >= 0 && dr2 < d.rc2;
-        if (BF) {
-          const double d2 = in[k] ? dr2 : 1.0;
-          const double inv_r = FR ? rsqrt_pair(d2) : rsqrt(d2);
+        for (int a = 0; a < 3; a++) {   // minimum image, cutoff, table index, table load
+          double dx = pi[a].x - pj[b].x, dy = pi[a].y - pj[b].y, dz = pi[a].z - pj[b].z;
+          dx = fma(-bx, floor(fma(dx, ibx, 0.5)), dx);
+          dy = fma(-by, floor(fma(dy, iby, 0.5)), dy);
+          dz = fma(-bz, floor(fma(dz, ibz, 0.5)), dz);
+          const double dr2 = fma(dz, dz, fma(dy, dy, dx * dx));
+          live[a] = ((mask >> (3 * a + b)) & 1u) && dr2 < d.rc2;
+          const double d2 = live[a] ? dr2 : 1.0;
+          const double inv_r = rsqrt_pair(d2);
+          // linear_interpolation_ewald_tables  pair_int_real_space.f90:740-759
           const double x1 = (d2 * inv_r) * d.inv_erfc_dx;
           const double ci = ceil(x1);
-          tb[k] = ldg256(&d.es2_t[in[k] ? (int)ci : 1]);
-          sc2[k] = (x1 + 1.0) - ci;
-          sinv[k] = inv_r;
-          sdx[k] = dx; sdy[k] = dy; sdz[k] = dz; sqq[k] = in[k] ? pi.w * p[k].w : 0.0;
-          continue;
+          tb[a] = ldg256(&d.es2_t[live[a] ? (int)ci : 1]);
+          sc2[a] = (x1 + 1.0) - ci;
+          sinv[a] = inv_r;
+          sdx[a] = dx; sdy[a] = dy; sdz[a] = dz;
+          sqq[a] = live[a] ? pi[a].w * pj[b].w : 0.0;
         }
-        tb[k] = make_double4(0.0, 0.0, 0.0, 0.0);
-        sdx[k] = dx; sdy[k] = dy; sdz[k] = dz; sqq[k] = pi.w * p[k].w;
-        sinv[k] = 1.0; sc2[k] = 0.0;
-        if (in[k]) {
-          const double inv_r = FR ? rsqrt_pair(dr2) : rsqrt(dr2);
-          // linear_interpolation_ewald_tables  pair_int_real_space.f90:740-759
-          const double x1 = (dr2 * inv_r) * d.inv_erfc_dx;
-          const double ci = ceil(x1);
-          tb[k] = ldg256(&d.es2_t[(int)ci]);
-          sc2[k] = (x1 + 1.0) - ci;
-          sinv[k] = inv_r;
-        }
-      }
 #pragma unroll
-      for (int k = 0; k < PAIR_B; k++) {   // energies and force of the in-cutoff pairs
-        if (!BF && !in[k]) continue;
-        const int pidx = BF ? (in[k] ? ti + (j[k] >> 24) : 0) : ti + (j[k] >> 24);
-        const double inv_r = sinv[k], inv_r2 = inv_r * inv_r, c1 = 1.0 - sc2[k];
-        const double qr = sqq[k] * inv_r;
-        e_el = fma(qr, fma(sc2[k], tb[k].z, c1 * tb[k].x), e_el);
-        double fs = (qr * inv_r2) * fma(sc2[k], tb[k].w, c1 * tb[k].y);
-        const int vt = (BF && !in[k]) ? -1 : sh_vt[pidx];
-        if (BF) {                            // LJ with the coefficients masked to zero for every lane that has no LJ term
-          const bool lj = vt == 0;
-          const double c12 = lj ? sh_par[6 * pidx] : 0.0, c6 = lj ? sh_par[6 * pidx + 1] : 0.0;
-          const double r6 = inv_r2 * inv_r2 * inv_r2, c12r6 = c12 * r6;
-          e_vdw = fma(r6, c12r6 - c6, e_vdw);
-          fs = fma(inv_r2 * r6, 12.0 * c12r6 - 6.0 * c6, fs);
-          if (vt == 1) sapt_pair(d.tt, d.dtt, d.tt_max, d.tt_grid, 1.0 / inv_r2, &sh_par[6 * pidx], e_vdw, fs);
-        } else if (vt == 0) {                // pairwise_real_space_LJ :621-645
-          const double c12 = sh_par[6 * pidx], c6 = sh_par[6 * pidx + 1];
-          const double r6 = inv_r2 * inv_r2 * inv_r2, c12r6 = c12 * r6;
-          e_vdw = fma(r6, c12r6 - c6, e_vdw);
-          fs = fma(inv_r2 * r6, 12.0 * c12r6 - 6.0 * c6, fs);
-        } else if (vt == 1) {                // pairwise_real_space_sapt :651-690 (generic path)
-          sapt_pair(d.tt, d.dtt, d.tt_max, d.tt_grid, 1.0 / inv_r2, &sh_par[6 * pidx], e_vdw, fs);
+        for (int a = 0; a < 3; a++) {   // energies and force
+          const double inv_r = sinv[a], inv_r2 = inv_r * inv_r, c1 = 1.0 - sc2[a];
+          const double qr = sqq[a] * inv_r;
+          e_el = fma(qr, fma(sc2[a], tb[a].z, c1 * tb[a].x), e_el);
+          double fs = (qr * inv_r2) * fma(sc2[a], tb[a].w, c1 * tb[a].y);
+          if (live[a]) {
+            const int pidx = ti[a] + tj[b];
+            const int vt = sh_vt[pidx];
+            if (vt == 0) {                       // pairwise_real_space_LJ :621-645
+              const double c12 = sh_par[6 * pidx], c6 = sh_par[6 * pidx + 1];
+              const double r6 = inv_r2 * inv_r2 * inv_r2, c12r6 = c12 * r6;
+              e_vdw = fma(r6, c12r6 - c6, e_vdw);
+              fs = fma(inv_r2 * r6, 12.0 * c12r6 - 6.0 * c6, fs);
+            } else if (vt == 1) {                // pairwise_real_space_sapt :651-690 (generic path)
+              sapt_pair(d.tt, d.dtt, d.tt_max, d.tt_grid, 1.0 / inv_r2, &sh_par[6 * pidx], e_vdw, fs);
+            }
+          }
+          f[a][0] = fma(sdx[a], fs, f[a][0]); f[a][1] = fma(sdy[a], fs, f[a][1]); f[a][2] = fma(sdz[a], fs, f[a][2]);
         }
-        fx = fma(sdx[k], fs, fx); fy = fma(sdy[k], fs, fy); fz = fma(sdz[k], fs, fz);
       }
     }
-    fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
-    if (lane == 0) { atomicAdd(&d.force[3 * i], fx); atomicAdd(&d.force[3 * i + 1], fy); atomicAdd(&d.force[3 * i + 2], fz); }   // one RED per component: the bonded branch adds to d.force concurrently
+  }
+  // F_I: lanes -> warp (xor shuffles), the WPC warps of the cluster -> one value through shared memory, fixed order
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      double x = f[a][k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if (lane == 0) sh_f[cib][part][3 * a + k] = x;
+    }
+  __syncthreads();
+  if (part == 0 && lane < 3 * ni && I < c_end) {
+    double x = 0.0;
+#pragma unroll
+    for (int p = 0; p < WPC; p++) x += sh_f[cib][p][lane];
+    atomicAdd(&d.force[3 * fi + lane], x);      // one ADD per component: the bonded branch and the PME gather add to d.force concurrently
   }
   e_el = block_sum(e_el, sh_red);
   e_vdw = block_sum(e_vdw, sh_red);
@@ -191,42 +200,29 @@ __global__ void k_molecule_terms(Dev d) {
   e = block_sum(E.e_dih, sh_red);  if (threadIdx.x == 0) atomicAdd(&d.en[E_DIH], e);
 }
 
-template <int B, int T, int M, int MODE = 0>
+template <int WPC, int T, int MINB>
 static void launch_pair_variant(rpb_ctx* c, bool shard) {
-  // state-sharded runs also shard the principal diabat's pair forces: rank r takes the atoms [N r / R, N (r+1) / R); the
-  // partial forces and energies ride the two all-reduces the sharded step has anyway
-  const int R = shard ? c->d.world : 1, r = shard ? c->d.rank : 0, N = c->d.N;
-  const int i0 = (int)((long long)N * r / R), i1 = (int)((long long)N * (r + 1) / R);
-  const int wpb = T / 32, blocks = std::max(1, (i1 - i0 + wpb - 1) / wpb);
+  // state-sharded runs also shard the principal diabat's pair forces: rank r takes the clusters [NC r / R, NC (r+1) / R); the
+  // partial forces and energies ride the two all-reduces the sharded step has anyway.  The number of clusters lives on the
+  // device (it changes with a committed hop); the grid is sized for the upper bound the host knows, surplus CTAs exit.
+  const int R = shard ? c->d.world : 1, r = shard ? c->d.rank : 0;
+  constexpr int CPB = T / 32 / WPC;
+  const int share = (c->n_clusters_bound + R - 1) / R + 1;
+  const int blocks = std::max(1, (share + CPB - 1) / CPB);
   const size_t shmem = (size_t)c->d.nT * c->d.nT * 6 * sizeof(double);
-  k_pair_verlet<B, T, M, MODE><<<blocks, T, shmem, c->stream>>>(c->d, i0, i1);
+  k_pair_tiles<WPC, T, MINB><<<blocks, T, shmem, c->stream>>>(c->d, r, R);
 }
 
 void launch_pair_verlet(rpb_ctx* c, bool shard) {
   ScopedTimer t(c, T_PAIR);
   static const int variant = getenv("RPB_PAIR_VARIANT") ? atoi(getenv("RPB_PAIR_VARIANT")) : 0;
   switch (variant) {
-    case 1: launch_pair_variant<2, 256, 3>(c, shard); break;
-    case 2: launch_pair_variant<2, 256, 4>(c, shard); break;
-    case 3: launch_pair_variant<3, 256, 2>(c, shard); break;
-    case 4: launch_pair_variant<3, 128, 5>(c, shard); break;
-    case 5: launch_pair_variant<4, 256, 2>(c, shard); break;
-    case 6: launch_pair_variant<2, 128, 6>(c, shard); break;
-    case 7: launch_pair_variant<4, 128, 3>(c, shard); break;
-    case 8: launch_pair_variant<3, 128, 3>(c, shard); break;
-    case 9: launch_pair_variant<3, 192, 2>(c, shard); break;
-    case 10: launch_pair_variant<2, 256, 2>(c, shard); break;
-    case 11: launch_pair_variant<2, 192, 3>(c, shard); break;
-    case 12: launch_pair_variant<2, 128, 4>(c, shard); break;
-    case 13: launch_pair_variant<2, 512, 1>(c, shard); break;
-    case 14: launch_pair_variant<2, 256, 2, 1>(c, shard); break;
-    case 15: launch_pair_variant<3, 256, 2, 1>(c, shard); break;
-    case 16: launch_pair_variant<2, 256, 2, 2>(c, shard); break;
-    case 17: launch_pair_variant<2, 256, 2, 3>(c, shard); break;
-    case 18: launch_pair_variant<3, 256, 2, 3>(c, shard); break;
-    default: launch_pair_variant<2, 256, 2, 2>(c, shard); break;   // best of the sweep on B200: batches of 2 x 32 neighbours fit 128 registers without
-                                                                // spills (3 x 32 spills loaded coordinates to local memory in the hot loop: ncu source
-                                                                // page, profiles/README.md); C2 107 -> 97 us, C4 260 -> 234 us; with the branch-free rsqrt_pair 94 / 228 us
+    case 1: launch_pair_variant<1, 128, 3>(c, shard); break;
+    case 2: launch_pair_variant<2, 128, 3>(c, shard); break;
+    case 3: launch_pair_variant<4, 128, 3>(c, shard); break;
+    case 4: launch_pair_variant<2, 256, 1>(c, shard); break;
+    case 5: launch_pair_variant<4, 256, 1>(c, shard); break;
+    default: launch_pair_variant<2, 128, 3>(c, shard); break;
   }
   c->n_launch += 1;
 }

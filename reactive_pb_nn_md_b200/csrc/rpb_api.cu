@@ -71,8 +71,8 @@ int calculate_total_force_energy(rpb_ctx* c, bool evb_principal) {
   stream_depend(c, 1, c->main_stream, c->aux[1]);
   // the long main-stream kernels are issued first: the host needs ~3 us per launch, and the GPU should not idle while
   // the side branches are being queued
-  launch_verlet_update(c);
-  int rc = 0;
+  int rc = launch_verlet_update(c);
+  if (rc) return rc;
   if (evb_principal) {
     // MS-EVB.  Two chains bound the time to the Hamiltonian: [pair forces -> candidate lists -> per-diabat real-space
     // deltas] on the main stream and [enumeration -> host -> per-step tables] on aux[0].  The host needs ~3 us per launch,
@@ -162,7 +162,7 @@ int rpb_create(rpb_ctx** out, const rpb_config* cfg) {
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++)
       if (i != j && std::fabs(cfg->box[i + 3 * j]) > 10e-6) { c->err = "code has been modified to assume orthorhombic box"; return RPB_ERR_UNSUPPORTED; }
-  if (cfg->n_atoms >= (1 << 24)) { c->err = "more than 2^24 atoms: the symmetric neighbour list packs the atom type into the top byte"; return RPB_ERR_UNSUPPORTED; }
+  if (cfg->n_atoms >= (1 << 23)) { c->err = "more than 2^23 atoms: a cluster-pair list entry packs the atom index into 23 bits"; return RPB_ERR_UNSUPPORTED; }
   if (cfg->evb_max_chain > RPB_MAXC || cfg->evb_max_states > RPB_MAXS) { c->err = "evb limits exceed compiled maxima"; return RPB_ERR_ARG; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { c->err = "no CUDA device: librpbmd.so has no CPU fallback"; return RPB_ERR_CUDA; }
@@ -231,12 +231,15 @@ int rpb_create(rpb_ctx** out, const rpb_config* cfg) {
   const size_t K3 = (size_t)K * K * K, Kh3 = (size_t)K * K * (K / 2 + 1);
   const int ncell = d.ncx * d.ncy * d.ncz;
 #define AL(p, n) if ((rc = dev_alloc(c, &(p), (n)))) return rc;
-  AL(d.xq, N); AL(d.vel, 3 * N); AL(d.force, 3 * N); AL(d.mass, N); AL(d.type, N); AL(d.mol_of_atom, N);
+  AL(d.xq, N + 4); AL(d.vel, 3 * N); AL(d.force, 3 * N); AL(d.mass, N); AL(d.type, N); AL(d.mol_of_atom, N);
   AL(d.mol_first, M); AL(d.mol_natom, M); AL(d.mol_type, M); AL(d.r_com, 3 * M); AL(d.hydronium, 1);
-  AL(d.verlet_point, N + 1); AL(d.neighbor_list, d.verlet_cap); AL(d.full_point, N + 1); AL(d.full_list, 2 * (size_t)d.verlet_cap);
-  AL(d.vrow_tmp, (size_t)N * 1024); AL(d.vsort_xq, N); AL(d.vsort_mol, N); AL(d.vsort_entry, N); AL(d.vstore, 3 * N); AL(d.vdisp, 3 * N);
+  AL(d.verlet_point, N + 1); AL(d.neighbor_list, d.verlet_cap);
+  d.tile_cap = 2 * (long long)d.verlet_cap;       // a tile holds at least one listed pair, and the listed pairs fit the reference's capacity
+  AL(d.tile_point, RPB_TILE_PARTS * (size_t)N + 4); AL(d.tile_list, (size_t)d.tile_cap); AL(d.cl_info, N + 1); AL(d.n_clusters, 1); AL(d.mol_cl_first, M + 1); AL(d.mol_ncl, M + 1);
+  AL(d.vbuild_xq, N); AL(d.csort_xq, 3 * (size_t)N); AL(d.csort_mol, N); AL(d.csort_info, N); AL(d.vstat, 4);
+  AL(d.vsort_xq, N); AL(d.vsort_mol, N); AL(d.vsort_entry, N); AL(d.vstore, 3 * N); AL(d.vdisp, 3 * N);
   AL(d.flag_verlet, 1); AL(d.rebuild_now, 1); AL(d.err_flag, 4); AL(d.vdone, 1);
-  AL(d.cell_count, 2 * (ncell + 1)); AL(d.cell_start, ncell + 1); AL(d.cell_atoms, N); AL(d.atom_cell, N); AL(d.row_count, N + 1); AL(d.row_count_full, N + 1);
+  AL(d.cell_count, 2 * (ncell + 1)); AL(d.cell_start, ncell + 1); AL(d.cell_atoms, N); AL(d.atom_cell, N); AL(d.row_count, RPB_TILE_PARTS * (size_t)N + 4);
   AL(d.maxd, 8 + 2 * ((N + 255) / 256 + 1) + 4 * ((N + 127) / 128 + 1));
   AL(d.uscale, 3 * N); AL(d.force_recip, 3 * N); AL(d.en, E_NSLOT);
   c->grid_capacity = 1;
@@ -253,7 +256,10 @@ int rpb_create(rpb_ctx** out, const rpb_config* cfg) {
   CK(cudaMemset(d.en, 0, E_NSLOT * sizeof(double)));
   CK(cudaMemset(d.force, 0, 3 * N * sizeof(double)));
   CK(cudaMemset(d.force_recip, 0, 3 * N * sizeof(double)));
-  return 0;
+  CK(cudaMemset(d.xq, 0, (N + 4) * sizeof(double4)));
+  CK(cudaMemset(d.vstat, 0, 4 * sizeof(unsigned long long)));
+  CK(cudaMemset(d.n_clusters, 0, sizeof(int)));
+  return verlet_setup(c);
 }
 
 void rpb_destroy(rpb_ctx* c) {
@@ -508,6 +514,14 @@ int rpb_upload_state(rpb_ctx* c, const double* xyz, const double* velocity, cons
   Staging st;
   int rc = staging_get(c, st);
   if (rc) return rc;
+  {   // validate the molecule table before anything is staged: a rejected upload must leave the change-detection cache alone
+    int expect = 0;
+    for (int m = 0; m < M; m++) {
+      if (mol_first_atom[m] - 1 != expect) { c->err = "molecules must be contiguous ascending atom ranges"; return RPB_ERR_ARG; }
+      expect += mol_n_atom[m];
+    }
+    if (expect != N) { c->err = "molecule table does not cover all atoms"; return RPB_ERR_ARG; }
+  }
   CK(cudaStreamSynchronize(c->stream));          // the staging area may still feed an earlier copy
   const bool all = !c->have_state || !c->state_cache_valid;   // a committed proton hop permuted the device tables
   bool type_changed = all, mass_changed = all, mol_changed = all;
@@ -517,17 +531,19 @@ int rpb_upload_state(rpb_ctx* c, const double* xyz, const double* velocity, cons
     if (st.type[i] != t) { st.type[i] = t; type_changed = true; }
     if (st.mass[i] != mass[i]) { st.mass[i] = mass[i]; mass_changed = true; }
   }
+  const bool had_state = c->have_state && (int)c->mol_first.size() == M;
   c->mol_first.resize(M); c->mol_natom.resize(M); c->mol_type.resize(M);
-  int expect = 0;
+  int expect = 0, ncl = 0;
   for (int m = 0; m < M; m++) {
     const int f = mol_first_atom[m] - 1, n = mol_n_atom[m], t = mol_type[m] - 1;
-    if (f != expect) { c->err = "molecules must be contiguous ascending atom ranges"; return RPB_ERR_ARG; }
     if (st.mol[m] != f || st.mol[M + m] != n || st.mol[2 * M + m] != t) { st.mol[m] = f; st.mol[M + m] = n; st.mol[2 * M + m] = t; mol_changed = true; }
+    if (had_state && (c->mol_first[m] != f || c->mol_natom[m] != n)) c->rebuild_forced = true;   // a different molecule table: the cluster table is stale
     c->mol_first[m] = f; c->mol_natom[m] = n; c->mol_type[m] = t;
     if (mol_changed) for (int a = 0; a < n; a++) st.moa[expect + a] = m;
     expect += n;
+    ncl += (n + 2) / 3;
   }
-  if (expect != N) { c->err = "molecule table does not cover all atoms"; return RPB_ERR_ARG; }
+  c->n_clusters_bound = std::min(N, ncl + 2);   // a hop moves one proton: the count changes by at most one either way
   memcpy(st.vel, velocity, 3 * (size_t)N * sizeof(double));
   if (c->hydronium_mol != hydronium_mol - 1) mol_changed = true;
   c->hydronium_mol = hydronium_mol - 1;
@@ -552,8 +568,9 @@ int rpb_upload_state(rpb_ctx* c, const double* xyz, const double* velocity, cons
 int rpb_initialize(rpb_ctx* c) {
   if (!(c->have_tables && c->have_ff && c->have_mt && c->have_state)) { c->err = "tables/forcefield/molecule types/state must be set first"; return RPB_ERR_STATE; }
   launch_update_com_shift(c, true);
-  launch_verlet_force_rebuild(c);
-  int rc = fetch_status(c);
+  int rc = launch_verlet_force_rebuild(c);
+  if (rc) return rc;
+  rc = fetch_status(c);
   if (rc) return rc;
   c->initialized = true;
   return 0;
@@ -665,8 +682,13 @@ int rpb_get_r_com(rpb_ctx* c, double* r_com) {
 
 int rpb_get_neighbor_list(rpb_ctx* c, int* verlet_point, int* neighbor_list, int capacity, int* n_pairs, int* flag) {
   const int N = c->d.N;
+  // the reference's half list in its row order is generated on demand from the positions of the last rebuild
+  int rc = launch_verlet_reference_list(c);
+  if (rc) return rc;
   CK(cudaStreamSynchronize(c->stream));
-  int last = 0, fl = 0;
+  int last = 0, fl = 0, ovf = 0;
+  CK(cudaMemcpy(&ovf, c->d.err_flag + 1, sizeof(int), cudaMemcpyDeviceToHost));
+  if (ovf) { c->err = "please increase size of verlet neighbor list"; return RPB_ERR_VERLET; }
   CK(cudaMemcpy(&last, c->d.verlet_point + N, sizeof(int), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(&fl, c->d.flag_verlet, sizeof(int), cudaMemcpyDeviceToHost));
   int np = last - 1;
@@ -676,6 +698,37 @@ int rpb_get_neighbor_list(rpb_ctx* c, int* verlet_point, int* neighbor_list, int
   if (neighbor_list) {
     if (capacity < np) { c->err = "neighbor_list buffer too small"; return RPB_ERR_ARG; }
     CK(cudaMemcpy(neighbor_list, c->d.neighbor_list, (size_t)np * sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+// The cluster-pair list the pair kernel actually consumes, expanded on the host into the half list it encodes:
+// pairs (i < j, 1-based) sorted by (i, j).  Parity accessor for tests: must equal the reference's half list as a set.
+int rpb_debug_tile_pairs(rpb_ctx* c, int* pair_i, int* pair_j, long long capacity, long long* n_pairs, long long* n_tiles) {
+  CK(cudaStreamSynchronize(c->stream));
+  int NC = 0;
+  CK(cudaMemcpy(&NC, c->d.n_clusters, sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<int> tp(RPB_TILE_PARTS * NC + 1), info(NC);
+  CK(cudaMemcpy(tp.data(), c->d.tile_point, tp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(info.data(), c->d.cl_info, NC * sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<unsigned> tl((size_t)tp[RPB_TILE_PARTS * NC]);
+  CK(cudaMemcpy(tl.data(), c->d.tile_list, tl.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  std::vector<std::pair<int, int>> pr;
+  for (int I = 0; I < NC; I++) {
+    const int fi = info[I] & 0xffffff;
+    for (int k = tp[RPB_TILE_PARTS * I]; k < tp[RPB_TILE_PARTS * (I + 1)]; k++) {
+      const int fj = tl[k] & 0x7fffff;
+      const unsigned mask = tl[k] >> 23;
+      for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++)
+        if (((mask >> (3 * a + b)) & 1u) && fi + a < fj + b) pr.emplace_back(fi + a + 1, fj + b + 1);
+    }
+  }
+  std::sort(pr.begin(), pr.end());
+  if (n_pairs) *n_pairs = (long long)pr.size();
+  if (n_tiles) *n_tiles = (long long)tl.size();
+  if (pair_i && pair_j) {
+    if (capacity < (long long)pr.size()) { c->err = "pair buffer too small"; return RPB_ERR_ARG; }
+    for (size_t k = 0; k < pr.size(); k++) { pair_i[k] = pr[k].first; pair_j[k] = pr[k].second; }
   }
   return 0;
 }

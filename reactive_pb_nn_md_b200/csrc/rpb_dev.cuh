@@ -21,6 +21,7 @@
 #define RPB_MA RPB_MAX_MOLE_ATOMS
 #define RPB_MAXB 8    // bonds / angles / dihedrals per molecule type
 #define RPB_CHAIN_MOLS (RPB_MAXC + 1)
+#define RPB_TILE_PARTS 4   // a cluster's row of the pair list is built and consumed in this many independent parts
 
 // energy accumulator slots (device doubles)
 enum { E_ELEC = 0, E_VDW, E_BOND, E_ANGLE, E_DIH, E_RECIP, E_KE, E_REP, E_NSLOT };
@@ -80,13 +81,26 @@ struct Dev {
   const double4* es2_t;  // es2_t[i] = {erfc_t[i-1], scale_t[i-1], erfc_t[i], scale_t[i]}: both table points of an interpolation in ONE 32-byte load
   double inv_erfc_dx;
   // verlet
+  // The reference's half list (verlet_point / neighbor_list, reference row order, 1-based) is a parity ACCESSOR: it is
+  // generated on demand from the positions of the last rebuild (vbuild_xq).  The step itself consumes the cluster-pair
+  // ("tile") list: clusters are runs of <= 3 consecutive atoms of one molecule (a water is one cluster), a tile is an
+  // ordered pair of clusters (I, J) with a 9-bit mask of the atom pairs that the reference's list holds
+  // (different molecule, |r_ij| < r_verlet at build time); both directions of every tile are stored.
   int* verlet_point; int* neighbor_list; int verlet_cap;
-  int* vrow_tmp; double4* vsort_xq; int* vsort_mol; int* vsort_entry;   // rebuild scratch: fixed-capacity rows, cell-sorted copies
-  int* full_point; int* full_list;   // symmetric (both directions) copy of the list, 0-based, for the atomic-free pair kernel
+  double4* vbuild_xq;                       // positions at the last rebuild
+  int* n_clusters;                          // device scalar
+  int* cl_info;                             // [cluster] first atom | n_atom << 24
+  int* mol_cl_first; int* mol_ncl;          // [M+1] first cluster of every molecule / [M] clusters per molecule
+  int* tile_point; unsigned* tile_list;     // CSR over (cluster, part) rows [RPB_TILE_PARTS * I + part]; entry = first atom of cluster J | mask << 23 (bit 3a+b: atom a of I with atom b of J)
+  long long tile_cap;
+  double4* csort_xq; int* csort_mol; int* csort_info;   // cell-sorted copies of the clusters for the sweep: [3 slot + b], [slot], [slot]
+  double4* vsort_xq; int* vsort_mol; int* vsort_entry;  // cell-sorted atom copies (reference-list accessor)
+  unsigned long long* vstat;                // [0] bits of the largest cluster extent  [1] listed (ordered) atom pairs  [2] rebuild counter
   double* vstore; double* vdisp; int* flag_verlet; int* rebuild_now;
   int* err_flag;  // [0] atom with |F|>1e5 (1-based, 0 none)  [1] verlet overflow  [2] too many diabats  [3] evb lookup failure
   int ncx, ncy, ncz, dia, dib, dic;
-  int* cell_count; int* cell_start; int* cell_atoms; int* atom_cell; int* row_count; int* row_count_full;
+  int coop_blocks;                          // grid of the cooperative rebuild kernels on this context's device
+  int* cell_count; int* cell_start; int* cell_atoms; int* atom_cell; int* row_count;
   double* maxd;  // two largest displacements
   int* vdone;    // arrival counter of the displacement kernel's blocks
   // PME

@@ -49,6 +49,8 @@ struct rpb_ctx {
   // host mirror of the molecule table (kept in sync on hop commit)
   std::vector<int> mol_first, mol_natom, mol_type;
   int hydronium_mol = -1;
+  bool rebuild_forced = false;  // rpb_upload_state brought a different molecule table: the next force evaluation rebuilds the list
+  int n_clusters_bound = 0;    // upper bound of the number of atom clusters (kernels_nlist.cu) for grid sizing; the count itself lives on the device
   // cuFFT
   std::map<int, cufftHandle> plan_fwd, plan_inv;   // keyed by (rounded) batch size
   char* fft_work = nullptr; size_t fft_work_bytes = 0;   // work area shared by every plan
@@ -122,13 +124,16 @@ int calculate_total_force_energy(rpb_ctx*, bool evb_principal);   // total_energ
 void launch_integrate_first(rpb_ctx*);      // md_integration.f90:469-491
 void launch_integrate_second(rpb_ctx*);     // md_integration.f90:507-532
 void launch_update_com_shift(rpb_ctx*, bool shift);
-void launch_verlet_update(rpb_ctx*);        // total_energy_forces.f90:30-39
-void launch_verlet_force_rebuild(rpb_ctx*); // construct_verlet_list + displacement init
+// ---- kernels_nlist.cu
+int verlet_setup(rpb_ctx*);                 // per-context sizing of the cooperative rebuild kernels
+int launch_verlet_update(rpb_ctx*);         // total_energy_forces.f90:30-39
+int launch_verlet_force_rebuild(rpb_ctx*);  // construct_verlet_list + displacement init
+int launch_verlet_reference_list(rpb_ctx*); // parity accessor: the reference's half list in its row order
 void launch_zero_forces(rpb_ctx*);
 void launch_kinetic_energy(rpb_ctx*);
 int measure_fp64_peak(rpb_ctx*, double* tflops);
 // ---- kernels_pair.cu
-void launch_pair_verlet(rpb_ctx*, bool shard_by_rank);   // pair_int_real_space.f90:135-371; shard: rank r takes atoms [N r/R, N (r+1)/R)
+void launch_pair_verlet(rpb_ctx*, bool shard_by_rank);   // pair_int_real_space.f90:135-371; shard: rank r takes clusters [NC r/R, NC (r+1)/R)
 void launch_molecule_terms(rpb_ctx*);       // pair_int_real_space.f90:386-588 + intra_bonded_interactions.f90:17-552
 // ---- kernels_pme.cu
 int pme_round_batch(int batch);

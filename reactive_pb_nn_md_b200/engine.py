@@ -301,6 +301,14 @@ class Simulation:
         self._check(self.dll.rpb_get_neighbor_list(self.ctx, iptr(vp), iptr(nl), n.value, C.byref(n), C.byref(flag)))
         return vp, nl[:n.value], flag.value
 
+    def tile_pairs(self):
+        """the pair list the force kernel consumes, as sorted (i, j) pairs, i < j, 1-based, and its size in list words"""
+        n, nt = C.c_longlong(), C.c_longlong()
+        self._check(self.dll.rpb_debug_tile_pairs(self.ctx, None, None, 0, C.byref(n), C.byref(nt)))
+        pi = np.zeros(max(n.value, 1), np.int32); pj = np.zeros(max(n.value, 1), np.int32)
+        self._check(self.dll.rpb_debug_tile_pairs(self.ctx, iptr(pi), iptr(pj), n.value, C.byref(n), C.byref(nt)))
+        return pi[:n.value], pj[:n.value], nt.value
+
     def pme(self, state=1):
         K, N = self.params.pme_grid, self.system.n_atoms
         Q = np.zeros((K, K, K), order="F"); th = np.zeros((K, K, K), order="F"); fr = np.zeros((N, 3))

@@ -27,6 +27,8 @@ def compare_state(sg, so):
     assert rel_rms(a["force"], b["force"]) < F_RTOL
     vg, ng, _ = sg.neighbor_list(); vo, no, _ = so.neighbor_list()
     assert np.array_equal(vg, vo) and np.array_equal(ng, no)
+    gi, gj, _ = sg.tile_pairs(); oi, oj, _ = so.tile_pairs()
+    assert np.array_equal(gi, oi) and np.array_equal(gj, oj)
 
 
 @pytest.mark.parametrize("order", ["h3o_first", "h3o_last"])
@@ -232,6 +234,8 @@ def test_reference_example_system_acid_in_water(cuda_lib, oracle_lib, ion_pair):
     _compare_full_state(sg, so)                                  # after a committed hop: permuted / retyped arrays identical
     vo, lo, _ = so.neighbor_list(); vg, lg, _ = sg.neighbor_list()
     assert np.array_equal(vo, vg) and np.array_equal(lo, lg)     # the commit rebuilds the list (ms_evb.f90:223-225)
+    gi, gj, _ = sg.tile_pairs(); oi, oj, _ = so.tile_pairs()     # clusters of the 5/6-site acid and its conjugate base
+    assert np.array_equal(gi, oi) and np.array_equal(gj, oj)
     so.md_integrate_atomic(12, ms_evb=True); sg.md_integrate_atomic(12, ms_evb=True)
     _compare_full_state(sg, so)
     assert sg.evb()["n_states"] == so.evb()["n_states"]

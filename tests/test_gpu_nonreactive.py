@@ -30,6 +30,8 @@ def test_neighbor_list_bit_exact(pair):
     assert np.array_equal(vpg, vpo)
     assert np.array_equal(nlg, nlo)      # same rows AND same order inside each row
     assert fg == fo
+    gi, gj, _ = sg.tile_pairs(); oi, oj, _ = so.tile_pairs()      # the cluster-pair list the pair kernel consumes: same set
+    assert np.array_equal(gi, oi) and np.array_equal(gj, oj)
 
 
 def test_com_and_wrap(pair):
@@ -72,6 +74,8 @@ def test_short_trajectory(oracle_lib, cuda_lib):
     # neighbour lists still identical after the on-device rebuild schedule
     vg, ng, fg = sg.neighbor_list(); vo, no, fo = so.neighbor_list()
     assert np.array_equal(vg, vo) and np.array_equal(ng, no) and fg == fo
+    gi, gj, _ = sg.tile_pairs(); oi, oj, _ = so.tile_pairs()
+    assert np.array_equal(gi, oi) and np.array_equal(gj, oj)
 
 
 def test_launch_counter(pair):

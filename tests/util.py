@@ -27,3 +27,14 @@ def assert_energies_close(eg, eo, keys=("potential_energy", "E_elec", "E_vdw", "
     scale = max(abs(eo["potential_energy"]), abs(eo["E_elec"]), 1.0)
     for k in keys:
         assert abs(eg[k] - eo[k]) <= rtol * max(abs(eo[k]), scale), (k, eg[k], eo[k])
+
+
+def assert_pair_lists_identical(sg, so):
+    """neighbour list: the reference-ordered half list (accessor) is bit-identical incl. row order, AND the cluster-pair
+    list the CUDA pair kernel actually consumes encodes exactly the same set of pairs"""
+    vo, lo, fo = so.neighbor_list(); vg, lg, fg = sg.neighbor_list()
+    assert np.array_equal(vo, vg) and np.array_equal(lo, lg) and fo == fg
+    gi, gj, n_words = sg.tile_pairs()
+    oi, oj, _ = so.tile_pairs()
+    assert len(gi) == len(lo) and np.array_equal(gi, oi) and np.array_equal(gj, oj)
+    return len(lo), n_words
