@@ -1919,89 +1919,151 @@ __global__ void k_copy(double* dst, const double* src, size_t n) {
 }
 
 // ================================================================================================
-// K15: hop commit -- permute the per-atom arrays exactly as shift_array_data_donor_acceptor_transfer
-// (ms_evb.f90:2677-2840) and retype / reorder the acceptor from the final-level snapshot.
+// K15: hop commit on the device -- when the solver selected a new hydronium molecule (plan.hop), permute the per-atom
+// arrays exactly as shift_array_data_donor_acceptor_transfer (ms_evb.f90:2677-2840), hop by hop of the new principal
+// diabat, and retype / re-order the chain molecules from its final-level snapshot (ms_evb.f90:806-1006).  Every kernel
+// of the sequence exits at once when no hop was selected, so the sequence is part of the fixed per-step launch list.
 // ================================================================================================
-__global__ void k_evb_commit_permute(Dev d, const int* __restrict__ perm, double4* xq_new, double* vel_new, double* force_new,
-                                     double* mass_new, int* type_new, int* moa_new, const int* __restrict__ moa_src) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= d.N) return;
-  int o = perm[i];
-  xq_new[i] = d.xq[o];
-  for (int k = 0; k < 3; k++) { vel_new[3 * i + k] = d.vel[3 * o + k]; force_new[3 * i + k] = d.force[3 * o + k]; }
-  mass_new[i] = d.mass[o];
-  type_new[i] = d.type[o];
-  moa_new[i] = moa_src[i];
-}
+struct CommitInfo {
+  int n_hops;
+  int from_g[MAXC], to_g[MAXC];     // global atom index the proton leaves / arrives at, in the index space BEFORE that hop
+  int m_from[MAXC], m_to[MAXC];
+  int n_mol; int mol[CM]; int new_first[CM]; int n_atom[CM];   // chain molecules of the new principal diabat after all hops
+  int hop_count;                    // committed hops since rpb_set_evb (the host notices permuted tables through it)
+};
 
-// after the permutation: write snapshot data (positions made whole, charges, types, centres of mass) of the chain molecules
-__global__ void k_evb_commit_patch(Dev d, EvbDev e, int state, int level, const int* __restrict__ new_first) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const Snapshot& S = e.snap[state * NLEV + level];
-  for (int k = 0; k < S.n_mol; k++) {
-    const MolImage& I = S.m[k];
-    int f = new_first[k];
-    for (int a = 0; a < I.n_atom; a++) {
-      d.xq[f + a] = make_double4(I.x[a][0], I.x[a][1], I.x[a][2], I.q[a]);
-      d.type[f + a] = I.type[a];
+// one thread: the hop parameters (host_shift of the previous version, replayed on the few molecules involved)
+__global__ void k_evb_commit_prepare(Dev d, EvbDev e, CommitInfo* ci) {
+  if (threadIdx.x != 0 || blockIdx.x != 0 || !e.plan->hop) return;
+  const int pdiab = e.result[0], nh = e.n_hops[pdiab];
+  const int* L = &e.proton_log[pdiab * MAXC * 5];
+  // first atom / atom count of molecule m after the hops applied so far
+  auto first_now = [&](int m, int upto) {
+    int f = d.mol_first[m];
+    for (int h = 0; h < upto; h++) {
+      if (ci->m_from[h] < ci->m_to[h]) { if (m > ci->m_from[h] && m <= ci->m_to[h]) f -= 1; }
+      else { if (m > ci->m_to[h] && m <= ci->m_from[h]) f += 1; }
     }
-    for (int c = 0; c < 3; c++) d.r_com[3 * I.mol + c] = I.r_com[c];
-    d.mol_first[I.mol] = f; d.mol_natom[I.mol] = I.n_atom; d.mol_type[I.mol] = I.mtype;
+    return f;
+  };
+  auto natom_now = [&](int m, int upto) {
+    int n = d.mol_natom[m];
+    for (int h = 0; h < upto; h++) { if (ci->m_from[h] == m) n -= 1; if (ci->m_to[h] == m) n += 1; }
+    return n;
+  };
+  int ima = *d.hydronium;
+  for (int k = 0; k < nh; k++) {
+    const int imd = ima, a_from = L[k * 5 + 1];
+    ima = L[k * 5 + 3];
+    ci->m_from[k] = imd; ci->m_to[k] = ima;
+    const int a_to = natom_now(ima, k);
+    ci->from_g[k] = first_now(imd, k) + a_from;
+    ci->to_g[k] = (imd < ima) ? first_now(ima, k) + a_to - 1 : first_now(ima, k) + a_to;
   }
-  *d.hydronium = S.m[S.hydronium].mol;
+  ci->n_hops = nh;
+  const Snapshot& S = e.snap[pdiab * NLEV + nh];
+  ci->n_mol = S.n_mol;
+  for (int k = 0; k < S.n_mol; k++) { ci->mol[k] = S.m[k].mol; ci->new_first[k] = first_now(S.m[k].mol, nh); ci->n_atom[k] = S.m[k].n_atom; }
 }
 
-// zero (or -1) every accumulator evb_build adds into: item energies, Vex, candidate counters, chain-atom corrections,
-// and the per-diabat force deltas / coupling forces of the S diabats in flight
-__global__ void k_evb_clear(Dev d, EvbDev e, int* cand_n, int s_begin, int s_end) {
-  const int S = s_end - s_begin;
-  e.dF += (size_t)s_begin * 3 * d.N; e.Foff += (size_t)s_begin * 3 * d.N;
-  e.corr_f += (size_t)s_begin * CM * MA * 3; e.corr_atom += (size_t)s_begin * CM * MA;
-  const size_t n3 = (size_t)3 * d.N, nbig = (size_t)S * n3;
+// thread i < N: source of new position i (hops undone last to first; chain molecules in snapshot order); thread m < M:
+// the molecule table and the atom -> molecule map after the hops
+__global__ void k_evb_commit_permute(Dev d, EvbDev e, const CommitInfo* __restrict__ ci, double4* xq_new, double* vel_new, double* force_new,
+                                     double* mass_new, int* type_new, int* moa_new) {
+  if (!e.plan->hop) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nh = ci->n_hops;
+  if (i < d.N) {
+    int src = i;
+    for (int h = nh - 1; h >= 0; h--) {
+      const int fg = ci->from_g[h], tg = ci->to_g[h];
+      if (src == tg) src = fg;
+      else if (fg < tg) { if (src >= fg && src < tg) src += 1; }
+      else { if (src > tg && src <= fg) src -= 1; }
+    }
+    const Snapshot& S = e.snap[e.result[0] * NLEV + nh];
+    for (int k = 0; k < ci->n_mol; k++)         // re-ordered acceptor: the snapshot lists the principal index of every position
+      if (i >= ci->new_first[k] && i < ci->new_first[k] + ci->n_atom[k]) src = S.m[k].atom[i - ci->new_first[k]];
+    xq_new[i] = d.xq[src];
+    for (int k = 0; k < 3; k++) { vel_new[3 * i + k] = d.vel[3 * src + k]; force_new[3 * i + k] = d.force[3 * src + k]; }
+    mass_new[i] = d.mass[src];
+    type_new[i] = d.type[src];
+  }
+  if (i < d.M) {
+    int f = d.mol_first[i], n = d.mol_natom[i];
+    for (int h = 0; h < nh; h++) {
+      if (ci->m_from[h] < ci->m_to[h]) { if (i > ci->m_from[h] && i <= ci->m_to[h]) f -= 1; }
+      else { if (i > ci->m_to[h] && i <= ci->m_from[h]) f += 1; }
+      if (ci->m_from[h] == i) n -= 1;
+      if (ci->m_to[h] == i) n += 1;
+    }
+    d.mol_first[i] = f; d.mol_natom[i] = n;     // (only this thread reads or writes entry i)
+    for (int a = 0; a < n; a++) moa_new[f + a] = i;
+  }
+}
+
+// copy back, then the snapshot data (positions made whole, charges, types, centres of mass, molecule types) of the chain
+// molecules and the new hydronium index
+__global__ void k_evb_commit_finish(Dev d, EvbDev e, CommitInfo* ci, const double4* __restrict__ xq_new, const double* __restrict__ vel_new,
+                                    const double* __restrict__ force_new, const double* __restrict__ mass_new, const int* __restrict__ type_new,
+                                    const int* __restrict__ moa_new) {
+  if (!e.plan->hop) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.N) return;
+  const Snapshot& S = e.snap[e.result[0] * NLEV + ci->n_hops];
+  double4 x = xq_new[i];
+  int ty = type_new[i];
+  for (int k = 0; k < ci->n_mol; k++)
+    if (i >= ci->new_first[k] && i < ci->new_first[k] + ci->n_atom[k]) {
+      const MolImage& I = S.m[k];
+      const int a = i - ci->new_first[k];
+      x = make_double4(I.x[a][0], I.x[a][1], I.x[a][2], I.q[a]);
+      ty = I.type[a];
+      if (a == 0) {
+        for (int c = 0; c < 3; c++) d.r_com[3 * I.mol + c] = I.r_com[c];
+        d.mol_type[I.mol] = I.mtype;
+      }
+    }
+  d.xq[i] = x; d.type[i] = ty;
+  for (int k = 0; k < 3; k++) { d.vel[3 * i + k] = vel_new[3 * i + k]; d.force[3 * i + k] = force_new[3 * i + k]; }
+  d.mass[i] = mass_new[i];
+  d.mol_of_atom[i] = moa_new[i];
+  if (i == 0) { *d.hydronium = S.m[S.hydronium].mol; ci->hop_count += 1; }
+}
+
+// zero every accumulator the build adds into.  mode 0 (ahead of the enumeration): item energies, Vex, and the per-diabat
+// force deltas / coupling forces of the diabats [0, plan.n_clear) -- the previous step's count plus a margin;
+// mode 1 (behind the enumeration): the diabats [plan.n_clear, S) of a step that gained more than the margin
+__global__ void k_evb_clear(Dev d, EvbDev e, int mode) {
+  const int s_begin = mode ? e.plan->n_clear : 0, s_end = mode ? *e.n_states : e.plan->n_clear;
   const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
-  for (size_t k = tid; k < nbig; k += nth) { e.dF[k] = 0.0; e.Foff[k] = 0.0; }
-  for (size_t k = tid; k < (size_t)S * CM * MA * 3; k += nth) e.corr_f[k] = 0.0;
-  for (size_t k = tid; k < (size_t)S * CM * MA; k += nth) e.corr_atom[k] = -1;
-  if (s_begin == 0) {   // the step-wide accumulators belong to the first (early) launch only: the coupling geometry of the
-                        // diabats it covers may already have added its Vex terms when a second launch clears [s_begin, S)
+  if (mode == 0) {
     for (size_t k = tid; k < RPB_MAX_ITEMS + 1; k += nth) e.item_energy[k] = 0.0;
     for (size_t k = tid; k < MAXS; k += nth) e.vex[k] = 0.0;
-    for (size_t k = tid; k < CAND_SLOTS; k += nth) cand_n[k] = 0;
   }
+  if (s_end <= s_begin) return;
+  const size_t n3 = (size_t)3 * d.N, nbig = (size_t)(s_end - s_begin) * n3;
+  double* dF = e.dF + (size_t)s_begin * n3; double* Fo = e.Foff + (size_t)s_begin * n3;
+  for (size_t k = tid; k < nbig; k += nth) { dF[k] = 0.0; Fo[k] = 0.0; }
 }
 
 // ================================================================================================
-// host orchestration
+// host orchestration: ENQUEUE ONLY.  Nothing below waits for the device inside a step; evb_readback (end of rpb_step /
+// rpb_force_energy) is the one synchronising read of the last step's results.
 // ================================================================================================
-// layout of the packed per-step upload (bytes)
 #define ENUM_BLOCK_INTS (16 + MAXS * (2 + MAXC * 5))
 // result[8 ints] | e_ground | evec[MAXS] | h_full[2 MAXS] | err_flag[4] as doubles | en[E_NSLOT]
 #define SOLVER_BLOCK_DOUBLES (5 + 3 * MAXS + 4 + E_NSLOT)
-#define PACK_OFF_ITEMS 0
-#define PACK_OFF_REAL (PACK_OFF_ITEMS + (RPB_MAX_ITEMS + 1) * (int)sizeof(EvbItem))
-#define PACK_OFF_SLOT_OF (PACK_OFF_REAL + (RPB_MAX_ITEMS + 1) * 4)
-#define PACK_OFF_SLOT_STATE (PACK_OFF_SLOT_OF + MAXS * 4)
-#define PACK_OFF_STATE_LIST (PACK_OFF_SLOT_STATE + MAXS * 4)
-#define PACK_OFF_UNIQ (PACK_OFF_STATE_LIST + MAXS * 4)
-#define PACK_OFF_LAST (PACK_OFF_UNIQ + CAND_SLOTS * 4)
-#define PACK_OFF_RMOL (PACK_OFF_LAST + MAXS * 4)
-#define PACK_OFF_RPAIR (PACK_OFF_RMOL + RA_MOLS * 4)
-#define PACK_BYTES (PACK_OFF_RPAIR + RA_MAXPAIR * 4)
 
-struct EvbScratch {   // device scratch owned by the context (allocated in evb_alloc)
-  char* pack_dev; char* pack_host;
+struct EvbScratch {   // device scratch owned by the context (allocated in evb_alloc, freed with it)
   CouplingGeo* geo;
-  int* slot_of_state;   // [MAXS]
-  int* slot_state;      // [MAXS] inverse map (slot -> state), -1 unused
-  int* state_list;      // [MAXS] owned diabats s>=1
   double* coeff_dev;    // [MAXS]
-  int* perm; int* new_first;
-  int* chain_slot; int* cand; int* cand_n; int* uniq_atom; int* last_item;
+  CommitInfo* commit;
+  int* chain_slot; int* cand; int* cand_n;
   double4* xq2; double* vel2; double* force2; double* mass2; int* type2; int* moa2;
-  RecipDev rd; double* gtab; int n_rmol, n_rpair;   // reciprocal-space delta algebra (default) ...
-  bool recip_grids;                                 // ... or one grid + FFT convolution per diabat (RPB_EVB_RECIP=grids, cross-check)
+  RecipDev rd; double* gtab;
+  int hop_count_seen = 0;
 };
-static std::map<rpb_ctx*, EvbScratch> g_scratch;
 
 #define CKE(call)                                                                 \
   do {                                                                            \
@@ -2012,6 +2074,8 @@ static std::map<rpb_ctx*, EvbScratch> g_scratch;
     }                                                                             \
   } while (0)
 
+static inline EvbScratch& scratch(rpb_ctx* c) { return *static_cast<EvbScratch*>(c->evb_scratch); }
+
 int evb_alloc(rpb_ctx* c) {
   if (c->e.n_states) return 0;
   EvbDev& e = c->e;
@@ -2019,54 +2083,41 @@ int evb_alloc(rpb_ctx* c) {
   const size_t K3 = (size_t)c->d.K * c->d.K * c->d.K;
   int rc;
 #define AL(p, n) if ((rc = dev_alloc(c, &(p), (size_t)(n)))) return rc;
-  {  // enumeration results are read back every step: one contiguous block, one copy (layout == EvbHost::pinned)
+  {  // enumeration results: one contiguous block, one copy (layout == EvbHost::pinned)
     int* blk;
     AL(blk, ENUM_BLOCK_INTS);
     e.n_states = blk; e.n_hops = blk + 16; e.parent = blk + 16 + MAXS; e.proton_log = blk + 16 + 2 * MAXS;
   }
-  AL(e.snap, MAXS * NLEV); AL(e.n_items, 1); AL(e.item_energy, RPB_MAX_ITEMS + 1);
-  AL(e.n_real, 1); AL(e.corr_f, (size_t)MAXS * CM * MA * 3); AL(e.corr_atom, MAXS * CM * MA);
+  AL(e.snap, MAXS * NLEV); AL(e.item_energy, RPB_MAX_ITEMS + 1); AL(e.plan, 1); AL(e.mol_slot, c->d.M);
   AL(e.dF, (size_t)MAXS * 3 * N); AL(e.Foff, (size_t)MAXS * 3 * N);
-  AL(e.vex, MAXS); AL(e.e_recip, MAXS); AL(e.h_diag, 3 * MAXS + E_NSLOT); AL(e.f_mix, 3 * N); AL(e.coef2, 3 * MAXS);
-  {  // solver results travel to the host every step: one contiguous block, one copy (SOLVER_BLOCK_DOUBLES)
+  AL(e.vex, MAXS); AL(e.e_recip, 4); AL(e.h_diag, 3 * MAXS + E_NSLOT); AL(e.f_mix, 3 * N); AL(e.coef2, 3 * MAXS);
+  {  // solver results: one contiguous block, one copy (SOLVER_BLOCK_DOUBLES)
     double* blk;
     AL(blk, SOLVER_BLOCK_DOUBLES);
     e.result = (int*)blk; e.e_ground = blk + 4; e.evec = blk + 5; e.h_full = blk + 5 + MAXS; e.status_copy = blk + 5 + 3 * MAXS;
-  } AL(e.theta_mix, K3); AL(e.jac_v, MAXS * MAXS); AL(e.jac_sig, 2 + MAXS * MAXC * 5); AL(e.tree_mu, 2);
-  EvbScratch s;
-  AL(s.geo, MAXS); AL(s.coeff_dev, MAXS);
-  // per-step host -> device tables travel as ONE packed copy from pinned memory (see PackLayout)
-  AL(s.pack_dev, PACK_BYTES);
-  CKE(cudaMallocHost(&s.pack_host, PACK_BYTES));
-  e.items = (EvbItem*)(s.pack_dev + PACK_OFF_ITEMS); e.real_list = (int*)(s.pack_dev + PACK_OFF_REAL);
-  s.slot_of_state = (int*)(s.pack_dev + PACK_OFF_SLOT_OF); s.slot_state = (int*)(s.pack_dev + PACK_OFF_SLOT_STATE);
-  s.state_list = (int*)(s.pack_dev + PACK_OFF_STATE_LIST); s.uniq_atom = (int*)(s.pack_dev + PACK_OFF_UNIQ);
-  s.last_item = (int*)(s.pack_dev + PACK_OFF_LAST);
-  AL(s.perm, N); AL(s.new_first, CM);
+  }
+  AL(e.jac_v, MAXS * MAXS); AL(e.jac_sig, 2 + MAXS * MAXC * 5); AL(e.tree_mu, 2);
+  EvbScratch* sp = new EvbScratch();
+  c->evb_scratch = sp;
+  EvbScratch& s = *sp;
+  AL(s.geo, MAXS); AL(s.coeff_dev, MAXS); AL(s.commit, 1);
   AL(s.chain_slot, N); AL(s.cand, (size_t)CAND_SLOTS * CAND_CAP); AL(s.cand_n, CAND_SLOTS + 2);
   AL(s.xq2, N); AL(s.vel2, 3 * N); AL(s.force2, 3 * N); AL(s.mass2, N); AL(s.type2, N); AL(s.moa2, N);
   {
     RecipDev& r = s.rd;
-    r.mol = (const int*)(s.pack_dev + PACK_OFF_RMOL); r.molpair = (const int*)(s.pack_dev + PACK_OFF_RPAIR);
-    AL(r.mol_slot, c->d.M); AL(r.P, RA_SLOTS); AL(r.G, 3 * RA_SLOTS); AL(r.Mx, (size_t)RA_SLOTS * RA_SLOTS); AL(r.Nx, (size_t)3 * RA_SLOTS * RA_SLOTS);
+    r.plan = e.plan; r.mol_slot = e.mol_slot;
+    AL(r.P, RA_SLOTS); AL(r.G, 3 * RA_SLOTS); AL(r.Mx, (size_t)RA_SLOTS * RA_SLOTS); AL(r.Nx, (size_t)3 * RA_SLOTS * RA_SLOTS);
     AL(r.D, RA_SLOTS); AL(r.st_n, MAXS); AL(r.st_slot, MAXS * RA_ENT); AL(r.st_dq, MAXS * RA_ENT);
     AL(r.sl_n, RA_SLOTS); AL(r.sl_state, RA_SLOTS * MAXS); AL(r.sl_dq, RA_SLOTS * MAXS);
     AL(s.gtab, K3); r.gtab = s.gtab;
     AL(e.rcp_dE, MAXS);
     CKE(cudaMemset(e.rcp_dE, 0, MAXS * sizeof(double)));
-    s.n_rmol = s.n_rpair = 0;
-    const char* rv = getenv("RPB_EVB_RECIP");
-    s.recip_grids = rv && std::string(rv) == "grids";
   }
 #undef AL
-  g_scratch[c] = s;
-  // cuFFT path only: every FFT batch size this context can meet (no plan is built inside a step)
+  // cuFFT path only (grid sizes with factors other than 2 and 3): the two plans a step needs (no plan is built inside a step)
   const int own_fft = fft_conv_supported(c);
   if (own_fft < 0) return own_fft;
-  for (int b = 1; b <= c->grid_capacity && !own_fft; b++) {
-    cufftHandle pf, pi;
-    if ((rc = pme_get_plans(c, b, &pf, &pi))) return rc;
-  }
+  if (!own_fft) { cufftHandle pf, pi; if ((rc = pme_get_plans(c, 1, &pf, &pi))) return rc; }
   {   // Green function of the reciprocal-space convolution, g = IDFT(CB): the convolution of a unit charge at the origin
     if (!c->have_tables) { c->err = "rpb_set_tables must precede rpb_set_evb"; return RPB_ERR_STATE; }
     const double one = 1.0;
@@ -2076,129 +2127,81 @@ int evb_alloc(rpb_ctx* c) {
     CKE(cudaMemcpyAsync(s.gtab, c->d.theta + K3, K3 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     CKE(cudaStreamSynchronize(c->stream));
   }
-  CKE(cudaMallocHost(&c->eh.pinned, ENUM_BLOCK_INTS * sizeof(int) + (SOLVER_BLOCK_DOUBLES + 8) * sizeof(double)));
+  CKE(cudaMallocHost(&c->eh.pinned, ENUM_BLOCK_INTS * sizeof(int) + (SOLVER_BLOCK_DOUBLES + 8) * sizeof(double) + sizeof(CommitInfo)));
   CKE(cudaMemset(e.n_states, 0, ENUM_BLOCK_INTS * sizeof(int)));
   CKE(cudaMemset(e.jac_sig, 0xff, (2 + MAXS * MAXC * 5) * sizeof(int)));
   CKE(cudaMemset(e.tree_mu, 0, 2 * sizeof(double)));
+  CKE(cudaMemset(e.mol_slot, 0xff, c->d.M * sizeof(int)));
+  CKE(cudaMemset(s.commit, 0, sizeof(CommitInfo)));
+  {
+    EvbPlan p0;
+    memset(&p0, 0, sizeof(p0));
+    p0.n_clear = MAXS;                  // the first step clears every diabat's accumulators
+    CKE(cudaMemcpy(e.plan, &p0, sizeof(p0), cudaMemcpyHostToDevice));
+  }
+  c->d.commit_hop = &e.plan->hop;
   CKE(cudaFuncSetAttribute(k_evb_enumerate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENUM_SMEM_BYTES));
+  CKE(cudaFuncSetAttribute(k_evb_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)3 * MAXS * MAXS + 2 * MAXS) * sizeof(double))));
   { const char* sv = getenv("RPB_EVB_SOLVER"); c->evb_solver = (sv && std::string(sv) == "jacobi") ? 1 : 0; }
   return 0;
 }
 
 void evb_free(rpb_ctx* c) {
-  auto it = g_scratch.find(c);
-  if (it == g_scratch.end()) return;
-  if (it->second.pack_host) cudaFreeHost(it->second.pack_host);
-  g_scratch.erase(it);
+  if (!c->evb_scratch) return;
+  delete static_cast<EvbScratch*>(c->evb_scratch);
+  c->evb_scratch = nullptr;
 }
 
-static void host_items(rpb_ctx* c, std::vector<EvbItem>& items) {
-  EvbHost& h = c->eh;
-  items.clear();
-  EvbItem p; p.state = 0; p.level = 0; p.donor_slot = -1; p.acceptor_slot = -1; p.sign = 1.0; p.pad = 0;
-  p.real = (c->d.rank == 0) ? 1 : 0;   // sharded runs: the principal diabat's repulsion / reference energy is counted once
-  items.push_back(p);   // principal diabat: EVB repulsion + reference energy (ms_evb.f90:418-426)
-  for (int s = 1; s < h.n_states; s++) {
-    if (!state_owned(s, c->d.rank, c->d.world)) continue;
-    int mols[CM], nm = 1;
-    mols[0] = c->hydronium_mol;
-    for (int k = 0; k < h.n_hops[s]; k++) {
-      int a = h.proton_log[s][k][3];
-      bool f = false;
-      for (int q = 0; q < nm; q++) f |= (mols[q] == a);
-      if (!f) mols[nm++] = a;
-    }
-    int cur = 0;
-    for (int k = 0; k < h.n_hops[s]; k++) {
-      int a = h.proton_log[s][k][3], as = 0;
-      for (int q = 0; q < nm; q++) if (mols[q] == a) as = q;
-      EvbItem it; it.state = s; it.donor_slot = cur; it.acceptor_slot = as; it.pad = 0;
-      it.real = (k == h.n_hops[s] - 1) ? 1 : 0;   // earlier hops' real-space deltas are the ancestors' (same images, same background)
-      it.level = k; it.sign = -1.0; items.push_back(it);
-      it.level = k + 1; it.sign = 1.0; items.push_back(it);
-      cur = as;
-    }
-  }
-}
+// grid bounds from a recent diabat count (performance only: every kernel loops over the device-side counts)
+static inline int s_bound(rpb_ctx* c) { return std::min(MAXS, std::max(c->eh.s_hint, 8) + 16); }
 
-// host-side wall clock of the orchestration phases (RPB_DEBUG_HOST=1): where the CPU thread spends a step
-#include <chrono>
-struct HostClock {
-  static bool on() { static const bool v = getenv("RPB_DEBUG_HOST") != nullptr; return v; }
-  static double now() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-  static thread_local double acc[8]; static thread_local long n;   // per host thread: rpb_ensemble_step drives one context per thread
-  static void report() {
-    if (!on() || ++n % 20) return;
-    fprintf(stderr, "[host us/step] principal-launch %.0f | wait-enumerate %.0f | build-launch %.0f | mix-launch %.0f | wait-mix %.0f | commit %.0f\n",
-            acc[0] / 20, acc[1] / 20, acc[2] / 20, acc[3] / 20, acc[4] / 20, acc[5] / 20);
-    for (int k = 0; k < 8; k++) acc[k] = 0;
-  }
-};
-thread_local double HostClock::acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-thread_local long HostClock::n = 0;
-
-#define CLEAR_MARGIN 8
 int evb_enumerate_async(rpb_ctx* c, int part) {
-  Dev& d = c->d; EvbDev& e = c->e; EvbHost& h = c->eh;
+  Dev& d = c->d; EvbDev& e = c->e;
+  EvbScratch& sc = scratch(c);
   if (part == 0) {   // the kernel alone: the caller queues the pair kernel on the main stream before the rest
     ScopedTimer t(c, T_EVB_ENUM);
-    k_evb_enumerate<<<1, ENUM_TPB, ENUM_SMEM_BYTES, c->stream>>>(d, e);
+    k_evb_enumerate<<<1, ENUM_TPB, ENUM_SMEM_BYTES, c->stream>>>(d, e, sc.cand_n);
     c->n_launch += 1;
     return 0;
   }
-  // read-back on its own stream: the images below must not queue behind two device-to-host copies
-  CKE(cudaEventRecord(c->ev_sync[10], c->stream));
-  CKE(cudaStreamWaitEvent(c->aux[3], c->ev_sync[10], 0));
-  CKE(cudaMemcpyAsync(h.pinned, e.n_states, ENUM_BLOCK_INTS * sizeof(int), cudaMemcpyDeviceToHost, c->aux[3]));
-  CKE(cudaMemcpyAsync(c->h_flags, d.err_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->aux[3]));
-  CKE(cudaEventRecord(c->ev_enum, c->aux[3]));
-  // the diabat images need nothing from the host: built for however many diabats the enumeration found (grid sized
-  // for evb_max_states, surplus warps exit)
-  { ScopedTimer t(c, T_EVB_SNAP); k_evb_snapshots<<<(MAXS + SNAP_WPB - 1) / SNAP_WPB, 32 * SNAP_WPB, 0, c->stream>>>(d, e, -1, g_scratch[c].recip_grids ? 0 : 1); }   // delta algebra: every rank needs the charges of every diabat
+  // diabat images for however many diabats the enumeration found (grid sized for evb_max_states, surplus warps exit)
+  { ScopedTimer t(c, T_EVB_SNAP); k_evb_snapshots<<<(MAXS + SNAP_WPB - 1) / SNAP_WPB, 32 * SNAP_WPB, 0, c->stream>>>(d, e, -1, 1); }   // every rank needs the charges of every diabat
   c->n_launch += 1;
+  CKE(cudaEventRecord(c->ev_sync[18], c->stream));            // "images ready"
   {
-    // geometry factors of the couplings need the images only (and the early clears: they add the Vex terms of the other
-    // chain molecules): launched for the diabats the early clears cover, before the host knows S; evb_build adds the rest
-    // in the rare step that gains more diabats than the margin
-    // On the read-back stream (idle once the enumeration has been copied): aux[0] must stay free for the per-step tables.
-    EvbScratch& sc = g_scratch[c];
-    const int cleared = std::min(MAXS, h.n_states_prev + CLEAR_MARGIN);
-    CKE(cudaEventRecord(c->ev_sync[18], c->stream));
+    // geometry factors of the couplings need the images and the clears (they add the Vex terms of the other chain
+    // molecules); on aux[3] so that aux[0] is free for the Vex kernel's wait
     StreamScope ss(c, c->aux[3]);
     CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[18], 0));
-    CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[11], 0));
+    CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[11], 0));   // the early clears (aux[1])
+    k_evb_clear<<<148, 256, 0, c->stream>>>(d, e, 1);         // the diabats beyond the early clears' margin (normally none)
     {
       ScopedTimer t(c, T_EVB_COUPLING_GEO);
-      k_evb_coupling_geo<<<(cleared + GEO_WPB - 1) / GEO_WPB, 32 * GEO_WPB, 0, c->stream>>>(d, e, sc.geo, 0, cleared);
+      const int sb = s_bound(c);
+      k_evb_coupling_geo<<<(sb + GEO_WPB - 1) / GEO_WPB, 32 * GEO_WPB, 0, c->stream>>>(d, e, sc.geo);
     }
-    CKE(cudaEventRecord(c->ev_sync[19], c->stream));
-    c->n_launch += 1;
+    CKE(cudaEventRecord(c->ev_sync[19], c->stream));          // "clears complete, coupling geometry ready"
+    c->n_launch += 2;
   }
   return 0;
 }
 
-// Accumulators of the build (per-diabat force deltas, coupling forces, item energies, Vex, candidate counters) for the
-// diabats [0, previous S + CLEAR_MARGIN): the number of diabats changes slowly, and evb_build clears the rest in the rare
-// step that gains more.  The bound comes from the host (the enumeration kernel is rewriting the device copy of S).
+// Accumulators of the build for the diabats [0, previous S + margin): ahead of the enumeration, on a stream with slack
 void evb_clear_early(rpb_ctx* c) {
-  const int cleared = std::min(MAXS, c->eh.n_states_prev + CLEAR_MARGIN);
-  k_evb_clear<<<148 * 2, 256, 0, c->stream>>>(c->d, c->e, g_scratch[c].cand_n, 0, cleared);
+  k_evb_clear<<<148 * 2, 256, 0, c->stream>>>(c->d, c->e, 0);
   c->n_launch += 1;
 }
 
 int evb_build(rpb_ctx* c) {
   Dev& d = c->d; EvbDev& e = c->e; EvbHost& h = c->eh;
-  EvbScratch& sc = g_scratch[c];
+  EvbScratch& sc = scratch(c);
   const int N = d.N;
   const size_t K3 = (size_t)d.K * d.K * d.K, n3 = (size_t)3 * N;
-  double hc0 = HostClock::now();
-  int rc = calculate_total_force_energy(c, true);   // principal diabat (+ enumeration)
+  int rc = calculate_total_force_energy(c, true);   // principal diabat (+ enumeration, images, coupling geometry)
   if (rc) return rc;
-  const bool algebra = !sc.recip_grids;
-  if (algebra) {
-    // delta algebra: the principal grid is the only one convolved before the solver -- queued right behind the
-    // spreading, while the host is still waiting for the enumeration; its copy in slot 1 later receives the
-    // Hellmann-Feynman averaged charge deltas (evb_mix)
+  {
+    // the principal grid is the only one convolved before the solver -- queued right behind the spreading; its copy in
+    // slot 1 later receives the Hellmann-Feynman averaged charge deltas (evb_mix)
     StreamScope ss(c, c->aux[1]);
     k_copy<<<(unsigned)((K3 + 255) / 256), 256, 0, c->stream>>>(d.Q + K3, d.Q, K3);
     c->n_launch += 1;
@@ -2207,328 +2210,208 @@ int evb_build(rpb_ctx* c) {
     k_copy<<<1, 32, 0, c->stream>>>(d.en + E_RECIP, e.e_recip, 1);   // E_rec of the principal diabat (pme.f90:127)
     c->n_launch += 1;
   }
-  double hc1 = HostClock::now();
+  const int sb = s_bound(c);
+  // Branches from here (joined before the Hamiltonian is assembled):
+  //   aux[4] : candidate lists -> real-space / repulsion / bonded deltas of every (diabat, last hop, topology)
+  //   aux[0] : [enumeration, images] -> Vex of the couplings
+  //   aux[1] : [principal grid spread + convolution] -> reciprocal-space algebra (P_a, G_a; energies)
+  //   aux[2] : [bonded terms of the principal diabat] -> pair matrix of the chain atoms
   {
-    int* pin = h.pinned;
-    CKE(cudaEventSynchronize(c->ev_enum));           // only the enumeration: the pair forces etc. are still running
-    HostClock::acc[0] += hc1 - hc0; hc0 = HostClock::now(); HostClock::acc[1] += hc0 - hc1;
-    if (c->h_flags[2]) { c->err = "Found more diabat states than the current setting of evb_max_states"; return RPB_ERR_DIABATS; }
-    if (c->h_flags[3] >= 30) { c->err = "peer-memory exchange: rank " + std::to_string(c->h_flags[3] - 30) + " did not arrive"; return RPB_ERR_CUDA; }
-    if (c->h_flags[3]) { c->err = "error in subroutine find_bonded_atom_hydrogen"; return RPB_ERR_STATE; }
-    h.n_states = pin[0];
-    memcpy(h.n_hops, pin + 16, MAXS * sizeof(int));
-    memcpy(h.parent, pin + 16 + MAXS, MAXS * sizeof(int));
-    memcpy(h.proton_log, pin + 16 + 2 * MAXS, MAXS * MAXC * 5 * sizeof(int));
-  }
-  const int S = h.n_states;
-  std::vector<EvbItem> items;
-  host_items(c, items);
-  h.n_items = (int)items.size();
-  int* real_list = (int*)(sc.pack_host + PACK_OFF_REAL);
-  int n_real = 0;
-  int* last_item = (int*)(sc.pack_host + PACK_OFF_LAST);
-  for (int i = 0; i < MAXS; i++) last_item[i] = 1;
-  for (int i = 0; i < h.n_items; i++)
-    if (items[i].real) {
-      real_list[n_real++] = i;
-      if (items[i].sign > 0 && items[i].state > 0) last_item[items[i].state] = i;
-    }
-  memcpy(sc.pack_host + PACK_OFF_ITEMS, items.data(), items.size() * sizeof(EvbItem));
-  // distinct chain atoms of the owned diabats (principal indices, from the host mirror of the molecule table)
-  int* uniq_atom = (int*)(sc.pack_host + PACK_OFF_UNIQ);
-  int n_uniq = 0;
-  {
-    std::vector<int> um(1, c->hydronium_mol);
-    for (int s = 1; s < S; s++) {
-      if (!state_owned(s, d.rank, d.world)) continue;
-      for (int k = 0; k < h.n_hops[s]; k++) {
-        int a = h.proton_log[s][k][3];
-        if (std::find(um.begin(), um.end(), a) == um.end()) um.push_back(a);
-      }
-    }
-    for (int m : um)
-      for (int a = 0; a < c->mol_natom[m]; a++) {
-        if (n_uniq >= CAND_SLOTS) { c->err = "more distinct chain atoms than CAND_SLOTS"; return RPB_ERR_DIABATS; }
-        uniq_atom[n_uniq++] = c->mol_first[m] + a;
-      }
-  }
-  if (algebra) {
-    // distinct chain molecules over ALL diabats (every rank evaluates the cheap reciprocal-space algebra of every diabat)
-    // and the ordered pairs of them that share a diabat
-    int* rmol = (int*)(sc.pack_host + PACK_OFF_RMOL);
-    int* rpair = (int*)(sc.pack_host + PACK_OFF_RPAIR);
-    int nm = 0, np = 0;
-    static thread_local std::vector<unsigned char> seen;
-    seen.assign((size_t)RA_MOLS * RA_MOLS, 0);
-    auto mol_index = [&](int m) { for (int k = 0; k < nm; k++) if (rmol[k] == m) return k; rmol[nm] = m; return nm++; };
-    mol_index(c->hydronium_mol);
-    for (int s = 1; s < S; s++) {
-      int idx[CM], ni = 0;
-      idx[ni++] = 0;
-      for (int k = 0; k < h.n_hops[s]; k++) {
-        const int mi = mol_index(h.proton_log[s][k][3]);
-        bool dup = false;
-        for (int q = 0; q < ni; q++) dup |= (idx[q] == mi);
-        if (!dup) idx[ni++] = mi;
-      }
-      for (int a = 0; a < ni; a++)
-        for (int b = 0; b < ni; b++) {
-          const int key = idx[a] * RA_MOLS + idx[b];
-          if (!seen[key]) {
-            if (np >= RA_MAXPAIR) { c->err = "more chain-molecule pairs than RA_MAXPAIR"; return RPB_ERR_DIABATS; }
-            seen[key] = 1; rpair[np++] = key;
-          }
-        }
-    }
-    sc.n_rmol = nm; sc.n_rpair = np;
-    c->evb_may_reorder = false;
-    for (int k = 0; k < nm; k++) if (c->mt_multi_basic[c->mol_type[rmol[k]]]) c->evb_may_reorder = true;
-  }
-  int* slot_of_state = (int*)(sc.pack_host + PACK_OFF_SLOT_OF);
-  int* slot_state = (int*)(sc.pack_host + PACK_OFF_SLOT_STATE);
-  int* state_list = (int*)(sc.pack_host + PACK_OFF_STATE_LIST);
-  for (int i = 0; i < MAXS; i++) { slot_of_state[i] = 0; slot_state[i] = -1; state_list[i] = 0; }
-  slot_state[0] = (d.rank == 0) ? 0 : -1;   // slot 0 = principal grid on every rank; it enters theta_mix on rank 0 only
-  int n_own = 0;
-  for (int s = 1; s < S; s++)
-    if (state_owned(s, d.rank, d.world)) { state_list[n_own++] = s; slot_of_state[s] = n_own; slot_state[n_own] = s; }
-  if (n_own + 1 > c->grid_capacity) { c->err = "grid capacity exceeded"; return RPB_ERR_DIABATS; }
-  // The host part is done; from here three branches run concurrently (joined before the Hamiltonian is assembled):
-  //   main   : [pair forces of the principal diabat, already queued] -> candidate lists -> real-space / repulsion /
-  //            bonded deltas of every (diabat, last hop, topology)
-  //   aux[0] : [enumeration, images, bonded terms, already queued] -> per-step tables upload -> off-diagonal couplings
-  //            (geometry factor, Vex with all atoms)
-  //   aux[1] : [principal grid spread, already queued] -> delta grids, ONE batched D2Z -> (x CB, E_rec) -> Z2D over the
-  //            principal grid (slot 0) and every owned diabat, chain-atom force corrections
-  {
-    StreamScope ss(c, c->aux[0]);
-    CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[11], 0));      // the early clears (aux[1])
-    const int cleared = std::min(MAXS, h.n_states_prev + CLEAR_MARGIN);
-    if (S > cleared) {
-      k_evb_clear<<<148 * 2, 256, 0, c->stream>>>(d, e, sc.cand_n, cleared, S);
-      k_evb_coupling_geo<<<(S - cleared + GEO_WPB - 1) / GEO_WPB, 32 * GEO_WPB, 0, c->stream>>>(d, e, sc.geo, cleared, S);
-      c->n_launch += 2;
-    }
-    CKE(cudaMemcpyAsync(sc.pack_dev, sc.pack_host, PACK_BYTES, cudaMemcpyHostToDevice, c->stream));
-  }
-  h.n_states_prev = S;
-  if (n_own > 0 && !algebra) {
-    // the copies of the principal grid need only the NUMBER of owned diabats: queued behind the spreading right away,
-    // they run while the diabat images and the per-step tables are still on their way
-    StreamScope ss(c, c->aux[1]);
-    ScopedTimer t(c, T_EVB_BCAST);
-    k_evb_broadcast_grid<<<(unsigned)((K3 / 2 + 255) / 256), 256, 0, c->stream>>>(d.Q, d.Q + K3, K3, n_own);
-    c->n_launch += 1;
-  }
-  stream_depend(c, 4, c->aux[0], c->main_stream);
-  stream_depend(c, 5, c->aux[0], c->aux[1]);
-  stream_depend(c, 12, c->aux[0], c->aux[4]);
-  // issued first: the per-diabat real-space deltas are the longest branch between the tables and the Hamiltonian
-  {
-    // aux[4] (NOT behind the pair forces: needs the tables, images and clears only): candidate lists -> real-space /
-    // repulsion / bonded deltas
     StreamScope ss(c, c->aux[4]);
+    CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[19], 0));      // images, clears (incl. the enumeration's candidate counters)
     {
       ScopedTimer t(c, T_EVB_CAND);
-      dim3 g((N + 255) / 256, n_uniq);
-      k_evb_candidates<<<g, 256, 0, c->stream>>>(d, sc.uniq_atom, c->evb_rcand * c->evb_rcand, sc.chain_slot, sc.cand, sc.cand_n);
+      dim3 g((N + 255) / 256, std::min(CAND_SLOTS, 4 * sb + 8));
+      k_evb_candidates<<<g, 256, 0, c->stream>>>(d, e, c->evb_rcand * c->evb_rcand, sc.chain_slot, sc.cand, sc.cand_n);
     }
-    if (n_real > 0) { ScopedTimer t(c, T_EVB_ITEMS_BG); k_evb_items<<<dim3(n_real, ITEM_SPLIT), ITEM_TPB, 0, c->stream>>>(d, e, sc.chain_slot, sc.cand, sc.cand_n, c->evb_rcand, c->evb_rep_reach); }
+    { ScopedTimer t(c, T_EVB_ITEMS_BG); k_evb_items<<<dim3(2 * sb - 1, ITEM_SPLIT), ITEM_TPB, 0, c->stream>>>(d, e, sc.chain_slot, sc.cand, sc.cand_n, c->evb_rcand, c->evb_rep_reach); }
     c->n_launch += 2;
   }
-  if (algebra) {
-    if (S > 1) {
-      {   // the pair matrix needs the tables and the scaled coordinates only, not theta_1: on aux[2] (idle since the bonded
-          // terms), next to the principal convolution instead of behind it
-        StreamScope ss(c, c->aux[2]);
-        stream_depend(c, 14, c->aux[0], c->aux[2]);
-        CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[15], 0));
-        ScopedTimer t(c, T_EVB_CORR);
-        const int pw = sc.n_rpair * MA * MA;
-        k_evb_rcp_pairs<<<(pw + 3) / 4, 128, 0, c->stream>>>(d, sc.rd, sc.n_rpair);
-        CKE(cudaEventRecord(c->ev_sync[16], c->stream));
-      }
-      StreamScope ss(c, c->aux[1]);
+  {
+    {   // the pair matrix needs the plan and the scaled coordinates only, not theta_1
+      StreamScope ss(c, c->aux[2]);
+      CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[18], 0));    // enumeration (plan)
+      CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[15], 0));    // scaled coordinates
       ScopedTimer t(c, T_EVB_CORR);
-      k_evb_rcp_atoms<<<(sc.n_rmol * MA * 32 + 255) / 256, 256, 0, c->stream>>>(d, sc.rd, sc.n_rmol);
-      CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[16], 0));
-      k_evb_rcp_energy<<<(S + 3) / 4, 128, 0, c->stream>>>(d, e, sc.rd);
-      c->n_launch += 3;
+      k_evb_rcp_pairs<<<std::min(4 * sb * MA * MA / 4 + 1, 148 * 8), 128, 0, c->stream>>>(d, sc.rd);
+      CKE(cudaEventRecord(c->ev_sync[16], c->stream));
     }
-  } else {
     StreamScope ss(c, c->aux[1]);
-    if (n_own > 0) {
-      int warps = h.n_items * 2 * MA;
-      ScopedTimer t(c, T_EVB_PATCH);
-      k_evb_item_pme<<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(d, e, h.n_items, sc.slot_of_state, 0);
-      c->n_launch += 1;
-    }
-    rc = launch_convolve(c, 0, n_own + 1, e.e_recip, true);
-    if (rc) return rc;
-    k_copy<<<1, 32, 0, c->stream>>>(d.en + E_RECIP, e.e_recip, 1);   // E_rec of the principal diabat (pme.f90:127)
-    c->n_launch += 1;
-    if (n_own > 0) {
-      ScopedTimer t(c, T_EVB_CORR);
-      int warps = h.n_items * 2 * MA;
-      k_evb_item_pme<<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(d, e, h.n_items, sc.slot_of_state, 1);
-      c->n_launch += 1;
-    }
+    ScopedTimer t(c, T_EVB_CORR);
+    CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[18], 0));      // enumeration (plan), images
+    k_evb_rcp_atoms<<<((sb + 1) * MA * 32 + 255) / 256, 256, 0, c->stream>>>(d, sc.rd);
+    CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[16], 0));
+    k_evb_rcp_energy<<<(sb + 3) / 4, 128, 0, c->stream>>>(d, e, sc.rd);
+    c->n_launch += 3;
   }
   {
-    // aux[0] (behind images, clears and the per-step tables): off-diagonal couplings
     StreamScope ss(c, c->aux[0]);
-    if (n_own > 0) {
-      CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[19], 0));     // coupling geometry (aux[3])
-      ScopedTimer t(c, T_EVB_COUPLING);
-      dim3 g(n_own, (N + 256 * VEX_APT - 1) / (256 * VEX_APT));
-      k_evb_coupling_vex<<<g, 256, 0, c->stream>>>(d, e, sc.geo, sc.state_list);
-      c->n_launch += 1;
-    }
+    CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[19], 0));       // coupling geometry (aux[3])
+    ScopedTimer t(c, T_EVB_COUPLING);
+    const int own_bound = (sb + d.world - 1) / d.world + 1;
+    dim3 g(own_bound, (N + 256 * VEX_APT - 1) / (256 * VEX_APT));
+    k_evb_coupling_vex<<<g, 256, 0, c->stream>>>(d, e, sc.geo);
+    c->n_launch += 1;
   }
-  // Single rank, tree solver, delta algebra: the ground state needs only energies RELATIVE to H_11, so the solver (and the
-  // averaged-grid convolution behind it) must not wait for the principal diabat's pair forces -- the longest kernel of the
-  // step on large boxes.  The branches join on aux[0], where evb_mix runs the solver; the main stream (pair forces) is
-  // joined only by k_evb_finalize_principal and the force mixing.
-  h.overlap_solver = (d.world == 1 && c->evb_solver == 0 && algebra);
-  if (h.overlap_solver) {
+  // Single rank, tree solver: the ground state needs only energies RELATIVE to H_11, so the solver (and the averaged-grid
+  // convolution behind it) must not wait for the principal diabat's pair forces -- the longest kernel of the step on large
+  // boxes.  The branches join on aux[0], where evb_mix runs the solver; the main stream (pair forces) is joined only by
+  // k_evb_finalize_principal and the force mixing.
+  c->evb_overlap_solver = (d.world == 1 && c->evb_solver == 0);
+  if (c->evb_overlap_solver) {
     stream_depend(c, 7, c->aux[1], c->aux[0]);
     stream_depend(c, 13, c->aux[4], c->aux[0]);
-    CKE(cudaStreamWaitEvent(c->aux[0], c->ev_sync[19], 0));          // coupling geometry (aux[3])
   } else {
     stream_depend(c, 6, c->aux[0], c->main_stream);
     stream_depend(c, 7, c->aux[1], c->main_stream);
     stream_depend(c, 13, c->aux[4], c->main_stream);
   }
-  if (d.rank == 0) stream_depend(c, 9, c->aux[2], c->main_stream);   // bonded terms of the principal diabat
+  if (d.rank == 0) stream_depend(c, 9, c->aux[2], c->main_stream);   // bonded terms of the principal diabat (+ pair matrix)
+  else stream_depend(c, 9, c->aux[2], c->evb_overlap_solver ? c->aux[0] : c->main_stream);
   if (d.world > 1 || c->evb_solver != 0) {
     ScopedTimer t(c, T_EVB_ASSEMBLE);
-    k_evb_assemble<<<(MAXS + 31) / 32, 32, 0, c->stream>>>(d, e, sc.geo, sc.last_item, algebra ? nullptr : sc.slot_of_state);
+    k_evb_assemble<<<(MAXS + 31) / 32, 32, 0, c->stream>>>(d, e, sc.geo);
     c->n_launch += 1;
-  } else h.assemble_pending = true;   // single rank, tree solver: assembled in the solver's prologue
+    c->evb_assemble_pending = false;
+  } else c->evb_assemble_pending = true;   // single rank, tree solver: assembled in the solver's prologue
   // keep the principal-diabat force (incl. EVB repulsion, without reciprocal part) in dF slot 0: d.force is
-  // overwritten with the adiabatic force at commit time
+  // overwritten with the adiabatic force
   if (d.world > 1) { k_copy<<<(unsigned)((n3 + 255) / 256), 256, 0, c->stream>>>(e.dF, d.force, n3); c->n_launch++; }   // single rank: saved by k_evb_mix_forces
   h.built = true;
-  HostClock::acc[2] += HostClock::now() - hc0;
   return 0;
 }
 
 int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_host) {
   Dev& d = c->d; EvbDev& e = c->e; EvbHost& h = c->eh;
-  EvbScratch& sc = g_scratch[c];
+  EvbScratch& sc = scratch(c);
   if (!h.built) { c->err = "evb_mix before evb_build"; return RPB_ERR_STATE; }
-  double hm0 = HostClock::now();
-  const int N = d.N, S = h.n_states;
+  const int N = d.N;
   const size_t K3 = (size_t)d.K * d.K * d.K, n3 = (size_t)3 * N;
-  int n_own = 0;
-  for (int s = 1; s < S; s++) if (state_owned(s, d.rank, d.world)) n_own++;
   const double* coeff_dev = nullptr;
   if (coeff_override_host) {
-    CKE(cudaMemcpyAsync(sc.coeff_dev, coeff_override_host, S * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CKE(cudaMemcpyAsync(sc.coeff_dev, coeff_override_host, MAXS * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     coeff_dev = sc.coeff_dev;
   }
-  const bool fuse = (c->evb_solver == 0 && d.world == 1 && !coeff_override_host && h.assemble_pending);
-  const bool overlap = fuse && h.overlap_solver;
+  const bool fuse = (c->evb_solver == 0 && d.world == 1 && !coeff_override_host && c->evb_assemble_pending);
+  const bool overlap = fuse && c->evb_overlap_solver;
+  const int sb = s_bound(c);
   if (overlap) {
     {
       StreamScope ss(c, c->aux[0]);
       ScopedTimer t(c, T_EVB_DIAG);
-      k_evb_tree_solver<<<1, TREE_TPB, 0, c->stream>>>(d, e, nullptr, sc.geo, sc.last_item, nullptr, 1);
+      k_evb_tree_solver<<<1, TREE_TPB, 0, c->stream>>>(d, e, nullptr, sc.geo, 1);
       CKE(cudaEventRecord(c->ev_sync[6], c->stream));               // "ground state known"
     }
-    // H_11, absolute energies and the read-back block: on the read-back stream, behind the solver and behind what the main
-    // stream holds so far (pair forces; bonded terms were joined by evb_build) -- not in the chain of the force mixing
+    // H_11, absolute energies and the status block: behind the solver and behind what the main stream holds so far (pair
+    // forces; bonded terms were joined by evb_build) -- on aux[3], not in the chain of the force mixing
     CKE(cudaEventRecord(c->ev_sync[0], c->main_stream));
     CKE(cudaStreamWaitEvent(c->aux[3], c->ev_sync[6], 0));
     CKE(cudaStreamWaitEvent(c->aux[3], c->ev_sync[0], 0));
     k_evb_finalize_principal<<<1, MAXS, 0, c->aux[3]>>>(d, e);
     CKE(cudaStreamWaitEvent(c->main_stream, c->ev_sync[6], 0));     // main: [pair forces, bonded terms] + ground state -> mixing
     c->n_launch += 2;
-    h.assemble_pending = false;
+    c->evb_assemble_pending = false;
   } else {
     ScopedTimer t(c, T_EVB_DIAG);
     if (c->evb_solver == 0) {
-      k_evb_tree_solver<<<1, TREE_TPB, 0, c->stream>>>(d, e, coeff_dev, fuse ? sc.geo : nullptr, sc.last_item, sc.recip_grids ? sc.slot_of_state : nullptr, 0);
-      c->n_launch++;
-      h.assemble_pending = false;
+      k_evb_tree_solver<<<1, TREE_TPB, 0, c->stream>>>(d, e, coeff_dev, fuse ? sc.geo : nullptr, 0);
+      c->evb_assemble_pending = false;
     } else {
-    const int np = S + (S & 1);
-    size_t shmem = ((size_t)3 * np * np + 2 * np) * sizeof(double);
-    if (shmem > 48 * 1024) cudaFuncSetAttribute(k_evb_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
-    const int nbp = np / 2, work = nbp * (nbp - 1) / 2 + nbp * nbp;   // 2x2 blocks of A (upper) and V per round
-    const int nthr = std::min(JAC_TPB, std::max(64, (work + 31) / 32 * 32));
-    k_evb_jacobi<<<1, nthr, shmem, c->stream>>>(d, e, coeff_dev);
-    c->n_launch++;
+      const size_t shmem = ((size_t)3 * MAXS * MAXS + 2 * MAXS) * sizeof(double);
+      k_evb_jacobi<<<1, JAC_TPB, shmem, c->stream>>>(d, e, coeff_dev);
     }
-  }
-  double* pd = (double*)(h.pinned + ENUM_BLOCK_INTS + (ENUM_BLOCK_INTS & 1));   // solver read-back block (8-byte aligned)
-  const int* pres = (const int*)pd;
-  if (!coeff_override_host) {
-  // read back what the host needs for the commit decision and the accessors right behind the solver: the host waits
-  // for THIS event only, while the mixing kernels queued below are still running
-  if (!overlap) {
-    CKE(cudaEventRecord(c->ev_sync[17], c->stream));
-    CKE(cudaStreamWaitEvent(c->aux[3], c->ev_sync[17], 0));
-  }
-  CKE(cudaMemcpyAsync(pd, e.result, SOLVER_BLOCK_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, c->aux[3]));   // copy stream: the mixing kernels do not queue behind it
-  CKE(cudaEventRecord(c->ev_enum, c->aux[3]));
+    c->n_launch++;
+    CKE(cudaEventRecord(c->ev_sync[6], c->stream));
   }
   {
-    int include_principal = 1;            // every rank holds its share of the principal-diabat force (pair forces are sharded by atoms)
-    // slot 0 (principal theta) only contributes on rank 0: mask it on the other ranks through slot_state
-    // theta_mix (grids) runs on aux[1] next to the force mixing (per-atom arrays) on the main stream; the gather of
-    // the mixed grid then adds into the mixed force
-    const bool algebra = !sc.recip_grids;
+    const int include_principal = 1;      // every rank holds its share of the principal-diabat force (pair forces are sharded by clusters)
     const int in_place = (d.world == 1 && !coeff_override_host) ? 1 : 0;
     double* out = in_place ? d.force : e.f_mix;
-    if (overlap) CKE(cudaStreamWaitEvent(c->aux[1], c->ev_sync[6], 0));   // the averaged grid needs the ground state, not the pair forces
-    else stream_depend(c, 0, c->main_stream, c->aux[1]);
-    if (algebra) {
-      // aux[1]: averaged charge deltas -> patch the copy of the principal grid -> ONE convolution; main: force mixing and the
-      // chain atoms' own reciprocal terms; then the mixed grid is gathered once (sharded runs: this rank's slice of atoms)
+    CKE(cudaStreamWaitEvent(c->aux[1], c->ev_sync[6], 0));   // the averaged grid needs the ground state, not the pair forces
+    // aux[1]: averaged charge deltas -> patch the copy of the principal grid -> ONE convolution; main: force mixing and the
+    // chain atoms' own reciprocal terms; then the mixed grid is gathered once (sharded runs: this rank's slice of atoms)
+    {
+      StreamScope ss(c, c->aux[1]);
+      if (coeff_override_host) { k_copy<<<(unsigned)((K3 + 255) / 256), 256, 0, c->stream>>>(d.Q + K3, d.Q, K3); c->n_launch++; }   // debug re-mix: fresh copy
       {
-        StreamScope ss(c, c->aux[1]);
-        if (coeff_override_host) { k_copy<<<(unsigned)((K3 + 255) / 256), 256, 0, c->stream>>>(d.Q + K3, d.Q, K3); c->n_launch++; }   // debug re-mix: fresh copy
-        if (S > 1) {
-          ScopedTimer t(c, T_EVB_PATCH);
-          k_evb_rcp_patch<<<(sc.n_rmol * MA * 32 + 255) / 256, 256, 0, c->stream>>>(d, e, sc.rd, d.Q + K3, sc.n_rmol);
-          c->n_launch += 1;
-        }
-        int rc2 = launch_convolve(c, 1, 1, e.e_recip, true);
-        if (rc2) return rc2;
+        ScopedTimer t(c, T_EVB_PATCH);
+        k_evb_rcp_patch<<<((sb + 1) * MA * 32 + 255) / 256, 256, 0, c->stream>>>(d, e, sc.rd, d.Q + K3);
+        c->n_launch += 1;
       }
-      { ScopedTimer t(c, T_EVB_MIXF); k_evb_mix_forces<<<(unsigned)((n3 + 255) / 256), 256, 0, c->stream>>>(d, e, sc.state_list, n_own, include_principal, in_place);
-        if (S > 1 && d.rank == 0) { k_evb_rcp_mix<<<(S * RA_ENT + 127) / 128, 128, 0, c->stream>>>(d, e, sc.rd, out); c->n_launch++; }
-        if (S > 1 && c->evb_may_reorder) { k_evb_reorder_quirk<<<(S + 3) / 4, 128, 0, c->stream>>>(d, e, sc.rd, out, 1); c->n_launch++; } }
-      stream_depend(c, 1, c->aux[1], c->main_stream);
-      const int i0 = (int)((long long)N * d.rank / d.world), i1 = (int)((long long)N * (d.rank + 1) / d.world);
-      { ScopedTimer t(c, T_EVB_GATHERMIX); k_evb_gather_range<<<((i1 - i0) * 32 + 255) / 256, 256, 0, c->stream>>>(d, d.theta + K3, out, i0, i1); }
-      c->n_launch += 2;
-    } else {
-    { StreamScope ss(c, c->aux[1]); ScopedTimer t(c, T_EVB_THETAMIX); k_evb_theta_mix<<<(unsigned)((K3 / 2 + 255) / 256), 256, 0, c->stream>>>(d, e, sc.slot_state, n_own + 1); }
-    { ScopedTimer t(c, T_EVB_MIXF); k_evb_mix_forces<<<(unsigned)((n3 + 255) / 256), 256, 0, c->stream>>>(d, e, sc.state_list, n_own, include_principal, in_place);
-      if (n_own > 0) { k_evb_add_corr<<<(n_own * CM * MA + 127) / 128, 128, 0, c->stream>>>(d, e, sc.state_list, n_own, out); c->n_launch++; } }
-    stream_depend(c, 1, c->aux[1], c->main_stream);
-    { ScopedTimer t(c, T_EVB_GATHERMIX); k_evb_gather_mix<<<(N * 32 + 255) / 256, 256, 0, c->stream>>>(d, e, out); }
-    c->n_launch += 3;
+      int rc2 = launch_convolve(c, 1, 1, e.e_recip, true);
+      if (rc2) return rc2;
     }
+    {
+      ScopedTimer t(c, T_EVB_MIXF);
+      k_evb_mix_forces<<<(unsigned)((n3 + 255) / 256), 256, 0, c->stream>>>(d, e, include_principal, in_place);
+      if (d.rank == 0) { k_evb_rcp_mix<<<(sb * RA_ENT + 127) / 128, 128, 0, c->stream>>>(d, e, sc.rd, out); c->n_launch++; }
+      if (c->evb_any_multi_basic) { k_evb_reorder_quirk<<<(sb + 3) / 4, 128, 0, c->stream>>>(d, e, sc.rd, out, 1); c->n_launch++; }
+    }
+    stream_depend(c, 1, c->aux[1], c->main_stream);
+    const int i0 = (int)((long long)N * d.rank / d.world), i1 = (int)((long long)N * (d.rank + 1) / d.world);
+    { ScopedTimer t(c, T_EVB_GATHERMIX); k_evb_gather_range<<<((i1 - i0) * 32 + 255) / 256, 256, 0, c->stream>>>(d, d.theta + K3, out, i0, i1); }
+    c->n_launch += 2;
   }
   if (coeff_override_host) {
     CKE(cudaStreamSynchronize(c->stream));
     CKE(cudaMemcpy(force_out_host, e.f_mix, n3 * sizeof(double), cudaMemcpyDeviceToHost));
-    return 0;
   }
-  double hm1 = HostClock::now();
-  CKE(cudaEventSynchronize(c->ev_enum));
-  HostClock::acc[3] += hm1 - hm0; HostClock::acc[4] += HostClock::now() - hm1;
+  return 0;
+}
+
+// Hop commit (evb_change_diabat_data_structure_topology, ms_evb.f90:806-834, + the forced list rebuild of :223-225):
+// device kernels that act only when the solver selected a new hydronium molecule.  Also queues the read-back of the
+// step's results (enumeration block, solver block, commit counter) into pinned memory -- nobody waits for it here.
+int evb_commit(rpb_ctx* c) {
+  Dev& d = c->d; EvbDev& e = c->e; EvbHost& h = c->eh;
+  EvbScratch& sc = scratch(c);
+  const int N = d.N;
+  if (d.world > 1 && !c->peer.f_reduced_in_place) { k_copy<<<(3 * N + 255) / 256, 256, 0, c->stream>>>(d.force, e.f_mix, (size_t)3 * N); c->n_launch++; }   // single rank: mixed in place; peer exchange: reduced into d.force
+  c->peer.f_reduced_in_place = false;
+  // the status block must be complete before it is copied: k_evb_finalize_principal runs on aux[3]
+  const int nb = (std::max(N, d.M) + 255) / 256;
+  k_evb_commit_prepare<<<1, 32, 0, c->stream>>>(d, e, sc.commit);
+  k_evb_commit_permute<<<nb, 256, 0, c->stream>>>(d, e, sc.commit, sc.xq2, sc.vel2, sc.force2, sc.mass2, sc.type2, sc.moa2);
+  k_evb_commit_finish<<<(N + 255) / 256, 256, 0, c->stream>>>(d, e, sc.commit, sc.xq2, sc.vel2, sc.force2, sc.mass2, sc.type2, sc.moa2);
+  c->n_launch += 3;
+  int rc = launch_verlet_commit_rebuild(c);     // construct_verlet_list + update_verlet_displacements(init), only after a hop
+  if (rc) return rc;
+  // read-back (aux[3], behind the main stream's commit kernels and its own finalize kernel)
+  CKE(cudaEventRecord(c->ev_sync[17], c->stream));
+  CKE(cudaStreamWaitEvent(c->aux[3], c->ev_sync[17], 0));
+  int* pin = h.pinned;
+  double* pd = (double*)(pin + ENUM_BLOCK_INTS + (ENUM_BLOCK_INTS & 1));
+  CKE(cudaMemcpyAsync(pin, e.n_states, ENUM_BLOCK_INTS * sizeof(int), cudaMemcpyDeviceToHost, c->aux[3]));
+  CKE(cudaMemcpyAsync(pd, e.result, SOLVER_BLOCK_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, c->aux[3]));
+  CKE(cudaMemcpyAsync(pd + SOLVER_BLOCK_DOUBLES + 1, sc.commit, sizeof(CommitInfo), cudaMemcpyDeviceToHost, c->aux[3]));
+  stream_depend(c, 2, c->aux[3], c->main_stream);
+  return 0;
+}
+
+// The one synchronising read of a call: results of the LAST step (accessors), sticky error flags of all of them.
+int evb_readback(rpb_ctx* c) {
+  EvbHost& h = c->eh;
+  EvbScratch& sc = scratch(c);
+  CKE(cudaStreamSynchronize(c->main_stream));
+  const int* pin = h.pinned;
+  const double* pd = (const double*)(pin + ENUM_BLOCK_INTS + (ENUM_BLOCK_INTS & 1));
+  const int* pres = (const int*)pd;
+  h.n_states = pin[0];
+  h.s_hint = std::max(1, h.n_states);
+  memcpy(h.n_hops, pin + 16, MAXS * sizeof(int));
+  memcpy(h.parent, pin + 16 + MAXS, MAXS * sizeof(int));
+  memcpy(h.proton_log, pin + 16 + 2 * MAXS, MAXS * MAXC * 5 * sizeof(int));
   for (int k = 0; k < 4; k++) c->h_flags[k] = (int)pd[5 + 3 * MAXS + k];
   for (int k = 0; k < E_NSLOT; k++) c->h_en[k] = pd[5 + 3 * MAXS + 4 + k];
   if (c->h_flags[1]) { c->err = "please increase size of verlet neighbor list"; return RPB_ERR_VERLET; }
+  if (c->h_flags[2]) { c->err = "Found more diabat states than the current setting of evb_max_states"; return RPB_ERR_DIABATS; }
   if (c->h_flags[3] >= 30) { c->err = "peer-memory exchange: rank " + std::to_string(c->h_flags[3] - 30) + " did not arrive"; return RPB_ERR_CUDA; }
+  if (c->h_flags[3] == 1) { c->err = "error in subroutine find_bonded_atom_hydrogen"; return RPB_ERR_STATE; }
   if (c->h_flags[3]) { c->err = "couldn't find index in subroutine 'get_index_atom_set' (code " + std::to_string(c->h_flags[3]) + ")"; return RPB_ERR_STATE; }
   if (pres[2]) { c->err = "too many iterations in jacobi"; return RPB_ERR_STATE; }
   static const bool dbg_jacobi = getenv("RPB_DEBUG_JACOBI") != nullptr;
-  if (dbg_jacobi) fprintf(stderr, "[evb solver %s] S=%d %s=%d\n", c->evb_solver ? "jacobi" : "tree", S, c->evb_solver ? "sweeps" : "evaluations", pres[4]);
+  if (dbg_jacobi) fprintf(stderr, "[evb solver %s] S=%d %s=%d\n", c->evb_solver ? "jacobi" : "tree", h.n_states, c->evb_solver ? "sweeps" : "evaluations", pres[4]);
+  const int S = h.n_states;
   h.principal_diabat = pres[0]; h.new_hydronium = pres[1];
   h.adiabatic_potential = pd[4];
   memcpy(h.evec, pd + 5, MAXS * sizeof(double));
@@ -2537,29 +2420,6 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
     h.hamiltonian[s][s] = pd[5 + MAXS + s];
     if (s > 0) h.hamiltonian[h.parent[s]][s] = pd[5 + 2 * MAXS + s];
   }
-  return 0;
-}
-
-// shift_array_data_donor_acceptor_transfer on a permutation vector (ms_evb.f90:2677-2840)
-static void host_shift(std::vector<int>& perm, std::vector<int>& first, std::vector<int>& natom, int m_from, int a_from, int m_to, int a_to) {
-  int from_g = first[m_from] + a_from;
-  int to_g = (m_from < m_to) ? first[m_to] + a_to - 1 : first[m_to] + a_to;
-  int saved = perm[from_g];
-  if (from_g < to_g) for (int i = from_g; i < to_g; i++) perm[i] = perm[i + 1];
-  else for (int i = from_g; i > to_g; i--) perm[i] = perm[i - 1];
-  perm[to_g] = saved;
-  if (from_g < to_g) { for (int m = m_from + 1; m <= m_to; m++) first[m] -= 1; }
-  else { for (int m = m_to + 1; m <= m_from; m++) first[m] += 1; }
-  natom[m_to] += 1; natom[m_from] -= 1;
-}
-
-int evb_commit(rpb_ctx* c) {
-  HostClock::report();
-  Dev& d = c->d; EvbDev& e = c->e; EvbHost& h = c->eh;
-  EvbScratch& sc = g_scratch[c];
-  const int N = d.N, M = d.M;
-  if (d.world > 1 && !c->peer.f_reduced_in_place) { k_copy<<<(3 * N + 255) / 256, 256, 0, c->stream>>>(d.force, e.f_mix, (size_t)3 * N); c->n_launch++; }   // single rank: mixed in place; peer exchange: reduced into d.force
-  c->peer.f_reduced_in_place = false;
   // energies as the reference leaves them: potential = adiabatic energy, components = principal diabat's
   {
     rpb_energies& en = c->last_en;
@@ -2569,68 +2429,9 @@ int evb_commit(rpb_ctx* c) {
     en.E_vdw = s[E_VDW]; en.E_bond = s[E_BOND]; en.E_angle = s[E_ANGLE]; en.E_dihedral = s[E_DIH];
     en.potential_energy = h.adiabatic_potential;
   }
-  if (h.new_hydronium == c->hydronium_mol) return 0;
-  // ---- proton hop accepted: evb_change_diabat_data_structure_topology (ms_evb.f90:806-834)
-  c->state_cache_valid = false;
-  const int pdiab = h.principal_diabat;
-  if (d.world > 1 && !state_owned(pdiab, d.rank, d.world)) {
-    // every rank needs the final snapshot of the new principal diabat; non-owned diabats were not built in evb_build
-    k_evb_snapshots<<<1, 32, 0, c->stream>>>(d, e, pdiab, 0);
-    c->n_launch++;
-  }
-  std::vector<int> perm(N), first = c->mol_first, natom = c->mol_natom;
-  for (int i = 0; i < N; i++) perm[i] = i;
-  int nh = h.n_hops[pdiab];
-  // replay the hops on (first, n_atom) to obtain the atom permutation; the per-molecule reordering of the acceptor
-  // (reorder_molecule_data_structures) is taken from the snapshot, whose atom[] lists give the final order
-  int ima = c->hydronium_mol;
-  std::vector<int> cur_first = first, cur_natom = natom;
-  for (int k = 0; k < nh; k++) {
-    int imd = ima;
-    int i_atom_donor = h.proton_log[pdiab][k][1];
-    ima = h.proton_log[pdiab][k][3];
-    host_shift(perm, cur_first, cur_natom, imd, i_atom_donor, ima, cur_natom[ima]);
-  }
-  // chain molecule list (same construction as on the device)
-  int mols[CM], nm = 1;
-  mols[0] = c->hydronium_mol;
-  for (int k = 0; k < nh; k++) {
-    int a = h.proton_log[pdiab][k][3];
-    bool f = false;
-    for (int q = 0; q < nm; q++) f |= (mols[q] == a);
-    if (!f) mols[nm++] = a;
-  }
-  // final atom order inside each chain molecule comes from the snapshot (download it: tiny)
-  Snapshot snap;
-  CKE(cudaMemcpyAsync(&snap, e.snap + pdiab * NLEV + nh, sizeof(Snapshot), cudaMemcpyDeviceToHost, c->stream));
-  CKE(cudaStreamSynchronize(c->stream));
-  int new_first[CM] = {0, 0, 0, 0};
-  for (int k = 0; k < snap.n_mol; k++) {
-    int m = snap.m[k].mol;
-    new_first[k] = cur_first[m];
-    for (int a = 0; a < snap.m[k].n_atom; a++) perm[cur_first[m] + a] = snap.m[k].atom[a];
-  }
-  std::vector<int> moa(N);
-  for (int m = 0; m < M; m++) for (int a = 0; a < cur_natom[m]; a++) moa[cur_first[m] + a] = m;
-  CKE(cudaMemcpyAsync(sc.perm, perm.data(), N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  CKE(cudaMemcpyAsync(sc.moa2, moa.data(), N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  CKE(cudaMemcpyAsync(sc.new_first, new_first, CM * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  CKE(cudaMemcpyAsync(d.mol_first, cur_first.data(), M * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  CKE(cudaMemcpyAsync(d.mol_natom, cur_natom.data(), M * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  k_evb_commit_permute<<<(N + 255) / 256, 256, 0, c->stream>>>(d, sc.perm, sc.xq2, sc.vel2, sc.force2, sc.mass2, sc.type2, d.mol_of_atom, sc.moa2);
-  CKE(cudaMemcpyAsync(d.xq, sc.xq2, N * sizeof(double4), cudaMemcpyDeviceToDevice, c->stream));
-  CKE(cudaMemcpyAsync(d.vel, sc.vel2, 3 * N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-  CKE(cudaMemcpyAsync(d.force, sc.force2, 3 * N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-  CKE(cudaMemcpyAsync(d.mass, sc.mass2, N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-  CKE(cudaMemcpyAsync(d.type, sc.type2, N * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
-  k_evb_commit_patch<<<1, 1, 0, c->stream>>>(d, e, pdiab, nh, sc.new_first);
-  c->n_launch += 2;
-  // host mirror
-  c->mol_first = cur_first; c->mol_natom = cur_natom;
-  for (int k = 0; k < snap.n_mol; k++) c->mol_type[snap.m[k].mol] = snap.m[k].mtype;
-  c->hydronium_mol = h.new_hydronium;
-  // construct_verlet_list + update_verlet_displacements(init)  (ms_evb.f90:223-225)
-  { int rcv = launch_verlet_force_rebuild(c); if (rcv) return rcv; }
-  CKE(cudaStreamSynchronize(c->stream));
+  // committed hops permuted the per-atom / per-molecule tables: the host mirrors and the upload cache are stale
+  CommitInfo ci;
+  memcpy(&ci, pd + SOLVER_BLOCK_DOUBLES + 1, sizeof(ci));
+  if (ci.hop_count != sc.hop_count_seen) { sc.hop_count_seen = ci.hop_count; c->state_cache_valid = false; c->mirror_stale = true; }
   return 0;
 }

@@ -25,10 +25,11 @@ namespace cg = cooperative_groups;
 #define TPB 256
 
 // per-block two largest |accumulated displacement|; the last block merges them and sets the flag (:1293-1326)
-__global__ void k_verlet_disp(Dev d, double* blk_top2, int* done_counter) {
+__global__ void k_verlet_disp(Dev d, double* blk_top2, int* done_counter, int only_if_rebuilt) {
   __shared__ double s1[TPB], s2[TPB];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int rebuild = *d.rebuild_now;
+  if (only_if_rebuilt && !rebuild) return;       // hop-commit call of a step without a hop
   double nrm = 0.0;
   if (i < d.N) {
     double4 p = d.xq[i];
@@ -243,8 +244,9 @@ __device__ __forceinline__ void tile_sweep(const Dev& d, const int I, const int 
 // rebuild it costs a single launch that exits at once.
 __global__ void __launch_bounds__(TPB) k_verlet_rebuild(Dev d, int force_rebuild, int ncell) {
   cg::grid_group grid = cg::this_grid();
-  // forced (init / hop commit): flag_verlet_list untouched (flag_junk, ms_evb.f90:223-225)
-  const int rb = force_rebuild ? 2 : ((*d.flag_verlet == 1) ? 1 : 0);
+  // forced (init / hop commit): flag_verlet_list untouched (flag_junk, ms_evb.f90:223-225).  force_rebuild == 2: the
+  // hop-commit call of the fixed per-step launch list -- forced if and only if the solver selected a hop this step
+  const int rb = (force_rebuild == 2) ? ((d.commit_hop && *d.commit_hop) ? 2 : 0) : (force_rebuild ? 2 : ((*d.flag_verlet == 1) ? 1 : 0));
   if (blockIdx.x == 0 && threadIdx.x == 0) { *d.rebuild_now = rb; d.maxd[0] = 0.0; d.maxd[1] = 0.0; }
   if (!rb) return;
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
@@ -436,6 +438,7 @@ int verlet_setup(rpb_ctx* c) {     // per context: the cooperative grid of THIS 
     return RPB_ERR_CUDA;
   }
   c->d.coop_blocks = std::max(2, std::min(std::min(per_sm, per_sm2), 4) * sms);
+  c->n_sm = sms;
   return 0;
 }
 
@@ -448,7 +451,7 @@ static int verlet_common(rpb_ctx* c, int force_rebuild) {
   void* args[] = {(void*)&d, (void*)&force_rebuild, (void*)&ncell};
   cudaError_t e = cudaLaunchCooperativeKernel((void*)k_verlet_rebuild, dim3(d.coop_blocks), dim3(TPB), args, 0, c->stream);
   if (e != cudaSuccess) { c->err = std::string("neighbour-list rebuild launch: ") + cudaGetErrorString(e); return RPB_ERR_CUDA; }
-  k_verlet_disp<<<nb, TPB, 0, c->stream>>>(d, blk_top2, d.vdone);
+  k_verlet_disp<<<nb, TPB, 0, c->stream>>>(d, blk_top2, d.vdone, force_rebuild == 2 ? 1 : 0);
   e = cudaGetLastError();
   if (e != cudaSuccess) { c->err = std::string("k_verlet_disp launch: ") + cudaGetErrorString(e); return RPB_ERR_CUDA; }
   c->n_launch += 2;
@@ -457,6 +460,8 @@ static int verlet_common(rpb_ctx* c, int force_rebuild) {
 
 int launch_verlet_update(rpb_ctx* c) { const int f = c->rebuild_forced ? 1 : 0; c->rebuild_forced = false; return verlet_common(c, f); }
 int launch_verlet_force_rebuild(rpb_ctx* c) { c->rebuild_forced = false; return verlet_common(c, 1); }
+
+int launch_verlet_commit_rebuild(rpb_ctx* c) { return verlet_common(c, 2); }
 
 // the reference-ordered half list of the last rebuild -> d.verlet_point / d.neighbor_list (accessor only)
 int launch_verlet_reference_list(rpb_ctx* c) {

@@ -118,7 +118,8 @@ int calculate_total_force_energy(rpb_ctx* c, bool evb_principal) {
   return 0;
 }
 
-static int force_energy(rpb_ctx* c, int ms_evb, bool sync) {
+// enqueue one force evaluation (no host synchronisation)
+static int enqueue_force(rpb_ctx* c, int ms_evb) {
   int rc;
   if (ms_evb) {
     if (!c->have_evb) { c->err = "rpb_set_evb not called"; return RPB_ERR_STATE; }
@@ -128,16 +129,27 @@ static int force_energy(rpb_ctx* c, int ms_evb, bool sync) {
     if (sharded) { rc = peer_allreduce(c, PEER_H); if (rc) return rc; peer_begin(c, PEER_F); }
     rc = evb_mix(c, nullptr, nullptr); if (rc) return rc;
     if (sharded) { rc = peer_allreduce(c, PEER_F); if (rc) return rc; }
-    rc = evb_commit(c); if (rc) return rc;
-    return 0;
+    return evb_commit(c);
   }
-  rc = calculate_total_force_energy(c, false);
+  return calculate_total_force_energy(c, false);
+}
+
+// synchronise and collect what the accessors serve: error flags, energies, (MS-EVB) the last step's diabat set and solution
+static int collect_results(rpb_ctx* c, int ms_evb) {
+  int rc = fetch_status(c);
   if (rc) return rc;
-  if (sync) {
-    rc = fetch_status(c);
-    if (rc) return rc;
-    energies_from_slots(c);
-  }
+  if (ms_evb) return evb_readback(c);
+  energies_from_slots(c);
+  return 0;
+}
+
+// md_integrate_atomic (md_integration.f90:438-541), one step, enqueue only
+static int enqueue_step(rpb_ctx* c, int ms_evb) {
+  ScopedTimer t(c, T_STEP);
+  launch_integrate_first(c);
+  int rc = enqueue_force(c, ms_evb);
+  if (rc) return rc;
+  launch_integrate_second(c);
   return 0;
 }
 
@@ -373,7 +385,7 @@ int rpb_set_molecule_types(rpb_ctx* c, const int* n_atom, const int* atom_type, 
       m.reactive_basic[a] = evb_reactive_basic_atoms ? evb_reactive_basic_atoms[t * MA + a] : 0;
       for (int b = 0; b < MA; b++) m.pair_excl[a][b] = pair_exclusions[t * MA * MA + a + MA * b];
     }
-    { int nb = 0; for (int a = 0; a < MA; a++) nb += (m.reactive_basic[a] == 1); c->mt_multi_basic.resize(c->d.nMT, 0); c->mt_multi_basic[t] = nb > 1; }
+    { int nb = 0; for (int a = 0; a < MA; a++) nb += (m.reactive_basic[a] == 1); c->mt_multi_basic.resize(c->d.nMT, 0); c->mt_multi_basic[t] = nb > 1; if (nb > 1) c->evb_any_multi_basic = true; }
     m.n_bond = n_bond[t]; m.n_angle = n_angle[t]; m.n_dih = n_dihedral[t];
     for (int b = 0; b < m.n_bond; b++) {
       int i = bonds[2 * (ob + b)] - 1, j = bonds[2 * (ob + b) + 1] - 1;
@@ -507,6 +519,24 @@ static int staging_get(rpb_ctx* c, Staging& st) {
   return 0;
 }
 
+// committed hops permute the molecule table on the device; the host mirror (served by rpb_download_state, compared by
+// rpb_upload_state) is refreshed from the device when evb_readback has seen a new hop
+static int refresh_mirror(rpb_ctx* c) {
+  if (!c->mirror_stale) return 0;
+  const int M = c->d.M;
+  CK(cudaStreamSynchronize(c->stream));
+  c->mol_first.resize(M); c->mol_natom.resize(M); c->mol_type.resize(M);
+  CK(cudaMemcpy(c->mol_first.data(), c->d.mol_first, M * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(c->mol_natom.data(), c->d.mol_natom, M * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(c->mol_type.data(), c->d.mol_type, M * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&c->hydronium_mol, c->d.hydronium, sizeof(int), cudaMemcpyDeviceToHost));
+  int ncl = 0;
+  for (int m = 0; m < M; m++) ncl += (c->mol_natom[m] + 2) / 3;
+  c->n_clusters_bound = std::min(c->d.N, ncl + 2);
+  c->mirror_stale = false;
+  return 0;
+}
+
 int rpb_upload_state(rpb_ctx* c, const double* xyz, const double* velocity, const double* mass, const double* charge,
                      const int* atom_type_index, const int* mol_first_atom, const int* mol_n_atom, const int* mol_type,
                      int hydronium_mol) {
@@ -523,6 +553,7 @@ int rpb_upload_state(rpb_ctx* c, const double* xyz, const double* velocity, cons
     if (expect != N) { c->err = "molecule table does not cover all atoms"; return RPB_ERR_ARG; }
   }
   CK(cudaStreamSynchronize(c->stream));          // the staging area may still feed an earlier copy
+  if ((rc = refresh_mirror(c))) return rc;
   const bool all = !c->have_state || !c->state_cache_valid;   // a committed proton hop permuted the device tables
   bool type_changed = all, mass_changed = all, mol_changed = all;
   for (int i = 0; i < N; i++) {
@@ -579,7 +610,9 @@ int rpb_initialize(rpb_ctx* c) {
 int rpb_force_energy(rpb_ctx* c, int ms_evb) {
   if (!c->initialized) { c->err = "rpb_initialize not called"; return RPB_ERR_STATE; }
   if (ms_evb && c->d.world > 1 && !c->peer.on) { c->err = "world_size>1: set up the peer-memory exchange (rpb_peer_*) or use the phase calls"; return RPB_ERR_STATE; }
-  return force_energy(c, ms_evb, true);
+  int rc = enqueue_force(c, ms_evb);
+  if (rc) return rc;
+  return collect_results(c, ms_evb);
 }
 
 int rpb_step_begin(rpb_ctx* c) { launch_integrate_first(c); return 0; }
@@ -591,7 +624,7 @@ int rpb_step_end(rpb_ctx* c) {
 // the phase calls always use the library's own exchange buffers (the caller runs the collectives), never the peer arena
 int rpb_evb_phase_build(rpb_ctx* c) { if (c->peer.h_local) c->e.h_diag = c->peer.h_local; return evb_build(c); }
 int rpb_evb_phase_mix(rpb_ctx* c) { if (c->peer.f_local) c->e.f_mix = c->peer.f_local; c->peer.f_reduced_in_place = false; return evb_mix(c, nullptr, nullptr); }
-int rpb_evb_phase_commit(rpb_ctx* c) { return evb_commit(c); }
+int rpb_evb_phase_commit(rpb_ctx* c) { int rc = evb_commit(c); return rc ? rc : evb_readback(c); }
 int rpb_evb_exchange_h(rpb_ctx* c, void** ptr, int* n) { *ptr = c->e.h_diag; *n = 3 * RPB_MAXS + E_NSLOT; return 0; }
 int rpb_evb_exchange_f(rpb_ctx* c, void** ptr, int* n) { *ptr = c->e.f_mix; *n = 3 * c->d.N; return 0; }
 
@@ -599,16 +632,10 @@ int rpb_step(rpb_ctx* c, int n_steps, int ms_evb) {
   if (!c->initialized) { c->err = "rpb_initialize not called"; return RPB_ERR_STATE; }
   if (ms_evb && c->d.world > 1 && !c->peer.on) { c->err = "world_size>1: set up the peer-memory exchange (rpb_peer_*) or use the phase calls"; return RPB_ERR_STATE; }
   for (int s = 0; s < n_steps; s++) {
-    ScopedTimer t(c, T_STEP);
-    launch_integrate_first(c);
-    int rc = force_energy(c, ms_evb, false);
+    int rc = enqueue_step(c, ms_evb);
     if (rc) return rc;
-    launch_integrate_second(c);
   }
-  int rc = fetch_status(c);
-  if (rc) return rc;
-  if (!ms_evb) energies_from_slots(c);
-  return 0;
+  return collect_results(c, ms_evb);
 }
 
 // Independent replicas (BASELINE config 5, "replicas only": no communication): every context is driven by its own host
@@ -645,6 +672,7 @@ int rpb_download_state(rpb_ctx* c, double* xyz, double* velocity, double* force,
   Staging st;
   int rc = staging_get(c, st);
   if (rc) return rc;
+  if ((rc = refresh_mirror(c))) return rc;
   // a separate pinned block would be needed to keep the upload cache valid: downloads use the tail halves only where they
   // do not alias cached tables (xq, vel, force are re-sent on every upload anyway)
   if (xyz || charge) CK(cudaMemcpyAsync(st.xq, c->d.xq, N * sizeof(double4), cudaMemcpyDeviceToHost, c->stream));

@@ -97,6 +97,7 @@ struct Dev {
   double4* vsort_xq; int* vsort_mol; int* vsort_entry;  // cell-sorted atom copies (reference-list accessor)
   unsigned long long* vstat;                // [0] bits of the largest cluster extent  [1] listed (ordered) atom pairs  [2] rebuild counter
   double* vstore; double* vdisp; int* flag_verlet; int* rebuild_now;
+  const int* commit_hop;                    // device flag: the MS-EVB solver selected a new hydronium molecule this step (null without MS-EVB)
   int* err_flag;  // [0] atom with |F|>1e5 (1-based, 0 none)  [1] verlet overflow  [2] too many diabats  [3] evb lookup failure
   int ncx, ncy, ncz, dia, dib, dic;
   int coop_blocks;                          // grid of the cooperative rebuild kernels on this context's device

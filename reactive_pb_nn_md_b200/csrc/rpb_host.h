@@ -50,18 +50,22 @@ struct rpb_ctx {
   std::vector<int> mol_first, mol_natom, mol_type;
   int hydronium_mol = -1;
   bool rebuild_forced = false;  // rpb_upload_state brought a different molecule table: the next force evaluation rebuilds the list
+  int n_sm = 148;              // multiprocessors of this context's device (persistent grids)
   int n_clusters_bound = 0;    // upper bound of the number of atom clusters (kernels_nlist.cu) for grid sizing; the count itself lives on the device
   // cuFFT
   std::map<int, cufftHandle> plan_fwd, plan_inv;   // keyed by (rounded) batch size
   char* fft_work = nullptr; size_t fft_work_bytes = 0;   // work area shared by every plan
   // EVB
   EvbDev e;                    // device pointers of the EVB working set
-  EvbHost eh;                  // pinned host read-back area + per-step host state
+  EvbHost eh;                  // pinned host read-back area + the last evaluated step's results
+  void* evb_scratch = nullptr; // EvbScratch (kernels_evb.cu): device scratch of the MS-EVB build, owned by this context
+  bool evb_overlap_solver = false;    // the branches of evb_build were joined on aux[0] (not on the main stream): evb_mix runs the solver there
+  bool evb_assemble_pending = false;  // evb_build left the Hamiltonian assembly to the solver kernel
+  bool evb_any_multi_basic = false;   // some molecule type has more than one atom that can be protonated (reference re-ordering quirk possible)
+  bool mirror_stale = false;          // a committed hop changed the molecule table on the device: the host mirror is refreshed before use
   int grid_capacity = 0;       // number of K^3 grids usable in d.Q / d.theta (4 spare ones follow for the rounded FFT batch)
   int evb_solver = 0;          // 0: tree-structured ground-state solver (default)  1: block Jacobi (RPB_EVB_SOLVER=jacobi)
   std::vector<char> mt_multi_basic;   // per molecule type: more than one atom that can be protonated
-  bool evb_may_reorder = false; // this step, some chain molecule has such a type: a protonated acceptor may be re-ordered to its
-                               // template (reference quirk handled by k_evb_reorder_quirk)
   double evb_rcand = 0.0;      // candidate-list radius of the diabat real-space deltas
   double evb_rep_reach = 0.0;  // largest cutoff of the EVB proton-acceptor repulsion
   // pinned scratch
@@ -128,6 +132,7 @@ void launch_update_com_shift(rpb_ctx*, bool shift);
 int verlet_setup(rpb_ctx*);                 // per-context sizing of the cooperative rebuild kernels
 int launch_verlet_update(rpb_ctx*);         // total_energy_forces.f90:30-39
 int launch_verlet_force_rebuild(rpb_ctx*);  // construct_verlet_list + displacement init
+int launch_verlet_commit_rebuild(rpb_ctx*); // the forced rebuild of a committed hop (ms_evb.f90:223-225); acts only if the device-side hop flag is set
 int launch_verlet_reference_list(rpb_ctx*); // parity accessor: the reference's half list in its row order
 void launch_zero_forces(rpb_ctx*);
 void launch_kinetic_energy(rpb_ctx*);
@@ -158,3 +163,4 @@ void evb_clear_early(rpb_ctx*);      // accumulators of the build for the previo
 int evb_build(rpb_ctx*);
 int evb_mix(rpb_ctx*, const double* coeff_override_host, double* force_out_host);
 int evb_commit(rpb_ctx*);
+int evb_readback(rpb_ctx*);          // synchronising read of the last step's results + sticky error flags
