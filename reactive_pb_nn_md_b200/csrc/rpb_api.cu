@@ -285,6 +285,7 @@ void rpb_destroy(rpb_ctx* c) {
   for (void* p : c->allocs) cudaFree(p);
   if (c->h_en) cudaFreeHost(c->h_en);
   if (c->h_flags) cudaFreeHost(c->h_flags);
+  for (int k = 0; k < 2; k++) if (c->graph[k].exec) cudaGraphExecDestroy(c->graph[k].exec);
   if (c->staging) cudaFreeHost(c->staging);
   if (c->eh.pinned) cudaFreeHost(c->eh.pinned);
   if (c->stream) {
@@ -628,21 +629,101 @@ int rpb_evb_phase_commit(rpb_ctx* c) { int rc = evb_commit(c); return rc ? rc : 
 int rpb_evb_exchange_h(rpb_ctx* c, void** ptr, int* n) { *ptr = c->e.h_diag; *n = 3 * RPB_MAXS + E_NSLOT; return 0; }
 int rpb_evb_exchange_f(rpb_ctx* c, void** ptr, int* n) { *ptr = c->e.f_mix; *n = 3 * c->d.N; return 0; }
 
-int rpb_step(rpb_ctx* c, int n_steps, int ms_evb) {
-  if (!c->initialized) { c->err = "rpb_initialize not called"; return RPB_ERR_STATE; }
-  if (ms_evb && c->d.world > 1 && !c->peer.on) { c->err = "world_size>1: set up the peer-memory exchange (rpb_peer_*) or use the phase calls"; return RPB_ERR_STATE; }
-  for (int s = 0; s < n_steps; s++) {
+// One MD step is a fixed launch sequence (every data-dependent decision -- number of diabats, list rebuild, proton hop --
+// is taken on the device), so it is captured once into a CUDA graph and replayed: ~45 kernel nodes on six streams cost
+// one launch call per step instead of ~60 API calls.  Not used while the per-kernel timers run, for state-sharded ranks
+// (the peer exchange alternates its buffers from step to step) or when RPB_GRAPH=0.
+static bool graph_allowed(rpb_ctx* c, int ms_evb) {
+  static const bool off = getenv("RPB_GRAPH") && atoi(getenv("RPB_GRAPH")) == 0;
+  return !off && !c->timers_on && !c->serial_streams && !(ms_evb && c->d.world > 1) && !c->graph_failed;
+}
+
+static int graph_get(rpb_ctx* c, int ms_evb, cudaGraphExec_t* out) {
+  StepGraph& g = c->graph[ms_evb ? 1 : 0];
+  const int hint = ms_evb ? c->eh.s_hint : 0;
+  if (g.exec && (hint > g.s_hint + 12 || hint < g.s_hint - 24 || g.n_clusters_bound != c->n_clusters_bound)) {   // grids sized for another diabat count
+    cudaGraphExecDestroy(g.exec); g.exec = nullptr;
+  }
+  if (!g.exec) {
+    const long long l0 = c->n_launch;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(c->main_stream, cudaStreamCaptureModeThreadLocal);
+    int rc = 0;
+    if (e == cudaSuccess) {
+      rc = enqueue_step(c, ms_evb);
+      e = cudaStreamEndCapture(c->main_stream, &graph);
+    }
+    if (e == cudaSuccess && rc == 0) e = cudaGraphInstantiate(&g.exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (e != cudaSuccess || rc != 0 || !g.exec) {
+      cudaGetLastError();
+      g.exec = nullptr;
+      c->graph_failed = true;              // fall back to plain launches for the rest of this context's life
+      c->n_launch = l0;
+      static const bool dbg = getenv("RPB_DEBUG_GRAPH") != nullptr;
+      if (dbg) fprintf(stderr, "[rpbmd] step graph capture failed (%s, rc %d): plain launches\n", cudaGetErrorString(e), rc);
+      if (rc) return rc;
+      *out = nullptr;
+      return 0;
+    }
+    g.launches = (int)(c->n_launch - l0);
+    c->n_launch = l0;
+    g.s_hint = hint; g.n_clusters_bound = c->n_clusters_bound;
+  }
+  *out = g.exec;
+  return 0;
+}
+
+static int enqueue_steps(rpb_ctx* c, int n_steps, int ms_evb) {
+  int s = 0;
+  if (graph_allowed(c, ms_evb) && !c->rebuild_forced && n_steps > 0) {
+    cudaGraphExec_t exec = nullptr;
+    int rc = graph_get(c, ms_evb, &exec);
+    if (rc) return rc;
+    if (exec) {
+      const StepGraph& g = c->graph[ms_evb ? 1 : 0];
+      for (; s < n_steps; s++) {
+        CK(cudaGraphLaunch(exec, c->main_stream));
+        c->n_launch += g.launches;
+      }
+    }
+  }
+  for (; s < n_steps; s++) {
     int rc = enqueue_step(c, ms_evb);
     if (rc) return rc;
   }
+  return 0;
+}
+
+int rpb_step(rpb_ctx* c, int n_steps, int ms_evb) {
+  if (!c->initialized) { c->err = "rpb_initialize not called"; return RPB_ERR_STATE; }
+  if (ms_evb && c->d.world > 1 && !c->peer.on) { c->err = "world_size>1: set up the peer-memory exchange (rpb_peer_*) or use the phase calls"; return RPB_ERR_STATE; }
+  int rc = enqueue_steps(c, n_steps, ms_evb);
+  if (rc) return rc;
   return collect_results(c, ms_evb);
 }
 
-// Independent replicas (BASELINE config 5, "replicas only": no communication): every context is driven by its own host
-// thread, so the replicas' kernels -- most of them latency-bound single-CTA or small-grid launches -- overlap on the
-// device through the contexts' own streams.  Returns the first non-zero status.
+// Independent replicas (BASELINE config 5, "replicas only": no communication).  A step needs no host decision, so ONE host
+// thread queues every replica's steps round-robin (one graph launch per replica and step) and the replicas' kernels --
+// most of them latency-bound single-CTA or small-grid launches -- overlap on the device through the contexts' own streams;
+// the results are collected once at the end.  Contexts on several devices, or without step graphs, are driven by one host
+// thread each.  Returns the first non-zero status.
 int rpb_ensemble_step(rpb_ctx** replicas, int n_replicas, int n_steps, int ms_evb) {
   if (!replicas || n_replicas < 1) return RPB_ERR_ARG;
+  bool one_thread = true;
+  for (int r = 0; r < n_replicas; r++) {
+    rpb_ctx* c = replicas[r];
+    if (!c->initialized) { c->err = "rpb_initialize not called"; return RPB_ERR_STATE; }
+    one_thread = one_thread && c->cfg.device == replicas[0]->cfg.device && graph_allowed(c, ms_evb) && !c->rebuild_forced;
+  }
+  if (one_thread) {
+    if (cudaSetDevice(replicas[0]->cfg.device) != cudaSuccess) { replicas[0]->err = "cudaSetDevice failed"; return RPB_ERR_CUDA; }
+    for (int s = 0; s < n_steps; s++)
+      for (int r = 0; r < n_replicas; r++) { int rc = enqueue_steps(replicas[r], 1, ms_evb); if (rc) return rc; }
+    int first = 0;
+    for (int r = 0; r < n_replicas; r++) { int rc = collect_results(replicas[r], ms_evb); if (rc && !first) first = rc; }
+    return first;
+  }
   std::vector<int> rc(n_replicas, 0);
   std::vector<std::thread> th;
   th.reserve(n_replicas);

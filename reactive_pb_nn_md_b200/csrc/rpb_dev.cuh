@@ -131,6 +131,18 @@ __device__ __forceinline__ double4 ldg256(const double4* p) {
 //      only where the summation order is free) ----
 __device__ __forceinline__ double min_image(double d, double L) { return d - L * floor(d / L + 0.5); }
 
+// floor / ceil of |t| < 2^51 on the FP64 pipe (two DADDs with directed rounding around 1.5 * 2^52) instead of the
+// conversion unit's FRND.F64, which runs at a fraction of the FP64 rate on sm_100 (ncu: the XU pipe, not the FP64 pipe,
+// was the busiest unit of the pair kernel).  Exact: t + M lies in [2^52, 2^53), where the spacing of doubles is 1.
+#define RPB_MAGIC_2P52 6755399441055744.0
+__device__ __forceinline__ double floor_fp64pipe(double t) { return __dadd_rn(__dadd_rd(t, RPB_MAGIC_2P52), -RPB_MAGIC_2P52); }
+// ceil(t) as a double and as an int (the low word of the biased sum), 0 <= t < 2^31
+__device__ __forceinline__ double ceil_fp64pipe(double t, int& i) {
+  const double b = __dadd_ru(t, RPB_MAGIC_2P52);
+  i = __double2loint(b);
+  return __dadd_rn(b, -RPB_MAGIC_2P52);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);

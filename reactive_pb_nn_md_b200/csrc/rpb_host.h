@@ -28,6 +28,9 @@ struct PeerExchange {
   int n[2] = {0, 0}, n_act[2] = {0, 0};    // stride / length in doubles of one partial
 };
 
+// one MD step captured as a CUDA graph (rpb_api.cu)
+struct StepGraph { cudaGraphExec_t exec = nullptr; int launches = 0; int s_hint = 0; int n_clusters_bound = 0; };
+
 struct rpb_ctx {
   rpb_config cfg;
   std::string err;
@@ -73,6 +76,8 @@ struct rpb_ctx {
   int* h_flags = nullptr;      // [8]
   void* staging = nullptr;     // pinned staging area of rpb_upload_state / rpb_download_state (also caches the last uploaded tables)
   bool serial_streams = false;
+  StepGraph graph[2];          // [0] non-reactive step, [1] MS-EVB step
+  bool graph_failed = false;   // stream capture of a step did not work on this context: plain launches
   bool state_cache_valid = false;   // the staging area mirrors the per-atom / per-molecule tables on the device
   // measurement
   long long n_launch = 0, n_fft = 0;
