@@ -59,7 +59,6 @@ __host__ __device__ inline bool state_owned(int s, int rank, int world) {
 #define ENUM_HITS 12           // acceptor atoms inside the reactive-pair distance of one proton (10 are kept)
 #define ENUM_COMPACT 2048
 #define ENUM_SMEM_BYTES (ENUM_COMPACT * (3 * sizeof(double) + 3 * sizeof(int)))
-struct EnumFrame { int mol, v, diabat, count, ip, cursor; int log[MAXC][5]; };
 
 __global__ void __launch_bounds__(ENUM_TPB) k_evb_enumerate(Dev d, EvbDev e, int* __restrict__ cand_n) {
   extern __shared__ double compact_com[];        // dynamic: [ENUM_COMPACT][3] centres of mass of the compacted molecules, then their
@@ -76,7 +75,6 @@ __global__ void __launch_bounds__(ENUM_TPB) k_evb_enumerate(Dev d, EvbDev e, int
   __shared__ unsigned char nb_v[ENUM_MAXMOL][ENUM_MAXP][RPB_EVB_MAX_NEIGHBORS];
   __shared__ int s_ncomp, s_nvis, s_fail;
   __shared__ double vis_com[ENUM_MAXMOL][3];
-  __shared__ EnumFrame fr[MAXC + 1];
   const int tid = threadIdx.x, nth = blockDim.x;
   const int hyd = *d.hydronium;
   EvbPlan& plan = *e.plan;
@@ -210,43 +208,91 @@ __global__ void __launch_bounds__(ENUM_TPB) k_evb_enumerate(Dev d, EvbDev e, int
     __syncthreads();
     lvl_begin = lvl_end; lvl_end = s_nvis;
   }
-  // ---- 3. DFS replay (pre-order; new diabat id = ++counter, :557)
+  // ---- 3. the reference's pre-order DFS numbering (new diabat id = ++counter, :557), level-parallel.  A diabat is a path
+  //         root -> child j1 -> child j2 -> child j3 over the memoised lists: the children of a node whose acceptor is the
+  //         visited molecule v are its (proton, neighbour) pairs in (ip, k) order; a node recurses unless its acceptor is
+  //         the hydronium or the chain is full (flag_cycle :573,596 ; "if ( count < evb_max_chain )" :538).  With
+  //         size(node) = 1 + sum of its children's sizes, id(first child) = id(node) + 1 and id(next sibling) = id + size.
+  static_assert(MAXC == 3, "three levels of diabats are spelled out below");
+  __shared__ int s_size1[ENUM_MAXP * RPB_EVB_MAX_NEIGHBORS], s_id1[ENUM_MAXP * RPB_EVB_MAX_NEIGHBORS + 1];
+  auto n_children = [&](int v) { int t = 0; for (int ip = 0; ip < prot_n[v]; ip++) t += nb_n[v][ip]; return t; };
+  auto decode = [&](int v, int j, int& ip, int& k) { ip = 0; while (j >= nb_n[v][ip]) { j -= nb_n[v][ip]; ip++; } k = j; };
+  auto make_row = [&](int v, int ip, int k, int row[5]) {
+    const int pk = nb[v][ip][k];
+    row[0] = vis_mol[v]; row[1] = prot[v][ip]; row[2] = heavy[v][ip]; row[3] = pk >> 4; row[4] = pk & 15;
+    if (row[2] == 255) { atomicMax(&d.err_flag[3], 1); row[2] = -1; }   // find_bonded_atom_hydrogen failed
+  };
+  auto write_state = [&](int id, int parent, int nh, const int (*rows)[5]) {
+    if (id >= d.max_states || id >= MAXS) return;
+    e.parent[id] = parent; e.n_hops[id] = nh;
+    for (int h = 0; h < nh; h++) for (int q = 0; q < 5; q++) e.proton_log[(id * MAXC + h) * 5 + q] = rows[h][q];
+  };
+  const bool enum_ok = (s_fail == 0);
   if (tid == 0) {
-    int s_count = 1, depth = 0;
-    if (s_fail == 1) { atomicMax(&d.err_flag[2], 1); depth = -1; }            // more molecules than evb_max_states diabats
-    else if (s_fail) { atomicMax(&d.err_flag[3], 9); depth = -1; }            // compiled enumeration limits exceeded
-    fr[0].mol = hyd; fr[0].v = 0; fr[0].diabat = 0; fr[0].count = 0; fr[0].ip = -1; fr[0].cursor = 0;
-    while (depth >= 0) {
-      EnumFrame& f = fr[depth];
-      if (f.ip >= 0 && f.cursor < nb_n[f.v][f.ip]) {
-        const int pk = nb[f.v][f.ip][f.cursor];
-        const int acc_mol = pk >> 4, acc_atom = pk & 15;
-        const int acc_v = nb_v[f.v][f.ip][f.cursor];
-        f.cursor++;
-        if (s_count >= d.max_states) { atomicMax(&d.err_flag[2], 1); break; }
-        const int da = s_count++;
-        e.parent[da] = f.diabat;
-        int row[5] = {f.mol, (int)prot[f.v][f.ip], (int)heavy[f.v][f.ip], acc_mol, acc_atom};
-        if (row[2] == 255) { atomicMax(&d.err_flag[3], 1); row[2] = -1; }   // find_bonded_atom_hydrogen failed
-        for (int h = 0; h < f.count; h++)
-          for (int q = 0; q < 5; q++) e.proton_log[(da * MAXC + h) * 5 + q] = f.log[h][q];
-        for (int q = 0; q < 5; q++) e.proton_log[(da * MAXC + f.count) * 5 + q] = row[q];
-        e.n_hops[da] = f.count + 1;
-        if (acc_mol != hyd && f.count + 1 < d.max_chain) {          // flag_cycle :573,596 ; "if ( count < evb_max_chain )" :538
-          EnumFrame& g = fr[depth + 1];
-          g.mol = acc_mol; g.v = acc_v; g.diabat = da; g.count = f.count + 1; g.ip = -1; g.cursor = 0;
-          for (int h = 0; h < f.count; h++) for (int q = 0; q < 5; q++) g.log[h][q] = f.log[h][q];
-          for (int q = 0; q < 5; q++) g.log[f.count][q] = row[q];
-          depth++;
-        }
-        continue;
+    if (s_fail == 1) atomicMax(&d.err_flag[2], 1);              // more molecules than evb_max_states diabats
+    else if (s_fail) atomicMax(&d.err_flag[3], 9);              // compiled enumeration limits exceeded
+  }
+  const int n1 = enum_ok ? n_children(0) : 0;
+  for (int j1 = tid; j1 < n1; j1 += nth) {                       // subtree sizes of the root's children
+    int ip1, k1;
+    decode(0, j1, ip1, k1);
+    const int acc1 = nb[0][ip1][k1] >> 4;
+    int size = 1;
+    if (acc1 != hyd && 1 < d.max_chain) {
+      const int v1 = nb_v[0][ip1][k1], n2 = n_children(v1);
+      for (int j2 = 0; j2 < n2; j2++) {
+        int ip2, k2;
+        decode(v1, j2, ip2, k2);
+        const int acc2 = nb[v1][ip2][k2] >> 4;
+        size += 1 + ((acc2 != hyd && 2 < d.max_chain) ? n_children(nb_v[v1][ip2][k2]) : 0);
       }
-      if (f.ip + 1 < prot_n[f.v]) { f.ip++; f.cursor = 0; }   // next reactive proton of this donor
-      else depth--;
     }
-    *e.n_states = s_count;
-    s_S = s_count; s_ncmol = 1; s_npair = 0;
+    s_size1[j1] = size;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int run = 1;
+    for (int j1 = 0; j1 < n1; j1++) { s_id1[j1] = run; run += s_size1[j1]; }
+    s_id1[n1] = run;
+    if (run > d.max_states) { atomicMax(&d.err_flag[2], 1); run = d.max_states; }   // "Found more diabat states than ... evb_max_states"
+    *e.n_states = run;
+    s_S = run; s_ncmol = 1; s_npair = 0;
     e.mol_slot[hyd] = 0;
+  }
+  __syncthreads();
+  constexpr int NCH = ENUM_MAXP * RPB_EVB_MAX_NEIGHBORS;        // children of one node at most
+  for (int idx = tid; idx < n1 * (NCH + 1); idx += nth) {
+    const int j1 = idx / (NCH + 1), j2 = idx % (NCH + 1) - 1;    // j2 == -1: the level-1 diabat itself
+    int rows[MAXC][5];
+    int ip1, k1;
+    decode(0, j1, ip1, k1);
+    make_row(0, ip1, k1, rows[0]);
+    const int id1 = s_id1[j1];
+    if (j2 < 0) { write_state(id1, 0, 1, rows); continue; }
+    const int acc1 = rows[0][3];
+    if (!(acc1 != hyd && 1 < d.max_chain)) continue;
+    const int v1 = nb_v[0][ip1][k1];
+    if (j2 >= n_children(v1)) continue;
+    int id2 = id1 + 1;                                           // ids of the earlier siblings' subtrees
+    for (int j = 0; j < j2; j++) {
+      int ipj, kj;
+      decode(v1, j, ipj, kj);
+      const int accj = nb[v1][ipj][kj] >> 4;
+      id2 += 1 + ((accj != hyd && 2 < d.max_chain) ? n_children(nb_v[v1][ipj][kj]) : 0);
+    }
+    int ip2, k2;
+    decode(v1, j2, ip2, k2);
+    make_row(v1, ip2, k2, rows[1]);
+    write_state(id2, id1, 2, rows);
+    const int acc2 = rows[1][3];
+    if (!(acc2 != hyd && 2 < d.max_chain)) continue;
+    const int v2 = nb_v[v1][ip2][k2], n3 = n_children(v2);
+    for (int j3 = 0; j3 < n3; j3++) {
+      int ip3, k3;
+      decode(v2, j3, ip3, k3);
+      make_row(v2, ip3, k3, rows[2]);
+      write_state(id2 + 1 + j3, id2, 3, rows);
+    }
   }
   // ---- 4. this step's work lists (what the host used to derive from the read-back hop logs).  The enumeration's own
   //         dynamic shared arrays are dead from here on: the pair-seen bit matrix, the ownership marks and the atom
@@ -660,7 +706,7 @@ __global__ void __launch_bounds__(256) k_evb_candidates(Dev d, EvbDev e, double 
   }
 }
 
-#define ITEM_SPLIT 4          // CTAs per item (the candidate chunks of an item are dealt round-robin to 4 x 8 warps)
+#define ITEM_SPLIT 8          // CTAs per item (the candidate chunks of an item are dealt round-robin to 8 x 8 warps)
 struct ItemBlock {
   ItemShared sh;
   int d_ci[MA], a_ci[MA], h_ci[MA];       // position of every image atom in sh.chain_atoms
@@ -2174,7 +2220,7 @@ int evb_enumerate_async(rpb_ctx* c, int part) {
     StreamScope ss(c, c->aux[3]);
     CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[18], 0));
     CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[11], 0));   // the early clears (aux[1])
-    k_evb_clear<<<148, 256, 0, c->stream>>>(d, e, 1);         // the diabats beyond the early clears' margin (normally none)
+    k_evb_clear<<<32, 256, 0, c->stream>>>(d, e, 1);          // the diabats beyond the early clears' margin (normally none)
     {
       ScopedTimer t(c, T_EVB_COUPLING_GEO);
       const int sb = s_bound(c);

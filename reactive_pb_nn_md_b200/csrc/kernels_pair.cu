@@ -50,8 +50,8 @@ __device__ __forceinline__ double rsqrt_pair(double x) {
   return y;
 }
 
-// Persistent warps with a work counter: a warp fetches the next row part (cluster I, part) of the tile list until none is
-// left (rank r of R works on the clusters [NC r / R, NC (r+1) / R)).  Two phases per row part:
+// A warp works on a few consecutive row parts (cluster I, part) of the tile list; rank r of R works on the clusters
+// [NC r / R, NC (r+1) / R).  Two phases per row part:
 //   1. candidate test -- a lane takes one ATOM of a cluster J per iteration (three consecutive lanes share a list word) and
 //      tests its three pairs with the atoms of I: mask bit, minimum image, r^2 < r_c^2.  42 % of the listed pairs lie
 //      between the cutoff and the list radius and 18 % of a tile's slots are not listed at all, so the pairs that pass
@@ -67,7 +67,7 @@ __device__ __forceinline__ double rsqrt_pair(double x) {
 struct PairQueue { double dx[PAIR_QCAP], dy[PAIR_QCAP], dz[PAIR_QCAP], r2[PAIR_QCAP], qq[PAIR_QCAP]; int meta[PAIR_QCAP]; };
 
 template <int TPB_, int MINB, int NB>
-__global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int world, unsigned int* __restrict__ counters) {
+__global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int world, int ppw) {
   extern __shared__ double sh_par[];           // [nT*nT][6] vdw parameters, then the warps' queues
   __shared__ int sh_vt[RPB_MAXT * RPB_MAXT];   // atype_vdw_type; 2 = SAPT row with all-zero coefficients (contributes exactly 0)
   __shared__ double sh_red[32];
@@ -82,22 +82,6 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int 
       if (P[0] == 0.0 && P[2] == 0.0 && P[3] == 0.0 && P[4] == 0.0 && P[5] == 0.0) vt = 2;
     }
     sh_vt[k] = vt;
-  }
-  // Cold-L2 warm-up: the working set of this kernel (Ewald tables 3.2 MB, tile list, coordinates) is a few MB that the
-  // loop touches through small dependent gathers -- served from DRAM (first touch after the L2 was flushed or simply
-  // evicted by other work) nearly every warp-wide gather waits for at least one DRAM miss.  Every thread prefetches a few
-  // 128-byte lines of it into L2 first: bulk, independent requests at DRAM bandwidth (~2 us) instead of latency-bound misses.
-  {
-    const size_t gtid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, gth = (size_t)gridDim.x * blockDim.x;
-    const char* t0 = reinterpret_cast<const char*>(d.es2_t);
-    const size_t tbytes = (size_t)(min((int)ceil(sqrt(d.rc2) * d.inv_erfc_dx), 2000000) + 3) * sizeof(double4);
-    for (size_t o = gtid * 128; o < tbytes; o += gth * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(t0 + o));
-    const int ncl = *d.n_clusters;
-    const char* l0 = reinterpret_cast<const char*>(d.tile_list);
-    const size_t lbytes = (size_t)d.tile_point[RPB_TILE_PARTS * ncl] * sizeof(unsigned);
-    for (size_t o = gtid * 128; o < lbytes; o += gth * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(l0 + o));
-    const char* x0 = reinterpret_cast<const char*>(d.xq);
-    for (size_t o = gtid * 128; o < (size_t)d.N * sizeof(double4); o += gth * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(x0 + o));
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -114,9 +98,10 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int 
   const bool shift_per_atom = sqrt(d.rc2) + ext < 0.5 * fmin(bx, fmin(by, bz));
   const unsigned* __restrict__ L = d.tile_list;
   double e_el = 0.0, e_vdw = 0.0;
-  // Work pieces are fetched TWO ahead and their headers ONE ahead: a piece's header is a chain of dependent loads
-  // (cluster -> first atom -> types / coordinates; row pointers -> first list words) that would otherwise be paid in
-  // full at every switch -- with ~7 iterations per piece that chain was a fifth of the kernel (ncu source view).
+  // A warp works on PPW consecutive pieces (row parts); the header of the next piece -- a chain of dependent loads
+  // (cluster -> first atom -> types / coordinates; row pointers) -- is fetched while the current piece is processed.
+  // The grid is NOT persistent: CTAs live ~15 us, so the short kernels of the high-priority side streams (enumeration,
+  // images, PME, bonded terms) get SM resources as CTAs retire instead of waiting for the whole pair kernel.
   struct Header { int info, vs, vf, tpack; double4 p; };
   auto load_header = [&](int wk, Header& h) {
     h.info = 0; h.vs = 0; h.vf = 0; h.tpack = 0; h.p = make_double4(0.0, 0.0, 0.0, 0.0);
@@ -128,14 +113,11 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int 
       if (lane < 3) { const int ia = fi + (lane < ni ? lane : 0); h.p = d.xq[ia]; h.tpack = d.type[ia]; }
     }
   };
-  int w = 0, w1 = 0, w2 = 0;
-  if (lane == 0) { w = (int)atomicAdd(&counters[0], 1u); w1 = (int)atomicAdd(&counters[0], 1u); }
-  w = __shfl_sync(0xffffffffu, w, 0); w1 = __shfl_sync(0xffffffffu, w1, 0);
+  const int w_first = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * ppw;
   Header H, H1;
-  load_header(w, H);
-  while (w < n_work) {
-    if (lane == 0) w2 = (int)atomicAdd(&counters[0], 1u);      // consumed two pieces from now
-    load_header(w1, H1);                                        // consumed at the next switch
+  load_header(w_first, H);
+  for (int w = w_first; w < w_first + ppw && w < n_work; w++) {
+    load_header(w + 1 < w_first + ppw ? w + 1 : n_work, H1);   // consumed at the next switch
     const int fi = H.info & 0xffffff, ni = H.info >> 24;
     const int vs = H.vs, vf = H.vf;
     int ti[3];
@@ -259,17 +241,11 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int 
         if (lane == 3 * a + c) mine = x;
       }
     if (lane < 3 * ni) atomicAdd(&d.force[3 * fi + lane], mine);
-    w = w1; H = H1;
-    w1 = __shfl_sync(0xffffffffu, w2, 0);
+    H = H1;
   }
   e_el = block_sum(e_el, sh_red);
   e_vdw = block_sum(e_vdw, sh_red);
-  if (threadIdx.x == 0) {
-    atomicAdd(&d.en[E_ELEC], 0.5 * e_el); atomicAdd(&d.en[E_VDW], 0.5 * e_vdw);
-    // the last CTA to finish re-arms the work counter for the next launch
-    __threadfence();
-    if (atomicAdd(&counters[1], 1u) == gridDim.x - 1) { counters[0] = 0u; counters[1] = 0u; __threadfence(); }
-  }
+  if (threadIdx.x == 0) { atomicAdd(&d.en[E_ELEC], 0.5 * e_el); atomicAdd(&d.en[E_VDW], 0.5 * e_vdw); }
 }
 
 // one thread per molecule: intramolecular non-bonded (exclusion correction, 1-4) + bonds/angles/dihedrals
@@ -301,16 +277,19 @@ __global__ void k_molecule_terms(Dev d) {
 }
 
 template <int T, int MINB, int NB>
-static int launch_pair_variant(rpb_ctx* c, bool shard, int ctas_per_sm) {
+static int launch_pair_variant(rpb_ctx* c, bool shard, int ppw, int pad_kb = 0) {
   // state-sharded runs also shard the principal diabat's pair forces: rank r takes the clusters [NC r / R, NC (r+1) / R); the
-  // partial forces and energies ride the two all-reduces the sharded step has anyway.  Persistent warps: a fixed grid.
+  // partial forces and energies ride the two all-reduces the sharded step has anyway.
   const int R = shard ? c->d.world : 1, r = shard ? c->d.rank : 0;
   const long long pieces = (long long)RPB_TILE_PARTS * ((c->n_clusters_bound + R - 1) / R + 1);
-  const int blocks = (int)std::max(1LL, std::min((long long)c->n_sm * ctas_per_sm, (pieces * 32 + T - 1) / T));
-  const size_t shmem = (size_t)((c->d.nT * c->d.nT * 6 + 1) & ~1) * sizeof(double) + (T / 32) * sizeof(PairQueue);
+  const int wpb = T / 32;
+  const int blocks = (int)std::max(1LL, (pieces + (long long)wpb * ppw - 1) / ((long long)wpb * ppw));
+  // pad_kb: shared memory requested beyond what the kernel uses, to cap the CTAs resident per SM -- at full occupancy the
+  // pair kernel holds every register of an SM, and each short kernel of the MS-EVB chain then waits for a pair CTA to retire
+  const size_t shmem = std::max((size_t)((c->d.nT * c->d.nT * 6 + 1) & ~1) * sizeof(double) + wpb * sizeof(PairQueue), (size_t)pad_kb * 1024);
   static bool attr_set = false;     // (same for every context: a function attribute)
   if (!attr_set) { cudaFuncSetAttribute(k_pair_tiles<T, MINB, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr_set = true; }
-  k_pair_tiles<T, MINB, NB><<<blocks, T, shmem, c->stream>>>(c->d, r, R, reinterpret_cast<unsigned int*>(c->d.vstat + 3));
+  k_pair_tiles<T, MINB, NB><<<blocks, T, shmem, c->stream>>>(c->d, r, R, ppw);
   return 0;
 }
 
@@ -318,12 +297,12 @@ void launch_pair_verlet(rpb_ctx* c, bool shard) {
   ScopedTimer t(c, T_PAIR);
   static const int variant = getenv("RPB_PAIR_VARIANT") ? atoi(getenv("RPB_PAIR_VARIANT")) : 0;
   switch (variant) {
-    case 1: launch_pair_variant<128, 3, 3>(c, shard, 3); break;      // 168 registers, three pairs per lane in flight
-    case 2: launch_pair_variant<128, 3, 4>(c, shard, 3); break;
-    case 3: launch_pair_variant<128, 4, 2>(c, shard, 4); break;      // 128 registers
-    case 4: launch_pair_variant<128, 2, 6>(c, shard, 2); break;      // 255 registers
-    case 5: launch_pair_variant<128, 4, 3>(c, shard, 4); break;
-    default: launch_pair_variant<128, 3, 3>(c, shard, 3); break;
+    case 1: launch_pair_variant<128, 3, 3>(c, shard, 2); break;      // 168 registers, three pairs per lane in flight
+    case 2: launch_pair_variant<128, 3, 3>(c, shard, 4); break;
+    case 3: launch_pair_variant<128, 3, 3>(c, shard, 4, 80); break;      // two CTAs per SM
+    case 4: launch_pair_variant<128, 3, 3>(c, shard, 2, 80); break;
+    case 5: launch_pair_variant<128, 3, 3>(c, shard, 4, 120); break;     // one CTA per SM
+    default: launch_pair_variant<128, 3, 3>(c, shard, 4); break;
   }
   c->n_launch += 1;
 }

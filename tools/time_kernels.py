@@ -18,7 +18,8 @@ sim.md_integrate_atomic(5, ms_evb=evb)
 flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
 sim.timers_enable(True); sim.timers(reset=True)
 for k in range(n):
-    flush.fill_(float(k)); torch.cuda.synchronize()
+    if not os.environ.get("NO_FLUSH"):
+        flush.fill_(float(k)); torch.cuda.synchronize()
     sim.md_integrate_atomic(1, ms_evb=evb)
 tm = sim.timers()
 tot = tm["step_total"][0] / n
