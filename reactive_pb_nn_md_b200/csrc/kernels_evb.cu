@@ -26,6 +26,7 @@
 #include "rpb_host.h"
 #include "rpb_bonded.cuh"
 #include "rpb_pme.cuh"
+#include "rpb_commit.cuh"
 
 #define MAXS RPB_MAXS
 #define MAXC RPB_MAXC
@@ -79,6 +80,12 @@ __global__ void __launch_bounds__(ENUM_TPB) k_evb_enumerate(Dev d, EvbDev e, int
   const int hyd = *d.hydronium;
   EvbPlan& plan = *e.plan;
   __shared__ int s_S, s_ncmol, s_npair;
+  __shared__ signed char mt_rp[RPB_MAXM][MA], mt_rb[RPB_MAXM][MA], mt_bh[RPB_MAXM][MA];   // reactive proton / basic atom flags, bonded heavy atom per molecule type
+  for (int k = tid; k < d.nMT * MA; k += nth) {
+    const MolTypeDev& T = d.mt[k / MA];
+    mt_rp[k / MA][k % MA] = (signed char)T.reactive_proton[k % MA]; mt_rb[k / MA][k % MA] = (signed char)T.reactive_basic[k % MA];
+    mt_bh[k / MA][k % MA] = (signed char)T.bonded_heavy[k % MA];
+  }
   // the chain molecules of the previous step give their slots back
   for (int k = tid; k < plan.n_cmol; k += nth) e.mol_slot[plan.cmol[k]] = -1;
   for (int i = tid; i < MAXS * MAXC * 5; i += nth) e.proton_log[i] = -1;
@@ -92,9 +99,11 @@ __global__ void __launch_bounds__(ENUM_TPB) k_evb_enumerate(Dev d, EvbDev e, int
     double R = (double)d.max_chain * sqrt(d.cut_solv2) + 0.5;
     double R2 = R * R;
     double c0 = d.r_com[3 * hyd], c1 = d.r_com[3 * hyd + 1], c2 = d.r_com[3 * hyd + 2];
-    for (int jm = tid; jm < d.M; jm += nth) {
-      double a0 = min_image(d.r_com[3 * jm] - c0, d.box[0]), a1 = min_image(d.r_com[3 * jm + 1] - c1, d.box[1]),
-             a2 = min_image(d.r_com[3 * jm + 2] - c2, d.box[2]);
+    for (int jm = tid; jm < d.M; jm += nth) {      // (a superset with a 0.5 A margin: the reciprocal-box minimum image is exact enough)
+      double a0 = d.r_com[3 * jm] - c0, a1 = d.r_com[3 * jm + 1] - c1, a2 = d.r_com[3 * jm + 2] - c2;
+      a0 -= d.box[0] * floor_fp64pipe(fma(a0, d.inv_box[0], 0.5));
+      a1 -= d.box[1] * floor_fp64pipe(fma(a1, d.inv_box[1], 0.5));
+      a2 -= d.box[2] * floor_fp64pipe(fma(a2, d.inv_box[2], 0.5));
       if (a0 * a0 + a1 * a1 + a2 * a2 < R2) {
         int slot = atomicAdd(&s_ncomp, 1);
         if (slot < ENUM_COMPACT) {
@@ -118,13 +127,13 @@ __global__ void __launch_bounds__(ENUM_TPB) k_evb_enumerate(Dev d, EvbDev e, int
     // reactive protons of the molecules of this level (principal-topology molecule type, ms_evb.f90:542-546)
     for (int vv = lvl_begin + tid; vv < lvl_end; vv += nth) {
       int mol = vis_mol[vv];
-      const MolTypeDev& T = d.mt[d.mol_type[mol]];
+      const int mty = d.mol_type[mol];
       int n = d.mol_natom[mol], np = 0;
       for (int ia = 0; ia < n; ia++)
-        if (T.reactive_proton[ia] == 1) {
+        if (mt_rp[mty][ia] == 1) {
           if (np >= ENUM_MAXP) { s_fail = 2; break; }
           prot[vv][np] = (unsigned char)ia;
-          int hv = T.bonded_heavy[ia];
+          int hv = mt_bh[mty][ia];
           heavy[vv][np] = (unsigned char)(hv < 0 ? 255 : hv);
           np++;
         }
@@ -163,10 +172,10 @@ __global__ void __launch_bounds__(ENUM_TPB) k_evb_enumerate(Dev d, EvbDev e, int
         double dr = compact_com[3 * cs + k] - vis_com[vv][k];
         shift[k] = floor(d.inv_box[k] * dr + 0.5) * d.box[k];
       }
-      const MolTypeDev& TJ = d.mt[compact_type[cs]];
+      const int tyj = compact_type[cs];
       const int fj = compact_first[cs], nj = compact_nat[cs];
       for (int ja = 0; ja < nj; ja++) {
-        if (TJ.reactive_basic[ja] != 1) continue;
+        if (mt_rb[tyj][ja] != 1) continue;
         double4 pj = d.xq[fj + ja];
         double r0 = pj.x - ph.x - shift[0], r1 = pj.y - ph.y - shift[1], r2 = pj.z - ph.z - shift[2];
         if (r0 * r0 + r1 * r1 + r2 * r2 < d.cut_pair2) {
@@ -188,22 +197,38 @@ __global__ void __launch_bounds__(ENUM_TPB) k_evb_enumerate(Dev d, EvbDev e, int
       nb_n[vv][ip] = min(n, RPB_EVB_MAX_NEIGHBORS);
     }
     __syncthreads();
-    // d) next level: acceptors not seen before (their protons are searched only if a diabat can still hop from them)
-    if (tid == 0 && L + 1 < d.max_chain) {
-      int nv = s_nvis;
-      for (int vv = lvl_begin; vv < lvl_end; vv++)
-        for (int ip = 0; ip < prot_n[vv]; ip++)
-          for (int k = 0; k < nb_n[vv][ip]; k++) {
-            int acc = nb[vv][ip][k] >> 4, at = -1;
-            if (acc == hyd) { nb_v[vv][ip][k] = 0; continue; }
-            for (int q = 0; q < nv; q++) if (vis_mol[q] == acc) { at = q; break; }
-            if (at < 0) {
-              if (nv >= ENUM_MAXMOL) { s_fail = 1; at = 0; }
-              else { vis_mol[nv] = acc; at = nv++; }
+    // d) next level: acceptors not seen before (their protons are searched only if a diabat can still hop from them).
+    //    Every (molecule, proton, neighbour) entry looks its acceptor up in parallel; one thread then appends the unseen
+    //    ones (few) in entry order.
+    if (L + 1 < d.max_chain) {
+      const int nv0 = s_nvis;
+      for (int idx = tid; idx < nlvl * ENUM_MAXP * RPB_EVB_MAX_NEIGHBORS; idx += nth) {
+        const int vv = lvl_begin + idx / (ENUM_MAXP * RPB_EVB_MAX_NEIGHBORS), ip = (idx / RPB_EVB_MAX_NEIGHBORS) % ENUM_MAXP, k = idx % RPB_EVB_MAX_NEIGHBORS;
+        if (ip >= prot_n[vv] || k >= nb_n[vv][ip]) continue;
+        const int acc = nb[vv][ip][k] >> 4;
+        int at = 255;
+        if (acc == hyd) at = 0;
+        else for (int q = 0; q < nv0; q++) if (vis_mol[q] == acc) { at = q; break; }
+        nb_v[vv][ip][k] = (unsigned char)at;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int nv = nv0;
+        for (int vv = lvl_begin; vv < lvl_end; vv++)
+          for (int ip = 0; ip < prot_n[vv]; ip++)
+            for (int k = 0; k < nb_n[vv][ip]; k++) {
+              if (nb_v[vv][ip][k] != 255) continue;
+              const int acc = nb[vv][ip][k] >> 4;
+              int at = -1;
+              for (int q = nv0; q < nv; q++) if (vis_mol[q] == acc) { at = q; break; }
+              if (at < 0) {
+                if (nv >= ENUM_MAXMOL) { s_fail = 1; at = 0; }
+                else { vis_mol[nv] = acc; at = nv++; }
+              }
+              nb_v[vv][ip][k] = (unsigned char)at;
             }
-            nb_v[vv][ip][k] = (unsigned char)at;
-          }
-      s_nvis = nv;
+        s_nvis = nv;
+      }
     }
     __syncthreads();
     lvl_begin = lvl_end; lvl_end = s_nvis;
@@ -1237,6 +1262,7 @@ struct TreeShared {
   double delta[MAXS], beta[MAXS], b2[MAXS], dv[MAXS], d1[MAXS], d2[MAXS], invd[MAXS], y[MAXS], b[MAXS];
   int parent[MAXS], level[MAXS], child_start[MAXS + 1], child[MAXS];
   double red[2][4];
+  int redi[4];
 };
 
 // sums two values over the CTA; every thread returns the same (deterministically ordered) totals
@@ -1303,24 +1329,40 @@ __global__ void __launch_bounds__(TREE_TPB) k_evb_tree_solver(Dev d, EvbDev e, c
     T.y[i] = 1.0;
   }
   __syncthreads();
-  if (tid == 0) {   // children in ascending order (deterministic summation)
-    for (int k = 0; k <= S; k++) T.child_start[k] = 0;
-    for (int k = 1; k < S; k++) T.child_start[T.parent[k] + 1]++;
-    for (int k = 0; k < S; k++) T.child_start[k + 1] += T.child_start[k];
-    int fill[MAXS];
-    for (int k = 0; k < S; k++) fill[k] = T.child_start[k];
-    for (int k = 1; k < S; k++) T.child[fill[T.parent[k]]++] = k;
+  // children of every diabat in ascending order (deterministic summation), levels, Gershgorin bound: one thread per diabat
+  if (i < S) {
+    int before = 0, nch = 0;
+    const int p = T.parent[i];
+    for (int k = 1; k < S; k++) { const int pk = T.parent[k]; before += (k < i && pk == p) ? 1 : 0; nch += (pk == i) ? 1 : 0; }
+    T.child_start[i + 1] = nch;        // counts first; scanned below
+    T.b[i] = (double)before;           // (scratch) rank among the siblings
   }
+  if (tid == 0) T.child_start[0] = 0;
   __syncthreads();
-  int mlev = 0;
-  for (int k = 0; k < S; k++) mlev = max(mlev, T.level[k]);
-  // Gershgorin lower bound of the spectrum and the magnitude of the problem
-  double gers = 1e300, mag = 0.0;
-  for (int k = 0; k < S; k++) {
-    double g = T.delta[k] - fabs(T.beta[k]);
-    for (int q = T.child_start[k]; q < T.child_start[k + 1]; q++) g -= fabs(T.beta[T.child[q]]);
-    gers = fmin(gers, g); mag = fmax(mag, fabs(T.delta[k]));
+  if (tid == 0) for (int k = 0; k < S; k++) T.child_start[k + 1] += T.child_start[k];
+  __syncthreads();
+  if (i >= 1 && i < S) T.child[T.child_start[T.parent[i]] + (int)T.b[i]] = i;
+  __syncthreads();
+  // deepest level, Gershgorin lower bound of the spectrum and the magnitude of the problem (block reductions in shared memory)
+  {
+    double g = 1e300, m = 0.0;
+    int lv = 0;
+    if (i < S) {
+      g = T.delta[i] - fabs(T.beta[i]);
+      for (int q = T.child_start[i]; q < T.child_start[i + 1]; q++) g -= fabs(T.beta[T.child[q]]);
+      m = fabs(T.delta[i]); lv = T.level[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      g = fmin(g, __shfl_xor_sync(0xffffffffu, g, o)); m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o)); lv = max(lv, __shfl_xor_sync(0xffffffffu, lv, o));
+    }
+    if ((tid & 31) == 0) { T.red[0][tid >> 5] = g; T.red[1][tid >> 5] = m; T.redi[tid >> 5] = lv; }
+    __syncthreads();
   }
+  const double gers = fmin(T.red[0][0], fmin(T.red[0][1], T.red[0][2]));
+  const double mag = fmax(T.red[1][0], fmax(T.red[1][1], T.red[1][2]));
+  const int mlev = max(T.redi[0], max(T.redi[1], T.redi[2]));
+  __syncthreads();
   double lo = gers - 1e-3 * (1.0 + fabs(gers)), hi = 1e300;
   const double tol = 1e-10 * fmax(fmax(mag, fabs(lo)), 1.0);   // the inverse iteration + Rayleigh quotient finish the job
   double x = lo;
@@ -1379,7 +1421,9 @@ __global__ void __launch_bounds__(TREE_TPB) k_evb_tree_solver(Dev d, EvbDev e, c
       double change = 0.0;
       if (i < S) { const double yn = T.b[i] * inv; change = fabs(fabs(yn) - fabs(T.y[i])); T.y[i] = yn; }
       n_eval++;
-      if (__syncthreads_and(change < 1e-15)) break;
+      // the shift sits ~1e-10 (relative) below the eigenvalue, so one solve contracts the error by ~1e-9: once a solve
+      // changed the vector by less than 1e-8 the vector before it was already that close, and this one is converged
+      if (__syncthreads_and(change < (rep >= 1 ? 1e-8 : 1e-15))) break;
     }
     double r1 = 0.0, r2 = 0.0;
     if (i < S) { r1 = T.delta[i] * T.y[i] * T.y[i]; if (i > 0) r2 = 2.0 * T.beta[i] * T.y[i] * T.y[T.parent[i]]; }
@@ -1964,119 +2008,6 @@ __global__ void k_copy(double* dst, const double* src, size_t n) {
   if (i < n) dst[i] = src[i];
 }
 
-// ================================================================================================
-// K15: hop commit on the device -- when the solver selected a new hydronium molecule (plan.hop), permute the per-atom
-// arrays exactly as shift_array_data_donor_acceptor_transfer (ms_evb.f90:2677-2840), hop by hop of the new principal
-// diabat, and retype / re-order the chain molecules from its final-level snapshot (ms_evb.f90:806-1006).  Every kernel
-// of the sequence exits at once when no hop was selected, so the sequence is part of the fixed per-step launch list.
-// ================================================================================================
-struct CommitInfo {
-  int n_hops;
-  int from_g[MAXC], to_g[MAXC];     // global atom index the proton leaves / arrives at, in the index space BEFORE that hop
-  int m_from[MAXC], m_to[MAXC];
-  int n_mol; int mol[CM]; int new_first[CM]; int n_atom[CM];   // chain molecules of the new principal diabat after all hops
-  int hop_count;                    // committed hops since rpb_set_evb (the host notices permuted tables through it)
-};
-
-// one thread: the hop parameters (host_shift of the previous version, replayed on the few molecules involved)
-__global__ void k_evb_commit_prepare(Dev d, EvbDev e, CommitInfo* ci) {
-  if (threadIdx.x != 0 || blockIdx.x != 0 || !e.plan->hop) return;
-  const int pdiab = e.result[0], nh = e.n_hops[pdiab];
-  const int* L = &e.proton_log[pdiab * MAXC * 5];
-  // first atom / atom count of molecule m after the hops applied so far
-  auto first_now = [&](int m, int upto) {
-    int f = d.mol_first[m];
-    for (int h = 0; h < upto; h++) {
-      if (ci->m_from[h] < ci->m_to[h]) { if (m > ci->m_from[h] && m <= ci->m_to[h]) f -= 1; }
-      else { if (m > ci->m_to[h] && m <= ci->m_from[h]) f += 1; }
-    }
-    return f;
-  };
-  auto natom_now = [&](int m, int upto) {
-    int n = d.mol_natom[m];
-    for (int h = 0; h < upto; h++) { if (ci->m_from[h] == m) n -= 1; if (ci->m_to[h] == m) n += 1; }
-    return n;
-  };
-  int ima = *d.hydronium;
-  for (int k = 0; k < nh; k++) {
-    const int imd = ima, a_from = L[k * 5 + 1];
-    ima = L[k * 5 + 3];
-    ci->m_from[k] = imd; ci->m_to[k] = ima;
-    const int a_to = natom_now(ima, k);
-    ci->from_g[k] = first_now(imd, k) + a_from;
-    ci->to_g[k] = (imd < ima) ? first_now(ima, k) + a_to - 1 : first_now(ima, k) + a_to;
-  }
-  ci->n_hops = nh;
-  const Snapshot& S = e.snap[pdiab * NLEV + nh];
-  ci->n_mol = S.n_mol;
-  for (int k = 0; k < S.n_mol; k++) { ci->mol[k] = S.m[k].mol; ci->new_first[k] = first_now(S.m[k].mol, nh); ci->n_atom[k] = S.m[k].n_atom; }
-}
-
-// thread i < N: source of new position i (hops undone last to first; chain molecules in snapshot order); thread m < M:
-// the molecule table and the atom -> molecule map after the hops
-__global__ void k_evb_commit_permute(Dev d, EvbDev e, const CommitInfo* __restrict__ ci, double4* xq_new, double* vel_new, double* force_new,
-                                     double* mass_new, int* type_new, int* moa_new) {
-  if (!e.plan->hop) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int nh = ci->n_hops;
-  if (i < d.N) {
-    int src = i;
-    for (int h = nh - 1; h >= 0; h--) {
-      const int fg = ci->from_g[h], tg = ci->to_g[h];
-      if (src == tg) src = fg;
-      else if (fg < tg) { if (src >= fg && src < tg) src += 1; }
-      else { if (src > tg && src <= fg) src -= 1; }
-    }
-    const Snapshot& S = e.snap[e.result[0] * NLEV + nh];
-    for (int k = 0; k < ci->n_mol; k++)         // re-ordered acceptor: the snapshot lists the principal index of every position
-      if (i >= ci->new_first[k] && i < ci->new_first[k] + ci->n_atom[k]) src = S.m[k].atom[i - ci->new_first[k]];
-    xq_new[i] = d.xq[src];
-    for (int k = 0; k < 3; k++) { vel_new[3 * i + k] = d.vel[3 * src + k]; force_new[3 * i + k] = d.force[3 * src + k]; }
-    mass_new[i] = d.mass[src];
-    type_new[i] = d.type[src];
-  }
-  if (i < d.M) {
-    int f = d.mol_first[i], n = d.mol_natom[i];
-    for (int h = 0; h < nh; h++) {
-      if (ci->m_from[h] < ci->m_to[h]) { if (i > ci->m_from[h] && i <= ci->m_to[h]) f -= 1; }
-      else { if (i > ci->m_to[h] && i <= ci->m_from[h]) f += 1; }
-      if (ci->m_from[h] == i) n -= 1;
-      if (ci->m_to[h] == i) n += 1;
-    }
-    d.mol_first[i] = f; d.mol_natom[i] = n;     // (only this thread reads or writes entry i)
-    for (int a = 0; a < n; a++) moa_new[f + a] = i;
-  }
-}
-
-// copy back, then the snapshot data (positions made whole, charges, types, centres of mass, molecule types) of the chain
-// molecules and the new hydronium index
-__global__ void k_evb_commit_finish(Dev d, EvbDev e, CommitInfo* ci, const double4* __restrict__ xq_new, const double* __restrict__ vel_new,
-                                    const double* __restrict__ force_new, const double* __restrict__ mass_new, const int* __restrict__ type_new,
-                                    const int* __restrict__ moa_new) {
-  if (!e.plan->hop) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= d.N) return;
-  const Snapshot& S = e.snap[e.result[0] * NLEV + ci->n_hops];
-  double4 x = xq_new[i];
-  int ty = type_new[i];
-  for (int k = 0; k < ci->n_mol; k++)
-    if (i >= ci->new_first[k] && i < ci->new_first[k] + ci->n_atom[k]) {
-      const MolImage& I = S.m[k];
-      const int a = i - ci->new_first[k];
-      x = make_double4(I.x[a][0], I.x[a][1], I.x[a][2], I.q[a]);
-      ty = I.type[a];
-      if (a == 0) {
-        for (int c = 0; c < 3; c++) d.r_com[3 * I.mol + c] = I.r_com[c];
-        d.mol_type[I.mol] = I.mtype;
-      }
-    }
-  d.xq[i] = x; d.type[i] = ty;
-  for (int k = 0; k < 3; k++) { d.vel[3 * i + k] = vel_new[3 * i + k]; d.force[3 * i + k] = force_new[3 * i + k]; }
-  d.mass[i] = mass_new[i];
-  d.mol_of_atom[i] = moa_new[i];
-  if (i == 0) { *d.hydronium = S.m[S.hydronium].mol; ci->hop_count += 1; }
-}
-
 // zero every accumulator the build adds into.  mode 0 (ahead of the enumeration): item energies, Vex, and the per-diabat
 // force deltas / coupling forces of the diabats [0, plan.n_clear) -- the previous step's count plus a margin;
 // mode 1 (behind the enumeration): the diabats [plan.n_clear, S) of a step that gained more than the margin
@@ -2221,6 +2152,7 @@ int evb_enumerate_async(rpb_ctx* c, int part) {
     CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[18], 0));
     CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[11], 0));   // the early clears (aux[1])
     k_evb_clear<<<32, 256, 0, c->stream>>>(d, e, 1);          // the diabats beyond the early clears' margin (normally none)
+    CKE(cudaEventRecord(c->ev_sync[14], c->stream));          // "images ready, every accumulator cleared"
     {
       ScopedTimer t(c, T_EVB_COUPLING_GEO);
       const int sb = s_bound(c);
@@ -2264,7 +2196,7 @@ int evb_build(rpb_ctx* c) {
   //   aux[2] : [bonded terms of the principal diabat] -> pair matrix of the chain atoms
   {
     StreamScope ss(c, c->aux[4]);
-    CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[19], 0));      // images, clears (incl. the enumeration's candidate counters)
+    CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[14], 0));      // images, clears (incl. the enumeration's candidate counters) -- not the coupling geometry
     {
       ScopedTimer t(c, T_EVB_CAND);
       dim3 g((N + 255) / 256, std::min(CAND_SLOTS, 4 * sb + 8));
@@ -2414,13 +2346,9 @@ int evb_commit(rpb_ctx* c) {
   const int N = d.N;
   if (d.world > 1 && !c->peer.f_reduced_in_place) { k_copy<<<(3 * N + 255) / 256, 256, 0, c->stream>>>(d.force, e.f_mix, (size_t)3 * N); c->n_launch++; }   // single rank: mixed in place; peer exchange: reduced into d.force
   c->peer.f_reduced_in_place = false;
-  // the status block must be complete before it is copied: k_evb_finalize_principal runs on aux[3]
-  const int nb = (std::max(N, d.M) + 255) / 256;
-  k_evb_commit_prepare<<<1, 32, 0, c->stream>>>(d, e, sc.commit);
-  k_evb_commit_permute<<<nb, 256, 0, c->stream>>>(d, e, sc.commit, sc.xq2, sc.vel2, sc.force2, sc.mass2, sc.type2, sc.moa2);
-  k_evb_commit_finish<<<(N + 255) / 256, 256, 0, c->stream>>>(d, e, sc.commit, sc.xq2, sc.vel2, sc.force2, sc.mass2, sc.type2, sc.moa2);
-  c->n_launch += 3;
-  int rc = launch_verlet_commit_rebuild(c);     // construct_verlet_list + update_verlet_displacements(init), only after a hop
+  CommitArgs ca;
+  ca.e = e; ca.ci = sc.commit; ca.xq2 = sc.xq2; ca.vel2 = sc.vel2; ca.force2 = sc.force2; ca.mass2 = sc.mass2; ca.type2 = sc.type2; ca.moa2 = sc.moa2;
+  int rc = launch_commit_and_rebuild(c, &ca);   // permutation, retyping, construct_verlet_list + update_verlet_displacements(init): only after a hop
   if (rc) return rc;
   // read-back (aux[3], behind the main stream's commit kernels and its own finalize kernel)
   CKE(cudaEventRecord(c->ev_sync[17], c->stream));

@@ -20,16 +20,16 @@
 #include <algorithm>
 #include <cooperative_groups.h>
 #include "rpb_host.h"
+#include "rpb_commit.cuh"
 namespace cg = cooperative_groups;
 
 #define TPB 256
 
 // per-block two largest |accumulated displacement|; the last block merges them and sets the flag (:1293-1326)
-__global__ void k_verlet_disp(Dev d, double* blk_top2, int* done_counter, int only_if_rebuilt) {
+__global__ void k_verlet_disp(Dev d, double* blk_top2, int* done_counter) {
   __shared__ double s1[TPB], s2[TPB];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int rebuild = *d.rebuild_now;
-  if (only_if_rebuilt && !rebuild) return;       // hop-commit call of a step without a hop
   double nrm = 0.0;
   if (i < d.N) {
     double4 p = d.xq[i];
@@ -166,7 +166,9 @@ __device__ __forceinline__ void tile_sweep(const Dev& d, const int I, const int 
   offset_range((int)floor(R / wy) + 1, d.ncy, ylo, yhi, py);
   offset_range((int)floor(R / wz) + 1, d.ncz, zlo, zhi, pz);
   const double slack = 1e-6, R2 = R * R;
-  unsigned* __restrict__ out = WRITE ? d.tile_list + d.tile_point[RPB_TILE_PARTS * I + part] : nullptr;
+  // WRITE: straight into the row of the final list; otherwise into this row's fixed-capacity scratch (the entries beyond
+  // the capacity are only counted: such a row is swept a second time once its place in the list is known)
+  unsigned* __restrict__ out = WRITE ? d.tile_list + d.tile_point[RPB_TILE_PARTS * I + part] : d.tile_tmp + (size_t)(RPB_TILE_PARTS * I + part) * RPB_TILE_TMPCAP;
   int n_tile = 0;
   unsigned long long n_pair = 0;
   const int ny = yhi - ylo + 1, ncol = (xhi - xlo + 1) * ny;
@@ -202,9 +204,9 @@ __device__ __forceinline__ void tile_sweep(const Dev& d, const int I, const int 
           if (slot < e && d.csort_mol[slot] != mi) {     // first atoms farther apart than R: no atom pair can be listed
             const double4 p0 = ldg256(&d.csort_xq[3 * slot]);
             double r0 = pi[0].x - p0.x, r1 = pi[0].y - p0.y, r2 = pi[0].z - p0.z;
-            r0 = r0 - d.box[0] * floor(r0 * d.inv_box[0] + 0.5);
-            r1 = r1 - d.box[1] * floor(r1 * d.inv_box[1] + 0.5);
-            r2 = r2 - d.box[2] * floor(r2 * d.inv_box[2] + 0.5);
+            r0 = r0 - d.box[0] * floor_fp64pipe(r0 * d.inv_box[0] + 0.5);
+            r1 = r1 - d.box[1] * floor_fp64pipe(r1 * d.inv_box[1] + 0.5);
+            r2 = r2 - d.box[2] * floor_fp64pipe(r2 * d.inv_box[2] + 0.5);
             near = (r0 * r0 + r1 * r1 + r2 * r2) < R2;
           }
           if (near) {
@@ -217,17 +219,17 @@ __device__ __forceinline__ void tile_sweep(const Dev& d, const int I, const int 
 #pragma unroll
                 for (int a = 0; a < 3; a++) {
                   double r0 = pi[a].x - pj.x, r1 = pi[a].y - pj.y, r2 = pi[a].z - pj.z;
-                  r0 = r0 - d.box[0] * floor(r0 * d.inv_box[0] + 0.5);
-                  r1 = r1 - d.box[1] * floor(r1 * d.inv_box[1] + 0.5);
-                  r2 = r2 - d.box[2] * floor(r2 * d.inv_box[2] + 0.5);
+                  r0 = r0 - d.box[0] * floor_fp64pipe(r0 * d.inv_box[0] + 0.5);
+                  r1 = r1 - d.box[1] * floor_fp64pipe(r1 * d.inv_box[1] + 0.5);
+                  r2 = r2 - d.box[2] * floor_fp64pipe(r2 * d.inv_box[2] + 0.5);
                   if (a < ni && (r0 * r0 + r1 * r1 + r2 * r2) < d.rv2) mask |= 1u << (3 * a + b);
                 }
               }
             }
           }
           const unsigned hit = __ballot_sync(0xffffffffu, mask != 0);
-          if (WRITE) { if (mask) out[n_tile + __popc(hit & ((1u << lane) - 1u))] = (unsigned)fj | (mask << 23); }
-          else n_pair += __popc(mask);
+          if (mask) { const int pos = n_tile + __popc(hit & ((1u << lane) - 1u)); if (WRITE || pos < RPB_TILE_TMPCAP) out[pos] = (unsigned)fj | (mask << 23); }
+          if (!WRITE) n_pair += __popc(mask);
           n_tile += __popc(hit);
         }
       }
@@ -242,13 +244,7 @@ __device__ __forceinline__ void tile_sweep(const Dev& d, const int I, const int 
 
 // The whole rebuild as ONE cooperative kernel (grid-wide barriers between the phases): on the ~95 % of steps without a
 // rebuild it costs a single launch that exits at once.
-__global__ void __launch_bounds__(TPB) k_verlet_rebuild(Dev d, int force_rebuild, int ncell) {
-  cg::grid_group grid = cg::this_grid();
-  // forced (init / hop commit): flag_verlet_list untouched (flag_junk, ms_evb.f90:223-225).  force_rebuild == 2: the
-  // hop-commit call of the fixed per-step launch list -- forced if and only if the solver selected a hop this step
-  const int rb = (force_rebuild == 2) ? ((d.commit_hop && *d.commit_hop) ? 2 : 0) : (force_rebuild ? 2 : ((*d.flag_verlet == 1) ? 1 : 0));
-  if (blockIdx.x == 0 && threadIdx.x == 0) { *d.rebuild_now = rb; d.maxd[0] = 0.0; d.maxd[1] = 0.0; }
-  if (!rb) return;
+__device__ __forceinline__ void rebuild_phases(const Dev& d, cg::grid_group& grid, const int ncell) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
   const int gwarp = gtid >> 5, nwarps = gthreads >> 5, lane = threadIdx.x & 31;
   int* cursor = d.cell_count + (ncell + 1);
@@ -290,8 +286,8 @@ __global__ void __launch_bounds__(TPB) k_verlet_rebuild(Dev d, int force_rebuild
     d.csort_info[s] = info; d.csort_mol[s] = d.mol_of_atom[f];
     for (int b = 0; b < 3; b++) d.csort_xq[3 * s + b] = d.xq[f + (b < n ? b : 0)];
   }
-  const double R = sqrt(d.rv2) + 2.0 * __longlong_as_double((long long)d.vstat[0]) + 1e-9;
   grid.sync();
+  const double R = sqrt(d.rv2) + 2.0 * __longlong_as_double((long long)d.vstat[0]) + 1e-9;
   for (int w = gwarp; w < RPB_TILE_PARTS * NC; w += nwarps) tile_sweep<false>(d, w / RPB_TILE_PARTS, w % RPB_TILE_PARTS, lane, R);
   grid.sync();
   if (blockIdx.x == 0) {
@@ -301,7 +297,43 @@ __global__ void __launch_bounds__(TPB) k_verlet_rebuild(Dev d, int force_rebuild
   }
   grid.sync();
   if (d.err_flag[1]) return;
-  for (int w = gwarp; w < RPB_TILE_PARTS * NC; w += nwarps) tile_sweep<true>(d, w / RPB_TILE_PARTS, w % RPB_TILE_PARTS, lane, R);
+  for (int w = gwarp; w < RPB_TILE_PARTS * NC; w += nwarps) {
+    const int n = d.row_count[w];
+    if (n <= RPB_TILE_TMPCAP) {                      // the usual case: copy the row out of its scratch
+      const unsigned* __restrict__ src = d.tile_tmp + (size_t)w * RPB_TILE_TMPCAP;
+      unsigned* __restrict__ dst = d.tile_list + d.tile_point[w];
+      for (int k = lane; k < n; k += 32) dst[k] = src[k];
+    } else tile_sweep<true>(d, w / RPB_TILE_PARTS, w % RPB_TILE_PARTS, lane, R);
+  }
+}
+
+__global__ void __launch_bounds__(TPB) k_verlet_rebuild(Dev d, int force_rebuild, int ncell) {
+  cg::grid_group grid = cg::this_grid();
+  // forced (init): flag_verlet_list untouched (flag_junk, ms_evb.f90:223-225)
+  const int rb = force_rebuild ? 2 : ((*d.flag_verlet == 1) ? 1 : 0);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *d.rebuild_now = rb; d.maxd[0] = 0.0; d.maxd[1] = 0.0; }
+  if (!rb) return;
+  rebuild_phases(d, grid, ncell);
+}
+
+// Hop commit (rpb_commit.cuh) + the forced rebuild + update_verlet_displacements(init) of ms_evb.f90:218-227 as ONE
+// cooperative kernel at the end of every MS-EVB force evaluation: exits at once unless the solver selected a hop.
+__global__ void __launch_bounds__(TPB) k_commit_and_rebuild(Dev d, CommitArgs a, int ncell) {
+  if (!*d.commit_hop) return;
+  cg::grid_group grid = cg::this_grid();
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  if (gtid == 0) commit_prepare(d, a.e, a.ci);
+  grid.sync();
+  for (int i = gtid; i < max(d.N, d.M); i += gthreads) commit_permute(d, a, i);
+  grid.sync();
+  for (int i = gtid; i < d.N; i += gthreads) commit_finish(d, a, i);
+  grid.sync();
+  rebuild_phases(d, grid, ncell);
+  for (int i = gtid; i < d.N; i += gthreads) {       // update_verlet_displacements(init): flag_verlet_list untouched (flag_junk)
+    const double4 p = d.xq[i];
+    d.vstore[3 * i] = p.x; d.vstore[3 * i + 1] = p.y; d.vstore[3 * i + 2] = p.z;
+    d.vdisp[3 * i] = 0.0; d.vdisp[3 * i + 1] = 0.0; d.vdisp[3 * i + 2] = 0.0;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -364,16 +396,16 @@ __device__ __forceinline__ void verlet_rows_atom(const Dev& d, const int i, cons
           bool hit0 = false, hit1 = false;
           if (m0 != mi && i < j0) {
             double r0 = pi.x - p0.x, r1 = pi.y - p0.y, r2 = pi.z - p0.z;
-            r0 = r0 - d.box[0] * floor(r0 * d.inv_box[0] + 0.5);
-            r1 = r1 - d.box[1] * floor(r1 * d.inv_box[1] + 0.5);
-            r2 = r2 - d.box[2] * floor(r2 * d.inv_box[2] + 0.5);
+            r0 = r0 - d.box[0] * floor_fp64pipe(r0 * d.inv_box[0] + 0.5);
+            r1 = r1 - d.box[1] * floor_fp64pipe(r1 * d.inv_box[1] + 0.5);
+            r2 = r2 - d.box[2] * floor_fp64pipe(r2 * d.inv_box[2] + 0.5);
             hit0 = (r0 * r0 + r1 * r1 + r2 * r2) < d.rv2;
           }
           if (m1 != mi && i < j1) {
             double r0 = pi.x - p1.x, r1 = pi.y - p1.y, r2 = pi.z - p1.z;
-            r0 = r0 - d.box[0] * floor(r0 * d.inv_box[0] + 0.5);
-            r1 = r1 - d.box[1] * floor(r1 * d.inv_box[1] + 0.5);
-            r2 = r2 - d.box[2] * floor(r2 * d.inv_box[2] + 0.5);
+            r0 = r0 - d.box[0] * floor_fp64pipe(r0 * d.inv_box[0] + 0.5);
+            r1 = r1 - d.box[1] * floor_fp64pipe(r1 * d.inv_box[1] + 0.5);
+            r2 = r2 - d.box[2] * floor_fp64pipe(r2 * d.inv_box[2] + 0.5);
             hit1 = (r0 * r0 + r1 * r1 + r2 * r2) < d.rv2;
           }
           const unsigned below = (1u << lane) - 1u;
@@ -430,14 +462,17 @@ __global__ void __launch_bounds__(TPB) k_verlet_reference_list(Dev d, int ncell)
 
 // ------------------------------------------------------------------------------------------------
 int verlet_setup(rpb_ctx* c) {     // per context: the cooperative grid of THIS context's device
-  int per_sm = 0, per_sm2 = 0, sms = 0;
+  int per_sm = 0, per_sm2 = 0, per_sm3 = 0, sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device) != cudaSuccess ||
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_verlet_rebuild, TPB, 0) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_verlet_reference_list, TPB, 0) != cudaSuccess || per_sm < 1 || per_sm2 < 1) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_verlet_reference_list, TPB, 0) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm3, k_commit_and_rebuild, TPB, 0) != cudaSuccess || per_sm < 1 || per_sm2 < 1 || per_sm3 < 1) {
     c->err = "cannot size the cooperative neighbour-list kernels on this device";
     return RPB_ERR_CUDA;
   }
-  c->d.coop_blocks = std::max(2, std::min(std::min(per_sm, per_sm2), 4) * sms);
+  // ONE block per SM: a cooperative grid starts only when all of its blocks can be resident, and the single-CTA enumeration
+  // kernel (512 threads, 117 KB of shared memory) that runs next to it must not make it wait for an SM
+  c->d.coop_blocks = std::max(2, sms);
   c->n_sm = sms;
   return 0;
 }
@@ -451,7 +486,7 @@ static int verlet_common(rpb_ctx* c, int force_rebuild) {
   void* args[] = {(void*)&d, (void*)&force_rebuild, (void*)&ncell};
   cudaError_t e = cudaLaunchCooperativeKernel((void*)k_verlet_rebuild, dim3(d.coop_blocks), dim3(TPB), args, 0, c->stream);
   if (e != cudaSuccess) { c->err = std::string("neighbour-list rebuild launch: ") + cudaGetErrorString(e); return RPB_ERR_CUDA; }
-  k_verlet_disp<<<nb, TPB, 0, c->stream>>>(d, blk_top2, d.vdone, force_rebuild == 2 ? 1 : 0);
+  k_verlet_disp<<<nb, TPB, 0, c->stream>>>(d, blk_top2, d.vdone);
   e = cudaGetLastError();
   if (e != cudaSuccess) { c->err = std::string("k_verlet_disp launch: ") + cudaGetErrorString(e); return RPB_ERR_CUDA; }
   c->n_launch += 2;
@@ -461,7 +496,15 @@ static int verlet_common(rpb_ctx* c, int force_rebuild) {
 int launch_verlet_update(rpb_ctx* c) { const int f = c->rebuild_forced ? 1 : 0; c->rebuild_forced = false; return verlet_common(c, f); }
 int launch_verlet_force_rebuild(rpb_ctx* c) { c->rebuild_forced = false; return verlet_common(c, 1); }
 
-int launch_verlet_commit_rebuild(rpb_ctx* c) { return verlet_common(c, 2); }
+int launch_commit_and_rebuild(rpb_ctx* c, const CommitArgs* a) {
+  Dev& d = c->d;
+  int ncell = d.ncx * d.ncy * d.ncz;
+  void* args[] = {(void*)&d, (void*)a, (void*)&ncell};
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)k_commit_and_rebuild, dim3(d.coop_blocks), dim3(TPB), args, 0, c->stream);
+  if (e != cudaSuccess) { c->err = std::string("hop-commit launch: ") + cudaGetErrorString(e); return RPB_ERR_CUDA; }
+  c->n_launch += 1;
+  return 0;
+}
 
 // the reference-ordered half list of the last rebuild -> d.verlet_point / d.neighbor_list (accessor only)
 int launch_verlet_reference_list(rpb_ctx* c) {

@@ -67,7 +67,7 @@ __device__ __forceinline__ double rsqrt_pair(double x) {
 struct PairQueue { double dx[PAIR_QCAP], dy[PAIR_QCAP], dz[PAIR_QCAP], r2[PAIR_QCAP], qq[PAIR_QCAP]; int meta[PAIR_QCAP]; };
 
 template <int TPB_, int MINB, int NB>
-__global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int world, int ppw) {
+__global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int world, int ppw, unsigned int* __restrict__ counters) {
   extern __shared__ double sh_par[];           // [nT*nT][6] vdw parameters, then the warps' queues
   __shared__ int sh_vt[RPB_MAXT * RPB_MAXT];   // atype_vdw_type; 2 = SAPT row with all-zero coefficients (contributes exactly 0)
   __shared__ double sh_red[32];
@@ -113,11 +113,16 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int 
       if (lane < 3) { const int ia = fi + (lane < ni ? lane : 0); h.p = d.xq[ia]; h.tpack = d.type[ia]; }
     }
   };
-  const int w_first = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * ppw;
+  // pieces are handed out by a counter (balance: the last CTAs of the grid find nothing left and exit), ppw per warp
+  int w = 0, w1 = 0;
+  if (lane == 0) { w = (int)atomicAdd(&counters[0], 1u); if (ppw > 1) w1 = (int)atomicAdd(&counters[0], 1u); }
+  w = __shfl_sync(0xffffffffu, w, 0); w1 = ppw > 1 ? __shfl_sync(0xffffffffu, w1, 0) : n_work;
   Header H, H1;
-  load_header(w_first, H);
-  for (int w = w_first; w < w_first + ppw && w < n_work; w++) {
-    load_header(w + 1 < w_first + ppw ? w + 1 : n_work, H1);   // consumed at the next switch
+  load_header(w, H);
+  for (int it = 0; it < ppw && w < n_work; it++) {
+    int w2 = n_work;
+    if (it + 2 < ppw && lane == 0) w2 = (int)atomicAdd(&counters[0], 1u);   // consumed two pieces from now
+    load_header(w1, H1);                                                    // consumed at the next switch
     const int fi = H.info & 0xffffff, ni = H.info >> 24;
     const int vs = H.vs, vf = H.vf;
     int ti[3];
@@ -241,11 +246,17 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int 
         if (lane == 3 * a + c) mine = x;
       }
     if (lane < 3 * ni) atomicAdd(&d.force[3 * fi + lane], mine);
-    H = H1;
+    H = H1; w = w1;
+    w1 = (it + 2 < ppw) ? __shfl_sync(0xffffffffu, w2, 0) : n_work;
   }
   e_el = block_sum(e_el, sh_red);
   e_vdw = block_sum(e_vdw, sh_red);
-  if (threadIdx.x == 0) { atomicAdd(&d.en[E_ELEC], 0.5 * e_el); atomicAdd(&d.en[E_VDW], 0.5 * e_vdw); }
+  if (threadIdx.x == 0) {
+    atomicAdd(&d.en[E_ELEC], 0.5 * e_el); atomicAdd(&d.en[E_VDW], 0.5 * e_vdw);
+    // the last CTA to finish re-arms the work counter for the next launch
+    __threadfence();
+    if (atomicAdd(&counters[1], 1u) == gridDim.x - 1) { counters[0] = 0u; counters[1] = 0u; __threadfence(); }
+  }
 }
 
 // one thread per molecule: intramolecular non-bonded (exclusion correction, 1-4) + bonds/angles/dihedrals
@@ -289,7 +300,7 @@ static int launch_pair_variant(rpb_ctx* c, bool shard, int ppw, int pad_kb = 0) 
   const size_t shmem = std::max((size_t)((c->d.nT * c->d.nT * 6 + 1) & ~1) * sizeof(double) + wpb * sizeof(PairQueue), (size_t)pad_kb * 1024);
   static bool attr_set = false;     // (same for every context: a function attribute)
   if (!attr_set) { cudaFuncSetAttribute(k_pair_tiles<T, MINB, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr_set = true; }
-  k_pair_tiles<T, MINB, NB><<<blocks, T, shmem, c->stream>>>(c->d, r, R, ppw);
+  k_pair_tiles<T, MINB, NB><<<blocks, T, shmem, c->stream>>>(c->d, r, R, ppw, reinterpret_cast<unsigned int*>(c->d.vstat + 3));
   return 0;
 }
 

@@ -247,7 +247,7 @@ int rpb_create(rpb_ctx** out, const rpb_config* cfg) {
   AL(d.mol_first, M); AL(d.mol_natom, M); AL(d.mol_type, M); AL(d.r_com, 3 * M); AL(d.hydronium, 1);
   AL(d.verlet_point, N + 1); AL(d.neighbor_list, d.verlet_cap);
   d.tile_cap = 2 * (long long)d.verlet_cap;       // a tile holds at least one listed pair, and the listed pairs fit the reference's capacity
-  AL(d.tile_point, RPB_TILE_PARTS * (size_t)N + 4); AL(d.tile_list, (size_t)d.tile_cap); AL(d.cl_info, N + 1); AL(d.n_clusters, 1); AL(d.mol_cl_first, M + 1); AL(d.mol_ncl, M + 1);
+  AL(d.tile_point, RPB_TILE_PARTS * (size_t)N + 4); AL(d.tile_tmp, (RPB_TILE_PARTS * (size_t)N + 4) * RPB_TILE_TMPCAP); AL(d.tile_list, (size_t)d.tile_cap); AL(d.cl_info, N + 1); AL(d.n_clusters, 1); AL(d.mol_cl_first, M + 1); AL(d.mol_ncl, M + 1);
   AL(d.vbuild_xq, N); AL(d.csort_xq, 3 * (size_t)N); AL(d.csort_mol, N); AL(d.csort_info, N); AL(d.vstat, 4);
   AL(d.vsort_xq, N); AL(d.vsort_mol, N); AL(d.vsort_entry, N); AL(d.vstore, 3 * N); AL(d.vdisp, 3 * N);
   AL(d.flag_verlet, 1); AL(d.rebuild_now, 1); AL(d.err_flag, 4); AL(d.vdone, 1);

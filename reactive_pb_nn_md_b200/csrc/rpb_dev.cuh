@@ -22,6 +22,7 @@
 #define RPB_MAXB 8    // bonds / angles / dihedrals per molecule type
 #define RPB_CHAIN_MOLS (RPB_MAXC + 1)
 #define RPB_TILE_PARTS 4   // a cluster's row of the pair list is built and consumed in this many independent parts
+#define RPB_TILE_TMPCAP 160 // entries of a row part kept in the rebuild's scratch (longer rows are swept twice; water at r_v = 12 A: ~70)
 
 // energy accumulator slots (device doubles)
 enum { E_ELEC = 0, E_VDW, E_BOND, E_ANGLE, E_DIH, E_RECIP, E_KE, E_REP, E_NSLOT };
@@ -91,6 +92,7 @@ struct Dev {
   int* n_clusters;                          // device scalar
   int* cl_info;                             // [cluster] first atom | n_atom << 24
   int* mol_cl_first; int* mol_ncl;          // [M+1] first cluster of every molecule / [M] clusters per molecule
+  unsigned* tile_tmp;                       // rebuild scratch: [row part][RPB_TILE_TMPCAP]
   int* tile_point; unsigned* tile_list;     // CSR over (cluster, part) rows [RPB_TILE_PARTS * I + part]; entry = first atom of cluster J | mask << 23 (bit 3a+b: atom a of I with atom b of J)
   long long tile_cap;
   double4* csort_xq; int* csort_mol; int* csort_info;   // cell-sorted copies of the clusters for the sweep: [3 slot + b], [slot], [slot]

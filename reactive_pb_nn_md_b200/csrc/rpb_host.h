@@ -137,7 +137,8 @@ void launch_update_com_shift(rpb_ctx*, bool shift);
 int verlet_setup(rpb_ctx*);                 // per-context sizing of the cooperative rebuild kernels
 int launch_verlet_update(rpb_ctx*);         // total_energy_forces.f90:30-39
 int launch_verlet_force_rebuild(rpb_ctx*);  // construct_verlet_list + displacement init
-int launch_verlet_commit_rebuild(rpb_ctx*); // the forced rebuild of a committed hop (ms_evb.f90:223-225); acts only if the device-side hop flag is set
+struct CommitArgs;
+int launch_commit_and_rebuild(rpb_ctx*, const CommitArgs*);   // hop commit + the forced rebuild of ms_evb.f90:223-225 in ONE cooperative launch; acts only if the device-side hop flag is set
 int launch_verlet_reference_list(rpb_ctx*); // parity accessor: the reference's half list in its row order
 void launch_zero_forces(rpb_ctx*);
 void launch_kinetic_energy(rpb_ctx*);

@@ -1,2 +1,3 @@
-for v in 2 3 4 5; do RPB_PAIR_VARIANT=$v python bench.py --steps 40 --warmup 10 --no-cpu-baseline --workload c3 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('c3 variant $v', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'pair', d['kernels']['pair_real_space']['ms_per_step'], d['config']['n_states'])"; done
-RPB_PAIR_VARIANT=3 python tools/diag_timeline.py 20 2>&1 | tail -1 | tr ' ' '\n' | grep ":" > gpurun_out/r02_timeline_v3.txt; cat gpurun_out/r02_timeline_v3.txt
+python -m pytest tests/test_gpu_nonreactive.py -m gpu -q -x 2>&1 | tail -2
+for v in 1 2; do RPB_PAIR_VARIANT=$v python tools/time_kernels.py c2 10 2>&1 | grep -E "variant|pair_real"; done
+for v in 1 2; do RPB_PAIR_VARIANT=$v python tools/time_kernels.py c4 5 2>&1 | grep -E "variant|pair_real"; done
