@@ -20,11 +20,20 @@ CUDA-event time is its own and not inflated by whatever overlapped it; ALGORITHM
 DESIGN.md section 4.  `roofline` is the dominant kernel of the step (the fp64 real-space pair kernel, against
 the fp64 FMA peak measured in this process); `roofline_hbm` is the largest HBM-class PME kernel against the measured copy
 bandwidth (BASELINE.json: "PME spread/gather GB/s vs HBM"); `roofline_fp64` always names the pair kernel.
-`traffic` (DRAM bytes per launch) is read from profiles/r01_dram_traffic.json (ncu --set full of the same command).
+`traffic` (DRAM bytes per launch) is read from profiles/r02_dram_traffic.json (ncu --set full of the same command).
+The pair kernel's algorithmic flops use SURVEY 8(d)'s formula 24 P_v + 28 P_c + 28 P_c,LJ with the three pair counts
+COUNTED on the step's own pair list and positions (per rank: the rank's share of the clusters).  `config.n_states` is the
+number of diabats at step warmup+steps in both arms; the CPU leg re-runs exactly that trajectory with the oracle and the
+bench ASSERTS that the diabat count and the positions agree (`parity_check`).  `other_workloads` carries short runs of
+BASELINE configs[1], [3] and [4] (c2, c4, c5) measured the same way, so that they appear in driver records.
 """
 import argparse
 import json
 import os
+
+# more hardware work queues than the default 8: the step's six streams, and the replicas of an ensemble (6 streams each),
+# must not alias onto the same queue (false serialisation); read by the CUDA driver at initialisation
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import subprocess
 import sys
 import threading
@@ -112,7 +121,7 @@ def run_reference(args):
     sim = engine.Simulation(s, params_for(args.workload, n_threads=cores), library=lib)
     evb = wl["ms_evb"]
     (sim.ms_evb_calculate_total_force_energy if evb else sim.calculate_total_force_energy)()
-    sim.md_integrate_atomic(args.warmup, ms_evb=evb)
+    sim.md_integrate_atomic(max(args.warmup, 3), ms_evb=evb)      # same warm-up count as the CUDA arm: same trajectory point
     t0 = time.perf_counter()
     sim.md_integrate_atomic(args.steps, ms_evb=evb)
     dt = time.perf_counter() - t0
@@ -120,7 +129,7 @@ def run_reference(args):
     n_states = sim.evb()["n_states"] if evb else 1
     line = {
         "impl": "reference", "metric": "ms_evb_steps_per_s", "value": sps, "unit": "steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "ns_per_day": sps * DT_PS * 86.4,
         "config": {"workload": args.workload, "description": wl["desc"], "n_atoms": s.n_atoms, "pme_grid": wl["pme_grid"],
                    "n_states": n_states, "delta_t_ps": DT_PS},
@@ -133,28 +142,16 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def run_ensemble(args):
-    """--workload c5: R independent replicas per GPU ("replicas only": weak scaling, no collective on the data path).
-    value = replica-steps/s summed over all replicas of all ranks."""
-    import torch
+def ensemble_run(torch, lib, R, steps, warmup, rank, world, local_rank):
+    """R independent C3 replicas per GPU ("replicas only": weak scaling, no collective on the data path), driven by ONE
+    host thread per GPU (a graph launch per replica and step); returns replica-steps/s summed over all replicas of all ranks."""
     from reactive_pb_nn_md_b200 import engine, system
-    from reactive_pb_nn_md_b200._binding import load_cuda
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
-    lib = load_cuda()
-    R = args.replicas
     sims = []
     for r in range(R):
         s = system.config_c3(seed=20171017 + rank * R + r)
         sim = engine.Simulation(s, params_for("c5"), library=lib, device=local_rank)
         sim.ms_evb_calculate_total_force_energy()
         sims.append(sim)
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
 
     def barrier():
         torch.cuda.synchronize()
@@ -162,16 +159,12 @@ def run_ensemble(args):
             import torch.distributed as dist
             dist.barrier(); torch.cuda.synchronize()
 
-    engine.Simulation.ensemble_step(sims, max(args.warmup, 3), ms_evb=True)
+    engine.Simulation.ensemble_step(sims, max(warmup, 3), ms_evb=True)
     l0 = sum(s.launch_counts()[0] for s in sims)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start(); time.sleep(0.3)
-    flush.fill_(1.0)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    engine.Simulation.ensemble_step(sims, args.steps, ms_evb=True)      # returns when every replica's last step has completed
+    engine.Simulation.ensemble_step(sims, steps, ms_evb=True)      # returns when every replica's last step has completed
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -181,21 +174,47 @@ def run_ensemble(args):
         import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    clocks = sampler.finish() if rank == 0 else None
     # one replica alone, same device, for the concurrency gain
-    t0 = time.perf_counter(); sims[0].md_integrate_atomic(args.steps, ms_evb=True); torch.cuda.synchronize(); single = args.steps / (time.perf_counter() - t0)
+    torch.cuda.synchronize(); t0 = time.perf_counter(); sims[0].md_integrate_atomic(steps, ms_evb=True); torch.cuda.synchronize()
+    single = steps / (time.perf_counter() - t0)
+    total = world * R * steps / (ms * 1e-3)
+    out = {"workload": "c5", "description": WORKLOADS["c5"]["desc"], "value": total, "unit": "replica-steps/s", "n_gpus": world,
+           "replicas_per_gpu": R, "steps": steps, "warmup": max(warmup, 3), "ms_per_ensemble_step": ms / steps,
+           "n_atoms": sims[0].system.n_atoms, "pme_grid": 48, "n_states": [s.evb()["n_states"] for s in sims],
+           "gpu_launches": int(l1 - l0), "single_replica_steps_per_s_same_device": single,
+           "concurrency_gain": (R * steps / (ms * 1e-3)) / single,
+           "parallelism": "%d independent replicas per GPU x %d GPUs, one host thread per GPU, one CUDA-graph launch per replica and step (rpb_ensemble_step)" % (R, world),
+           "l2": "working set of %d replicas exceeds L2" % R, "timing": "cuda events around the K ensemble steps, max over ranks"}
+    for sim in sims:
+        sim.close()
+    return out
+
+
+def run_ensemble(args):
+    """--workload c5 as the headline."""
+    import torch
+    from reactive_pb_nn_md_b200._binding import load_cuda
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    lib = load_cuda()
+    sampler = ClockSampler(local_rank)
     if rank == 0:
-        total = world * R * args.steps / (ms * 1e-3)
+        sampler.start(); time.sleep(0.3)
+    r = ensemble_run(torch, lib, args.replicas, args.steps, args.warmup, rank, world, local_rank)
+    clocks = sampler.finish() if rank == 0 else None
+    if rank == 0:
         print(json.dumps({
-            "metric": "ms_evb_steps_per_s", "value": total, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "ns_per_day": total * DT_PS * 86.4,
-            "config": {"workload": "c5", "description": WORKLOADS["c5"]["desc"], "replicas_per_gpu": R, "n_atoms": sims[0].system.n_atoms,
-                       "pme_grid": 48, "n_states": [s.evb()["n_states"] for s in sims], "delta_t_ps": DT_PS,
-                       "parallelism": "%d independent replicas per GPU x %d GPUs, one host thread per replica (rpb_ensemble_step)" % (R, world),
-                       "l2": "working set of %d replicas exceeds L2" % R, "timing": "cuda events around the K ensemble steps, max over ranks"},
-            "clocks": clocks, "gpu_launches": int(l1 - l0), "single_replica_steps_per_s_same_device": single,
-            "concurrency_gain": (R * args.steps / (ms * 1e-3)) / single, "e2e": None, "roofline": None, "cpu_baseline": None}), flush=True)
+            "metric": "ms_evb_steps_per_s", "value": r["value"], "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": r["warmup"], "ms_per_step": r["ms_per_ensemble_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "ns_per_day": r["value"] * DT_PS * 86.4,
+            "config": {k: r[k] for k in ("workload", "description", "replicas_per_gpu", "n_atoms", "pme_grid", "n_states", "parallelism", "l2", "timing")},
+            "clocks": clocks, "gpu_launches": r["gpu_launches"], "single_replica_steps_per_s_same_device": r["single_replica_steps_per_s_same_device"],
+            "concurrency_gain": r["concurrency_gain"], "e2e": None, "roofline": None, "cpu_baseline": None}), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -221,6 +240,101 @@ def algorithmic_model(name, N, K, S, n_own, pairs_listed, pairs_cut):
     return m
 
 
+def count_pairs(sim, s, rc=10.0):
+    """P_v (listed pairs), P_c (listed and inside the cutoff), P_c,LJ (of those, with an LJ term) of the pair list and
+    positions the library holds right now -- the counts SURVEY 8(d)'s flop formula needs."""
+    pi, pj, _ = sim.tile_pairs()
+    st = sim.download_state()
+    x = st["xyz"]; L = s.box_length
+    d = x[pi - 1] - x[pj - 1]
+    d -= L * np.floor(d / L + 0.5)
+    r2 = (d * d).sum(axis=1)
+    inc = r2 < rc * rc
+    t = st["atom_type"]
+    lj = s.ff.vdw_type[t[pi - 1] - 1, t[pj - 1] - 1] == 0
+    return int(len(pi)), int(inc.sum()), int((inc & lj).sum())
+
+
+def timed_steps(torch, sim, evb, steps, warmup, flush, stream, world):
+    """W untimed + K timed steps, CUDA events per step on the library's stream, L2 flushed between steps outside the
+    timed intervals; returns total ms (max over ranks) and the launch-count deltas."""
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            torch.cuda.synchronize()
+    for _ in range(warmup):
+        sim.md_integrate_atomic(1, ms_evb=evb)
+    own0, fft0 = sim.launch_counts()
+    barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    wall0 = time.perf_counter()
+    for k in range(steps):
+        flush.fill_(float(k))                     # L2 flush (256 MiB > 126 MB L2), outside the timed interval
+        torch.cuda.synchronize()
+        evs[k][0].record(stream)
+        sim.md_integrate_atomic(1, ms_evb=evb)
+        evs[k][1].record(stream)
+    barrier()
+    wall = time.perf_counter() - wall0
+    ms_total = sum(a.elapsed_time(b) for a, b in evs)
+    own1, fft1 = sim.launch_counts()
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), wall, int(own1 - own0), int(fft1 - fft0)
+
+
+def e2e_steps(torch, sim, s, evb, n, world):
+    """the same step through the reference-facing calls with HOST buffers: upload x,v,topology -> step -> download x,v,F,
+    topology + energies, every step; wall clock around the loop (max over ranks)."""
+    st = sim.download_state()
+    for _ in range(3):
+        sim.upload_state(st["xyz"], st["velocity"], st); sim.md_integrate_atomic(1, ms_evb=evb); st = sim.download_state(out=st); sim.energies()
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        sim.upload_state(st["xyz"], st["velocity"], st)   # host buffers -> device (positions, velocities, topology)
+        sim.md_integrate_atomic(1, ms_evb=evb)
+        st = sim.download_state(out=st)                   # device -> host into the same host arrays: x, v, F, topology after possible hops
+        sim.energies()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    N = s.n_atoms
+    return {"value": n / float(t.item()), "unit": "steps/s",
+            "h2d_bytes_per_step": (N + 4) * 32 + 3 * N * 8, "d2h_bytes_per_step": (N + 4) * 32 + 2 * 3 * N * 8 + 8 * 8,
+            "call": "rpb_upload_state + rpb_step(1) + rpb_download_state + rpb_get_energies per step; caller-owned host arrays, one pinned "
+                    "copy each way ({x,q,v} up, {x,q,v,F} down); per-atom / per-molecule tables are re-sent only when they changed"}
+
+
+def quick_workload(torch, lib, name, steps, warmup, flush, rank, world, local_rank, pg):
+    """a short run of another BASELINE configuration, measured like the headline"""
+    from reactive_pb_nn_md_b200 import engine
+    wl = WORKLOADS[name]
+    evb = wl["ms_evb"]
+    sh = evb and world > 1
+    s = build_system(name)
+    sim = engine.Simulation(s, params_for(name), library=lib, device=local_rank, rank=rank if sh else 0,
+                            world_size=world if sh else 1, process_group=pg if sh else None)
+    (sim.ms_evb_calculate_total_force_energy if evb else sim.calculate_total_force_energy)()
+    stream = torch.cuda.ExternalStream(sim.dll.rpb_get_stream(sim.ctx), device=torch.device("cuda", local_rank))
+    ms, _, launches, _ = timed_steps(torch, sim, evb, steps, warmup, flush, stream, world if sh else 1)
+    out = {"workload": name, "description": wl["desc"], "n_atoms": s.n_atoms, "pme_grid": wl["pme_grid"], "steps": steps, "warmup": warmup,
+           "value": steps / (ms * 1e-3), "unit": "steps/s", "ms_per_step": ms / steps, "gpu_launches": launches,
+           "n_gpus": world if sh else 1, "n_states": sim.evb()["n_states"] if evb else 1}
+    sim.close()
+    return out
+
+
 def run_ours(args):
     import torch
     from reactive_pb_nn_md_b200 import engine
@@ -240,54 +354,25 @@ def run_ours(args):
     lib = load_cuda()
     wl = WORKLOADS[args.workload]
     evb = wl["ms_evb"]
+    W = max(args.warmup, 3)
     s = build_system(args.workload)
     sim = engine.Simulation(s, params_for(args.workload), library=lib, device=local_rank, rank=rank if evb else 0,
                             world_size=world if evb else 1, process_group=pg)
-    first = sim.ms_evb_calculate_total_force_energy if evb else sim.calculate_total_force_energy
-    first()
-    step = lambda n=1: sim.md_integrate_atomic(n, ms_evb=evb)
+    (sim.ms_evb_calculate_total_force_energy if evb else sim.calculate_total_force_energy)()
     stream = torch.cuda.ExternalStream(sim.dll.rpb_get_stream(sim.ctx), device=torch.device("cuda", local_rank))
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    own0, fft0 = sim.launch_counts()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    barrier()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.fill_(float(k))                     # L2 flush (256 MiB > 126 MB L2), outside the timed interval
-        torch.cuda.synchronize()
-        evs[k][0].record(stream)
-        step()
-        evs[k][1].record(stream)
-    barrier()
-    wall = time.perf_counter() - wall0
-    ms_total = sum(a.elapsed_time(b) for a, b in evs)
-    own1, fft1 = sim.launch_counts()
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total, wall, launches, fft_execs = timed_steps(torch, sim, evb, args.steps, W, flush, stream, world)
     clocks = sampler.finish() if rank == 0 else None
     sps = args.steps / (ms_total * 1e-3)
+    n_states = sim.evb()["n_states"] if evb else 1          # at step W + K: what the reference arm reports too
+    st_now = sim.download_state()
 
     # ---- per-kernel pass: a second context with every branch on ONE stream (clean per-kernel event times), started from
     #      the state the headline loop reached
-    n_states = sim.evb()["n_states"] if evb else 1
-    st_now = sim.download_state()
     os.environ["RPB_SERIAL_STREAMS"] = "1"
     sim2 = engine.Simulation(s, params_for(args.workload), library=lib, device=local_rank, rank=rank if evb else 0,
                              world_size=world if evb else 1, process_group=pg)
@@ -295,22 +380,23 @@ def run_ours(args):
     sim2.upload_state(st_now["xyz"], st_now["velocity"], st_now)
     sim2._check(sim2.dll.rpb_initialize(sim2.ctx))
     (sim2.ms_evb_calculate_total_force_energy if evb else sim2.calculate_total_force_energy)()
-    step2 = lambda n=1: sim2.md_integrate_atomic(n, ms_evb=evb)
     for _ in range(3):
-        step2()
+        sim2.md_integrate_atomic(1, ms_evb=evb)
     sim2.timers_enable(True)
     sim2.timers(reset=True)
     n_prof = min(args.steps, 20)
     for k in range(n_prof):
         flush.fill_(float(k)); torch.cuda.synchronize()
-        step2()
+        sim2.md_integrate_atomic(1, ms_evb=evb)
     tm = sim2.timers()
     sim2.timers_enable(False)
-    n_states = sim2.evb()["n_states"] if evb else 1
-    n_own = len([x for x in range(1, n_states) if (x - 1) % world == rank]) if evb else 0
-    vp, nl, _ = sim2.neighbor_list()
-    pairs_listed = len(nl)
-    model = algorithmic_model(args.workload, s.n_atoms, wl["pme_grid"], n_states, n_own, pairs_listed, int(0.58 * pairs_listed))
+    n_states_prof = sim2.evb()["n_states"] if evb else 1
+    n_own = len([x for x in range(1, n_states_prof) if (x - 1) % world == rank]) if evb else 0
+    P_v, P_c, P_lj = count_pairs(sim2, s)
+    share = 1.0 / world if evb else 1.0                     # a state-sharded run shards the pair kernel by clusters
+    model = algorithmic_model(args.workload, s.n_atoms, wl["pme_grid"], n_states_prof, n_own, P_v, P_c)
+    model["pair_real_space"] = ("fp64", int(share * (24 * P_v + 28 * P_c + 28 * P_lj)))
+    sim2.close()
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -337,7 +423,7 @@ def run_ours(args):
         kernels[name] = ent
     traffic = {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json"))).get(args.workload, {})
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_dram_traffic.json"))).get(args.workload, {})
     except Exception:
         pass
 
@@ -360,50 +446,49 @@ def run_ours(args):
     top = max(timed, key=lambda k: timed[k]["ms_per_step"]) if timed else None
     roofline = roof(top) if top else None
     if roofline and roofline["bound"] == "fp64":
-        roofline["bound_note"] = ("FP64-pipe-bound kernel (neither 'hbm' nor 'tensor'): achieved = reference operation count "
-                                  "(24 per listed + 56 per in-cutoff pair, each pair once) / launch time; ncu fp64 pipe utilisation "
-                                  "in profiles/r01_v5_ncu_full_summary.csv")
+        roofline["pair_counts"] = {"P_v": P_v, "P_c": P_c, "P_c_LJ": P_lj, "rank_share": share}
+        roofline["bound_note"] = ("FP64-pipe-bound kernel (neither 'hbm' nor 'tensor'): achieved = SURVEY 8(d) operation count "
+                                  "24 P_v + 28 P_c + 28 P_c,LJ (each pair once; counts taken from this run's pair list and positions) "
+                                  "/ launch time; ncu fp64 pipe utilisation in profiles/")
 
-    # ---- end-to-end through the reference-facing call with HOST buffers: upload x,v -> step -> download x,v,F + energies
-    e2e = None
+    # ---- end-to-end through the reference-facing call with HOST buffers (every rank of a sharded run moves its replica)
+    e2e = e2e_steps(torch, sim, s, evb, min(args.steps, 50), world)
+
+    # ---- CPU leg (rank 0, N = 1): the oracle re-runs EXACTLY the headline trajectory (first evaluation + W + K steps); its
+    #      last K steps are the reported CPU baseline, and its end point must be the CUDA run's
     cpu_baseline = None
-    if world == 1:
-        st = sim.download_state()
-        n_e2e = min(args.steps, 50)
-        N = s.n_atoms
-        h2d = 2 * 3 * N * 8 + 2 * N * 8 + N * 4 + 3 * s.n_mole * 4
-        d2h = 3 * 3 * N * 8 + 8 * 8
-        for _ in range(3):
-            sim.upload_state(st["xyz"], st["velocity"], st); step(); st = sim.download_state(out=st); sim.energies()
-        torch.cuda.synchronize()
+    parity_check = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        olib = Library(os.path.join(ROOT, "oracle", "librpbmd_oracle.so"))
+        so = engine.Simulation(s, params_for(args.workload, n_threads=cores), library=olib)
+        (so.ms_evb_calculate_total_force_energy if evb else so.calculate_total_force_energy)()
+        so.md_integrate_atomic(W, ms_evb=evb)
         t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            sim.upload_state(st["xyz"], st["velocity"], st)   # host buffers -> device (positions, velocities, topology)
-            step()
-            st = sim.download_state(out=st)         # device -> host into the same host arrays: x, v, F, topology after possible hops
-            sim.energies()
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        e2e = {"value": n_e2e / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "call": "rpb_upload_state + rpb_step(1) + rpb_download_state + rpb_get_energies; caller-owned host arrays, staged through the library's pinned buffer"}
-        # ---- CPU baseline: bounded sample of the same workload on the host cores (oracle = port of the reference algorithm)
-        if not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            olib = Library(os.path.join(ROOT, "oracle", "librpbmd_oracle.so"))
-            so = engine.Simulation(s, params_for(args.workload, n_threads=cores), library=olib)
-            (so.ms_evb_calculate_total_force_energy if evb else so.calculate_total_force_energy)()
-            so.md_integrate_atomic(2, ms_evb=evb)
-            n_cpu = args.cpu_steps
-            t0 = time.perf_counter()
-            so.md_integrate_atomic(n_cpu, ms_evb=evb)
-            cdt = time.perf_counter() - t0
-            cpu_baseline = {"value": n_cpu / cdt, "unit": "steps/s", "cores": cores, "kind": "port",
-                            "sample": "%d full MD steps of the same workload with the CPU restatement of the reference "
-                                      "algorithm (oracle/, g++ -O2 -fopenmp)" % n_cpu}
+        so.md_integrate_atomic(args.steps, ms_evb=evb)
+        cdt = time.perf_counter() - t0
+        cpu_baseline = {"value": args.steps / cdt, "unit": "steps/s", "cores": cores, "kind": "port",
+                        "sample": "the %d timed MD steps of the same trajectory with the CPU restatement of the reference "
+                                  "algorithm (oracle/, g++ -O2 -fopenmp, %d threads)" % (args.steps, cores)}
+        xo = so.download_state()
+        S_o = so.evb()["n_states"] if evb else 1
+        dx = float(np.abs(xo["xyz"] - st_now["xyz"]).max())
+        parity_check = {"n_states_cuda": n_states, "n_states_oracle": S_o, "hydronium_cuda": int(st_now["hydronium_mol"]),
+                        "hydronium_oracle": int(xo["hydronium_mol"]), "max_abs_dx_angstrom": dx, "after_steps": W + args.steps}
+        assert S_o == n_states and xo["hydronium_mol"] == st_now["hydronium_mol"] and dx < 1e-8, parity_check
+
+    # ---- the other BASELINE configurations, short runs
+    other = None
+    if args.workload == "c3" and not args.no_extra:
+        other = {}
+        if world == 1:
+            other["c2"] = quick_workload(torch, lib, "c2", 20, 5, flush, rank, world, local_rank, pg)
+        other["c4"] = quick_workload(torch, lib, "c4", 20, 5, flush, rank, world, local_rank, pg)
+        other["c5"] = ensemble_run(torch, lib, args.replicas, 20, 5, rank, world, local_rank)
     if rank == 0:
         line = {
             "metric": "ms_evb_steps_per_s", "value": sps, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "warmup": W, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "ns_per_day": sps * DT_PS * 86.4,
             "config": {"workload": args.workload, "description": wl["desc"], "n_atoms": s.n_atoms, "pme_grid": wl["pme_grid"],
@@ -411,10 +496,10 @@ def run_ours(args):
                        "exchange": {"none": "single GPU", "peer": "peer-memory all-reduce kernels over NVLink (in-library, rank-ordered sums)",
                                     "collective": "torch.distributed all-reduce (NCCL) between the phase calls"}[sim.exchange],
                        "l2": "flushed between timed steps (256 MiB write)", "timing": "cuda events per step on the library stream, max over ranks"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(own1 - own0), "cufft_execs": int(fft1 - fft0),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "cufft_execs": fft_execs,
             "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_fp64": roofline_fp64, "kernels": kernels,
-            "kernels_note": "per-kernel CUDA-event times from a serial-stream context (RPB_SERIAL_STREAMS=1); the headline value runs three concurrent streams", "fp64_peak_tflops_measured": fp64_peak,
-            "cpu_baseline": cpu_baseline, "wall_s_timed_region": wall,
+            "kernels_note": "per-kernel CUDA-event times from a serial-stream context (RPB_SERIAL_STREAMS=1, plain launches); the headline value replays the step as a CUDA graph on six streams", "fp64_peak_tflops_measured": fp64_peak,
+            "cpu_baseline": cpu_baseline, "parity_check": parity_check, "other_workloads": other, "wall_s_timed_region": wall,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -431,6 +516,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short c2 / c4 / c5 runs of the default c3 line")
     ap.add_argument("--replicas", type=int, default=16, help="replicas per GPU of --workload c5")
     args = ap.parse_args()
     if args.impl == "reference":

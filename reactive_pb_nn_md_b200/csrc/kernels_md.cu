@@ -99,11 +99,20 @@ __global__ void k_remove_com_momentum(Dev d, const double* psum, int n_partial) 
   for (int k = 0; k < 4; k++) { double v = block_sum(a[k], sh); if (threadIdx.x == 0) tot[k] = v; }
   __syncthreads();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= d.N || d.freeze[d.type[i]] == 1) return;
-  double n = tot[3], m = d.mass[i];
-  d.vel[3 * i] = d.vel[3 * i] - (tot[0] / n) / m;
-  d.vel[3 * i + 1] = d.vel[3 * i + 1] - (tot[1] / n) / m;
-  d.vel[3 * i + 2] = d.vel[3 * i + 2] - (tot[2] / n) / m;
+  double ke = 0.0;
+  if (i < d.N) {
+    double v0 = d.vel[3 * i], v1 = d.vel[3 * i + 1], v2 = d.vel[3 * i + 2];
+    const double m = d.mass[i];
+    if (d.freeze[d.type[i]] != 1) {
+      const double n = tot[3];
+      v0 = v0 - (tot[0] / n) / m; v1 = v1 - (tot[1] / n) / m; v2 = v2 - (tot[2] / n) / m;
+      d.vel[3 * i] = v0; d.vel[3 * i + 1] = v1; d.vel[3 * i + 2] = v2;
+    }
+    ke = 0.5 * m * (v0 * v0 + v1 * v1 + v2 * v2) / d.conv_kin;      // calculate_kinetic_energy total_energy_forces.f90:106-121
+  }
+  // the step's kinetic energy rides along (slot zeroed by k_integrate_first): rpb_get_energies after a step needs no kernel
+  ke = block_sum(ke, sh);
+  if (threadIdx.x == 0) atomicAdd(&d.en[E_KE], ke);
 }
 
 __global__ void k_kinetic(Dev d) {

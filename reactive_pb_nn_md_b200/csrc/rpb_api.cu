@@ -41,6 +41,7 @@ static int fetch_status(rpb_ctx* c) {
   CK(cudaMemcpyAsync(c->h_en, c->d.en, E_NSLOT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaMemcpyAsync(c->h_flags, c->d.err_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  c->last_en.kinetic_energy = c->h_en[E_KE];
   if (c->h_flags[1]) { c->err = "please increase size of verlet neighbor list"; return RPB_ERR_VERLET; }
   if (c->h_flags[2]) { c->err = "Found more diabat states than the current setting of evb_max_states"; return RPB_ERR_DIABATS; }
   if (c->h_flags[3] >= 30) { c->err = "peer-memory exchange: rank " + std::to_string(c->h_flags[3] - 30) + " did not arrive"; return RPB_ERR_CUDA; }
@@ -121,6 +122,7 @@ int calculate_total_force_energy(rpb_ctx* c, bool evb_principal) {
 // enqueue one force evaluation (no host synchronisation)
 static int enqueue_force(rpb_ctx* c, int ms_evb) {
   int rc;
+  c->image_valid = false; c->ke_valid = false;
   if (ms_evb) {
     if (!c->have_evb) { c->err = "rpb_set_evb not called"; return RPB_ERR_STATE; }
     const bool sharded = c->d.world > 1;   // peer-memory exchange (kernels_peer.cu); checked by the callers
@@ -243,7 +245,14 @@ int rpb_create(rpb_ctx** out, const rpb_config* cfg) {
   const size_t K3 = (size_t)K * K * K, Kh3 = (size_t)K * K * (K / 2 + 1);
   const int ncell = d.ncx * d.ncy * d.ncz;
 #define AL(p, n) if ((rc = dev_alloc(c, &(p), (n)))) return rc;
-  AL(d.xq, N + 4); AL(d.vel, 3 * N); AL(d.force, 3 * N); AL(d.mass, N); AL(d.type, N); AL(d.mol_of_atom, N);
+  {   // xq | vel | force contiguous: one copy per state transfer
+    const size_t bytes = (size_t)(N + 4) * sizeof(double4) + 2 * (size_t)3 * N * sizeof(double);
+    AL(c->state_block, bytes);
+    d.xq = reinterpret_cast<double4*>(c->state_block);
+    d.vel = reinterpret_cast<double*>(c->state_block + (size_t)(N + 4) * sizeof(double4));
+    d.force = d.vel + 3 * (size_t)N;
+  }
+  AL(d.mass, N); AL(d.type, N); AL(d.mol_of_atom, N);
   AL(d.mol_first, M); AL(d.mol_natom, M); AL(d.mol_type, M); AL(d.r_com, 3 * M); AL(d.hydronium, 1);
   AL(d.verlet_point, N + 1); AL(d.neighbor_list, d.verlet_cap);
   d.tile_cap = 2 * (long long)d.verlet_cap;       // a tile holds at least one listed pair, and the listed pairs fit the reference's capacity
@@ -287,6 +296,7 @@ void rpb_destroy(rpb_ctx* c) {
   if (c->h_flags) cudaFreeHost(c->h_flags);
   for (int k = 0; k < 2; k++) if (c->graph[k].exec) cudaGraphExecDestroy(c->graph[k].exec);
   if (c->staging) cudaFreeHost(c->staging);
+  for (int k = 0; k < 2; k++) { if (c->staging_up[k]) cudaFreeHost(c->staging_up[k]); if (c->ev_up[k]) cudaEventDestroy(c->ev_up[k]); }
   if (c->eh.pinned) cudaFreeHost(c->eh.pinned);
   if (c->stream) {
     for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
@@ -504,13 +514,13 @@ struct Staging {
 };
 static int staging_get(rpb_ctx* c, Staging& st) {
   const size_t N = c->d.N, M = c->d.M;
-  const size_t bytes = N * sizeof(double4) + (3 * N + 3 * N + N) * sizeof(double) + (2 * N + 3 * M) * sizeof(int);
+  const size_t bytes = (N + 4) * sizeof(double4) + (3 * N + 3 * N + N) * sizeof(double) + (2 * N + 3 * M) * sizeof(int);   // xq | vel | force laid out as on the device
   if (!c->staging) {
     CK(cudaMallocHost(&c->staging, bytes));
     memset(c->staging, 0xff, bytes);
   }
   char* p = (char*)c->staging;
-  st.xq = (double4*)p; p += N * sizeof(double4);
+  st.xq = (double4*)p; p += (N + 4) * sizeof(double4);
   st.vel = (double*)p; p += 3 * N * sizeof(double);
   st.force = (double*)p; p += 3 * N * sizeof(double);
   st.mass = (double*)p; p += N * sizeof(double);
@@ -553,34 +563,51 @@ int rpb_upload_state(rpb_ctx* c, const double* xyz, const double* velocity, cons
     }
     if (expect != N) { c->err = "molecule table does not cover all atoms"; return RPB_ERR_ARG; }
   }
-  CK(cudaStreamSynchronize(c->stream));          // the staging area may still feed an earlier copy
   if ((rc = refresh_mirror(c))) return rc;
+  // {xq, vel} travel from one of two pinned images in ONE copy: no wait for the previous upload, only for the one before it
+  const size_t up_bytes = (size_t)(N + 4) * sizeof(double4) + (size_t)3 * N * sizeof(double);
+  const int par = c->up_parity; c->up_parity ^= 1;
+  if (!c->staging_up[par]) {
+    CK(cudaMallocHost(&c->staging_up[par], up_bytes));
+    memset(c->staging_up[par], 0, up_bytes);
+    CK(cudaEventCreateWithFlags(&c->ev_up[par], cudaEventDisableTiming));
+  } else CK(cudaEventSynchronize(c->ev_up[par]));
+  double4* up_xq = reinterpret_cast<double4*>(c->staging_up[par]);
+  double* up_vel = reinterpret_cast<double*>(reinterpret_cast<char*>(c->staging_up[par]) + (size_t)(N + 4) * sizeof(double4));
   const bool all = !c->have_state || !c->state_cache_valid;   // a committed proton hop permuted the device tables
-  bool type_changed = all, mass_changed = all, mol_changed = all;
-  for (int i = 0; i < N; i++) {
-    st.xq[i] = make_double4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], charge[i]);
-    const int t = atom_type_index[i] - 1;
-    if (st.type[i] != t) { st.type[i] = t; type_changed = true; }
-    if (st.mass[i] != mass[i]) { st.mass[i] = mass[i]; mass_changed = true; }
-  }
-  const bool had_state = c->have_state && (int)c->mol_first.size() == M;
-  c->mol_first.resize(M); c->mol_natom.resize(M); c->mol_type.resize(M);
-  int expect = 0, ncl = 0;
-  for (int m = 0; m < M; m++) {
-    const int f = mol_first_atom[m] - 1, n = mol_n_atom[m], t = mol_type[m] - 1;
-    if (st.mol[m] != f || st.mol[M + m] != n || st.mol[2 * M + m] != t) { st.mol[m] = f; st.mol[M + m] = n; st.mol[2 * M + m] = t; mol_changed = true; }
-    if (had_state && (c->mol_first[m] != f || c->mol_natom[m] != n)) c->rebuild_forced = true;   // a different molecule table: the cluster table is stale
-    c->mol_first[m] = f; c->mol_natom[m] = n; c->mol_type[m] = t;
-    if (mol_changed) for (int a = 0; a < n; a++) st.moa[expect + a] = m;
-    expect += n;
-    ncl += (n + 2) / 3;
-  }
+  // change detection on raw copies of the caller's tables (one memcmp each): unchanged tables are neither converted nor sent
+  c->raw_type.resize(N); c->raw_mass.resize(N); c->raw_mol.resize(3 * (size_t)M);
+  bool type_changed = all || memcmp(c->raw_type.data(), atom_type_index, N * sizeof(int)) != 0;
+  bool mass_changed = all || memcmp(c->raw_mass.data(), mass, N * sizeof(double)) != 0;
+  bool mol_changed = all || memcmp(c->raw_mol.data(), mol_first_atom, M * sizeof(int)) != 0 ||
+                     memcmp(c->raw_mol.data() + M, mol_n_atom, M * sizeof(int)) != 0 || memcmp(c->raw_mol.data() + 2 * (size_t)M, mol_type, M * sizeof(int)) != 0;
+  if (type_changed || mass_changed || mol_changed) CK(cudaStreamSynchronize(c->stream));   // the cached tables below may still feed an earlier copy
+  for (int i = 0; i < N; i++) up_xq[i] = make_double4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], charge[i]);
+  if (type_changed) { memcpy(c->raw_type.data(), atom_type_index, N * sizeof(int)); for (int i = 0; i < N; i++) st.type[i] = atom_type_index[i] - 1; }
+  if (mass_changed) { memcpy(c->raw_mass.data(), mass, N * sizeof(double)); memcpy(st.mass, mass, N * sizeof(double)); }
+  int ncl = 0;
+  if (mol_changed) {
+    memcpy(c->raw_mol.data(), mol_first_atom, M * sizeof(int)); memcpy(c->raw_mol.data() + M, mol_n_atom, M * sizeof(int));
+    memcpy(c->raw_mol.data() + 2 * (size_t)M, mol_type, M * sizeof(int));
+    const bool had_state = c->have_state && (int)c->mol_first.size() == M;
+    c->mol_first.resize(M); c->mol_natom.resize(M); c->mol_type.resize(M);
+    int expect = 0;
+    for (int m = 0; m < M; m++) {
+      const int f = mol_first_atom[m] - 1, n = mol_n_atom[m], t = mol_type[m] - 1;
+      st.mol[m] = f; st.mol[M + m] = n; st.mol[2 * M + m] = t;
+      if (had_state && (c->mol_first[m] != f || c->mol_natom[m] != n)) c->rebuild_forced = true;   // a different molecule table: the cluster table is stale
+      c->mol_first[m] = f; c->mol_natom[m] = n; c->mol_type[m] = t;
+      for (int a = 0; a < n; a++) st.moa[expect + a] = m;
+      expect += n;
+      ncl += (n + 2) / 3;
+    }
+  } else for (int m = 0; m < M; m++) ncl += (c->mol_natom[m] + 2) / 3;
   c->n_clusters_bound = std::min(N, ncl + 2);   // a hop moves one proton: the count changes by at most one either way
-  memcpy(st.vel, velocity, 3 * (size_t)N * sizeof(double));
+  memcpy(up_vel, velocity, 3 * (size_t)N * sizeof(double));
   if (c->hydronium_mol != hydronium_mol - 1) mol_changed = true;
   c->hydronium_mol = hydronium_mol - 1;
-  CK(cudaMemcpyAsync(c->d.xq, st.xq, N * sizeof(double4), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d.vel, st.vel, 3 * (size_t)N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->state_block, c->staging_up[par], up_bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaEventRecord(c->ev_up[par], c->stream));
   if (mass_changed) CK(cudaMemcpyAsync(c->d.mass, st.mass, N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   if (type_changed) CK(cudaMemcpyAsync(c->d.type, st.type, N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   if (mol_changed) {
@@ -592,6 +619,7 @@ int rpb_upload_state(rpb_ctx* c, const double* xyz, const double* velocity, cons
     *hp = c->hydronium_mol;
     CK(cudaMemcpyAsync(c->d.hydronium, hp, sizeof(int), cudaMemcpyHostToDevice, c->stream));
   }
+  c->ke_valid = false; c->image_valid = false;
   c->have_state = true;
   c->state_cache_valid = true;
   return 0;
@@ -599,6 +627,7 @@ int rpb_upload_state(rpb_ctx* c, const double* xyz, const double* velocity, cons
 
 int rpb_initialize(rpb_ctx* c) {
   if (!(c->have_tables && c->have_ff && c->have_mt && c->have_state)) { c->err = "tables/forcefield/molecule types/state must be set first"; return RPB_ERR_STATE; }
+  c->image_valid = false;
   launch_update_com_shift(c, true);
   int rc = launch_verlet_force_rebuild(c);
   if (rc) return rc;
@@ -616,7 +645,7 @@ int rpb_force_energy(rpb_ctx* c, int ms_evb) {
   return collect_results(c, ms_evb);
 }
 
-int rpb_step_begin(rpb_ctx* c) { launch_integrate_first(c); return 0; }
+int rpb_step_begin(rpb_ctx* c) { c->image_valid = false; c->ke_valid = false; launch_integrate_first(c); return 0; }
 int rpb_step_end(rpb_ctx* c) {
   launch_integrate_second(c);
   int rc = fetch_status(c);
@@ -682,6 +711,7 @@ static int enqueue_steps(rpb_ctx* c, int n_steps, int ms_evb) {
     if (rc) return rc;
     if (exec) {
       const StepGraph& g = c->graph[ms_evb ? 1 : 0];
+      c->image_valid = false; c->ke_valid = false;
       for (; s < n_steps; s++) {
         CK(cudaGraphLaunch(exec, c->main_stream));
         c->n_launch += g.launches;
@@ -700,7 +730,19 @@ int rpb_step(rpb_ctx* c, int n_steps, int ms_evb) {
   if (ms_evb && c->d.world > 1 && !c->peer.on) { c->err = "world_size>1: set up the peer-memory exchange (rpb_peer_*) or use the phase calls"; return RPB_ERR_STATE; }
   int rc = enqueue_steps(c, n_steps, ms_evb);
   if (rc) return rc;
-  return collect_results(c, ms_evb);
+  // a caller that downloads the state after every call (a host driver that owns the arrays): the copy is queued right
+  // behind the steps and completes under the one synchronisation below, instead of costing a second round trip
+  c->image_valid = false;
+  if (c->download_streak >= 2) {
+    Staging st;
+    if ((rc = staging_get(c, st))) return rc;
+    CK(cudaMemcpyAsync(st.xq, c->state_block, (size_t)(c->d.N + 4) * sizeof(double4) + 2 * (size_t)3 * c->d.N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    c->image_valid = true;
+  }
+  c->download_streak = std::max(0, c->download_streak - 1);   // (raised by two per download: a streak survives as long as every call is followed by one)
+  rc = collect_results(c, ms_evb);
+  c->ke_valid = (rc == 0 && n_steps > 0);     // the last kernel of a step leaves the kinetic energy in its slot
+  return rc;
 }
 
 // Independent replicas (BASELINE config 5, "replicas only": no communication).  A step needs no host decision, so ONE host
@@ -739,6 +781,7 @@ int rpb_ensemble_step(rpb_ctx** replicas, int n_replicas, int n_steps, int ms_ev
 }
 
 int rpb_get_energies(rpb_ctx* c, rpb_energies* e) {
+  if (c->ke_valid) { *e = c->last_en; return 0; }
   launch_kinetic_energy(c);
   CK(cudaMemcpyAsync(c->h_en, c->d.en, E_NSLOT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -756,15 +799,24 @@ int rpb_download_state(rpb_ctx* c, double* xyz, double* velocity, double* force,
   if ((rc = refresh_mirror(c))) return rc;
   // a separate pinned block would be needed to keep the upload cache valid: downloads use the tail halves only where they
   // do not alias cached tables (xq, vel, force are re-sent on every upload anyway)
-  if (xyz || charge) CK(cudaMemcpyAsync(st.xq, c->d.xq, N * sizeof(double4), cudaMemcpyDeviceToHost, c->stream));
-  if (velocity) CK(cudaMemcpyAsync(st.vel, c->d.vel, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  if (force) CK(cudaMemcpyAsync(st.force, c->d.force, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  const bool full = (xyz || charge) && velocity && force;
+  if (full) c->download_streak = std::min(4, c->download_streak + 2);
+  if (full && c->image_valid) {
+    // the image was copied behind the last step (see rpb_step) and nothing touched the device state since
+  } else if (full) {     // the usual full download: xq | vel | force are one block on both sides
+    CK(cudaMemcpyAsync(st.xq, c->state_block, (size_t)(N + 4) * sizeof(double4) + 2 * (size_t)3 * N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    if (xyz || charge) CK(cudaMemcpyAsync(st.xq, c->d.xq, N * sizeof(double4), cudaMemcpyDeviceToHost, c->stream));
+    if (velocity) CK(cudaMemcpyAsync(st.vel, c->d.vel, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (force) CK(cudaMemcpyAsync(st.force, c->d.force, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
   // masses and atom types only change when a proton hop is committed: while the staging area still mirrors the device
   // tables (state_cache_valid, see rpb_upload_state) they are served from it without a copy
   const bool cached = c->state_cache_valid;
+  const bool need_sync = !(full && c->image_valid) || ((mass || atom_type_index) && !cached);
   if (mass && !cached) CK(cudaMemcpyAsync(st.mass, c->d.mass, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   if (atom_type_index && !cached) CK(cudaMemcpyAsync(st.type, c->d.type, N * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  if (need_sync) CK(cudaStreamSynchronize(c->stream));
   if (xyz || charge)
     for (int i = 0; i < N; i++) {
       if (xyz) { xyz[3 * i] = st.xq[i].x; xyz[3 * i + 1] = st.xq[i].y; xyz[3 * i + 2] = st.xq[i].z; }

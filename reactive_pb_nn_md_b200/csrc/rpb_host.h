@@ -75,6 +75,13 @@ struct rpb_ctx {
   double* h_en = nullptr;      // [E_NSLOT]
   int* h_flags = nullptr;      // [8]
   void* staging = nullptr;     // pinned staging area of rpb_upload_state / rpb_download_state (also caches the last uploaded tables)
+  void* staging_up[2] = {nullptr, nullptr};   // double-buffered pinned images of {xq, vel} for uploads: no wait for the previous upload's copy
+  cudaEvent_t ev_up[2] = {nullptr, nullptr}; int up_parity = 0;
+  char* state_block = nullptr; // device: xq | vel | force in ONE allocation, so that a state transfer is one copy each way
+  std::vector<int> raw_type, raw_mol; std::vector<double> raw_mass;   // the caller's tables as last uploaded (change detection by memcmp)
+  bool image_valid = false;    // the pinned staging area holds the device state {xq, vel, force} as of the end of the last rpb_step
+  int download_streak = 0;     // > 1: the caller downloads the full state after every call
+  bool ke_valid = false;       // last_en.kinetic_energy belongs to the current velocities (computed by the step's last kernel)
   bool serial_streams = false;
   StepGraph graph[2];          // [0] non-reactive step, [1] MS-EVB step
   bool graph_failed = false;   // stream capture of a step did not work on this context: plain launches

@@ -1,3 +1,6 @@
-python -m pytest tests/test_gpu_nonreactive.py -m gpu -q -x 2>&1 | tail -2
-for v in 1 2; do RPB_PAIR_VARIANT=$v python tools/time_kernels.py c2 10 2>&1 | grep -E "variant|pair_real"; done
-for v in 1 2; do RPB_PAIR_VARIANT=$v python tools/time_kernels.py c4 5 2>&1 | grep -E "variant|pair_real"; done
+python -m pytest tests -m gpu -q -x 2>&1 | tail -4
+python tools/diag_e2e.py c3 2>&1 | tail -1
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
+import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('c3', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['value']/d['value'])
+for k,v in d['other_workloads'].items(): print(k, v['value'], v.get('ms_per_step'), v.get('concurrency_gain'))
+"
