@@ -311,7 +311,7 @@ def e2e_steps(torch, sim, s, evb, n, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     N = s.n_atoms
     return {"value": n / float(t.item()), "unit": "steps/s",
-            "h2d_bytes_per_step": (N + 4) * 32 + 3 * N * 8, "d2h_bytes_per_step": (N + 4) * 32 + 2 * 3 * N * 8 + 8 * 8,
+            "h2d_bytes_per_step": (N + 4) * 32 + (3 * N * 8 + 31) // 32 * 32, "d2h_bytes_per_step": (N + 4) * 32 + (3 * N * 8 + 31) // 32 * 32 + 3 * N * 8 + 8 * 8,
             "call": "rpb_upload_state + rpb_step(1) + rpb_download_state + rpb_get_energies per step; caller-owned host arrays, one pinned "
                     "copy each way ({x,q,v} up, {x,q,v,F} down); per-atom / per-molecule tables are re-sent only when they changed"}
 

@@ -25,6 +25,12 @@ static const char* k_timer_names[T_NTIMER] = {
     }                                                                             \
   } while (0)
 
+// layout of the contiguous state block, device and pinned images alike: xq[N + 4] | vel[3N] (padded to 32 bytes) | force[3N]
+static inline size_t sb_xq_bytes(int N) { return (size_t)(N + 4) * sizeof(double4); }
+static inline size_t sb_vel_bytes(int N) { return ((size_t)3 * N * sizeof(double) + 31) & ~(size_t)31; }   // force stays 32-byte aligned (peer all-reduce: 16-byte accesses)
+static inline size_t sb_bytes_up(int N) { return sb_xq_bytes(N) + sb_vel_bytes(N); }
+static inline size_t sb_bytes_all(int N) { return sb_xq_bytes(N) + sb_vel_bytes(N) + (size_t)3 * N * sizeof(double); }
+
 template <typename T>
 static int upload(rpb_ctx* c, T** dst, const T* src, size_t n) {
   int rc = dev_alloc(c, dst, n);
@@ -246,11 +252,10 @@ int rpb_create(rpb_ctx** out, const rpb_config* cfg) {
   const int ncell = d.ncx * d.ncy * d.ncz;
 #define AL(p, n) if ((rc = dev_alloc(c, &(p), (n)))) return rc;
   {   // xq | vel | force contiguous: one copy per state transfer
-    const size_t bytes = (size_t)(N + 4) * sizeof(double4) + 2 * (size_t)3 * N * sizeof(double);
-    AL(c->state_block, bytes);
+    AL(c->state_block, sb_bytes_all(N));
     d.xq = reinterpret_cast<double4*>(c->state_block);
-    d.vel = reinterpret_cast<double*>(c->state_block + (size_t)(N + 4) * sizeof(double4));
-    d.force = d.vel + 3 * (size_t)N;
+    d.vel = reinterpret_cast<double*>(c->state_block + sb_xq_bytes(N));
+    d.force = reinterpret_cast<double*>(c->state_block + sb_xq_bytes(N) + sb_vel_bytes(N));
   }
   AL(d.mass, N); AL(d.type, N); AL(d.mol_of_atom, N);
   AL(d.mol_first, M); AL(d.mol_natom, M); AL(d.mol_type, M); AL(d.r_com, 3 * M); AL(d.hydronium, 1);
@@ -514,14 +519,14 @@ struct Staging {
 };
 static int staging_get(rpb_ctx* c, Staging& st) {
   const size_t N = c->d.N, M = c->d.M;
-  const size_t bytes = (N + 4) * sizeof(double4) + (3 * N + 3 * N + N) * sizeof(double) + (2 * N + 3 * M) * sizeof(int);   // xq | vel | force laid out as on the device
+  const size_t bytes = sb_bytes_all((int)N) + N * sizeof(double) + (2 * N + 3 * M) * sizeof(int);   // xq | vel | force laid out as on the device
   if (!c->staging) {
     CK(cudaMallocHost(&c->staging, bytes));
     memset(c->staging, 0xff, bytes);
   }
   char* p = (char*)c->staging;
   st.xq = (double4*)p; p += (N + 4) * sizeof(double4);
-  st.vel = (double*)p; p += 3 * N * sizeof(double);
+  st.vel = (double*)p; p += sb_vel_bytes((int)N);
   st.force = (double*)p; p += 3 * N * sizeof(double);
   st.mass = (double*)p; p += N * sizeof(double);
   st.type = (int*)p; p += N * sizeof(int);
@@ -565,7 +570,7 @@ int rpb_upload_state(rpb_ctx* c, const double* xyz, const double* velocity, cons
   }
   if ((rc = refresh_mirror(c))) return rc;
   // {xq, vel} travel from one of two pinned images in ONE copy: no wait for the previous upload, only for the one before it
-  const size_t up_bytes = (size_t)(N + 4) * sizeof(double4) + (size_t)3 * N * sizeof(double);
+  const size_t up_bytes = sb_bytes_up(N);
   const int par = c->up_parity; c->up_parity ^= 1;
   if (!c->staging_up[par]) {
     CK(cudaMallocHost(&c->staging_up[par], up_bytes));
@@ -573,7 +578,7 @@ int rpb_upload_state(rpb_ctx* c, const double* xyz, const double* velocity, cons
     CK(cudaEventCreateWithFlags(&c->ev_up[par], cudaEventDisableTiming));
   } else CK(cudaEventSynchronize(c->ev_up[par]));
   double4* up_xq = reinterpret_cast<double4*>(c->staging_up[par]);
-  double* up_vel = reinterpret_cast<double*>(reinterpret_cast<char*>(c->staging_up[par]) + (size_t)(N + 4) * sizeof(double4));
+  double* up_vel = reinterpret_cast<double*>(reinterpret_cast<char*>(c->staging_up[par]) + sb_xq_bytes(N));
   const bool all = !c->have_state || !c->state_cache_valid;   // a committed proton hop permuted the device tables
   // change detection on raw copies of the caller's tables (one memcmp each): unchanged tables are neither converted nor sent
   c->raw_type.resize(N); c->raw_mass.resize(N); c->raw_mol.resize(3 * (size_t)M);
@@ -736,7 +741,7 @@ int rpb_step(rpb_ctx* c, int n_steps, int ms_evb) {
   if (c->download_streak >= 2) {
     Staging st;
     if ((rc = staging_get(c, st))) return rc;
-    CK(cudaMemcpyAsync(st.xq, c->state_block, (size_t)(c->d.N + 4) * sizeof(double4) + 2 * (size_t)3 * c->d.N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(st.xq, c->state_block, sb_bytes_all(c->d.N), cudaMemcpyDeviceToHost, c->stream));
     c->image_valid = true;
   }
   c->download_streak = std::max(0, c->download_streak - 1);   // (raised by two per download: a streak survives as long as every call is followed by one)
@@ -804,7 +809,7 @@ int rpb_download_state(rpb_ctx* c, double* xyz, double* velocity, double* force,
   if (full && c->image_valid) {
     // the image was copied behind the last step (see rpb_step) and nothing touched the device state since
   } else if (full) {     // the usual full download: xq | vel | force are one block on both sides
-    CK(cudaMemcpyAsync(st.xq, c->state_block, (size_t)(N + 4) * sizeof(double4) + 2 * (size_t)3 * N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(st.xq, c->state_block, sb_bytes_all(N), cudaMemcpyDeviceToHost, c->stream));
   } else {
     if (xyz || charge) CK(cudaMemcpyAsync(st.xq, c->d.xq, N * sizeof(double4), cudaMemcpyDeviceToHost, c->stream));
     if (velocity) CK(cudaMemcpyAsync(st.vel, c->d.vel, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

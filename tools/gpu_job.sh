@@ -1,6 +1,7 @@
-python -m pytest tests -m gpu -q -x 2>&1 | tail -4
-python tools/diag_e2e.py c3 2>&1 | tail -1
-python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
-import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('c3', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['value']/d['value'])
+python -m pytest tests/test_gpu_full_size.py tests/test_gpu_evb_cases.py -m gpu -q -x -k "real_peers or peer_memory" 2>&1 | tail -6 > gpurun_out/r02_gputest_2gpu.log; cat gpurun_out/r02_gputest_2gpu.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 5 2>gpurun_out/bench2_err.log > gpurun_out/r02_bench_c3_n2.json; tail -3 gpurun_out/bench2_err.log
+python -c "
+import json; d=json.loads(open('gpurun_out/r02_bench_c3_n2.json').read().strip().splitlines()[-1]); print('c3 n2', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['config']['n_states'], d['config']['exchange'])
+print(d['roofline'])
 for k,v in d['other_workloads'].items(): print(k, v['value'], v.get('ms_per_step'), v.get('concurrency_gain'))
 "
