@@ -2377,6 +2377,7 @@ int evb_readback(rpb_ctx* c) {
   memcpy(h.proton_log, pin + 16 + 2 * MAXS, MAXS * MAXC * 5 * sizeof(int));
   for (int k = 0; k < 4; k++) c->h_flags[k] = (int)pd[5 + 3 * MAXS + k];
   for (int k = 0; k < E_NSLOT; k++) c->h_en[k] = pd[5 + 3 * MAXS + 4 + k];
+  if (c->h_flags[1] == 2) { c->err = "a molecule's atoms are farther apart than the box allows (r_cutoff + extent of three consecutive atoms >= L/2)"; return RPB_ERR_VERLET; }
   if (c->h_flags[1]) { c->err = "please increase size of verlet neighbor list"; return RPB_ERR_VERLET; }
   if (c->h_flags[2]) { c->err = "Found more diabat states than the current setting of evb_max_states"; return RPB_ERR_DIABATS; }
   if (c->h_flags[3] >= 30) { c->err = "peer-memory exchange: rank " + std::to_string(c->h_flags[3] - 30) + " did not arrive"; return RPB_ERR_CUDA; }

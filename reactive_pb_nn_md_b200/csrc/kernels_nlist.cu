@@ -34,6 +34,17 @@ __global__ void k_verlet_disp(Dev d, double* blk_top2, int* done_counter) {
   if (i < d.N) {
     double4 p = d.xq[i];
     double xn[3] = {p.x, p.y, p.z};
+    {
+      // current extent of the atom's cluster (distance to the cluster's first atom; molecules are never split by the
+      // periodic wrap): the pair kernel culls whole tiles with the largest one.  d.vstat[4] is reset by k_verlet_rebuild, which precedes every launch of this kernel.
+      const int f = d.mol_first[d.mol_of_atom[i]], k = (i - f) % 3;
+      if (k) {
+        const double4 p0 = d.xq[i - k];
+        const double e2 = (p.x - p0.x) * (p.x - p0.x) + (p.y - p0.y) * (p.y - p0.y) + (p.z - p0.z) * (p.z - p0.z);
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(sqrt(e2));
+        if (bits > d.vstat[4]) atomicMax(&d.vstat[4], bits);      // non-negative doubles order like their bit patterns
+      }
+    }
     if (rebuild) {
       for (int k = 0; k < 3; k++) { d.vstore[3 * i + k] = xn[k]; d.vdisp[3 * i + k] = 0.0; }
     } else {
@@ -201,7 +212,11 @@ __device__ __forceinline__ void tile_sweep(const Dev& d, const int I, const int 
           unsigned mask = 0;
           int fj = 0;
           bool near = false;
-          if (slot < e && d.csort_mol[slot] != mi) {     // first atoms farther apart than R: no atom pair can be listed
+          // HALF list of tiles: the unordered cluster pair {I, J} is stored in the row of I when I + J is odd and I < J, or
+          // I + J is even and I > J (balanced rows without any ordering of the clusters in space)
+          bool mine = false;
+          if (slot < e && d.csort_mol[slot] != mi) { const int J = d.cell_atoms[slot]; mine = ((I + J) & 1) ? (I < J) : (I > J); }
+          if (mine) {     // first atoms farther apart than R: no atom pair can be listed
             const double4 p0 = ldg256(&d.csort_xq[3 * slot]);
             double r0 = pi[0].x - p0.x, r1 = pi[0].y - p0.y, r2 = pi[0].z - p0.z;
             r0 = r0 - d.box[0] * floor_fp64pipe(r0 * d.inv_box[0] + 0.5);
@@ -292,8 +307,8 @@ __device__ __forceinline__ void rebuild_phases(const Dev& d, cg::grid_group& gri
   grid.sync();
   if (blockIdx.x == 0) {
     block_scan_exclusive(d.row_count, d.tile_point, RPB_TILE_PARTS * NC, 0);
-    // allocate_verlet_list / the overflow stop of :1562-1565: the reference's half list holds each listed pair once
-    if (threadIdx.x == 0 && (long long)(d.vstat[1] / 2ull) > (long long)d.verlet_cap) atomicMax(&d.err_flag[1], 1);
+    // allocate_verlet_list / the overflow stop of :1562-1565: like the reference's half list, the tiles hold each listed pair once
+    if (threadIdx.x == 0 && (long long)d.vstat[1] > (long long)d.verlet_cap) atomicMax(&d.err_flag[1], 1);
   }
   grid.sync();
   if (d.err_flag[1]) return;
@@ -311,7 +326,8 @@ __global__ void __launch_bounds__(TPB) k_verlet_rebuild(Dev d, int force_rebuild
   cg::grid_group grid = cg::this_grid();
   // forced (init): flag_verlet_list untouched (flag_junk, ms_evb.f90:223-225)
   const int rb = force_rebuild ? 2 : ((*d.flag_verlet == 1) ? 1 : 0);
-  if (blockIdx.x == 0 && threadIdx.x == 0) { *d.rebuild_now = rb; d.maxd[0] = 0.0; d.maxd[1] = 0.0; }
+  // (d.vstat[4]: the largest cluster extent, re-accumulated by the k_verlet_disp that follows on this stream)
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *d.rebuild_now = rb; d.maxd[0] = 0.0; d.maxd[1] = 0.0; d.vstat[4] = 0ull; }
   if (!rb) return;
   rebuild_phases(d, grid, ncell);
 }

@@ -5,16 +5,14 @@
 //   intra_molecular_pairwise_energy_force src/pair_int_real_space.f90:386-588
 //   intra_molecular_energy_force          src/intra_bonded_interactions.f90:17-552
 //
-// Pair kernel (k_pair_tiles): a warp per row part of a cluster I (<= 3 consecutive atoms of one molecule, held in
-// registers); a lane takes one atom of a cluster J per iteration -- its (up to) three pairs with the atoms of I, whose
-// listed subset are three bits of the tile's 9-bit mask (kernels_nlist.cu: exactly the reference's listed pairs).  A list
-// word serves nine atom pairs.  Both directions of a tile are stored, so F_I is reduced in registers + shuffles and added
-// to d.force once per row part: no j-scatter (bonded terms and the PME gather add to d.force too).  Energies are halved.  Per listed pair: minimum image with a reciprocal box (the shift can only differ from the reference's
-// division for |dr| ~ L/2, far outside the cutoff) and the cutoff test dr^2 < r_c^2.  Per in-cutoff pair: ONE rsqrt
-// replaces the sqrt and the six divisions of pair_int_real_space.f90:621-645,698-759 (relative differences ~1e-16,
-// the interpolated tables are continuous across bins), and the erfc / ewaldscale tables are read interleaved
-// (one 32-byte load per pair).  Pairs outside the mask or the cutoff run the same Coulomb arithmetic on harmless
-// operands (r^2 = 1, q_i q_j = 0, table entry 1) instead of diverging.  FP64-pipe bound -- see DESIGN.md.
+// Pair kernel (k_pair_tiles): works on the HALF list of cluster-pair tiles (kernels_nlist.cu: a tile = cluster I x cluster J,
+// <= 3 consecutive atoms of one molecule each, with a 9-bit mask of exactly the reference's listed atom pairs; one list
+// word serves nine atom pairs, every listed pair is stored and evaluated once).  Per listed pair: minimum image with a
+// reciprocal box (the shift can only differ from the reference's division for |dr| ~ L/2, far outside the cutoff) and
+// the cutoff test dr^2 < r_c^2.  Per in-cutoff pair: ONE rsqrt replaces the sqrt and the six divisions of
+// pair_int_real_space.f90:621-645,698-759 (relative differences ~1e-16, the interpolated tables are continuous across
+// bins), and the erfc / ewaldscale tables are read interleaved (one 32-byte load per pair).  FP64 work -- see DESIGN.md.
+#include <cmath>
 #include <cstdlib>
 #include "rpb_host.h"
 #include "rpb_bonded.cuh"
@@ -50,30 +48,79 @@ __device__ __forceinline__ double rsqrt_pair(double x) {
   return y;
 }
 
-// A warp works on a few consecutive row parts (cluster I, part) of the tile list; rank r of R works on the clusters
-// [NC r / R, NC (r+1) / R).  Two phases per row part:
-//   1. candidate test -- a lane takes one ATOM of a cluster J per iteration (three consecutive lanes share a list word) and
-//      tests its three pairs with the atoms of I: mask bit, minimum image, r^2 < r_c^2.  42 % of the listed pairs lie
-//      between the cutoff and the list radius and 18 % of a tile's slots are not listed at all, so the pairs that pass
-//      are COMPACTED (ballot + prefix count) into a per-warp queue in shared memory;
-//   2. interaction -- whenever the queue holds NB x 32 pairs, every lane pops NB of them: rsqrt, table index, ONE 32-byte
-//      gather of the interleaved erfc / ewaldscale entries per pair, Coulomb, LJ / SAPT, force.  All lanes carry real
-//      pairs, and a lane has NB independent dependency chains (and NB table gathers) in flight: the loop is bound by the
-//      latency of that chain, not by a pipe.
+// sum of nine per-lane values over the warp; on return lane k (k < 9) holds the total of v[k].  Transposing butterfly:
+// at each of the first three levels a lane keeps half of its values and hands the other half to its partner, so the
+// eight values v[0..7] cost 4 + 2 + 1 + 2 = 9 exchanges instead of 40 (v[8]: a plain butterfly).
+__device__ __forceinline__ double warp_sum9(const double (&v)[9], const int lane) {
+  double w4[4], w2[2], w1;
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const double keep = up ? v[k + 4] : v[k], give = up ? v[k] : v[k + 4]; w4[k] = keep + __shfl_xor_sync(0xffffffffu, give, 16); }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int k = 0; k < 2; k++) { const double keep = up ? w4[k + 2] : w4[k], give = up ? w4[k] : w4[k + 2]; w2[k] = keep + __shfl_xor_sync(0xffffffffu, give, 8); }
+  }
+  {
+    const bool up = lane & 4;
+    const double keep = up ? w2[1] : w2[0], give = up ? w2[0] : w2[1];
+    w1 = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+  }
+  w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
+  w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+  // lane l now holds the total of value 4*(l>>4 & 1) + 2*(l>>3 & 1) + (l>>2 & 1)
+  double x = v[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  // bring value k to lane k
+  const int src = ((lane & 4) ? 16 : 0) | ((lane & 2) ? 8 : 0) | ((lane & 1) ? 4 : 0);
+  const double t = __shfl_sync(0xffffffffu, w1, src);
+  return lane == 8 ? x : t;
+}
+
+// Ampere-style asynchronous copies global -> shared (LDGSTS): no register staging, no scoreboard stall at the issue
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// The grid is one resident wave; warp g takes the g-th of (warps of the grid) equal, contiguous ranges of the tile list
+// (balanced in tiles whatever the row lengths; a work counter would cost one same-address atomic per piece, which the L2
+// serialises).  A range is cut into pieces at the cluster boundaries: within a piece the cluster I (<= 3 atoms) is
+// broadcast from shared memory.  Every listed pair is stored ONCE (the list is a half list of tiles, kernels_nlist.cu),
+// so a pair is evaluated once: F_I accumulates in registers over the piece, F_J of a lane's atom goes to d.force with
+// three atomic adds per visit.
+//   1. tile cull -- a lane takes one tile (cluster J): minimum-image distance of the two first atoms against
+//      r_c + 2 x (largest cluster extent now).  ~37 % of the listed tiles lie wholly between the cutoff and the list
+//      radius and are dropped here at the cost of one 32-byte gather and ~20 fp64 operations per NINE pair slots; the
+//      survivors' list words are compacted (ballot + prefix count) into a per-warp ring in shared memory, and the
+//      coordinates / types of their (up to) three atoms are fetched into the ring by asynchronous copies;
+//   2. interaction, one cull iteration behind (the copies have landed) -- ten tiles per round: lane 3t + b takes atom b
+//      of tile t and its three pairs with the atoms of I (three independent dependency chains per lane; b, and with it the
+//      bit positions of the tile mask, are per-lane constants).  A pair that is not listed or outside the cutoff runs the
+//      same Coulomb arithmetic on harmless operands (r^2 = 1, q_i q_j = 0) instead of diverging: ~77 % of the slots of a
+//      surviving tile are live.
 // One minimum-image shift per (I, J atom) from I's first atom instead of one per pair: identical results whenever
 // r_cutoff + (largest cluster extent) < L/2 (a pair inside the cutoff then has that very shift, and a pair that would
 // need another one is outside the cutoff with either); checked per launch on the device, per-pair shifts otherwise.
-#define PAIR_QCAP 256            // pairs a warp's queue can hold: < NB x 32 left over + 96 from one chunk
-struct PairQueue { double dx[PAIR_QCAP], dy[PAIR_QCAP], dz[PAIR_QCAP], r2[PAIR_QCAP], qq[PAIR_QCAP]; int meta[PAIR_QCAP]; };
+#define PAIR_QT 80               // ring capacity in tiles: < 10 left over + 2 x 32 from two cull iterations
+struct PairRing { double4 xq[PAIR_QT][3]; int ty[PAIR_QT][4]; unsigned ent[PAIR_QT]; };
 
-template <int TPB_, int MINB, int NB>
-__global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int world, int ppw, unsigned int* __restrict__ counters) {
-  extern __shared__ double sh_par[];           // [nT*nT][6] vdw parameters, then the warps' queues
+template <int TPB_, int MINB, bool SPA>
+__global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int world) {
+  extern __shared__ __align__(16) unsigned char sh_dyn[];   // the warps' rings, then [nT*nT][6] vdw parameters
   __shared__ int sh_vt[RPB_MAXT * RPB_MAXT];   // atype_vdw_type; 2 = SAPT row with all-zero coefficients (contributes exactly 0)
   __shared__ double sh_red[32];
   __shared__ double4 sh_pi[TPB_ / 32][3];      // the warp's cluster I (uniform over the lanes: broadcast reads instead of registers)
+  PairRing& Q = reinterpret_cast<PairRing*>(sh_dyn)[threadIdx.x >> 5];
+  double* sh_par = reinterpret_cast<double*>(sh_dyn + (TPB_ / 32) * sizeof(PairRing));
   const int npar = d.nT * d.nT * 6;
-  PairQueue& Q = reinterpret_cast<PairQueue*>(sh_par + ((npar + 1) & ~1))[threadIdx.x >> 5];
   for (int k = threadIdx.x; k < npar; k += blockDim.x) sh_par[k] = d.vdw_param[k];
   for (int k = threadIdx.x; k < d.nT * d.nT; k += blockDim.x) {
     int vt = d.vdw_type[k];
@@ -86,85 +133,116 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int 
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
+  const int tl = lane / 3, b = lane - 3 * tl;  // phase 2: tile of the round, atom of J
   const double4* pi = sh_pi[threadIdx.x >> 5];
+  const int N = d.N;
   const int NC = *d.n_clusters;                // on the device: a committed hop can change it
   const int c_begin = (int)((long long)NC * rank / world), c_end = (int)((long long)NC * (rank + 1) / world);
-  const int n_work = RPB_TILE_PARTS * (c_end - c_begin);
   const double bx = d.box[0], by = d.box[1], bz = d.box[2];
   const double ibx = d.inv_box[0], iby = d.inv_box[1], ibz = d.inv_box[2];
   const double rc2 = d.rc2, inv_dx = d.inv_erfc_dx;
   const int nT = d.nT;
-  const double ext = __longlong_as_double((long long)d.vstat[0]);
-  const bool shift_per_atom = sqrt(d.rc2) + ext < 0.5 * fmin(bx, fmin(by, bz));
+  // largest cluster extent NOW (k_verlet_disp, every evaluation; bonds stretch between list builds)
+  const double ext = __longlong_as_double((long long)d.vstat[4]);
+  const double rc = sqrt(d.rc2);
+  // SPA (one minimum-image shift per (I, J atom)) is chosen by the host from the box and the cutoff; should a cluster be
+  // larger than that choice assumed, the step fails loudly instead of computing with a wrong image
+  constexpr bool shift_per_atom = SPA;
+  if (SPA && !(rc + ext < 0.5 * fmin(bx, fmin(by, bz)))) { if (threadIdx.x == 0) atomicMax(&d.err_flag[1], 2); return; }
+  const double cull2 = (rc + 2.0 * ext) * (rc + 2.0 * ext) * (1.0 + 1e-12);
   const unsigned* __restrict__ L = d.tile_list;
   double e_el = 0.0, e_vdw = 0.0;
-  // A warp works on PPW consecutive pieces (row parts); the header of the next piece -- a chain of dependent loads
-  // (cluster -> first atom -> types / coordinates; row pointers) -- is fetched while the current piece is processed.
-  // The grid is NOT persistent: CTAs live ~15 us, so the short kernels of the high-priority side streams (enumeration,
-  // images, PME, bonded terms) get SM resources as CTAs retire instead of waiting for the whole pair kernel.
-  struct Header { int info, vs, vf, tpack; double4 p; };
-  auto load_header = [&](int wk, Header& h) {
-    h.info = 0; h.vs = 0; h.vf = 0; h.tpack = 0; h.p = make_double4(0.0, 0.0, 0.0, 0.0);
-    if (wk < n_work) {
-      const int rp = RPB_TILE_PARTS * c_begin + wk;
-      h.info = d.cl_info[rp / RPB_TILE_PARTS];
-      h.vs = d.tile_point[rp]; h.vf = d.tile_point[rp + 1];
-      const int fi = h.info & 0xffffff, ni = h.info >> 24;
-      if (lane < 3) { const int ia = fi + (lane < ni ? lane : 0); h.p = d.xq[ia]; h.tpack = d.type[ia]; }
+  const int gwarp = blockIdx.x * (TPB_ / 32) + (threadIdx.x >> 5), nwarp = gridDim.x * (TPB_ / 32);
+  const int* __restrict__ tp = d.tile_point;
+  // this warp's range of the rank's tiles; the cluster holding its first tile by a 32-ary search over the row pointers
+  const int T0 = tp[RPB_TILE_PARTS * c_begin], T1 = tp[RPB_TILE_PARTS * c_end];
+  const int per = max(64, (T1 - T0 + nwarp - 1) / nwarp);
+  const long long tb64 = (long long)T0 + (long long)gwarp * per;
+  const int t_begin = (int)min(tb64, (long long)T1), t_end = min(T1, t_begin + per);
+  int I0 = c_begin;
+  if (t_begin < t_end) {
+    int lo = c_begin, hi = c_end;              // tp[PARTS * lo] <= t_begin < tp[PARTS * hi]
+    while (hi - lo > 1) {
+      const int probe = lo + (int)(((long long)(hi - lo) * (lane + 1)) / 33);
+      const unsigned le = __ballot_sync(0xffffffffu, tp[RPB_TILE_PARTS * probe] <= t_begin);   // monotone: a prefix of the lanes
+      const int nle = __popc(le);
+      const int nlo = __shfl_sync(0xffffffffu, probe, max(nle - 1, 0)), nhi = __shfl_sync(0xffffffffu, probe, min(nle, 31));
+      if (nle) lo = nlo;
+      if (nle < 32) hi = nhi;
     }
-  };
-  // pieces are handed out by a counter (balance: the last CTAs of the grid find nothing left and exit), ppw per warp
-  int w = 0, w1 = 0;
-  if (lane == 0) { w = (int)atomicAdd(&counters[0], 1u); if (ppw > 1) w1 = (int)atomicAdd(&counters[0], 1u); }
-  w = __shfl_sync(0xffffffffu, w, 0); w1 = ppw > 1 ? __shfl_sync(0xffffffffu, w1, 0) : n_work;
-  Header H, H1;
-  load_header(w, H);
-  for (int it = 0; it < ppw && w < n_work; it++) {
-    int w2 = n_work;
-    if (it + 2 < ppw && lane == 0) w2 = (int)atomicAdd(&counters[0], 1u);   // consumed two pieces from now
-    load_header(w1, H1);                                                    // consumed at the next switch
-    const int fi = H.info & 0xffffff, ni = H.info >> 24;
-    const int vs = H.vs, vf = H.vf;
+    I0 = lo;
+  }
+  for (int I = I0; I < c_end && t_begin < t_end; I++) {
+    const int rs = tp[RPB_TILE_PARTS * I], re = tp[RPB_TILE_PARTS * (I + 1)];
+    if (rs >= t_end) break;
+    const int vs = max(rs, t_begin), vf = min(re, t_end);
+    if (vs >= vf) continue;
+    const int info = d.cl_info[I], fi = info & 0xffffff, ni = info >> 24;
     int ti[3];
+    {
+      double4 hp = make_double4(0.0, 0.0, 0.0, 0.0);
+      int ht = 0;
+      if (lane < 3) { const int ia = fi + (lane < ni ? lane : 0); hp = d.xq[ia]; ht = d.type[ia]; }
 #pragma unroll
-    for (int a = 0; a < 3; a++) ti[a] = __shfl_sync(0xffffffffu, H.tpack, a) * nT;
-    __syncwarp();
-    if (lane < 3) sh_pi[threadIdx.x >> 5][lane] = H.p;
-    __syncwarp();
-    const int nslot = 3 * (vf - vs);
-    double f[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
-    int head = 0, cnt = 0;                     // queue state (uniform over the warp)
+      for (int a = 0; a < 3; a++) ti[a] = __shfl_sync(0xffffffffu, ht, a) * nT;
+      __syncwarp();
+      if (lane < 3) sh_pi[threadIdx.x >> 5][lane] = hp;
+      __syncwarp();
+    }
+    double f[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    int qh = 0, qn = 0;                        // ring head and fill, in tiles (uniform over the warp)
 
-    // phase 2: NB pairs per lane (fewer in the last round of a row part)
-    auto interact = [&]() {
-      const int n = min(cnt, 32 * NB);
-      double dx[NB], dy[NB], dz[NB], inv_r[NB], c2[NB], qq[NB];
-      int meta[NB];
-      bool on[NB];
-      double4 tb[NB];
+    // phase 2: (up to) ten tiles of the ring
+    auto interact = [&](const int avail) {
+      const int nt = min(avail, 10);
+      const int slot = (qh + tl) % PAIR_QT;
+      const unsigned ent = tl < nt ? Q.ent[slot] : 0u;
+      const unsigned mb = (ent >> (23 + b)) & 0x49u;          // bit 3a: pair (a, b) is listed
+      double4 pj = make_double4(0.0, 0.0, 0.0, 0.0);
+      int tj = 0;
+      const int g = (int)(ent & 0x7fffffu) + b;
+      if (mb) { pj = Q.xq[slot][b]; tj = Q.ty[slot][b]; }
+      double sx = 0.0, sy = 0.0, sz = 0.0;
+      if (shift_per_atom) {
+        const double4 p0 = pi[0];
+        sx = bx * floor_fp64pipe(fma(p0.x - pj.x, ibx, 0.5));
+        sy = by * floor_fp64pipe(fma(p0.y - pj.y, iby, 0.5));
+        sz = bz * floor_fp64pipe(fma(p0.z - pj.z, ibz, 0.5));
+      }
+      double dx[3], dy[3], dz[3], inv_r[3], c2[3], qq[3];
+      bool live[3];
+      double4 tb[3];
 #pragma unroll
-      for (int u = 0; u < NB; u++) {
-        on[u] = 32 * u + lane < n;
-        const int q = (head + 32 * u + lane) & (PAIR_QCAP - 1);
-        double r2 = 1.0;
-        dx[u] = dy[u] = dz[u] = 0.0; qq[u] = 0.0; meta[u] = 0;
-        if (on[u]) { dx[u] = Q.dx[q]; dy[u] = Q.dy[q]; dz[u] = Q.dz[q]; r2 = Q.r2[q]; qq[u] = Q.qq[q]; meta[u] = Q.meta[q]; }
-        inv_r[u] = rsqrt_pair(r2);
+      for (int a = 0; a < 3; a++) {
+        const double4 pa = pi[a];
+        dx[a] = pa.x - pj.x; dy[a] = pa.y - pj.y; dz[a] = pa.z - pj.z;
+        if (shift_per_atom) { dx[a] -= sx; dy[a] -= sy; dz[a] -= sz; }
+        else {
+          dx[a] = fma(-bx, floor_fp64pipe(fma(dx[a], ibx, 0.5)), dx[a]);
+          dy[a] = fma(-by, floor_fp64pipe(fma(dy[a], iby, 0.5)), dy[a]);
+          dz[a] = fma(-bz, floor_fp64pipe(fma(dz[a], ibz, 0.5)), dz[a]);
+        }
+        double r2 = fma(dz[a], dz[a], fma(dy[a], dy[a], dx[a] * dx[a]));
+        live[a] = ((mb >> (3 * a)) & 1u) && r2 < rc2;
+        qq[a] = live[a] ? pa.w * pj.w : 0.0;
+        r2 = live[a] ? r2 : 1.0;
+        inv_r[a] = rsqrt_pair(r2);
         // linear_interpolation_ewald_tables  pair_int_real_space.f90:740-759
-        const double x1 = (r2 * inv_r[u]) * inv_dx;
+        const double x1 = (r2 * inv_r[a]) * inv_dx;
         int ii;
         const double ci = ceil_fp64pipe(x1, ii);
-        tb[u] = ldg256(&d.es2_t[ii]);
-        c2[u] = (x1 + 1.0) - ci;
+        tb[a] = ldg256(&d.es2_t[ii]);
+        c2[a] = (x1 + 1.0) - ci;
       }
+      double fjx = 0.0, fjy = 0.0, fjz = 0.0;
 #pragma unroll
-      for (int u = 0; u < NB; u++) {
-        const double ir = inv_r[u], inv_r2 = ir * ir, c1 = 1.0 - c2[u];
-        const double qr = qq[u] * ir;
-        e_el = fma(qr, fma(c2[u], tb[u].z, c1 * tb[u].x), e_el);
-        double fs = (qr * inv_r2) * fma(c2[u], tb[u].w, c1 * tb[u].y);
-        const int pidx = meta[u] & 0xffff, a = meta[u] >> 16;
-        if (on[u]) {
+      for (int a = 0; a < 3; a++) {
+        const double ir = inv_r[a], inv_r2 = ir * ir, c1 = 1.0 - c2[a];
+        const double qr = qq[a] * ir;
+        e_el = fma(qr, fma(c2[a], tb[a].z, c1 * tb[a].x), e_el);
+        double fs = (qr * inv_r2) * fma(c2[a], tb[a].w, c1 * tb[a].y);
+        if (live[a]) {
+          const int pidx = ti[a] + tj;
           const int vt = sh_vt[pidx];
           if (vt == 0) {                         // pairwise_real_space_LJ :621-645
             const double c12 = sh_par[6 * pidx], c6 = sh_par[6 * pidx + 1];
@@ -176,87 +254,68 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int 
             e_vdw += sp.x; fs += sp.y;
           }
         }
-        const double gx = dx[u] * fs, gy = dy[u] * fs, gz = dz[u] * fs;      // (an empty slot has d = 0)
-        if (a == 0) { f[0][0] += gx; f[0][1] += gy; f[0][2] += gz; }
-        else if (a == 1) { f[1][0] += gx; f[1][1] += gy; f[1][2] += gz; }
-        else { f[2][0] += gx; f[2][1] += gy; f[2][2] += gz; }
+        const double gx = dx[a] * fs, gy = dy[a] * fs, gz = dz[a] * fs;      // (a dead slot has fs = 0)
+        f[3 * a] += gx; f[3 * a + 1] += gy; f[3 * a + 2] += gz;
+        fjx -= gx; fjy -= gy; fjz -= gz;
       }
-      head = (head + n) & (PAIR_QCAP - 1); cnt -= n;
+      if (live[0] || live[1] || live[2]) {
+        atomicAdd(&d.force[3 * g], fjx); atomicAdd(&d.force[3 * g + 1], fjy); atomicAdd(&d.force[3 * g + 2], fjz);
+      }
+      qh = (qh + nt) % PAIR_QT; qn -= nt;
     };
 
-    // software pipeline of the list: word of iteration +2, gathers of iteration +1
+    // phase 1, software-pipelined: list words two iterations ahead, first-atom gathers one ahead
     unsigned ent_c = 0u, ent_n = 0u;
-    double4 pj_c = make_double4(0.0, 0.0, 0.0, 0.0);
-    int tj_c = 0;
-    { const int k = lane; if (k < nslot) ent_c = L[vs + k / 3]; }
-    { const int k = 32 + lane; if (k < nslot) ent_n = L[vs + k / 3]; }
-    { const int k = lane; if (k < nslot) { const int g = (ent_c & 0x7fffff) + k % 3; pj_c = ldg256(&d.xq[g]); tj_c = __ldg(&d.type[g]); } }
-    for (int k0 = 0; k0 < nslot; k0 += 32) {
-      const int k = k0 + lane, b = k % 3;
-      double4 pj_n = make_double4(0.0, 0.0, 0.0, 0.0);
-      int tj_n = 0;
+    double4 p_c = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (vs + lane < vf) ent_c = L[vs + lane];
+    if (vs + 32 + lane < vf) ent_n = L[vs + 32 + lane];
+    if (vs + lane < vf) p_c = ldg256(&d.xq[ent_c & 0x7fffffu]);
+    int ready = 0;                             // tiles of the ring whose asynchronous copies have been waited for
+    for (int k0 = vs; k0 < vf; k0 += 32) {
       unsigned ent_nn = 0u;
-      if (k + 32 < nslot) { const int g = (ent_n & 0x7fffff) + (k + 32) % 3; pj_n = ldg256(&d.xq[g]); tj_n = __ldg(&d.type[g]); }
-      if (k + 64 < nslot) ent_nn = L[vs + (k + 64) / 3];
-      const unsigned mbits = (k < nslot) ? (ent_c >> (23 + b)) : 0u;     // bit 3a: pair (a, b) is listed
-      // ---- phase 1: the three candidate pairs of this J atom, compacted into the queue
-      double sx = 0.0, sy = 0.0, sz = 0.0;
-      if (shift_per_atom) {
-        const double4 p0 = pi[0];
-        sx = bx * floor_fp64pipe(fma(p0.x - pj_c.x, ibx, 0.5));
-        sy = by * floor_fp64pipe(fma(p0.y - pj_c.y, iby, 0.5));
-        sz = bz * floor_fp64pipe(fma(p0.z - pj_c.z, ibz, 0.5));
-      }
+      double4 p_n = make_double4(0.0, 0.0, 0.0, 0.0);
+      if (k0 + 64 + lane < vf) ent_nn = L[k0 + 64 + lane];
+      if (k0 + 32 + lane < vf) p_n = ldg256(&d.xq[ent_n & 0x7fffffu]);
+      const double4 p0 = pi[0];
+      double r0 = p0.x - p_c.x, r1 = p0.y - p_c.y, r2 = p0.z - p_c.z;
+      r0 = fma(-bx, floor_fp64pipe(fma(r0, ibx, 0.5)), r0);
+      r1 = fma(-by, floor_fp64pipe(fma(r1, iby, 0.5)), r1);
+      r2 = fma(-bz, floor_fp64pipe(fma(r2, ibz, 0.5)), r2);
+      const bool keep = (k0 + lane < vf) && fma(r2, r2, fma(r1, r1, r0 * r0)) < cull2;
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const int slot = (qh + qn + __popc(m & lt)) % PAIR_QT;
+        const int fj = (int)(ent_c & 0x7fffffu);
+        Q.ent[slot] = ent_c;
 #pragma unroll
-      for (int a = 0; a < 3; a++) {
-        const double4 pa = pi[a];
-        double dx = pa.x - pj_c.x, dy = pa.y - pj_c.y, dz = pa.z - pj_c.z;
-        if (shift_per_atom) { dx -= sx; dy -= sy; dz -= sz; }
-        else {
-          dx = fma(-bx, floor_fp64pipe(fma(dx, ibx, 0.5)), dx);
-          dy = fma(-by, floor_fp64pipe(fma(dy, iby, 0.5)), dy);
-          dz = fma(-bz, floor_fp64pipe(fma(dz, ibz, 0.5)), dz);
-        }
-        const double dr2 = fma(dz, dz, fma(dy, dy, dx * dx));
-        const bool live = ((mbits >> (3 * a)) & 1u) && dr2 < rc2;
-        const unsigned m = __ballot_sync(0xffffffffu, live);
-        if (live) {
-          const int q = (head + cnt + __popc(m & lt)) & (PAIR_QCAP - 1);
-          Q.dx[q] = dx; Q.dy[q] = dy; Q.dz[q] = dz; Q.r2[q] = dr2; Q.qq[q] = pa.w * pj_c.w;
-          Q.meta[q] = (ti[a] + tj_c) | (a << 16);
-        }
-        cnt += __popc(m);
+        for (int a = 0; a < 3; a++)
+          if (fj + a < N) {                      // (a cluster of fewer atoms: the slot is never read, its mask bits are 0)
+            cp_async_16(&Q.xq[slot][a], &d.xq[fj + a]);
+            cp_async_16(reinterpret_cast<char*>(&Q.xq[slot][a]) + 16, reinterpret_cast<const char*>(&d.xq[fj + a]) + 16);
+            cp_async_4(&Q.ty[slot][a], &d.type[fj + a]);
+          }
       }
+      cp_async_commit();
+      // the copies of the PREVIOUS iterations have landed once all but the newest group are complete
+      cp_async_wait<1>();
       __syncwarp();
-      // ---- phase 2 on full rounds
-      while (cnt >= 32 * NB) interact();
-      ent_c = ent_n; ent_n = ent_nn; pj_c = pj_n; tj_c = tj_n;
+      while (ready >= 10) { interact(ready); ready -= 10; }
+      qn += __popc(m);
+      ready = qn;                                // (this iteration's tiles become usable after the next wait)
+      ent_c = ent_n; ent_n = ent_nn; p_c = p_n;
     }
-    while (cnt > 0) interact();                // what is left at the end of the row part
-    // F_I of this row part: lanes -> lane 0..8 by xor shuffles; one ADD per component and part (the other parts of the
-    // row, the bonded branch and the PME gather add to d.force concurrently)
-    double mine = 0.0;
-#pragma unroll
-    for (int a = 0; a < 3; a++)
-#pragma unroll
-      for (int c = 0; c < 3; c++) {
-        double x = f[a][c];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 3 * a + c) mine = x;
-      }
+    cp_async_wait<0>();
+    __syncwarp();
+    while (qn > 0) interact(qn);               // what is left at the end of the piece
+    __syncwarp();
+    // F_I of this piece: one ADD per component (the other pieces of the row, the F_J of other rows, the bonded branch and
+    // the PME gather add to d.force concurrently)
+    const double mine = warp_sum9(f, lane);
     if (lane < 3 * ni) atomicAdd(&d.force[3 * fi + lane], mine);
-    H = H1; w = w1;
-    w1 = (it + 2 < ppw) ? __shfl_sync(0xffffffffu, w2, 0) : n_work;
   }
   e_el = block_sum(e_el, sh_red);
   e_vdw = block_sum(e_vdw, sh_red);
-  if (threadIdx.x == 0) {
-    atomicAdd(&d.en[E_ELEC], 0.5 * e_el); atomicAdd(&d.en[E_VDW], 0.5 * e_vdw);
-    // the last CTA to finish re-arms the work counter for the next launch
-    __threadfence();
-    if (atomicAdd(&counters[1], 1u) == gridDim.x - 1) { counters[0] = 0u; counters[1] = 0u; __threadfence(); }
-  }
+  if (threadIdx.x == 0) { atomicAdd(&d.en[E_ELEC], e_el); atomicAdd(&d.en[E_VDW], e_vdw); }
 }
 
 // one thread per molecule: intramolecular non-bonded (exclusion correction, 1-4) + bonds/angles/dihedrals
@@ -287,20 +346,26 @@ __global__ void k_molecule_terms(Dev d) {
   e = block_sum(E.e_dih, sh_red);  if (threadIdx.x == 0) atomicAdd(&d.en[E_DIH], e);
 }
 
-template <int T, int MINB, int NB>
-static int launch_pair_variant(rpb_ctx* c, bool shard, int ppw, int pad_kb = 0) {
+template <int T, int MINB>
+static int launch_pair_variant(rpb_ctx* c, bool shard, int waves_x4 = 4) {
   // state-sharded runs also shard the principal diabat's pair forces: rank r takes the clusters [NC r / R, NC (r+1) / R); the
   // partial forces and energies ride the two all-reduces the sharded step has anyway.
   const int R = shard ? c->d.world : 1, r = shard ? c->d.rank : 0;
-  const long long pieces = (long long)RPB_TILE_PARTS * ((c->n_clusters_bound + R - 1) / R + 1);
   const int wpb = T / 32;
-  const int blocks = (int)std::max(1LL, (pieces + (long long)wpb * ppw - 1) / ((long long)wpb * ppw));
-  // pad_kb: shared memory requested beyond what the kernel uses, to cap the CTAs resident per SM -- at full occupancy the
-  // pair kernel holds every register of an SM, and each short kernel of the MS-EVB chain then waits for a pair CTA to retire
-  const size_t shmem = std::max((size_t)((c->d.nT * c->d.nT * 6 + 1) & ~1) * sizeof(double) + wpb * sizeof(PairQueue), (size_t)pad_kb * 1024);
+  const int blocks = std::max(1, c->n_sm * MINB * waves_x4 / 4);     // one resident wave
+  const size_t shmem = (size_t)wpb * sizeof(PairRing) + (size_t)((c->d.nT * c->d.nT * 6 + 1) & ~1) * sizeof(double);
+  // one minimum-image shift per (I, J atom) needs r_cutoff + (cluster extent) < L/2: taken when the box leaves 4 A for the
+  // extent (three bonded atoms), verified against the actual extents on the device
+  const double half_box = 0.5 * std::min(c->d.box[0], std::min(c->d.box[1], c->d.box[2]));
+  const bool spa = half_box - std::sqrt(c->d.rc2) > 4.0;
   static bool attr_set = false;     // (same for every context: a function attribute)
-  if (!attr_set) { cudaFuncSetAttribute(k_pair_tiles<T, MINB, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr_set = true; }
-  k_pair_tiles<T, MINB, NB><<<blocks, T, shmem, c->stream>>>(c->d, r, R, ppw, reinterpret_cast<unsigned int*>(c->d.vstat + 3));
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_pair_tiles<T, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_pair_tiles<T, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr_set = true;
+  }
+  if (spa) k_pair_tiles<T, MINB, true><<<blocks, T, shmem, c->stream>>>(c->d, r, R);
+  else k_pair_tiles<T, MINB, false><<<blocks, T, shmem, c->stream>>>(c->d, r, R);
   return 0;
 }
 
@@ -308,12 +373,14 @@ void launch_pair_verlet(rpb_ctx* c, bool shard) {
   ScopedTimer t(c, T_PAIR);
   static const int variant = getenv("RPB_PAIR_VARIANT") ? atoi(getenv("RPB_PAIR_VARIANT")) : 0;
   switch (variant) {
-    case 1: launch_pair_variant<128, 3, 3>(c, shard, 2); break;      // 168 registers, three pairs per lane in flight
-    case 2: launch_pair_variant<128, 3, 3>(c, shard, 4); break;
-    case 3: launch_pair_variant<128, 3, 3>(c, shard, 4, 80); break;      // two CTAs per SM
-    case 4: launch_pair_variant<128, 3, 3>(c, shard, 2, 80); break;
-    case 5: launch_pair_variant<128, 3, 3>(c, shard, 4, 120); break;     // one CTA per SM
-    default: launch_pair_variant<128, 3, 3>(c, shard, 4); break;
+    case 1: launch_pair_variant<128, 3>(c, shard); break;
+    case 2: launch_pair_variant<128, 4>(c, shard); break;
+    case 3: launch_pair_variant<64, 6>(c, shard); break;
+    case 4: launch_pair_variant<64, 7>(c, shard); break;
+    case 5: launch_pair_variant<128, 3>(c, shard, 8); break;        // two waves of half-length ranges
+    case 6: launch_pair_variant<128, 3>(c, shard, 3); break;        // leaves a quarter of the CTA slots to the side streams
+    case 7: launch_pair_variant<256, 1>(c, shard); break;
+    default: launch_pair_variant<128, 3>(c, shard); break;
   }
   c->n_launch += 1;
 }

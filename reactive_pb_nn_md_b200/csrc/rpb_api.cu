@@ -48,6 +48,7 @@ static int fetch_status(rpb_ctx* c) {
   CK(cudaMemcpyAsync(c->h_flags, c->d.err_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   c->last_en.kinetic_energy = c->h_en[E_KE];
+  if (c->h_flags[1] == 2) { c->err = "a molecule's atoms are farther apart than the box allows (r_cutoff + extent of three consecutive atoms >= L/2)"; return RPB_ERR_VERLET; }
   if (c->h_flags[1]) { c->err = "please increase size of verlet neighbor list"; return RPB_ERR_VERLET; }
   if (c->h_flags[2]) { c->err = "Found more diabat states than the current setting of evb_max_states"; return RPB_ERR_DIABATS; }
   if (c->h_flags[3] >= 30) { c->err = "peer-memory exchange: rank " + std::to_string(c->h_flags[3] - 30) + " did not arrive"; return RPB_ERR_CUDA; }
@@ -262,7 +263,7 @@ int rpb_create(rpb_ctx** out, const rpb_config* cfg) {
   AL(d.verlet_point, N + 1); AL(d.neighbor_list, d.verlet_cap);
   d.tile_cap = 2 * (long long)d.verlet_cap;       // a tile holds at least one listed pair, and the listed pairs fit the reference's capacity
   AL(d.tile_point, RPB_TILE_PARTS * (size_t)N + 4); AL(d.tile_tmp, (RPB_TILE_PARTS * (size_t)N + 4) * RPB_TILE_TMPCAP); AL(d.tile_list, (size_t)d.tile_cap); AL(d.cl_info, N + 1); AL(d.n_clusters, 1); AL(d.mol_cl_first, M + 1); AL(d.mol_ncl, M + 1);
-  AL(d.vbuild_xq, N); AL(d.csort_xq, 3 * (size_t)N); AL(d.csort_mol, N); AL(d.csort_info, N); AL(d.vstat, 4);
+  AL(d.vbuild_xq, N); AL(d.csort_xq, 3 * (size_t)N); AL(d.csort_mol, N); AL(d.csort_info, N); AL(d.vstat, 8);
   AL(d.vsort_xq, N); AL(d.vsort_mol, N); AL(d.vsort_entry, N); AL(d.vstore, 3 * N); AL(d.vdisp, 3 * N);
   AL(d.flag_verlet, 1); AL(d.rebuild_now, 1); AL(d.err_flag, 4); AL(d.vdone, 1);
   AL(d.cell_count, 2 * (ncell + 1)); AL(d.cell_start, ncell + 1); AL(d.cell_atoms, N); AL(d.atom_cell, N); AL(d.row_count, RPB_TILE_PARTS * (size_t)N + 4);
@@ -283,7 +284,7 @@ int rpb_create(rpb_ctx** out, const rpb_config* cfg) {
   CK(cudaMemset(d.force, 0, 3 * N * sizeof(double)));
   CK(cudaMemset(d.force_recip, 0, 3 * N * sizeof(double)));
   CK(cudaMemset(d.xq, 0, (N + 4) * sizeof(double4)));
-  CK(cudaMemset(d.vstat, 0, 4 * sizeof(unsigned long long)));
+  CK(cudaMemset(d.vstat, 0, 8 * sizeof(unsigned long long)));
   CK(cudaMemset(d.n_clusters, 0, sizeof(int)));
   return verlet_setup(c);
 }
@@ -886,7 +887,7 @@ int rpb_debug_tile_pairs(rpb_ctx* c, int* pair_i, int* pair_j, long long capacit
       const int fj = tl[k] & 0x7fffff;
       const unsigned mask = tl[k] >> 23;
       for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++)
-        if (((mask >> (3 * a + b)) & 1u) && fi + a < fj + b) pr.emplace_back(fi + a + 1, fj + b + 1);
+        if ((mask >> (3 * a + b)) & 1u) pr.emplace_back(std::min(fi + a, fj + b) + 1, std::max(fi + a, fj + b) + 1);   // each pair is stored once
     }
   }
   std::sort(pr.begin(), pr.end());

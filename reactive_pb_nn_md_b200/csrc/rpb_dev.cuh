@@ -97,7 +97,7 @@ struct Dev {
   long long tile_cap;
   double4* csort_xq; int* csort_mol; int* csort_info;   // cell-sorted copies of the clusters for the sweep: [3 slot + b], [slot], [slot]
   double4* vsort_xq; int* vsort_mol; int* vsort_entry;  // cell-sorted atom copies (reference-list accessor)
-  unsigned long long* vstat;                // [0] bits of the largest cluster extent  [1] listed (ordered) atom pairs  [2] rebuild counter
+  unsigned long long* vstat;                // [0] bits of the largest cluster extent at the build  [1] listed atom pairs  [2] rebuild counter  [3] pair-kernel work counters  [4] bits of the largest cluster extent now
   double* vstore; double* vdisp; int* flag_verlet; int* rebuild_now;
   const int* commit_hop;                    // device flag: the MS-EVB solver selected a new hydronium molecule this step (null without MS-EVB)
   int* err_flag;  // [0] atom with |F|>1e5 (1-based, 0 none)  [1] verlet overflow  [2] too many diabats  [3] evb lookup failure
