@@ -555,31 +555,42 @@ struct ItemShared {
   int pa_row[MA][RPB_MAXT];             // Born-Mayer row per (hydronium atom, solvent atom type)
 };
 
-// executed by the whole CTA (tid 0 copies the images, threads t < RPB_MAXT resolve the parameter rows); caller syncs
+// executed by the whole CTA (>= 96 threads; one thread per copied element, threads t < RPB_MAXT resolve the parameter
+// rows); caller syncs
 __device__ void fill_item_shared(const Dev& d, const Snapshot& S, const int donor_slot, const int acceptor_slot, ItemShared& sh, int tid) {
   const MolImage& H = S.m[S.hydronium];
   const EvbTables& E = *d.evb;
-  if (tid == 0) {
-    sh.n_chain = 0;
-    for (int k = 0; k < S.n_mol; k++)
-      for (int a = 0; a < S.m[k].n_atom; a++) sh.chain_atoms[sh.n_chain++] = S.m[k].atom[a];
-    sh.nd = sh.na = 0;
-    if (donor_slot >= 0) {
+  if (tid < CM * MA) {                    // chain atoms, molecule by molecule
+    const int k = tid / MA, a = tid % MA;
+    if (k < S.n_mol && a < S.m[k].n_atom) {
+      int off = 0;
+      for (int k2 = 0; k2 < k; k2++) off += S.m[k2].n_atom;
+      sh.chain_atoms[off + a] = S.m[k].atom[a];
+    }
+    if (tid == 0) {
+      int n = 0;
+      for (int k2 = 0; k2 < S.n_mol; k2++) n += S.m[k2].n_atom;
+      sh.n_chain = n;
+      sh.nd = donor_slot >= 0 ? S.m[donor_slot].n_atom : 0;
+      sh.na = acceptor_slot >= 0 ? S.m[acceptor_slot].n_atom : 0;
+      sh.nh = H.n_atom;
+      sh.h_heavy = d.mt[H.mtype].heavy_acid_atom;
+      if (sh.h_heavy < 0) { atomicMax(&d.err_flag[3], 3); sh.h_heavy = 0; }
+      sh.h_type_H = H.type[H.n_atom - 1];
+      sh.h_type_heavy = H.type[sh.h_heavy];
+    }
+  }
+  if (tid >= 64 && tid < 64 + 3 * MA) {   // donor / acceptor / hydronium images
+    const int grp = (tid - 64) / MA, a = (tid - 64) % MA;
+    if (grp == 0 && donor_slot >= 0) {
       const MolImage& D = S.m[donor_slot];
-      sh.nd = D.n_atom;
-      for (int a = 0; a < D.n_atom; a++) { sh.d_atom[a] = D.atom[a]; sh.d_type[a] = D.type[a]; sh.d_q[a] = D.q[a]; for (int k = 0; k < 3; k++) sh.d_x[a][k] = D.x[a][k]; }
-    }
-    if (acceptor_slot >= 0) {
+      if (a < D.n_atom) { sh.d_atom[a] = D.atom[a]; sh.d_type[a] = D.type[a]; sh.d_q[a] = D.q[a]; for (int k = 0; k < 3; k++) sh.d_x[a][k] = D.x[a][k]; }
+    } else if (grp == 1 && acceptor_slot >= 0) {
       const MolImage& A = S.m[acceptor_slot];
-      sh.na = A.n_atom;
-      for (int a = 0; a < A.n_atom; a++) { sh.a_atom[a] = A.atom[a]; sh.a_type[a] = A.type[a]; sh.a_q[a] = A.q[a]; for (int k = 0; k < 3; k++) sh.a_x[a][k] = A.x[a][k]; }
+      if (a < A.n_atom) { sh.a_atom[a] = A.atom[a]; sh.a_type[a] = A.type[a]; sh.a_q[a] = A.q[a]; for (int k = 0; k < 3; k++) sh.a_x[a][k] = A.x[a][k]; }
+    } else if (grp == 2) {
+      if (a < H.n_atom) { sh.h_atom[a] = H.atom[a]; sh.h_type[a] = H.type[a]; for (int k = 0; k < 3; k++) sh.h_x[a][k] = H.x[a][k]; }
     }
-    sh.nh = H.n_atom;
-    for (int a = 0; a < H.n_atom; a++) { sh.h_atom[a] = H.atom[a]; sh.h_type[a] = H.type[a]; for (int k = 0; k < 3; k++) sh.h_x[a][k] = H.x[a][k]; }
-    sh.h_heavy = d.mt[H.mtype].heavy_acid_atom;
-    if (sh.h_heavy < 0) { atomicMax(&d.err_flag[3], 3); sh.h_heavy = 0; }
-    sh.h_type_H = H.type[H.n_atom - 1];
-    sh.h_type_heavy = H.type[sh.h_heavy];
   }
   if (tid >= 32 && tid < 32 + RPB_MAXT) {
     const int t = tid - 32;
@@ -776,7 +787,9 @@ __global__ void __launch_bounds__(ITEM_TPB) k_evb_items(Dev d, EvbDev e, const i
   const Snapshot& S = e.snap[it.state * NLEV + it.level];
   const EvbTables& E = *d.evb;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int part = blockIdx.y, nparts = gridDim.y;
+  // the last slice of an item does the chain-internal terms, the others share the (image atom, candidate chunk) tasks
+  const int part = blockIdx.y, nparts = gridDim.y - 1;
+  const bool internal = part == nparts;
   fill_item_shared(d, S, it.donor_slot, it.acceptor_slot, sh, tid);
   for (int k = tid; k < CM * MA * 3; k += blockDim.x) (&B.fl[0][0])[k] = 0.0;
   __syncthreads();
@@ -817,7 +830,7 @@ __global__ void __launch_bounds__(ITEM_TPB) k_evb_items(Dev d, EvbDev e, const i
 
   // ---------------- image atoms x candidate atoms ----------------
   const int n_tasks = B.task_first[n_img];
-  for (int t = part * (ITEM_TPB / 32) + w; t < n_tasks; t += nparts * (ITEM_TPB / 32)) {
+  for (int t = internal ? n_tasks : part * (ITEM_TPB / 32) + w; t < n_tasks; t += nparts * (ITEM_TPB / 32)) {
     int ia = 0;
     while (t >= B.task_first[ia + 1]) ia++;
     int side, a;
@@ -874,21 +887,27 @@ __global__ void __launch_bounds__(ITEM_TPB) k_evb_items(Dev d, EvbDev e, const i
     }
   }
 
-  // ---------------- chain-internal terms (first CTA of the item) ----------------
-  if (part != 0) {
+  // ---------------- chain-internal terms (last CTA slice of the item) ----------------
+  if (!internal) {
     // nothing
   } else if (ds >= 0) {
     if (tid == 0) en += (sign < 0) ? E.ref_energy[S.m[ds].mtype] : E.ref_energy[S.m[as].mtype];   // ms_evb.f90:1478,1520
-    if (tid == 0 || tid == 32) {
-      int sl = tid == 0 ? ds : as;
+    if (tid < 64) {
+      // bonded + intramolecular terms of the donor (warp 0) and acceptor (warp 1) images: one term (bond, angle, dihedral,
+      // atom pair) per lane
+      int sl = w == 0 ? ds : as;
       const MolImage& I = S.m[sl];
-      const int* cidx = tid == 0 ? B.d_ci : B.a_ci;
-      double f[MA][3];
-      for (int q = 0; q < MA; q++) f[q][0] = f[q][1] = f[q][2] = 0.0;
-      MolEnergies ME;
-      molecule_terms(d, d.mt[I.mtype], I.n_atom, I.x, I.type, I.q, f, ME, true, true);
-      en += ME.e_bond + ME.e_angle + ME.e_dih + ME.e_elec + ME.e_vdw;
-      for (int q = 0; q < I.n_atom; q++) for (int c = 0; c < 3; c++) atomicAdd(&B.fl[cidx[q]][c], f[q][c]);
+      const MolTypeDev& T = d.mt[I.mtype];
+      const int* cidx = w == 0 ? B.d_ci : B.a_ci;
+      const int n_terms = molecule_term_count(T, I.n_atom, true, true);
+      for (int term = lane; term < n_terms; term += 32) {
+        double f[MA][3];
+        for (int q = 0; q < MA; q++) f[q][0] = f[q][1] = f[q][2] = 0.0;
+        MolEnergies ME = {0.0, 0.0, 0.0, 0.0, 0.0};
+        molecule_term(d, T, I.n_atom, I.x, I.type, I.q, f, ME, true, true, term);
+        en += ME.e_bond + ME.e_angle + ME.e_dih + ME.e_elec + ME.e_vdw;
+        for (int q = 0; q < I.n_atom; q++) for (int c = 0; c < 3; c++) if (f[q][c] != 0.0) atomicAdd(&B.fl[cidx[q]][c], f[q][c]);
+      }
     }
     if (tid >= 64) {
       // donor atoms vs every other chain molecule; acceptor atoms vs chain molecules other than donor and acceptor
@@ -917,7 +936,7 @@ __global__ void __launch_bounds__(ITEM_TPB) k_evb_items(Dev d, EvbDev e, const i
   } else if (tid == 0) {
     en += E.ref_energy[S.m[S.hydronium].mtype];   // principal diabat: E_reference (ms_evb.f90:424)
   }
-  if (part == 0 && w == 7) {
+  if (internal && w == 7) {
     // repulsion of the hydronium image with the atoms of the other chain molecules
     int hs = S.hydronium;
     for (int t = lane; t < S.n_mol * MA; t += 32) {
@@ -2202,7 +2221,7 @@ int evb_build(rpb_ctx* c) {
       dim3 g((N + 255) / 256, std::min(CAND_SLOTS, 4 * sb + 8));
       k_evb_candidates<<<g, 256, 0, c->stream>>>(d, e, c->evb_rcand * c->evb_rcand, sc.chain_slot, sc.cand, sc.cand_n);
     }
-    { ScopedTimer t(c, T_EVB_ITEMS_BG); k_evb_items<<<dim3(2 * sb - 1, ITEM_SPLIT), ITEM_TPB, 0, c->stream>>>(d, e, sc.chain_slot, sc.cand, sc.cand_n, c->evb_rcand, c->evb_rep_reach); }
+    { ScopedTimer t(c, T_EVB_ITEMS_BG); k_evb_items<<<dim3(2 * sb - 1, ITEM_SPLIT + 1), ITEM_TPB, 0, c->stream>>>(d, e, sc.chain_slot, sc.cand, sc.cand_n, c->evb_rcand, c->evb_rep_reach); }
     c->n_launch += 2;
   }
   {
@@ -2358,8 +2377,15 @@ int evb_commit(rpb_ctx* c) {
   CKE(cudaMemcpyAsync(pin, e.n_states, ENUM_BLOCK_INTS * sizeof(int), cudaMemcpyDeviceToHost, c->aux[3]));
   CKE(cudaMemcpyAsync(pd, e.result, SOLVER_BLOCK_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, c->aux[3]));
   CKE(cudaMemcpyAsync(pd + SOLVER_BLOCK_DOUBLES + 1, sc.commit, sizeof(CommitInfo), cudaMemcpyDeviceToHost, c->aux[3]));
-  stream_depend(c, 2, c->aux[3], c->main_stream);
+  // the main stream joins these copies at the END of the step (evb_join_readback): the second half kick need not wait
+  c->evb_join_pending = true;
   return 0;
+}
+
+void evb_join_readback(rpb_ctx* c) {
+  if (!c->evb_join_pending) return;
+  stream_depend(c, 2, c->aux[3], c->main_stream);
+  c->evb_join_pending = false;
 }
 
 // The one synchronising read of a call: results of the LAST step (accessors), sticky error flags of all of them.

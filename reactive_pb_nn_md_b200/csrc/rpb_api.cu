@@ -127,7 +127,7 @@ int calculate_total_force_energy(rpb_ctx* c, bool evb_principal) {
 }
 
 // enqueue one force evaluation (no host synchronisation)
-static int enqueue_force(rpb_ctx* c, int ms_evb) {
+static int enqueue_force(rpb_ctx* c, int ms_evb, bool defer_join = false) {
   int rc;
   c->image_valid = false; c->ke_valid = false;
   if (ms_evb) {
@@ -138,7 +138,9 @@ static int enqueue_force(rpb_ctx* c, int ms_evb) {
     if (sharded) { rc = peer_allreduce(c, PEER_H); if (rc) return rc; peer_begin(c, PEER_F); }
     rc = evb_mix(c, nullptr, nullptr); if (rc) return rc;
     if (sharded) { rc = peer_allreduce(c, PEER_F); if (rc) return rc; }
-    return evb_commit(c);
+    rc = evb_commit(c);
+    if (!defer_join) evb_join_readback(c);     // (a step joins after its second half kick)
+    return rc;
   }
   return calculate_total_force_energy(c, false);
 }
@@ -156,9 +158,10 @@ static int collect_results(rpb_ctx* c, int ms_evb) {
 static int enqueue_step(rpb_ctx* c, int ms_evb) {
   ScopedTimer t(c, T_STEP);
   launch_integrate_first(c);
-  int rc = enqueue_force(c, ms_evb);
+  int rc = enqueue_force(c, ms_evb, true);
   if (rc) return rc;
   launch_integrate_second(c);
+  evb_join_readback(c);
   return 0;
 }
 
@@ -660,7 +663,7 @@ int rpb_step_end(rpb_ctx* c) {
 // the phase calls always use the library's own exchange buffers (the caller runs the collectives), never the peer arena
 int rpb_evb_phase_build(rpb_ctx* c) { if (c->peer.h_local) c->e.h_diag = c->peer.h_local; return evb_build(c); }
 int rpb_evb_phase_mix(rpb_ctx* c) { if (c->peer.f_local) c->e.f_mix = c->peer.f_local; c->peer.f_reduced_in_place = false; return evb_mix(c, nullptr, nullptr); }
-int rpb_evb_phase_commit(rpb_ctx* c) { int rc = evb_commit(c); return rc ? rc : evb_readback(c); }
+int rpb_evb_phase_commit(rpb_ctx* c) { int rc = evb_commit(c); evb_join_readback(c); return rc ? rc : evb_readback(c); }
 int rpb_evb_exchange_h(rpb_ctx* c, void** ptr, int* n) { *ptr = c->e.h_diag; *n = 3 * RPB_MAXS + E_NSLOT; return 0; }
 int rpb_evb_exchange_f(rpb_ctx* c, void** ptr, int* n) { *ptr = c->e.f_mix; *n = 3 * c->d.N; return 0; }
 

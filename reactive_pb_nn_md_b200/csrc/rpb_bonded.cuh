@@ -9,12 +9,18 @@ __device__ __forceinline__ double dot3(const double* a, const double* b) { retur
 
 struct MolEnergies { double e_bond, e_angle, e_dih, e_elec, e_vdw; };
 
-// x[a][3], f[a][3] (accumulated), type[a] actual atom types, q[a] charges
-__device__ inline void molecule_terms(const Dev& d, const MolTypeDev& T, int n_atom, const double (*x)[3], const int* type,
-                                      const double* q, double (*f)[3], MolEnergies& E, bool bonded, bool nonbonded) {
-  E.e_bond = E.e_angle = E.e_dih = E.e_elec = E.e_vdw = 0.0;
+// number of independent terms of a molecule: bonds, angles, dihedrals, intramolecular atom pairs (in that order)
+__device__ __forceinline__ int molecule_term_count(const MolTypeDev& T, int n_atom, bool bonded, bool nonbonded) {
+  return (bonded ? T.n_bond + T.n_angle + T.n_dih : 0) + ((nonbonded && n_atom > 1) ? n_atom * (n_atom - 1) / 2 : 0);
+}
+
+// ONE term (index as counted by molecule_term_count): x[a][3], f[a][3] and E are accumulated into, type[a] actual atom
+// types, q[a] charges.  molecule_terms() runs them in order on one thread; the MS-EVB item kernel gives a term to a lane.
+__device__ inline void molecule_term(const Dev& d, const MolTypeDev& T, int n_atom, const double (*x)[3], const int* type,
+                                     const double* q, double (*f)[3], MolEnergies& E, bool bonded, bool nonbonded, int term) {
   if (bonded) {
-    for (int b = 0; b < T.n_bond; b++) {
+    if (term < T.n_bond) {
+      const int b = term;
       int i = T.bond[b][0], j = T.bond[b][1];
       double r[3] = {x[i][0] - x[j][0], x[i][1] - x[j][1], x[i][2] - x[j][2]};
       double rm = sqrt(dot3(r, r));
@@ -34,8 +40,11 @@ __device__ inline void molecule_terms(const Dev& d, const MolTypeDev& T, int n_a
       }
       E.e_bond += e;
       for (int k = 0; k < 3; k++) { f[i][k] += s * r[k]; f[j][k] -= s * r[k]; }
+      return;
     }
-    for (int a = 0; a < T.n_angle; a++) {
+    term -= T.n_bond;
+    if (term < T.n_angle) {
+      const int a = term;
       int i = T.angle[a][0], j = T.angle[a][1], k = T.angle[a][2];
       double rij[3], rkj[3];
       for (int c = 0; c < 3; c++) { rij[c] = x[i][c] - x[j][c]; rkj[c] = x[k][c] - x[j][c]; }
@@ -58,8 +67,11 @@ __device__ inline void molecule_terms(const Dev& d, const MolTypeDev& T, int n_a
         double fkj = fac * (rij[c] / rijm / rkjm - cosine * rkj[c] / (rkjm * rkjm));
         f[i][c] += fij; f[k][c] += fkj; f[j][c] = f[j][c] - fij - fkj;
       }
+      return;
     }
-    for (int q4 = 0; q4 < T.n_dih; q4++) {
+    term -= T.n_angle;
+    if (term < T.n_dih) {
+      const int q4 = term;
       int i = T.dih[q4][0], j = T.dih[q4][1], k = T.dih[q4][2], l = T.dih[q4][3];
       double rji[3], rkj[3], rlk[3];
       for (int c = 0; c < 3; c++) { rji[c] = x[j][c] - x[i][c]; rkj[c] = x[k][c] - x[j][c]; rlk[c] = x[l][c] - x[k][c]; }
@@ -89,7 +101,7 @@ __device__ inline void molecule_terms(const Dev& d, const MolTypeDev& T, int n_a
         e = P[0] - P[1] * cosine + P[2] * c2 - P[3] * c3 + P[4] * c4 - P[5] * c5;
         fac = P[1] - 2.0 * P[2] * cosine + 3.0 * P[3] * c2 - 4.0 * P[4] * c3 + 5.0 * P[5] * c4;
       } else {
-        continue;
+        return;
       }
       E.e_dih += e;
       double aa15 = pow(aa, 1.5), bb15 = pow(bb, 1.5);
@@ -107,11 +119,16 @@ __device__ inline void molecule_terms(const Dev& d, const MolTypeDev& T, int n_a
         double flk = sgn * fac * (dab_lk / sa / sb - 0.5 * ab / aa15 / sb * 0.0 - 0.5 * ab / sa / bb15 * dbb_lk);
         f[i][c] -= fji; f[j][c] = f[j][c] + fji - fkj; f[k][c] = f[k][c] + fkj - flk; f[l][c] += flk;
       }
+      return;
     }
+    term -= T.n_dih;
   }
   if (nonbonded && n_atom > 1) {
-    for (int i = 0; i < n_atom; i++) {
-      for (int j = i + 1; j < n_atom; j++) {
+    {
+      {
+        int i = 0;
+        while (term >= n_atom - 1 - i) { term -= n_atom - 1 - i; i++; }     // pairs (i, j > i), row by row
+        const int j = i + 1 + term;
         double dr[3] = {x[i][0] - x[j][0], x[i][1] - x[j][1], x[i][2] - x[j][2]};
         double dr2 = dot3(dr, dr);
         double qq = q[i] * q[j];
@@ -130,4 +147,11 @@ __device__ inline void molecule_terms(const Dev& d, const MolTypeDev& T, int n_a
       }
     }
   }
+}
+
+__device__ inline void molecule_terms(const Dev& d, const MolTypeDev& T, int n_atom, const double (*x)[3], const int* type,
+                                      const double* q, double (*f)[3], MolEnergies& E, bool bonded, bool nonbonded) {
+  E.e_bond = E.e_angle = E.e_dih = E.e_elec = E.e_vdw = 0.0;
+  const int n = molecule_term_count(T, n_atom, bonded, nonbonded);
+  for (int t = 0; t < n; t++) molecule_term(d, T, n_atom, x, type, q, f, E, bonded, nonbonded, t);
 }

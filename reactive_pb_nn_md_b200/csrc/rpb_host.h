@@ -64,6 +64,7 @@ struct rpb_ctx {
   void* evb_scratch = nullptr; // EvbScratch (kernels_evb.cu): device scratch of the MS-EVB build, owned by this context
   bool evb_overlap_solver = false;    // the branches of evb_build were joined on aux[0] (not on the main stream): evb_mix runs the solver there
   bool evb_assemble_pending = false;  // evb_build left the Hamiltonian assembly to the solver kernel
+  bool evb_join_pending = false;      // evb_commit queued its read-back copies on aux[3]; the main stream has not joined them yet
   bool evb_any_multi_basic = false;   // some molecule type has more than one atom that can be protonated (reference re-ordering quirk possible)
   bool mirror_stale = false;          // a committed hop changed the molecule table on the device: the host mirror is refreshed before use
   int grid_capacity = 0;       // number of K^3 grids usable in d.Q / d.theta (4 spare ones follow for the rounded FFT batch)
@@ -176,4 +177,5 @@ void evb_clear_early(rpb_ctx*);      // accumulators of the build for the previo
 int evb_build(rpb_ctx*);
 int evb_mix(rpb_ctx*, const double* coeff_override_host, double* force_out_host);
 int evb_commit(rpb_ctx*);
+void evb_join_readback(rpb_ctx*);   // main stream waits for the read-back copies evb_commit queued on aux[3]
 int evb_readback(rpb_ctx*);          // synchronising read of the last step's results + sticky error flags
