@@ -2149,7 +2149,7 @@ void evb_free(rpb_ctx* c) {
 }
 
 // grid bounds from a recent diabat count (performance only: every kernel loops over the device-side counts)
-static inline int s_bound(rpb_ctx* c) { return std::min(MAXS, std::max(c->eh.s_hint, 8) + 16); }
+static inline int s_bound(rpb_ctx* c) { return c->evb_s_bound_fixed ? c->evb_s_bound_fixed : std::min(MAXS, std::max(c->eh.s_hint, 8) + 16); }
 
 int evb_enumerate_async(rpb_ctx* c, int part) {
   Dev& d = c->d; EvbDev& e = c->e;
@@ -2157,6 +2157,7 @@ int evb_enumerate_async(rpb_ctx* c, int part) {
   if (part == 0) {   // the kernel alone: the caller queues the pair kernel on the main stream before the rest
     ScopedTimer t(c, T_EVB_ENUM);
     k_evb_enumerate<<<1, ENUM_TPB, ENUM_SMEM_BYTES, c->stream>>>(d, e, sc.cand_n);
+    CKE(cudaEventRecord(c->ev_sync[20], c->stream));            // "plan ready, candidate counters zeroed"
     c->n_launch += 1;
     return 0;
   }
@@ -2164,21 +2165,22 @@ int evb_enumerate_async(rpb_ctx* c, int part) {
   { ScopedTimer t(c, T_EVB_SNAP); k_evb_snapshots<<<(MAXS + SNAP_WPB - 1) / SNAP_WPB, 32 * SNAP_WPB, 0, c->stream>>>(d, e, -1, 1); }   // every rank needs the charges of every diabat
   c->n_launch += 1;
   CKE(cudaEventRecord(c->ev_sync[18], c->stream));            // "images ready"
+  CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[11], 0));     // the early clears (aux[1])
+  k_evb_clear<<<32, 256, 0, c->stream>>>(d, e, 1);            // the diabats beyond the early clears' margin (normally none)
+  CKE(cudaEventRecord(c->ev_sync[14], c->stream));            // "images ready, every accumulator cleared"
+  c->n_launch += 1;
   {
     // geometry factors of the couplings need the images and the clears (they add the Vex terms of the other chain
     // molecules); on aux[3] so that aux[0] is free for the Vex kernel's wait
     StreamScope ss(c, c->aux[3]);
-    CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[18], 0));
-    CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[11], 0));   // the early clears (aux[1])
-    k_evb_clear<<<32, 256, 0, c->stream>>>(d, e, 1);          // the diabats beyond the early clears' margin (normally none)
-    CKE(cudaEventRecord(c->ev_sync[14], c->stream));          // "images ready, every accumulator cleared"
+    CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[14], 0));
     {
       ScopedTimer t(c, T_EVB_COUPLING_GEO);
       const int sb = s_bound(c);
       k_evb_coupling_geo<<<(sb + GEO_WPB - 1) / GEO_WPB, 32 * GEO_WPB, 0, c->stream>>>(d, e, sc.geo);
     }
     CKE(cudaEventRecord(c->ev_sync[19], c->stream));          // "clears complete, coupling geometry ready"
-    c->n_launch += 2;
+    c->n_launch += 1;
   }
   return 0;
 }
@@ -2215,12 +2217,13 @@ int evb_build(rpb_ctx* c) {
   //   aux[2] : [bonded terms of the principal diabat] -> pair matrix of the chain atoms
   {
     StreamScope ss(c, c->aux[4]);
-    CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[14], 0));      // images, clears (incl. the enumeration's candidate counters) -- not the coupling geometry
+    CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[20], 0));      // the candidate lists need the plan only: next to the images
     {
       ScopedTimer t(c, T_EVB_CAND);
       dim3 g((N + 255) / 256, std::min(CAND_SLOTS, 4 * sb + 8));
       k_evb_candidates<<<g, 256, 0, c->stream>>>(d, e, c->evb_rcand * c->evb_rcand, sc.chain_slot, sc.cand, sc.cand_n);
     }
+    CKE(cudaStreamWaitEvent(c->stream, c->ev_sync[14], 0));      // images, clears -- not the coupling geometry
     { ScopedTimer t(c, T_EVB_ITEMS_BG); k_evb_items<<<dim3(2 * sb - 1, ITEM_SPLIT + 1), ITEM_TPB, 0, c->stream>>>(d, e, sc.chain_slot, sc.cand, sc.cand_n, c->evb_rcand, c->evb_rep_reach); }
     c->n_launch += 2;
   }

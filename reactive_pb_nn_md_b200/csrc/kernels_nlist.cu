@@ -159,7 +159,7 @@ __device__ __forceinline__ void offset_range(int reach, int n, int& lo, int& hi,
 // A cluster's row is built (and later consumed) in RPB_TILE_PARTS independent parts: part p takes every RPB_TILE_PARTS-th
 // (x, y) column of the cell walk, so four warps share the sweep of one cluster and four warps share its pair forces.
 template <bool WRITE>
-__device__ __forceinline__ void tile_sweep(const Dev& d, const int I, const int part, const int lane, const double R) {
+__device__ __forceinline__ void tile_sweep(const Dev& d, const int I, const int part, const int lane, const double R, int* __restrict__ queue) {
   const int info = d.cl_info[I], fi = info & 0xffffff, ni = info >> 24;
   const int mi = d.mol_of_atom[fi];
   double4 pi[3];
@@ -183,72 +183,105 @@ __device__ __forceinline__ void tile_sweep(const Dev& d, const int I, const int 
   int n_tile = 0;
   unsigned long long n_pair = 0;
   const int ny = yhi - ylo + 1, ncol = (xhi - xlo + 1) * ny;
-  {
-    for (int col_id = part; col_id < ncol; col_id += RPB_TILE_PARTS) {
-      const int ox = xlo + col_id / ny, oy = ylo + col_id % ny;
-      const int g1 = wrap_cell(ix + ox, d.ncx);
-      double gx = 0.0;
-      if (px && ox != 0) gx = fmax(0.0, (ox > 0 ? (double)ox - fx : fx - (double)(ox + 1)) - slack) * wx;
-      double gy = 0.0;
-      if (py && oy != 0) gy = fmax(0.0, (oy > 0 ? (double)oy - fy : fy - (double)(oy + 1)) - slack) * wy;
-      const double rem = R2 - (gx * gx + gy * gy);
-      if (rem < 0.0) continue;
-      int z0 = zlo, z1 = zhi;
-      if (pz) {
-        const double zc = sqrt(rem) / wz + slack;
-        z1 = min(zhi, (int)floor(fz + zc));
-        z0 = -min(-zlo, (int)floor(1.0 - fz + zc));
-      }
-      const int g2 = wrap_cell(iy + oy, d.ncy);
-      const int col = d.ncz * ((g2 - 1) + d.ncy * (g1 - 1));
-      // [iz+z0, iz+z1] wrapped into 1..ncz: one or two contiguous ranges of the cell-sorted arrays
-      const int len = z1 - z0 + 1, start = wrap_cell(iz + z0, d.ncz);
-      int seg0[2] = {start, 1}, seg1[2] = {min(start + len - 1, d.ncz), start + len - 1 - d.ncz};
-      const int nseg = (start + len - 1 > d.ncz) ? 2 : 1;
-      for (int sg = 0; sg < nseg; sg++) {
-        const int s = d.cell_start[col + seg0[sg] - 1], e = d.cell_start[col + seg1[sg]];
-        for (int b0 = s; b0 < e; b0 += 32) {
-          const int slot = b0 + lane;
-          unsigned mask = 0;
-          int fj = 0;
-          bool near = false;
-          // HALF list of tiles: the unordered cluster pair {I, J} is stored in the row of I when I + J is odd and I < J, or
-          // I + J is even and I > J (balanced rows without any ordering of the clusters in space)
-          bool mine = false;
-          if (slot < e && d.csort_mol[slot] != mi) { const int J = d.cell_atoms[slot]; mine = ((I + J) & 1) ? (I < J) : (I > J); }
-          if (mine) {     // first atoms farther apart than R: no atom pair can be listed
-            const double4 p0 = ldg256(&d.csort_xq[3 * slot]);
-            double r0 = pi[0].x - p0.x, r1 = pi[0].y - p0.y, r2 = pi[0].z - p0.z;
+  int qh = 0, qn = 0;                       // the warp's queue of near candidates (cell-sorted slots), uniform over the warp
+  // the (up to) nine atom pairs of cluster I with the cluster in `slot` (-1: idle lane) -> one list word
+  auto pair_tests = [&](const int slot) {
+    unsigned mask = 0;
+    int fj = 0;
+    if (slot >= 0) {
+      const int jinfo = d.csort_info[slot], nj = jinfo >> 24;
+      fj = jinfo & 0xffffff;
+#pragma unroll
+      for (int b = 0; b < 3; b++) {
+        if (b < nj) {
+          const double4 pj = ldg256(&d.csort_xq[3 * slot + b]);
+#pragma unroll
+          for (int a = 0; a < 3; a++) {
+            double r0 = pi[a].x - pj.x, r1 = pi[a].y - pj.y, r2 = pi[a].z - pj.z;
             r0 = r0 - d.box[0] * floor_fp64pipe(r0 * d.inv_box[0] + 0.5);
             r1 = r1 - d.box[1] * floor_fp64pipe(r1 * d.inv_box[1] + 0.5);
             r2 = r2 - d.box[2] * floor_fp64pipe(r2 * d.inv_box[2] + 0.5);
-            near = (r0 * r0 + r1 * r1 + r2 * r2) < R2;
+            if (a < ni && (r0 * r0 + r1 * r1 + r2 * r2) < d.rv2) mask |= 1u << (3 * a + b);
           }
-          if (near) {
-            const int jinfo = d.csort_info[slot], nj = jinfo >> 24;
-            fj = jinfo & 0xffffff;
-#pragma unroll
-            for (int b = 0; b < 3; b++) {
-              if (b < nj) {
-                const double4 pj = ldg256(&d.csort_xq[3 * slot + b]);
-#pragma unroll
-                for (int a = 0; a < 3; a++) {
-                  double r0 = pi[a].x - pj.x, r1 = pi[a].y - pj.y, r2 = pi[a].z - pj.z;
-                  r0 = r0 - d.box[0] * floor_fp64pipe(r0 * d.inv_box[0] + 0.5);
-                  r1 = r1 - d.box[1] * floor_fp64pipe(r1 * d.inv_box[1] + 0.5);
-                  r2 = r2 - d.box[2] * floor_fp64pipe(r2 * d.inv_box[2] + 0.5);
-                  if (a < ni && (r0 * r0 + r1 * r1 + r2 * r2) < d.rv2) mask |= 1u << (3 * a + b);
-                }
-              }
-            }
-          }
-          const unsigned hit = __ballot_sync(0xffffffffu, mask != 0);
-          if (mask) { const int pos = n_tile + __popc(hit & ((1u << lane) - 1u)); if (WRITE || pos < RPB_TILE_TMPCAP) out[pos] = (unsigned)fj | (mask << 23); }
-          if (!WRITE) n_pair += __popc(mask);
-          n_tile += __popc(hit);
         }
       }
     }
+    const unsigned hit = __ballot_sync(0xffffffffu, mask != 0);
+    if (mask) { const int pos = n_tile + __popc(hit & ((1u << lane) - 1u)); if (WRITE || pos < RPB_TILE_TMPCAP) out[pos] = (unsigned)fj | (mask << 23); }
+    if (!WRITE) n_pair += __popc(mask);
+    n_tile += __popc(hit);
+    __syncwarp();
+  };
+  {
+    // The (x, y) columns of this part, 32 at a time: every lane works out the slot range(s) of ONE column (a column's cells
+    // within reach are contiguous in the cell-sorted arrays, in two pieces when the z range wraps), then the warp walks the
+    // concatenation of the 32 ranges with all lanes busy (a lane finds its column by a search over the ranges' offsets).
+    const int ncol_mine = (ncol - part + RPB_TILE_PARTS - 1) / RPB_TILE_PARTS;
+    for (int kb = 0; kb < ncol_mine; kb += 32) {
+      int s0 = 0, e0 = 0, s1 = 0, e1 = 0;
+      if (kb + lane < ncol_mine) {
+        const int col_id = part + RPB_TILE_PARTS * (kb + lane);
+        const int ox = xlo + col_id / ny, oy = ylo + col_id % ny;
+        const int g1 = wrap_cell(ix + ox, d.ncx);
+        double gx = 0.0;
+        if (px && ox != 0) gx = fmax(0.0, (ox > 0 ? (double)ox - fx : fx - (double)(ox + 1)) - slack) * wx;
+        double gy = 0.0;
+        if (py && oy != 0) gy = fmax(0.0, (oy > 0 ? (double)oy - fy : fy - (double)(oy + 1)) - slack) * wy;
+        const double rem = R2 - (gx * gx + gy * gy);
+        if (rem >= 0.0) {
+          int z0 = zlo, z1 = zhi;
+          if (pz) {
+            const double zc = sqrt(rem) / wz + slack;
+            z1 = min(zhi, (int)floor(fz + zc));
+            z0 = -min(-zlo, (int)floor(1.0 - fz + zc));
+          }
+          const int g2 = wrap_cell(iy + oy, d.ncy);
+          const int col = d.ncz * ((g2 - 1) + d.ncy * (g1 - 1));
+          // [iz+z0, iz+z1] wrapped into 1..ncz: one or two contiguous ranges of the cell-sorted arrays
+          const int len = z1 - z0 + 1, start = wrap_cell(iz + z0, d.ncz);
+          s0 = d.cell_start[col + start - 1]; e0 = d.cell_start[col + min(start + len - 1, d.ncz)];
+          if (start + len - 1 > d.ncz) { s1 = d.cell_start[col]; e1 = d.cell_start[col + start + len - 1 - d.ncz]; }
+        }
+      }
+      const int n0 = e0 - s0, len = n0 + (e1 - s1);
+      int incl = len;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      const int total = __shfl_sync(0xffffffffu, incl, 31), excl = incl - len;
+      for (int t0 = 0; t0 < total; t0 += 32) {
+        const int t = t0 + lane;
+        int owner = 0;                      // the last lane whose range starts at or before t (ranges of length 0 never win)
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          const int ex = __shfl_sync(0xffffffffu, excl, (owner + step) & 31);
+          if (ex <= t) owner += step;
+        }
+        const int off = t - __shfl_sync(0xffffffffu, excl, owner);
+        const int cs0 = __shfl_sync(0xffffffffu, s0, owner), cn0 = __shfl_sync(0xffffffffu, n0, owner), cs1 = __shfl_sync(0xffffffffu, s1, owner);
+        const int slot = off < cn0 ? cs0 + off : cs1 + (off - cn0);
+        // HALF list of tiles: the unordered cluster pair {I, J} is stored in the row of I when I + J is odd and I < J, or
+        // I + J is even and I > J (balanced rows without any ordering of the clusters in space)
+        bool mine = false;
+        if (t < total && d.csort_mol[slot] != mi) { const int J = d.cell_atoms[slot]; mine = ((I + J) & 1) ? (I < J) : (I > J); }
+        bool near = false;
+        if (mine) {     // first atoms farther apart than R: no atom pair can be listed
+          const double4 p0 = ldg256(&d.csort_xq[3 * slot]);
+          double r0 = pi[0].x - p0.x, r1 = pi[0].y - p0.y, r2 = pi[0].z - p0.z;
+          r0 = r0 - d.box[0] * floor_fp64pipe(r0 * d.inv_box[0] + 0.5);
+          r1 = r1 - d.box[1] * floor_fp64pipe(r1 * d.inv_box[1] + 0.5);
+          r2 = r2 - d.box[2] * floor_fp64pipe(r2 * d.inv_box[2] + 0.5);
+          near = (r0 * r0 + r1 * r1 + r2 * r2) < R2;
+        }
+        // ~1 candidate in 8 survives: the survivors are compacted into the warp's queue and the nine atom-pair tests run
+        // on full warps
+        const unsigned nm = __ballot_sync(0xffffffffu, near);
+        if (near) queue[(qn + __popc(nm & ((1u << lane) - 1u))) & 63] = slot;
+        qn += __popc(nm);
+        __syncwarp();
+        if (qn - qh >= 32) { pair_tests(queue[(qh + lane) & 63]); qh += 32; }
+      }
+    }
+    if (qn > qh) pair_tests(lane < qn - qh ? queue[(qh + lane) & 63] : -1);
   }
   if (!WRITE) {
 #pragma unroll
@@ -303,7 +336,9 @@ __device__ __forceinline__ void rebuild_phases(const Dev& d, cg::grid_group& gri
   }
   grid.sync();
   const double R = sqrt(d.rv2) + 2.0 * __longlong_as_double((long long)d.vstat[0]) + 1e-9;
-  for (int w = gwarp; w < RPB_TILE_PARTS * NC; w += nwarps) tile_sweep<false>(d, w / RPB_TILE_PARTS, w % RPB_TILE_PARTS, lane, R);
+  __shared__ int sweep_queue[TPB / 32][64];       // per warp: near candidates waiting for their pair tests
+  int* queue = sweep_queue[threadIdx.x >> 5];
+  for (int w = gwarp; w < RPB_TILE_PARTS * NC; w += nwarps) tile_sweep<false>(d, w / RPB_TILE_PARTS, w % RPB_TILE_PARTS, lane, R, queue);
   grid.sync();
   if (blockIdx.x == 0) {
     block_scan_exclusive(d.row_count, d.tile_point, RPB_TILE_PARTS * NC, 0);
@@ -318,7 +353,7 @@ __device__ __forceinline__ void rebuild_phases(const Dev& d, cg::grid_group& gri
       const unsigned* __restrict__ src = d.tile_tmp + (size_t)w * RPB_TILE_TMPCAP;
       unsigned* __restrict__ dst = d.tile_list + d.tile_point[w];
       for (int k = lane; k < n; k += 32) dst[k] = src[k];
-    } else tile_sweep<true>(d, w / RPB_TILE_PARTS, w % RPB_TILE_PARTS, lane, R);
+    } else tile_sweep<true>(d, w / RPB_TILE_PARTS, w % RPB_TILE_PARTS, lane, R, queue);
   }
 }
 

@@ -205,7 +205,7 @@ int rpb_create(rpb_ctx** out, const rpb_config* cfg) {
       else CK(cudaStreamCreateWithPriority(&c->aux[k], cudaStreamNonBlocking, prio_hi));
     }
   }
-  for (int k = 0; k < 20; k++) CK(cudaEventCreateWithFlags(&c->ev_sync[k], cudaEventDisableTiming));
+  for (int k = 0; k < 24; k++) CK(cudaEventCreateWithFlags(&c->ev_sync[k], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_enum, cudaEventDisableTiming));
   CK(cudaMallocHost(&c->h_en, E_NSLOT * sizeof(double)));
   CK(cudaMallocHost(&c->h_flags, 8 * sizeof(int)));
@@ -303,13 +303,13 @@ void rpb_destroy(rpb_ctx* c) {
   for (void* p : c->allocs) cudaFree(p);
   if (c->h_en) cudaFreeHost(c->h_en);
   if (c->h_flags) cudaFreeHost(c->h_flags);
-  for (int k = 0; k < 2; k++) if (c->graph[k].exec) cudaGraphExecDestroy(c->graph[k].exec);
+  for (int k = 0; k < 4; k++) if (c->graph[k].exec) cudaGraphExecDestroy(c->graph[k].exec);
   if (c->staging) cudaFreeHost(c->staging);
   for (int k = 0; k < 2; k++) { if (c->staging_up[k]) cudaFreeHost(c->staging_up[k]); if (c->ev_up[k]) cudaEventDestroy(c->ev_up[k]); }
   if (c->eh.pinned) cudaFreeHost(c->eh.pinned);
   if (c->stream) {
     for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
-    for (int k = 0; k < 20; k++) if (c->ev_sync[k]) cudaEventDestroy(c->ev_sync[k]);
+    for (int k = 0; k < 24; k++) if (c->ev_sync[k]) cudaEventDestroy(c->ev_sync[k]);
     if (c->ev_enum) cudaEventDestroy(c->ev_enum);
     for (int k = 0; k < 5; k++) if (c->aux[k] && !c->serial_streams) { cudaStreamSynchronize(c->aux[k]); cudaStreamDestroy(c->aux[k]); }
     cudaStreamDestroy(c->stream);
@@ -676,19 +676,35 @@ static bool graph_allowed(rpb_ctx* c, int ms_evb) {
   return !off && !c->timers_on && !c->serial_streams && !(ms_evb && c->d.world > 1) && !c->graph_failed;
 }
 
-static int graph_get(rpb_ctx* c, int ms_evb, cudaGraphExec_t* out) {
-  StepGraph& g = c->graph[ms_evb ? 1 : 0];
+static int graph_get(rpb_ctx* c, int ms_evb, cudaGraphExec_t* out, int* launches, int force_slot = 0) {
+  // The grids of the MS-EVB kernels are sized for a bound of the diabat count (the kernels loop over the device-side count,
+  // so a generous bound only costs idle CTAs).  The count of a trajectory wanders (20 ... 60 within 150 steps of the
+  // benchmark system) and a capture costs ~1.2 ms of host time, so up to three graphs -- bounds 32, 56, evb_max_states --
+  // are captured together on first use and KEPT; a step replays the smallest one that leaves 6 diabats of headroom.
+  static const int bounds[3] = {32, 56, RPB_MAXS};
   const int hint = ms_evb ? c->eh.s_hint : 0;
-  if (g.exec && (hint > g.s_hint + 12 || hint < g.s_hint - 24 || g.n_clusters_bound != c->n_clusters_bound)) {   // grids sized for another diabat count
-    cudaGraphExecDestroy(g.exec); g.exec = nullptr;
-  }
+  int slot = 0;
+  if (ms_evb) { slot = 1; while (slot < 3 && hint + 6 > bounds[slot - 1]) slot++; }
+  if (force_slot) slot = force_slot;
+  else if (ms_evb)
+    for (int k = 1; k <= 3; k++)             // (all three at once: no capture inside a later timed region)
+      if (k != slot && (!c->graph[k].exec || c->graph[k].n_clusters_bound != c->n_clusters_bound) && !c->graph_failed) {
+        cudaGraphExec_t dummy; int nl;
+        int rc = graph_get(c, ms_evb, &dummy, &nl, k);
+        if (rc) return rc;
+      }
+  StepGraph& g = c->graph[slot];
+  if (g.exec && g.n_clusters_bound != c->n_clusters_bound) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
   if (!g.exec) {
     const long long l0 = c->n_launch;
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamBeginCapture(c->main_stream, cudaStreamCaptureModeThreadLocal);
     int rc = 0;
+    const int bound = ms_evb ? std::min(RPB_MAXS, bounds[slot - 1]) : 0;
     if (e == cudaSuccess) {
+      c->evb_s_bound_fixed = bound;
       rc = enqueue_step(c, ms_evb);
+      c->evb_s_bound_fixed = 0;
       e = cudaStreamEndCapture(c->main_stream, &graph);
     }
     if (e == cudaSuccess && rc == 0) e = cudaGraphInstantiate(&g.exec, graph, 0);
@@ -706,9 +722,11 @@ static int graph_get(rpb_ctx* c, int ms_evb, cudaGraphExec_t* out) {
     }
     g.launches = (int)(c->n_launch - l0);
     c->n_launch = l0;
-    g.s_hint = hint; g.n_clusters_bound = c->n_clusters_bound;
+    g.s_bound = bound; g.n_clusters_bound = c->n_clusters_bound;
+    { static const bool dbg = getenv("RPB_DEBUG_GRAPH") != nullptr; if (dbg) fprintf(stderr, "[rpbmd] step graph captured: %d kernel launches, diabat bound %d (count %d)\n", g.launches, bound, hint); }
   }
   *out = g.exec;
+  *launches = g.launches;
   return 0;
 }
 
@@ -716,14 +734,14 @@ static int enqueue_steps(rpb_ctx* c, int n_steps, int ms_evb) {
   int s = 0;
   if (graph_allowed(c, ms_evb) && !c->rebuild_forced && n_steps > 0) {
     cudaGraphExec_t exec = nullptr;
-    int rc = graph_get(c, ms_evb, &exec);
+    int launches = 0;
+    int rc = graph_get(c, ms_evb, &exec, &launches);
     if (rc) return rc;
     if (exec) {
-      const StepGraph& g = c->graph[ms_evb ? 1 : 0];
       c->image_valid = false; c->ke_valid = false;
       for (; s < n_steps; s++) {
         CK(cudaGraphLaunch(exec, c->main_stream));
-        c->n_launch += g.launches;
+        c->n_launch += launches;
       }
     }
   }

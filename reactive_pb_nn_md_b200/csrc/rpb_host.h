@@ -29,7 +29,7 @@ struct PeerExchange {
 };
 
 // one MD step captured as a CUDA graph (rpb_api.cu)
-struct StepGraph { cudaGraphExec_t exec = nullptr; int launches = 0; int s_hint = 0; int n_clusters_bound = 0; };
+struct StepGraph { cudaGraphExec_t exec = nullptr; int launches = 0; int s_bound = 0; int n_clusters_bound = 0; };
 
 struct rpb_ctx {
   rpb_config cfg;
@@ -39,7 +39,7 @@ struct rpb_ctx {
   cudaStream_t stream = nullptr;        // stream the launchers use (normally the main stream; see StreamScope)
   cudaStream_t main_stream = nullptr;   // the library's main stream: host synchronisation and timing happen here
   cudaStream_t aux[5] = {};   // side streams for the independent branches of a force evaluation; MS-EVB: [2] bonded terms of the principal diabat, [3] read-backs, [4] per-diabat real-space deltas
-  cudaEvent_t ev_sync[20] = {};   // fork / join points
+  cudaEvent_t ev_sync[24] = {};   // fork / join points
   cudaEvent_t ev_enum = nullptr;        // enumeration results have reached pinned host memory
   Dev d;                       // device pointer table (host copy, passed by value to kernels)
   std::vector<void*> allocs;   // everything cudaMalloc'ed (freed in rpb_destroy)
@@ -64,6 +64,7 @@ struct rpb_ctx {
   void* evb_scratch = nullptr; // EvbScratch (kernels_evb.cu): device scratch of the MS-EVB build, owned by this context
   bool evb_overlap_solver = false;    // the branches of evb_build were joined on aux[0] (not on the main stream): evb_mix runs the solver there
   bool evb_assemble_pending = false;  // evb_build left the Hamiltonian assembly to the solver kernel
+  int evb_s_bound_fixed = 0;          // while a step graph is captured: the diabat-count bound its grids are sized for (0: from the last count)
   bool evb_join_pending = false;      // evb_commit queued its read-back copies on aux[3]; the main stream has not joined them yet
   bool evb_any_multi_basic = false;   // some molecule type has more than one atom that can be protonated (reference re-ordering quirk possible)
   bool mirror_stale = false;          // a committed hop changed the molecule table on the device: the host mirror is refreshed before use
@@ -84,7 +85,7 @@ struct rpb_ctx {
   int download_streak = 0;     // > 1: the caller downloads the full state after every call
   bool ke_valid = false;       // last_en.kinetic_energy belongs to the current velocities (computed by the step's last kernel)
   bool serial_streams = false;
-  StepGraph graph[2];          // [0] non-reactive step, [1] MS-EVB step
+  StepGraph graph[4];          // [0] non-reactive step, [1..3] MS-EVB step with grids sized for <= 32 / 56 / evb_max_states diabats
   bool graph_failed = false;   // stream capture of a step did not work on this context: plain launches
   bool state_cache_valid = false;   // the staging area mirrors the per-atom / per-molecule tables on the device
   // measurement

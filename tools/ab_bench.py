@@ -43,6 +43,9 @@ for r in range(rounds):
         torch.cuda.synchronize()
         t = np.array([a.elapsed_time(b) for a, b in evs])
         res[k].append((float(np.median(t)), float(t.mean())))
+        if os.environ.get("AB_SHOW_OUTLIERS"):
+            big = np.argsort(-t)[:8]
+            print("AB"[k], "round", r, "slowest steps:", ["%d:%.3f" % (i, t[i]) for i in sorted(big)], " p10 %.4f p90 %.4f" % (np.percentile(t, 10), np.percentile(t, 90)))
 for k in range(2):
     print("AB"[k], sys.argv[1 + k], " median ms/step per round:", ["%.4f" % m for m, _ in res[k]], " mean:", ["%.4f" % a for _, a in res[k]],
           " S=%s" % (sims[k].evb()["n_states"] if evb else 1))
