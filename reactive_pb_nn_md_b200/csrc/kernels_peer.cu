@@ -27,7 +27,8 @@ struct PeerArgs {
   const unsigned long long* my_flags;         // [kind][0..world) in the local arena
   double* out;
   int* err_flag;
-  unsigned long long seq;
+  unsigned long long* seq_ptr;                // device-side sequence number of this kind's LAST collective: a captured step graph replays with fresh numbers
+  unsigned int* done;                         // blocks of this launch that have finished (the last one publishes the new number)
   int n;                                      // number of doubles
   int world;
 };
@@ -57,16 +58,17 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 }
 
 __global__ void __launch_bounds__(256) k_peer_allreduce(PeerArgs a) {
+  const unsigned long long seq = *a.seq_ptr + 1ull;   // (updated by the last block of the previous collective of this kind)
   // (1) announce: everything the earlier kernels of this stream wrote into the local arena is complete
   if (blockIdx.x == 0 && threadIdx.x < a.world) {
     __threadfence_system();
-    st_release_sys(a.flag_at[threadIdx.x], a.seq);
+    st_release_sys(a.flag_at[threadIdx.x], seq);
   }
   // (2) wait for every rank's partial #seq
   if (threadIdx.x == 0) {
     const unsigned long long t0 = global_timer_ns();
     for (int r = 0; r < a.world; r++)
-      while (ld_acquire_sys(&a.my_flags[r]) < a.seq) {
+      while (ld_acquire_sys(&a.my_flags[r]) < seq) {
         if (global_timer_ns() - t0 > PEER_TIMEOUT_NS) { atomicMax(&a.err_flag[3], 30 + r); break; }
         __nanosleep(64);
       }
@@ -86,6 +88,12 @@ __global__ void __launch_bounds__(256) k_peer_allreduce(PeerArgs a) {
       s.x += v.x; s.y += v.y;
     }
     reinterpret_cast<double2*>(a.out)[i] = s;
+  }
+  // the last block to finish (every block has read the old number by then) publishes the new sequence number
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(a.done, 1u) == gridDim.x - 1) { *a.seq_ptr = seq; *a.done = 0u; __threadfence(); }
   }
 }
 
@@ -113,6 +121,8 @@ static int peer_alloc(rpb_ctx* c) {
   if (e != cudaSuccess) { c->err = std::string("peer arena cudaMalloc: ") + cudaGetErrorString(e); return RPB_ERR_CUDA; }
   e = cudaMemset(p.arena, 0, p.arena_doubles * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc((void**)&p.h_total, p.n[PEER_H] * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p.seq_dev, 4 * sizeof(unsigned long long));     // [2] numbers, [2] block counters
+  if (e == cudaSuccess) e = cudaMemset(p.seq_dev, 0, 4 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { c->err = std::string("peer arena init: ") + cudaGetErrorString(e); return RPB_ERR_CUDA; }
   p.h_local = c->e.h_diag; p.f_local = c->e.f_mix;
@@ -124,6 +134,7 @@ static int peer_enable(rpb_ctx* c, int world) {
   p.world = world;
   p.peer[c->d.rank] = p.arena;
   p.seq[PEER_H] = p.seq[PEER_F] = 0;
+  cudaMemset(p.seq_dev, 0, 4 * sizeof(unsigned long long));
   p.on = true;
   return 0;
 }
@@ -134,13 +145,14 @@ void peer_free(rpb_ctx* c) {
     if (p.opened[r] && p.peer[r]) { cudaIpcCloseMemHandle(p.peer[r]); p.peer[r] = nullptr; p.opened[r] = false; }
   if (p.arena) { cudaFree(p.arena); p.arena = nullptr; }
   if (p.h_total) { cudaFree(p.h_total); p.h_total = nullptr; }
+  if (p.seq_dev) { cudaFree(p.seq_dev); p.seq_dev = nullptr; }
   p.on = false;
 }
 
 // Called before the phase that produces partial `kind`: the producers write into this step's parity of the arena.
 void peer_begin(rpb_ctx* c, int kind) {
   PeerExchange& p = c->peer;
-  p.seq[kind]++;
+  p.seq[kind]++;                                                  // host mirror of the device-side number: selects the parity
   double* part = p.arena + p.off[kind] + (size_t)(p.seq[kind] & 1) * p.n[kind];
   if (kind == PEER_H) c->e.h_diag = part; else c->e.f_mix = part;
 }
@@ -159,7 +171,8 @@ int peer_allreduce(rpb_ctx* c, int kind) {
   a.my_flags = reinterpret_cast<const unsigned long long*>(p.arena + p.off_flags) + kind * RPB_MAX_RANKS;
   a.out = (kind == PEER_H) ? p.h_total : c->d.force;
   a.err_flag = c->d.err_flag;
-  a.seq = (unsigned long long)p.seq[kind];
+  a.seq_ptr = p.seq_dev + kind;
+  a.done = reinterpret_cast<unsigned int*>(p.seq_dev + 2 + kind);
   a.n = p.n_act[kind];
   a.world = p.world;
   const int blocks = std::max(1, std::min((a.n / 2 + 255) / 256, 148 * 2));

@@ -303,7 +303,7 @@ void rpb_destroy(rpb_ctx* c) {
   for (void* p : c->allocs) cudaFree(p);
   if (c->h_en) cudaFreeHost(c->h_en);
   if (c->h_flags) cudaFreeHost(c->h_flags);
-  for (int k = 0; k < 4; k++) if (c->graph[k].exec) cudaGraphExecDestroy(c->graph[k].exec);
+  for (int k = 0; k < 8; k++) if (c->graph[k].exec) cudaGraphExecDestroy(c->graph[k].exec);
   if (c->staging) cudaFreeHost(c->staging);
   for (int k = 0; k < 2; k++) { if (c->staging_up[k]) cudaFreeHost(c->staging_up[k]); if (c->ev_up[k]) cudaEventDestroy(c->ev_up[k]); }
   if (c->eh.pinned) cudaFreeHost(c->eh.pinned);
@@ -673,10 +673,10 @@ int rpb_evb_exchange_f(rpb_ctx* c, void** ptr, int* n) { *ptr = c->e.f_mix; *n =
 // (the peer exchange alternates its buffers from step to step) or when RPB_GRAPH=0.
 static bool graph_allowed(rpb_ctx* c, int ms_evb) {
   static const bool off = getenv("RPB_GRAPH") && atoi(getenv("RPB_GRAPH")) == 0;
-  return !off && !c->timers_on && !c->serial_streams && !(ms_evb && c->d.world > 1) && !c->graph_failed;
+  return !off && !c->timers_on && !c->serial_streams && !(ms_evb && c->d.world > 1 && !c->peer.on) && !c->graph_failed;
 }
 
-static int graph_get(rpb_ctx* c, int ms_evb, cudaGraphExec_t* out, int* launches, int force_slot = 0) {
+static int graph_get(rpb_ctx* c, int ms_evb, cudaGraphExec_t* out, int* launches, int force_slot = 0, int force_parity = -1) {
   // The grids of the MS-EVB kernels are sized for a bound of the diabat count (the kernels loop over the device-side count,
   // so a generous bound only costs idle CTAs).  The count of a trajectory wanders (20 ... 60 within 150 steps of the
   // benchmark system) and a capture costs ~1.2 ms of host time, so up to three graphs -- bounds 32, 56, evb_max_states --
@@ -685,15 +685,20 @@ static int graph_get(rpb_ctx* c, int ms_evb, cudaGraphExec_t* out, int* launches
   const int hint = ms_evb ? c->eh.s_hint : 0;
   int slot = 0;
   if (ms_evb) { slot = 1; while (slot < 3 && hint + 6 > bounds[slot - 1]) slot++; }
-  if (force_slot) slot = force_slot;
+  // state-sharded step: the producers of the exchanged partials write into the arena parity of the step's sequence number
+  // (pointers baked into the launches), so there is one graph per parity and the steps alternate between them
+  const bool sharded = ms_evb && c->d.world > 1;
+  int parity = sharded ? (int)((c->peer.seq[PEER_H] + 1) & 1) : 0;
+  if (force_slot) { slot = force_slot; parity = force_parity; }
   else if (ms_evb)
-    for (int k = 1; k <= 3; k++)             // (all three at once: no capture inside a later timed region)
-      if (k != slot && (!c->graph[k].exec || c->graph[k].n_clusters_bound != c->n_clusters_bound) && !c->graph_failed) {
-        cudaGraphExec_t dummy; int nl;
-        int rc = graph_get(c, ms_evb, &dummy, &nl, k);
-        if (rc) return rc;
-      }
-  StepGraph& g = c->graph[slot];
+    for (int k = 1; k <= 3; k++)             // (all at once: no capture inside a later timed region)
+      for (int q = 0; q < (sharded ? 2 : 1); q++)
+        if ((k != slot || q != parity) && (!c->graph[k + 4 * q].exec || c->graph[k + 4 * q].n_clusters_bound != c->n_clusters_bound) && !c->graph_failed) {
+          cudaGraphExec_t dummy; int nl;
+          int rc = graph_get(c, ms_evb, &dummy, &nl, k, q);
+          if (rc) return rc;
+        }
+  StepGraph& g = c->graph[slot + 4 * parity];
   if (g.exec && g.n_clusters_bound != c->n_clusters_bound) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
   if (!g.exec) {
     const long long l0 = c->n_launch;
@@ -702,9 +707,12 @@ static int graph_get(rpb_ctx* c, int ms_evb, cudaGraphExec_t* out, int* launches
     int rc = 0;
     const int bound = ms_evb ? std::min(RPB_MAXS, bounds[slot - 1]) : 0;
     if (e == cudaSuccess) {
+      const long long seq_h = c->peer.seq[PEER_H], seq_f = c->peer.seq[PEER_F];
+      if (sharded) c->peer.seq[PEER_H] = c->peer.seq[PEER_F] = parity ? 0 : 1;   // the captured step's numbers get this parity
       c->evb_s_bound_fixed = bound;
       rc = enqueue_step(c, ms_evb);
       c->evb_s_bound_fixed = 0;
+      c->peer.seq[PEER_H] = seq_h; c->peer.seq[PEER_F] = seq_f;                   // (nothing ran: the device-side numbers did not move)
       e = cudaStreamEndCapture(c->main_stream, &graph);
     }
     if (e == cudaSuccess && rc == 0) e = cudaGraphInstantiate(&g.exec, graph, 0);
@@ -733,16 +741,16 @@ static int graph_get(rpb_ctx* c, int ms_evb, cudaGraphExec_t* out, int* launches
 static int enqueue_steps(rpb_ctx* c, int n_steps, int ms_evb) {
   int s = 0;
   if (graph_allowed(c, ms_evb) && !c->rebuild_forced && n_steps > 0) {
-    cudaGraphExec_t exec = nullptr;
-    int launches = 0;
-    int rc = graph_get(c, ms_evb, &exec, &launches);
-    if (rc) return rc;
-    if (exec) {
-      c->image_valid = false; c->ke_valid = false;
-      for (; s < n_steps; s++) {
-        CK(cudaGraphLaunch(exec, c->main_stream));
-        c->n_launch += launches;
-      }
+    c->image_valid = false; c->ke_valid = false;
+    for (; s < n_steps; s++) {
+      cudaGraphExec_t exec = nullptr;
+      int launches = 0;
+      int rc = graph_get(c, ms_evb, &exec, &launches);     // (sharded steps alternate between the two parities' graphs)
+      if (rc) return rc;
+      if (!exec) break;
+      CK(cudaGraphLaunch(exec, c->main_stream));
+      c->n_launch += launches;
+      if (ms_evb && c->d.world > 1) { c->peer.seq[PEER_H]++; c->peer.seq[PEER_F]++; }
     }
   }
   for (; s < n_steps; s++) {

@@ -22,7 +22,8 @@ struct PeerExchange {
   bool opened[RPB_MAX_RANKS] = {};         // mapped with cudaIpcOpenMemHandle (closed in peer_free)
   double* h_total = nullptr;               // all-reduced Hamiltonian block
   double* h_local = nullptr; double* f_local = nullptr;   // the library's own (non-arena) exchange buffers
-  long long seq[2] = {0, 0};               // collectives issued per kind
+  long long seq[2] = {0, 0};               // collectives issued per kind (host mirror of seq_dev: selects the arena parity)
+  unsigned long long* seq_dev = nullptr;   // device-side sequence numbers, ticked by a kernel ahead of each collective
   bool f_reduced_in_place = false;         // the force all-reduce of this step wrote d.force directly (evb_commit skips its copy)
   size_t off_flags = 0, off[2] = {0, 0}, arena_doubles = 0;
   int n[2] = {0, 0}, n_act[2] = {0, 0};    // stride / length in doubles of one partial
@@ -85,7 +86,8 @@ struct rpb_ctx {
   int download_streak = 0;     // > 1: the caller downloads the full state after every call
   bool ke_valid = false;       // last_en.kinetic_energy belongs to the current velocities (computed by the step's last kernel)
   bool serial_streams = false;
-  StepGraph graph[4];          // [0] non-reactive step, [1..3] MS-EVB step with grids sized for <= 32 / 56 / evb_max_states diabats
+  StepGraph graph[8];          // [0] non-reactive step, [1..3] MS-EVB step with grids sized for <= 32 / 56 / evb_max_states diabats;
+                               // [4 + k]: the same for the odd arena parity of a state-sharded step (kernels_peer.cu)
   bool graph_failed = false;   // stream capture of a step did not work on this context: plain launches
   bool state_cache_valid = false;   // the staging area mirrors the per-atom / per-molecule tables on the device
   // measurement

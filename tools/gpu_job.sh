@@ -1,5 +1,6 @@
-(RPB_DEBUG_GRAPH=1 python tools/diag_hop_graph.py 150) > gpurun_out/r02_hop_graph3.log 2>&1; cat gpurun_out/r02_hop_graph3.log
-python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-python bench.py --steps 20 --warmup 5 --no-extra 2>/dev/null | python -c "
-import sys, json
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('c3', round(d['value'],1), 'ms', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value'],1), 'pair us', round(d['roofline']['us_per_launch'],1), 'frac', round(d['roofline']['frac'],4))"
+python -m pytest tests/test_gpu_full_size.py tests/test_gpu_evb_cases.py -m gpu -q -x -k "real_peers or peer_memory" 2>&1 | tail -6 > gpurun_out/r02_gputest_2gpu_v2.log; cat gpurun_out/r02_gputest_2gpu_v2.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 5 2>gpurun_out/bench2_err.log > gpurun_out/r02_bench_c3_n2_v2.json; tail -3 gpurun_out/bench2_err.log
+python -c "
+import json; d=json.loads(open('gpurun_out/r02_bench_c3_n2_v2.json').read().strip().splitlines()[-1]); print('c3 n2', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['config']['n_states'], d['config']['exchange'])
+for k,v in d['other_workloads'].items(): print(k, v['value'], v.get('ms_per_step'), v.get('concurrency_gain'))
+"
