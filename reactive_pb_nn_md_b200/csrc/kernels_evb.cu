@@ -703,6 +703,9 @@ __device__ inline double repulsion_with_atom(const Dev& d, const ItemShared& sh,
 }
 
 #define ITEM_TPB 256
+#ifndef ITEM_MINB
+#define ITEM_MINB 3            // CTAs per SM the item kernel is compiled for (registers <= 85)
+#endif
 #define CAND_CAP 2048        // atoms inside the candidate radius of one chain atom (~420 at 10 A in water)
 #define CAND_SLOTS RPB_CAND_SLOTS
 
@@ -742,7 +745,7 @@ __global__ void __launch_bounds__(256) k_evb_candidates(Dev d, EvbDev e, double 
   }
 }
 
-#define ITEM_SPLIT 8          // CTAs per item (the candidate chunks of an item are dealt round-robin to 8 x 8 warps)
+#define ITEM_SPLIT 7          // task CTAs per item (the candidate chunks of an item are dealt round-robin to 7 x 8 warps)
 struct ItemBlock {
   ItemShared sh;
   int d_ci[MA], a_ci[MA], h_ci[MA];       // position of every image atom in sh.chain_atoms
@@ -774,7 +777,7 @@ __device__ __forceinline__ bool item_describe(const Dev& d, const EvbDev& e, int
   return true;
 }
 
-__global__ void __launch_bounds__(ITEM_TPB) k_evb_items(Dev d, EvbDev e, const int* __restrict__ chain_slot,
+__global__ void __launch_bounds__(ITEM_TPB, ITEM_MINB) k_evb_items(Dev d, EvbDev e, const int* __restrict__ chain_slot,
                                                         const int* __restrict__ cand, const int* __restrict__ cand_n,
                                                         double rcand, double rep_reach) {
   __shared__ ItemBlock B;

@@ -382,7 +382,7 @@ void launch_pair_verlet(rpb_ctx* c, bool shard) {
     case 7: launch_pair_variant<256, 1>(c, shard); break;
     // MS-EVB evaluations (shard == true): the Hamiltonian chain on the side streams bounds the step, and its short kernels
     // need CTA slots while the pair kernel runs -- three quarters of a wave
-    default: launch_pair_variant<128, 3>(c, shard, shard ? 3 : 4); break;
+    default: launch_pair_variant<128, 3>(c, shard, (shard && !c->throughput_mode) ? 3 : 4); break;
   }
   c->n_launch += 1;
 }

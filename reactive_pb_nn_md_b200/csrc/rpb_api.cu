@@ -693,13 +693,13 @@ static int graph_get(rpb_ctx* c, int ms_evb, cudaGraphExec_t* out, int* launches
   else if (ms_evb)
     for (int k = 1; k <= 3; k++)             // (all at once: no capture inside a later timed region)
       for (int q = 0; q < (sharded ? 2 : 1); q++)
-        if ((k != slot || q != parity) && (!c->graph[k + 4 * q].exec || c->graph[k + 4 * q].n_clusters_bound != c->n_clusters_bound) && !c->graph_failed) {
+        if ((k != slot || q != parity) && (!c->graph[k + 4 * q].exec || c->graph[k + 4 * q].n_clusters_bound != c->n_clusters_bound || c->graph[k + 4 * q].throughput_mode != c->throughput_mode) && !c->graph_failed) {
           cudaGraphExec_t dummy; int nl;
           int rc = graph_get(c, ms_evb, &dummy, &nl, k, q);
           if (rc) return rc;
         }
   StepGraph& g = c->graph[slot + 4 * parity];
-  if (g.exec && g.n_clusters_bound != c->n_clusters_bound) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+  if (g.exec && (g.n_clusters_bound != c->n_clusters_bound || g.throughput_mode != c->throughput_mode)) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
   if (!g.exec) {
     const long long l0 = c->n_launch;
     cudaGraph_t graph = nullptr;
@@ -730,7 +730,7 @@ static int graph_get(rpb_ctx* c, int ms_evb, cudaGraphExec_t* out, int* launches
     }
     g.launches = (int)(c->n_launch - l0);
     c->n_launch = l0;
-    g.s_bound = bound; g.n_clusters_bound = c->n_clusters_bound;
+    g.s_bound = bound; g.n_clusters_bound = c->n_clusters_bound; g.throughput_mode = c->throughput_mode;
     { static const bool dbg = getenv("RPB_DEBUG_GRAPH") != nullptr; if (dbg) fprintf(stderr, "[rpbmd] step graph captured: %d kernel launches, diabat bound %d (count %d)\n", g.launches, bound, hint); }
   }
   *out = g.exec;
@@ -760,7 +760,12 @@ static int enqueue_steps(rpb_ctx* c, int n_steps, int ms_evb) {
   return 0;
 }
 
+static int step_impl(rpb_ctx* c, int n_steps, int ms_evb);
 int rpb_step(rpb_ctx* c, int n_steps, int ms_evb) {
+  if (c) c->throughput_mode = false;
+  return step_impl(c, n_steps, ms_evb);
+}
+static int step_impl(rpb_ctx* c, int n_steps, int ms_evb) {
   if (!c->initialized) { c->err = "rpb_initialize not called"; return RPB_ERR_STATE; }
   if (ms_evb && c->d.world > 1 && !c->peer.on) { c->err = "world_size>1: set up the peer-memory exchange (rpb_peer_*) or use the phase calls"; return RPB_ERR_STATE; }
   int rc = enqueue_steps(c, n_steps, ms_evb);
@@ -791,6 +796,7 @@ int rpb_ensemble_step(rpb_ctx** replicas, int n_replicas, int n_steps, int ms_ev
   for (int r = 0; r < n_replicas; r++) {
     rpb_ctx* c = replicas[r];
     if (!c->initialized) { c->err = "rpb_initialize not called"; return RPB_ERR_STATE; }
+    c->throughput_mode = n_replicas > 1;
     one_thread = one_thread && c->cfg.device == replicas[0]->cfg.device && graph_allowed(c, ms_evb) && !c->rebuild_forced;
   }
   if (one_thread) {
@@ -808,7 +814,7 @@ int rpb_ensemble_step(rpb_ctx** replicas, int n_replicas, int n_steps, int ms_ev
     th.emplace_back([&, r]() {
       rpb_ctx* c = replicas[r];
       if (cudaSetDevice(c->cfg.device) != cudaSuccess) { c->err = "cudaSetDevice failed"; rc[r] = RPB_ERR_CUDA; return; }   // the current device is per host thread
-      rc[r] = rpb_step(c, n_steps, ms_evb);
+      rc[r] = step_impl(c, n_steps, ms_evb);
     });
   for (auto& t : th) t.join();
   for (int r = 0; r < n_replicas; r++) if (rc[r]) return rc[r];

@@ -30,7 +30,7 @@ struct PeerExchange {
 };
 
 // one MD step captured as a CUDA graph (rpb_api.cu)
-struct StepGraph { cudaGraphExec_t exec = nullptr; int launches = 0; int s_bound = 0; int n_clusters_bound = 0; };
+struct StepGraph { cudaGraphExec_t exec = nullptr; int launches = 0; int s_bound = 0; int n_clusters_bound = 0; bool throughput_mode = false; };
 
 struct rpb_ctx {
   rpb_config cfg;
@@ -65,6 +65,7 @@ struct rpb_ctx {
   void* evb_scratch = nullptr; // EvbScratch (kernels_evb.cu): device scratch of the MS-EVB build, owned by this context
   bool evb_overlap_solver = false;    // the branches of evb_build were joined on aux[0] (not on the main stream): evb_mix runs the solver there
   bool evb_assemble_pending = false;  // evb_build left the Hamiltonian assembly to the solver kernel
+  bool throughput_mode = false;       // replica ensembles (rpb_ensemble_step): other replicas fill the SMs, so the pair kernel takes a full wave
   int evb_s_bound_fixed = 0;          // while a step graph is captured: the diabat-count bound its grids are sized for (0: from the last count)
   bool evb_join_pending = false;      // evb_commit queued its read-back copies on aux[3]; the main stream has not joined them yet
   bool evb_any_multi_basic = false;   // some molecule type has more than one atom that can be protonated (reference re-ordering quirk possible)

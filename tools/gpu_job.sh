@@ -1,6 +1,12 @@
-python -m pytest tests/test_gpu_full_size.py tests/test_gpu_evb_cases.py -m gpu -q -x -k "real_peers or peer_memory" 2>&1 | tail -6 > gpurun_out/r02_gputest_2gpu_v2.log; cat gpurun_out/r02_gputest_2gpu_v2.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 5 2>gpurun_out/bench2_err.log > gpurun_out/r02_bench_c3_n2_v2.json; tail -3 gpurun_out/bench2_err.log
-python -c "
-import json; d=json.loads(open('gpurun_out/r02_bench_c3_n2_v2.json').read().strip().splitlines()[-1]); print('c3 n2', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['config']['n_states'], d['config']['exchange'])
-for k,v in d['other_workloads'].items(): print(k, v['value'], v.get('ms_per_step'), v.get('concurrency_gain'))
-"
+cat > /tmp/few.py <<'PY'
+import sys, os
+sys.path.insert(0, os.getcwd())
+import bench
+from reactive_pb_nn_md_b200 import engine
+from reactive_pb_nn_md_b200._binding import load_cuda
+s = bench.build_system("c3")
+sim = engine.Simulation(s, bench.params_for("c3"), library=load_cuda())
+sim.ms_evb_calculate_total_force_energy()
+sim.md_integrate_atomic(6, ms_evb=True)
+PY
+ncu --metrics gpu__time_duration.sum,sm__cycles_active.avg,sm__cycles_elapsed.max,launch__grid_size,launch__block_size,launch__registers_per_thread --clock-control none --launch-skip 200 -c 60 --csv --log-file gpurun_out/r02_smtime.csv python /tmp/few.py > gpurun_out/r02_smtime.log 2>&1; tail -2 gpurun_out/r02_smtime.log
