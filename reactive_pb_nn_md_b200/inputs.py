@@ -5,6 +5,10 @@ Formats follow the reference's own read / write statements:
   read_gro                      src/general_routines.f90:215-313   '(I5,2A5,I5,3F8.3)', nm -> Angstrom, 3- or 9-number box line
   read_simulation_parameters    src/read_simulation_parameters.f90:46-146 (list-directed "name value" pairs in two blocks)
   write_gro_frame / write_log   src/general_routines.f90:870-945    (print_step, print_gro_file)
+  write_velocity_checkpoint     src/general_routines.f90:997-1026   (print_velocities_checkpoint, '(I5,2A5,I5,3F14.6)')
+  check_restart_trajectory      src/general_routines.f90:37-115     (restart iff trajectory, log and velocity files exist
+                                                                     and end at the same step > 0)
+  last_gro_frame / read_velocity_restart_checkpoint   src/general_routines.f90:120-178
 
 Input parsing only -- no force-path arithmetic lives here.
 """
@@ -130,3 +134,68 @@ def write_log_step(fh, i_step, time_ps, energies, ms_evb):
         fh.write(" Electrostatic ,   VDWs ,   Bond   ,   Angle  ,  Dihedral\n")
         fh.write("%16.6E%16.6E%16.6E%16.6E%16.6E\n" % tuple(energies[k] for k in ("E_elec", "E_vdw", "E_bond", "E_angle", "E_dihedral")))
     fh.write(" ------------------------------\n")
+
+
+def write_velocity_checkpoint(fh, i_step, ff, state, atom_names=None):
+    """print_velocities_checkpoint (general_routines.f90:997-1026): a ' step <i>' heading, then one
+    '(I5,2A5,I5,3F14.6)' record per atom -- molecule index, molecule name, atom name, atom index WITHIN the molecule
+    (the trajectory file counts atoms globally, this file does not), velocity in Angstrom/ps."""
+    fh.write(" step  %11d\n" % i_step)
+    for m, (f, na, t) in enumerate(zip(state["mol_first_atom"], state["mol_n_atom"], state["mol_type"])):
+        mt = ff.molecule_types[t - 1]
+        for a in range(na):
+            g = f - 1 + a
+            aname = atom_names[g] if atom_names is not None else ff.atype_name[state["atom_type"][g] - 1]
+            v = state["velocity"][g]
+            fh.write("%5d%-5s%5s%5d%14.6f%14.6f%14.6f\n" % ((m + 1) % 100000, mt.name[:5], aname[:5], (a + 1) % 100000, v[0], v[1], v[2]))
+
+
+def _step_headings(text):
+    """(line number, step) of every heading line whose first token is 'step' (read_file_find_heading + parse)"""
+    out = []
+    for k, ln in enumerate(text.splitlines()):
+        tok = ln.split()
+        if tok and tok[0] == "step":
+            out.append((k, int(tok[1])))
+    return out
+
+
+def check_restart_trajectory(traj_path, log_path, velocity_path):
+    """-> n_old_trajectory (0: a new run).  The reference restarts iff all three files exist (general_routines.f90:48-52);
+    the last step of the trajectory and of the velocity checkpoint must then be the same positive number, anything else is
+    its 'error restarting trajectory' stop (:86-97)."""
+    import os
+    if not (os.path.exists(traj_path) and os.path.exists(log_path) and os.path.exists(velocity_path)):
+        return 0
+    traj = _step_headings(open(traj_path).read())
+    vel = _step_headings(open(velocity_path).read())
+    i_traj = traj[-1][1] if traj else 0
+    i_vel = vel[-1][1] if vel else 0
+    if i_traj != i_vel or i_vel <= 0:
+        raise ValueError("error restarting trajectory.  last step is not the same in the trajectory output and velocity checkpointing files")
+    return i_traj
+
+
+def last_gro_frame(traj_text, n_old_trajectory):
+    """scan_grofile_restart (general_routines.f90:120-143): the text of the frame of step n_old_trajectory, headed by its
+    'step' line like a .gro title line (read_gro then reads it like the input configuration -- positions as printed,
+    F8.3 nm: a restart is lossy to 1e-3 nm, in the reference too)."""
+    lines = traj_text.splitlines()
+    for k, step in _step_headings(traj_text):
+        if step == n_old_trajectory:
+            n = int(lines[k + 1].split()[0])
+            return "\n".join(lines[k:k + n + 3]) + "\n"
+    raise ValueError("step %d not found in the trajectory file" % n_old_trajectory)
+
+
+def read_velocity_restart_checkpoint(velocity_text, n_old_trajectory, n_atoms):
+    """read_velocity_restart_checkpoint (general_routines.f90:148-178): the block of step n_old_trajectory -> [N,3]"""
+    lines = velocity_text.splitlines()
+    for k, step in _step_headings(velocity_text):
+        if step == n_old_trajectory:
+            v = np.zeros((n_atoms, 3))
+            for i in range(n_atoms):
+                ln = lines[k + 1 + i]
+                v[i] = [float(ln[20:34]), float(ln[34:48]), float(ln[48:62])]
+            return v
+    raise ValueError("step %d not found in the velocity checkpoint file" % n_old_trajectory)

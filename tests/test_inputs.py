@@ -78,3 +78,76 @@ def test_driver_runs_a_reference_deck_on_the_oracle(tmp_path, oracle_lib):
     assert frames == 3
     names, _, xyz, box, _ = inputs.read_gro((tmp_path / "traj.gro").read_text())     # first frame parses back
     assert names[0] == "h3o" and len(xyz) == s.n_atoms
+
+
+def _deck(tmp_path, s, simpmt):
+    data = os.path.join(ROOT, "reactive_pb_nn_md_b200", "data")
+    (tmp_path / "conf.gro").write_text(_gro_text(s))
+    (tmp_path / "sim.pmt").write_text(simpmt)
+    return [str(tmp_path / "conf.gro"), os.path.join(data, "CH3SO3H.pmt"), os.path.join(data, "CH3SO3H_H2O.top"),
+            str(tmp_path / "sim.pmt"), str(tmp_path / "traj.gro"), str(tmp_path / "md.log")]
+
+
+def test_velocity_checkpoint_format_round_trip():
+    """print_velocities_checkpoint / read_velocity_restart_checkpoint (general_routines.f90:148-178, 997-1026)"""
+    s = system.build_water_box(10, with_hydronium=True)
+    rng = np.random.default_rng(3)
+    v = rng.normal(size=(s.n_atoms, 3)) * 5.0
+    st = dict(xyz=s.xyz, velocity=v, mol_first_atom=s.mol_first_atom, mol_n_atom=s.mol_n_atom, mol_type=s.mol_type, atom_type=s.atom_type)
+    buf = io.StringIO()
+    inputs.write_velocity_checkpoint(buf, 2, s.ff, st)
+    inputs.write_velocity_checkpoint(buf, 4, s.ff, dict(st, velocity=2.0 * v))
+    text = buf.getvalue()
+    lines = text.splitlines()
+    assert lines[0].split() == ["step", "2"] and len(lines) == 2 * (s.n_atoms + 1)
+    assert len(lines[1]) == 5 + 5 + 5 + 5 + 3 * 14 and lines[1][5:10].strip() == "h3o"
+    assert [int(lines[1 + a][15:20]) for a in range(5)] == [1, 2, 3, 4, 1]            # atom index WITHIN the molecule
+    assert np.abs(inputs.read_velocity_restart_checkpoint(text, 2, s.n_atoms) - v).max() <= 0.5e-6
+    assert np.abs(inputs.read_velocity_restart_checkpoint(text, 4, s.n_atoms) - 2.0 * v).max() <= 0.5e-6
+    with pytest.raises(ValueError):
+        inputs.read_velocity_restart_checkpoint(text, 3, s.n_atoms)
+
+
+def test_restart_detection_rules(tmp_path):
+    """check_restart_trajectory (general_routines.f90:37-115)"""
+    t, l, v = (str(tmp_path / n) for n in ("traj.gro", "md.log", "velocity_checkpoint"))
+    assert inputs.check_restart_trajectory(t, l, v) == 0
+    open(t, "w").write(" step  0 time(ps) 0.0\n 1\n    1h2o     Ow    1   0.000   0.000   0.000\n 1 1 1 0 0 0 0 0 0\n step  4 time(ps) 0.002\n 1\n    1h2o     Ow    1   0.000   0.000   0.000\n 1 1 1 0 0 0 0 0 0\n")
+    open(l, "w").write("log\n")
+    assert inputs.check_restart_trajectory(t, l, v) == 0                 # no velocity file: a new run
+    open(v, "w").write(" step  2\n    1h2o     Ow    1      0.000000      0.000000      0.000000\n")
+    with pytest.raises(ValueError):
+        inputs.check_restart_trajectory(t, l, v)                         # last steps differ: the reference stops
+    open(v, "a").write(" step  4\n    1h2o     Ow    1      1.000000      0.000000      0.000000\n")
+    assert inputs.check_restart_trajectory(t, l, v) == 4
+    assert inputs.last_gro_frame(open(t).read(), 4).splitlines()[0].split()[1] == "4"
+
+
+def test_driver_checkpoints_and_restarts(tmp_path, oracle_lib):
+    """N3: a run of 4 steps that is continued to 8 appends to its files, carries the step numbers on, and follows the
+    uninterrupted 8-step run up to the precision the restart files hold (positions F8.3 nm, velocities F14.6 A/ps)."""
+    s = system.build_water_box(10, with_hydronium=True)
+    base = SIMPMT.replace("n_exclusions        3\n", "n_exclusions        3\ncheckpoint_velocity 2\n")
+    a = tmp_path / "a"; b = tmp_path / "b"
+    a.mkdir(); b.mkdir()
+    lib = ["--library", oracle_lib.path, "--seed", "7"]
+    assert run.main(_deck(a, s, base) + lib) == 0                                      # steps 0..4
+    vel = (a / "velocity_checkpoint").read_text()
+    assert [st for _, st in inputs._step_headings(vel)] == [2, 4]
+    assert run.main(_deck(a, s, base.replace("n_step              4", "n_step              8")) + lib) == 0   # continues 5..8
+    steps = [st for _, st in inputs._step_headings((a / "traj.gro").read_text())]
+    assert steps == [0, 2, 4, 6, 8]
+    assert [st for _, st in inputs._step_headings((a / "velocity_checkpoint").read_text())] == [2, 4, 6, 8]
+    rows = [ln for ln in (a / "md.log").read_text().splitlines() if ln.strip() and ln.strip()[0].isdigit()]
+    assert [int(r.split()[0]) for r in rows] == [0, 2, 4, 6, 8]
+    assert run.main(_deck(b, s, base.replace("n_step              4", "n_step              8")) + lib) == 0   # uninterrupted
+    fa = inputs.read_gro(inputs.last_gro_frame((a / "traj.gro").read_text(), 8))
+    fb = inputs.read_gro(inputs.last_gro_frame((b / "traj.gro").read_text(), 8))
+    assert fa[0] == fb[0] and np.abs(fa[2] - fb[2]).max() <= 0.03                    # 1e-3 nm print precision + 4 steps of drift
+    va = inputs.read_velocity_restart_checkpoint((a / "velocity_checkpoint").read_text(), 8, s.n_atoms)
+    vb = inputs.read_velocity_restart_checkpoint((b / "velocity_checkpoint").read_text(), 8, s.n_atoms)
+    # the restart reads positions rounded to 1e-2 A: forces change by O(k * 1e-2 A), velocities by ~1 A/ps over 4 steps
+    assert np.sqrt(((va - vb) ** 2).mean()) < 0.15 * np.sqrt((vb ** 2).mean())
+    # without checkpoint_velocity in the parameters a continuation is refused (read_simulation_parameters.f90:226-236)
+    with pytest.raises(SystemExit):
+        run.main(_deck(a, s, SIMPMT.replace("n_step              4", "n_step              12")) + lib)

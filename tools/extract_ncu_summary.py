@@ -41,7 +41,7 @@ with open(out_csv, "w") as f:
         n = len(a["duration_us"])
         f.write('"' + name + '",' + str(n) + "," + ",".join("%.4g" % (sum(a[k]) / len(a[k])) if a[k] else "" for k in cols) + "\n")
 # bench.py kernel names -> CUDA kernels
-mapping = {"pair_real_space": ["k_pair_verlet"], "pme_spread": ["k_spread"], "pme_fft": ["k_fft16_fwd_xy", "k_fft16_inv_xy", "k_fft_fwd_xy", "k_fft_inv_xy"],
+mapping = {"pair_real_space": ["k_pair_verlet", "k_pair_tiles"], "pme_spread": ["k_spread"], "pme_fft": ["k_fft16_fwd_xy", "k_fft16_inv_xy", "k_fft_fwd_xy", "k_fft_inv_xy"],
            "pme_convolve": ["k_fft16_z_conv", "k_fft_z_conv", "k_conv_energy"], "evb_grid_broadcast": ["k_evb_broadcast_grid"],
            "evb_theta_mix": ["k_evb_theta_mix"], "evb_mix_forces": ["k_evb_mix_forces"], "evb_gather_mix": ["k_evb_gather_mix", "k_evb_gather_range"], "pme_gather": ["k_gather"]}
 traffic = {}
