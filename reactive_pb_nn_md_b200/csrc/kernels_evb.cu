@@ -27,6 +27,7 @@
 #include "rpb_bonded.cuh"
 #include "rpb_pme.cuh"
 #include "rpb_commit.cuh"
+#include "rpb_peer.cuh"
 
 #define MAXS RPB_MAXS
 #define MAXC RPB_MAXC
@@ -1319,14 +1320,23 @@ __device__ __forceinline__ bool tree_pivots(TreeShared& T, int S, int maxlev, in
 // defer_principal: the ground state only needs the diabats' energies RELATIVE to H_11, so the solver can run while the
 // principal diabat's pair forces are still being computed; H_11 itself, the absolute energies and the status / energy
 // slots of the read-back block are then filled in by k_evb_finalize_principal.
-__global__ void __launch_bounds__(TREE_TPB) k_evb_tree_solver(Dev d, EvbDev e, const double* coeff_override, const CouplingGeo* geo,
-                                                                int defer_principal) {
+struct PeerArgsH { PeerArgs a; int on; };     // on = 0: no exchange in the solver (single rank, or done by k_peer_allreduce)
+
+__global__ void __launch_bounds__(TREE_TPB) k_evb_tree_solver(Dev d, EvbDev e_in, const double* coeff_override, const CouplingGeo* geo,
+                                                                int defer_principal, const PeerArgsH px) {
   __shared__ TreeShared T;
+  EvbDev e = e_in;
   const int S = *e.n_states;
   const int tid = threadIdx.x, nth = blockDim.x, i = tid;
   if (geo) {
     assemble_state(d, e, geo, tid, defer_principal != 0);
     __syncthreads();     // h_diag is read back below by the same CTA
+  }
+  if (px.on) {
+    // state-sharded step: this rank's partial Hamiltonian block (just assembled into its exchange arena) is summed with the
+    // peers' over NVLink right here -- no assembly kernel, no all-reduce kernel, no launch gaps between them and the solver
+    peer_allreduce_cta(px.a);
+    e.h_diag = px.a.out;
   }
   const double h11 = defer_principal ? 0.0 : e.h_diag[0];
   if (coeff_override) {
@@ -1697,7 +1707,7 @@ __global__ void k_evb_mix_forces(Dev d, EvbDev e, int include_principal, int in_
     f = fma(e.coef2[2 * MAXS + s], e.dF[(size_t)s * n3 + i], f);
     f = fma(e.coef2[MAXS + s], e.Foff[(size_t)s * n3 + i], f);
   }
-  (in_place ? d.force : e.f_mix)[i] = f;
+  (in_place == 1 ? d.force : e.f_mix)[i] = f;     // in_place == 2 (sharded): principal force read and saved as for 1, partial sum into the exchange arena
 }
 
 
@@ -2271,7 +2281,7 @@ int evb_build(rpb_ctx* c) {
   }
   if (d.rank == 0) stream_depend(c, 9, c->aux[2], c->main_stream);   // bonded terms of the principal diabat (+ pair matrix)
   else stream_depend(c, 9, c->aux[2], c->evb_overlap_solver ? c->aux[0] : c->main_stream);
-  if (d.world > 1 || c->evb_solver != 0) {
+  if ((d.world > 1 && !c->evb_h_exchange_in_solver) || c->evb_solver != 0) {
     ScopedTimer t(c, T_EVB_ASSEMBLE);
     k_evb_assemble<<<(MAXS + 31) / 32, 32, 0, c->stream>>>(d, e, sc.geo);
     c->n_launch += 1;
@@ -2279,7 +2289,7 @@ int evb_build(rpb_ctx* c) {
   } else c->evb_assemble_pending = true;   // single rank, tree solver: assembled in the solver's prologue
   // keep the principal-diabat force (incl. EVB repulsion, without reciprocal part) in dF slot 0: d.force is
   // overwritten with the adiabatic force
-  if (d.world > 1) { k_copy<<<(unsigned)((n3 + 255) / 256), 256, 0, c->stream>>>(e.dF, d.force, n3); c->n_launch++; }   // single rank: saved by k_evb_mix_forces
+  // (saved to dF slot 0 by k_evb_mix_forces itself)
   h.built = true;
   return 0;
 }
@@ -2296,13 +2306,16 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
     coeff_dev = sc.coeff_dev;
   }
   const bool fuse = (c->evb_solver == 0 && d.world == 1 && !coeff_override_host && c->evb_assemble_pending);
+  const bool fuse_peer = (c->evb_solver == 0 && d.world > 1 && c->evb_h_exchange_in_solver && !coeff_override_host && c->evb_assemble_pending);
   const bool overlap = fuse && c->evb_overlap_solver;
+  PeerArgsH no_px;
+  memset(&no_px, 0, sizeof(no_px));
   const int sb = s_bound(c);
   if (overlap) {
     {
       StreamScope ss(c, c->aux[0]);
       ScopedTimer t(c, T_EVB_DIAG);
-      k_evb_tree_solver<<<1, TREE_TPB, 0, c->stream>>>(d, e, nullptr, sc.geo, 1);
+      k_evb_tree_solver<<<1, TREE_TPB, 0, c->stream>>>(d, e, nullptr, sc.geo, 1, no_px);
       CKE(cudaEventRecord(c->ev_sync[6], c->stream));               // "ground state known"
     }
     // H_11, absolute energies and the status block: behind the solver and behind what the main stream holds so far (pair
@@ -2316,8 +2329,16 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
     c->evb_assemble_pending = false;
   } else {
     ScopedTimer t(c, T_EVB_DIAG);
-    if (c->evb_solver == 0) {
-      k_evb_tree_solver<<<1, TREE_TPB, 0, c->stream>>>(d, e, coeff_dev, fuse ? sc.geo : nullptr, 0);
+    if (c->evb_solver == 0 && fuse_peer) {
+      // sharded: assembly of this rank's partial block into its arena + the exchange + the solver, one kernel
+      PeerArgsH px;
+      const EvbDev e_part = c->e;                  // (h_diag = this step's arena parity; peer_args_h redirects c->e to the sum)
+      peer_args_h(c, &px.a);
+      px.on = 1;
+      k_evb_tree_solver<<<1, TREE_TPB, 0, c->stream>>>(d, e_part, nullptr, sc.geo, 0, px);
+      c->evb_assemble_pending = false;
+    } else if (c->evb_solver == 0) {
+      k_evb_tree_solver<<<1, TREE_TPB, 0, c->stream>>>(d, e, coeff_dev, fuse ? sc.geo : nullptr, 0, no_px);
       c->evb_assemble_pending = false;
     } else {
       const size_t shmem = ((size_t)3 * MAXS * MAXS + 2 * MAXS) * sizeof(double);
@@ -2328,8 +2349,8 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
   }
   {
     const int include_principal = 1;      // every rank holds its share of the principal-diabat force (pair forces are sharded by clusters)
-    const int in_place = (d.world == 1 && !coeff_override_host) ? 1 : 0;
-    double* out = in_place ? d.force : e.f_mix;
+    const int in_place = coeff_override_host ? 0 : (d.world == 1 ? 1 : 2);
+    double* out = in_place == 1 ? d.force : e.f_mix;
     CKE(cudaStreamWaitEvent(c->aux[1], c->ev_sync[6], 0));   // the averaged grid needs the ground state, not the pair forces
     // aux[1]: averaged charge deltas -> patch the copy of the principal grid -> ONE convolution; main: force mixing and the
     // chain atoms' own reciprocal terms; then the mixed grid is gathered once (sharded runs: this rank's slice of atoms)

@@ -18,44 +18,7 @@
 // never arrives (crashed rank) is reported after PEER_TIMEOUT_NS instead of hanging the device.
 #include <cstring>
 #include "rpb_host.h"
-
-#define PEER_TIMEOUT_NS 20000000000ull
-
-struct PeerArgs {
-  const double* part[RPB_MAX_RANKS];          // partial of rank r (this parity), as mapped into this process
-  unsigned long long* flag_at[RPB_MAX_RANKS]; // flag slot [kind][my rank] inside rank r's arena
-  const unsigned long long* my_flags;         // [kind][0..world) in the local arena
-  double* out;
-  int* err_flag;
-  unsigned long long* seq_ptr;                // device-side sequence number of this kind's LAST collective: a captured step graph replays with fresh numbers
-  unsigned int* done;                         // blocks of this launch that have finished (the last one publishes the new number)
-  int n;                                      // number of doubles
-  int world;
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ double2 ld_relaxed_sys_f64x2(const double* p) {
-  double2 v;
-  asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
-  double v;
-  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
+#include "rpb_peer.cuh"
 
 __global__ void __launch_bounds__(256) k_peer_allreduce(PeerArgs a) {
   const unsigned long long seq = *a.seq_ptr + 1ull;   // (updated by the last block of the previous collective of this kind)
@@ -159,9 +122,8 @@ void peer_begin(rpb_ctx* c, int kind) {
 
 // The collective itself, on the main stream.  PEER_H: the sum lands in a local block that the solver reads through
 // e.h_diag; PEER_F: the sum lands in d.force (the principal diabat's partial force was saved to dF slot 0 by evb_build).
-int peer_allreduce(rpb_ctx* c, int kind) {
+static void peer_fill_args(rpb_ctx* c, int kind, PeerArgs& a) {
   PeerExchange& p = c->peer;
-  PeerArgs a;
   memset(&a, 0, sizeof(a));
   const size_t part_off = p.off[kind] + (size_t)(p.seq[kind] & 1) * p.n[kind];
   for (int r = 0; r < p.world; r++) {
@@ -175,6 +137,15 @@ int peer_allreduce(rpb_ctx* c, int kind) {
   a.done = reinterpret_cast<unsigned int*>(p.seq_dev + 2 + kind);
   a.n = p.n_act[kind];
   a.world = p.world;
+}
+
+// argument block of the Hamiltonian exchange for the solver kernel, which runs the exchange in its prologue
+void peer_args_h(rpb_ctx* c, void* out) { peer_fill_args(c, PEER_H, *static_cast<PeerArgs*>(out)); c->e.h_diag = c->peer.h_total; }
+
+int peer_allreduce(rpb_ctx* c, int kind) {
+  PeerExchange& p = c->peer;
+  PeerArgs a;
+  peer_fill_args(c, kind, a);
   const int blocks = std::max(1, std::min((a.n / 2 + 255) / 256, 148 * 2));
   k_peer_allreduce<<<blocks, 256, 0, c->main_stream>>>(a);
   c->n_launch++;

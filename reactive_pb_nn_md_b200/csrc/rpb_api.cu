@@ -133,9 +133,11 @@ static int enqueue_force(rpb_ctx* c, int ms_evb, bool defer_join = false) {
   if (ms_evb) {
     if (!c->have_evb) { c->err = "rpb_set_evb not called"; return RPB_ERR_STATE; }
     const bool sharded = c->d.world > 1;   // peer-memory exchange (kernels_peer.cu); checked by the callers
+    // sharded, tree solver: the solver kernel assembles this rank's partial block and runs the Hamiltonian exchange itself
+    c->evb_h_exchange_in_solver = sharded && c->peer.on && c->evb_solver == 0;
     if (sharded) peer_begin(c, PEER_H);
     rc = evb_build(c); if (rc) return rc;
-    if (sharded) { rc = peer_allreduce(c, PEER_H); if (rc) return rc; peer_begin(c, PEER_F); }
+    if (sharded) { if (!c->evb_h_exchange_in_solver) { rc = peer_allreduce(c, PEER_H); if (rc) return rc; } peer_begin(c, PEER_F); }
     rc = evb_mix(c, nullptr, nullptr); if (rc) return rc;
     if (sharded) { rc = peer_allreduce(c, PEER_F); if (rc) return rc; }
     rc = evb_commit(c);
@@ -661,7 +663,7 @@ int rpb_step_end(rpb_ctx* c) {
   return rc;
 }
 // the phase calls always use the library's own exchange buffers (the caller runs the collectives), never the peer arena
-int rpb_evb_phase_build(rpb_ctx* c) { if (c->peer.h_local) c->e.h_diag = c->peer.h_local; return evb_build(c); }
+int rpb_evb_phase_build(rpb_ctx* c) { c->evb_h_exchange_in_solver = false; if (c->peer.h_local) c->e.h_diag = c->peer.h_local; return evb_build(c); }
 int rpb_evb_phase_mix(rpb_ctx* c) { if (c->peer.f_local) c->e.f_mix = c->peer.f_local; c->peer.f_reduced_in_place = false; return evb_mix(c, nullptr, nullptr); }
 int rpb_evb_phase_commit(rpb_ctx* c) { int rc = evb_commit(c); evb_join_readback(c); return rc ? rc : evb_readback(c); }
 int rpb_evb_exchange_h(rpb_ctx* c, void** ptr, int* n) { *ptr = c->e.h_diag; *n = 3 * RPB_MAXS + E_NSLOT; return 0; }

@@ -67,6 +67,7 @@ struct rpb_ctx {
   bool evb_assemble_pending = false;  // evb_build left the Hamiltonian assembly to the solver kernel
   bool throughput_mode = false;       // replica ensembles (rpb_ensemble_step): other replicas fill the SMs, so the pair kernel takes a full wave
   int evb_s_bound_fixed = 0;          // while a step graph is captured: the diabat-count bound its grids are sized for (0: from the last count)
+  bool evb_h_exchange_in_solver = false;   // sharded step, tree solver: assembly + Hamiltonian all-reduce run in the solver kernel's prologue
   bool evb_join_pending = false;      // evb_commit queued its read-back copies on aux[3]; the main stream has not joined them yet
   bool evb_any_multi_basic = false;   // some molecule type has more than one atom that can be protonated (reference re-ordering quirk possible)
   bool mirror_stale = false;          // a committed hop changed the molecule table on the device: the host mirror is refreshed before use
@@ -172,6 +173,7 @@ void fft_conv_free(rpb_ctx*);
 // ---- kernels_peer.cu
 void peer_begin(rpb_ctx*, int kind);      // producers of partial `kind` write into this step's parity of the arena
 int peer_allreduce(rpb_ctx*, int kind);   // one kernel: signal, wait, pull + add in rank order
+void peer_args_h(rpb_ctx*, void* peer_args_out);   // the Hamiltonian exchange as an argument block for the solver kernel (rpb_peer.cuh)
 void peer_free(rpb_ctx*);
 // ---- kernels_evb.cu
 int evb_alloc(rpb_ctx*);
