@@ -1728,7 +1728,7 @@ __global__ void k_evb_mix_forces(Dev d, EvbDev e, int include_principal, int in_
 // M_ab needs no grid at all: w is a product of 1-D splines, so <w_a, g * w_b> = sum over the 11^3 displacements t of
 // g(n_a - n_b - t) cx(t_x) cy(t_y) cz(t_z) with the 1-D cross-correlations c(t) = sum_{k-k'=t} w_a[k] w_b[k'].
 // Two convolutions per step instead of S+1, no per-diabat grid traffic; differences from the per-diabat transforms are
-// rounding only (~1e-13 relative, checked against the grid path, RPB_EVB_RECIP=grids, in tests/).
+// rounding only (~1e-13 relative, checked in tests/ against the oracle's literal per-diabat grids, every diabat's own force).
 // ================================================================================================
 #define RA_MOLS RPB_RA_MOLS           // distinct chain molecules of a step
 #define RA_SLOTS (RA_MOLS * MA)       // chain-atom slots: (chain molecule, atom offset inside the molecule)
