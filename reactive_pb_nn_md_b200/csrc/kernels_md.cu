@@ -14,26 +14,6 @@ __global__ void k_zero(double* p, size_t n) {
   if (i < n) p[i] = 0.0;
 }
 
-// v += dt/2/m * F * conv ; x += v*dt          (md_integration.f90:478,484)
-// The thread that consumed F_i also clears it (and thread 0 the energy slots), so the force evaluation that follows needs no zeroing launches.
-__global__ void k_integrate_first(Dev d) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { for (int k = 0; k < E_NSLOT; k++) d.en[k] = 0.0; }
-  if (i >= d.N) return;
-  const double f0 = d.force[3 * i], f1 = d.force[3 * i + 1], f2 = d.force[3 * i + 2];
-  d.force[3 * i] = 0.0; d.force[3 * i + 1] = 0.0; d.force[3 * i + 2] = 0.0;
-  if (d.freeze[d.type[i]] == 1) return;
-  double4 p = d.xq[i];
-  double m = d.mass[i];
-  double h = d.dt / 2.0 / m;
-  double v0 = d.vel[3 * i] + h * f0 * d.conv_kin;
-  double v1 = d.vel[3 * i + 1] + h * f1 * d.conv_kin;
-  double v2 = d.vel[3 * i + 2] + h * f2 * d.conv_kin;
-  d.vel[3 * i] = v0; d.vel[3 * i + 1] = v1; d.vel[3 * i + 2] = v2;
-  p.x = p.x + v0 * d.dt; p.y = p.y + v1 * d.dt; p.z = p.z + v2 * d.dt;
-  d.xq[i] = p;
-}
-
 // one thread per molecule: pos_com, then shift_molecules_into_box
 __global__ void k_com_shift(Dev d, int do_shift) {
   int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -65,6 +45,54 @@ __global__ void k_com_shift(Dev d, int do_shift) {
         d.xq[f + a] = p;
       }
   }
+  d.r_com[3 * m] = rc[0]; d.r_com[3 * m + 1] = rc[1]; d.r_com[3 * m + 2] = rc[2];
+}
+
+// First half kick  v += dt/2/m * F * conv ; x += v*dt  (md_integration.f90:478,484), centre of mass and shift into the box
+// (k_com_shift with do_shift = 1) by ONE thread per molecule (its <= RPB_MA atoms are contiguous): one launch and one
+// dependency edge at the head of every step instead of two.  The thread that consumed F_i also clears it (and thread 0
+// the energy slots), so the force evaluation that follows needs no zeroing launches.
+__global__ void k_integrate_first_mol(Dev d) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m == 0) { for (int k = 0; k < E_NSLOT; k++) d.en[k] = 0.0; }
+  if (m >= d.M) return;
+  const int f = d.mol_first[m], n = d.mol_natom[m];
+  double c0 = 0, c1 = 0, c2 = 0, mt = 0;
+  for (int a = 0; a < n; a++) {
+    const int i = f + a;
+    const double f0 = d.force[3 * i], f1 = d.force[3 * i + 1], f2 = d.force[3 * i + 2];
+    d.force[3 * i] = 0.0; d.force[3 * i + 1] = 0.0; d.force[3 * i + 2] = 0.0;
+    double4 p = d.xq[i];
+    const double ms = d.mass[i];
+    if (d.freeze[d.type[i]] != 1) {
+      const double h = d.dt / 2.0 / ms;
+      const double v0 = d.vel[3 * i] + h * f0 * d.conv_kin;
+      const double v1 = d.vel[3 * i + 1] + h * f1 * d.conv_kin;
+      const double v2 = d.vel[3 * i + 2] + h * f2 * d.conv_kin;
+      d.vel[3 * i] = v0; d.vel[3 * i + 1] = v1; d.vel[3 * i + 2] = v2;
+      p.x = p.x + v0 * d.dt; p.y = p.y + v1 * d.dt; p.z = p.z + v2 * d.dt;
+      d.xq[i] = p;
+    }
+    c0 = c0 + p.x * ms; c1 = c1 + p.y * ms; c2 = c2 + p.z * ms;
+    mt = mt + ms;
+  }
+  double rc[3] = {c0 / mt, c1 / mt, c2 / mt};
+  double t[3];
+  bool any = false;
+  for (int k = 0; k < 3; k++) {
+    const double db = d.inv_box[k] * rc[k];
+    double sh = 0.0;
+    if (db < 0.0) sh = 1.0; else if (db > 1.0) sh = -1.0;
+    t[k] = sh * d.box[k];
+    any |= (sh != 0.0);
+    rc[k] = rc[k] + t[k];
+  }
+  if (any)
+    for (int a = 0; a < n; a++) {
+      double4 p = d.xq[f + a];
+      p.x = p.x + t[0]; p.y = p.y + t[1]; p.z = p.z + t[2];
+      d.xq[f + a] = p;
+    }
   d.r_com[3 * m] = rc[0]; d.r_com[3 * m + 1] = rc[1]; d.r_com[3 * m + 2] = rc[2];
 }
 
@@ -139,9 +167,8 @@ void launch_zero_forces(rpb_ctx* c) {
 
 void launch_integrate_first(rpb_ctx* c) {
   ScopedTimer t(c, T_INTEGRATE);
-  k_integrate_first<<<nblk(c->d.N), TPB, 0, c->stream>>>(c->d);
-  k_com_shift<<<nblk(c->d.M), TPB, 0, c->stream>>>(c->d, 1);
-  c->n_launch += 2;
+  k_integrate_first_mol<<<nblk(c->d.M, 64), 64, 0, c->stream>>>(c->d);      // (small CTAs: a few thousand molecules spread over many SMs)
+  c->n_launch += 1;
   c->forces_zeroed = true;
 }
 
