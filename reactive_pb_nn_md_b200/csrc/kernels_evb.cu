@@ -2369,7 +2369,7 @@ int evb_mix(rpb_ctx* c, const double* coeff_override_host, double* force_out_hos
       ScopedTimer t(c, T_EVB_MIXF);
       k_evb_mix_forces<<<(unsigned)((n3 + 255) / 256), 256, 0, c->stream>>>(d, e, include_principal, in_place);
       if (d.rank == 0) { k_evb_rcp_mix<<<(sb * RA_ENT + 127) / 128, 128, 0, c->stream>>>(d, e, sc.rd, out); c->n_launch++; }
-      if (c->evb_any_multi_basic) { k_evb_reorder_quirk<<<(sb + 3) / 4, 128, 0, c->stream>>>(d, e, sc.rd, out, 1); c->n_launch++; }
+      if (c->evb_any_multi_basic && c->evb_quirk_types_present) { k_evb_reorder_quirk<<<(sb + 3) / 4, 128, 0, c->stream>>>(d, e, sc.rd, out, 1); c->n_launch++; }
     }
     stream_depend(c, 1, c->aux[1], c->main_stream);
     const int i0 = (int)((long long)N * d.rank / d.world), i1 = (int)((long long)N * (d.rank + 1) / d.world);

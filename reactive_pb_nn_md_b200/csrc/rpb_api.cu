@@ -482,6 +482,7 @@ int rpb_set_evb(rpb_ctx* c, const int* da_i, const double* da_p, const int* pa_i
     e.proton_index[i] = proton_index[i] - 1; e.heavy_acid_index[i] = heavy_acid_index[i] - 1;
   }
   (void)acid; (void)basic;
+  c->conj_pairs_host.assign(e.conj_pairs, e.conj_pairs + MM);
   {  // candidate radius of the diabat real-space deltas: the real-space cutoff (+ margin for the rounding of image
      // positions that were made whole), or the reach of the EVB repulsion terms if that is larger
     double da_rc = 0.0, pa_rc = 0.0;
@@ -614,6 +615,18 @@ int rpb_upload_state(rpb_ctx* c, const double* xyz, const double* velocity, cons
     }
   } else for (int m = 0; m < M; m++) ncl += (c->mol_natom[m] + 2) / 3;
   c->n_clusters_bound = std::min(N, ncl + 2);   // a hop moves one proton: the count changes by at most one either way
+  if (mol_changed && c->evb_any_multi_basic && !c->conj_pairs_host.empty()) {
+    // can the reference's re-ordering quirk (k_evb_reorder_quirk) occur at all?  Only if a molecule type with several basic
+    // atoms is present, or can appear by a proton transfer (the conjugate of a present type)
+    bool present = false;
+    for (int m = 0; m < M && !present; m++) {
+      const int t = c->mol_type[m], tc = (t >= 0 && t < (int)c->conj_pairs_host.size()) ? c->conj_pairs_host[t] : -1;
+      present = (t >= 0 && t < (int)c->mt_multi_basic.size() && c->mt_multi_basic[t]) || (tc >= 0 && tc < (int)c->mt_multi_basic.size() && c->mt_multi_basic[tc]);
+    }
+    if (present != c->evb_quirk_types_present)       // the step graphs hold the launch list of the other case
+      for (int k = 0; k < 8; k++) if (c->graph[k].exec) { cudaGraphExecDestroy(c->graph[k].exec); c->graph[k].exec = nullptr; }
+    c->evb_quirk_types_present = present;
+  }
   memcpy(up_vel, velocity, 3 * (size_t)N * sizeof(double));
   if (c->hydronium_mol != hydronium_mol - 1) mol_changed = true;
   c->hydronium_mol = hydronium_mol - 1;

@@ -69,6 +69,8 @@ struct rpb_ctx {
   int evb_s_bound_fixed = 0;          // while a step graph is captured: the diabat-count bound its grids are sized for (0: from the last count)
   bool evb_h_exchange_in_solver = false;   // sharded step, tree solver: assembly + Hamiltonian all-reduce run in the solver kernel's prologue
   bool evb_join_pending = false;      // evb_commit queued its read-back copies on aux[3]; the main stream has not joined them yet
+  bool evb_quirk_types_present = true; // ... and such a type (or the conjugate of a present type) occurs in the current molecule table (rpb_upload_state)
+  std::vector<int> conj_pairs_host;    // evb_conjugate_pairs, 0-based (-1 none)
   bool evb_any_multi_basic = false;   // some molecule type has more than one atom that can be protonated (reference re-ordering quirk possible)
   bool mirror_stale = false;          // a committed hop changed the molecule table on the device: the host mirror is refreshed before use
   int grid_capacity = 0;       // number of K^3 grids usable in d.Q / d.theta (4 spare ones follow for the rounded FFT batch)

@@ -193,6 +193,22 @@ class Simulation:
         except Exception:
             pass
 
+    _STATE_KEYS = ("xyz", "velocity", "force", "mass", "charge", "atom_type", "mol_first_atom", "mol_n_atom", "mol_type")
+
+    def _state_pointers(self, holder):
+        """ctypes pointers of a state dict's arrays, cached per dict while it keeps holding the SAME array objects (a
+        caller that owns its arrays passes the same ones every step; building nine ctypes pointers costs ~15 us)."""
+        cache = self.__dict__.setdefault("_ptr_cache", {})
+        ent = cache.get(id(holder))
+        if ent is not None and ent[0] is holder and all(holder.get(k) is a for k, a in zip(self._STATE_KEYS, ent[1])):
+            return ent[2]
+        arrs = tuple(holder.get(k) for k in self._STATE_KEYS)
+        ptrs = tuple(None if a is None else (dptr(a) if a.dtype == np.float64 else iptr(a)) for a in arrs)
+        if len(cache) >= 4:
+            cache.clear()
+        cache[id(holder)] = (holder, arrs, ptrs)      # (strong references: the ids cannot be recycled while cached)
+        return ptrs
+
     def upload_state(self, xyz, velocity, topology=None):
         """atom_data / molecule_data -> library.  `topology` (a dict as returned by download_state) carries the
         per-atom and per-molecule arrays after proton hops have permuted them; default: the initial system."""
@@ -200,6 +216,10 @@ class Simulation:
         t = topology if topology is not None else dict(
             mass=s.mass, charge=s.charge, atom_type=s.atom_type, mol_first_atom=s.mol_first_atom,
             mol_n_atom=s.mol_n_atom, mol_type=s.mol_type, hydronium_mol=s.hydronium_mol)
+        if topology is not None and xyz is topology.get("xyz") and velocity is topology.get("velocity") and "force" in topology:
+            p = self._state_pointers(topology)        # a dict from download_state handed back unchanged in identity
+            self._check(self.dll.rpb_upload_state(self.ctx, p[0], p[1], p[3], p[4], p[5], p[6], p[7], p[8], int(t["hydronium_mol"])))
+            return
         xyz = np.ascontiguousarray(xyz, np.float64)
         velocity = np.ascontiguousarray(velocity, np.float64)
         self._check(self.dll.rpb_upload_state(
@@ -275,10 +295,8 @@ class Simulation:
                        charge=np.zeros(N), atom_type=np.zeros(N, np.int32), mol_first_atom=np.zeros(M, np.int32),
                        mol_n_atom=np.zeros(M, np.int32), mol_type=np.zeros(M, np.int32))
         h = C.c_int()
-        self._check(self.dll.rpb_download_state(
-            self.ctx, dptr(out["xyz"]), dptr(out["velocity"]), dptr(out["force"]), dptr(out["mass"]),
-            dptr(out["charge"]), iptr(out["atom_type"]), iptr(out["mol_first_atom"]), iptr(out["mol_n_atom"]),
-            iptr(out["mol_type"]), C.byref(h)))
+        p = self._state_pointers(out)
+        self._check(self.dll.rpb_download_state(self.ctx, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], C.byref(h)))
         out["hydronium_mol"] = h.value
         return out
 
