@@ -208,3 +208,43 @@ def test_state_sharding_on_real_peers(oracle_lib, world, workload):
         assert rel_rms(q["force"], xr["force"]) < F_RTOL
         for k in ("xyz", "vel", "force"):
             assert np.array_equal(q[k], z[0][k]), k                    # replicated state: bit-identical on every rank
+
+
+# ---- small boxes: the pair kernel's per-pair minimum-image instantiation ------------------------------------------------
+def _small_box_params(**kw):
+    p = small_params(pme_grid=32, na_nslist=18, nb_nslist=18, nc_nslist=18, **kw)
+    p.real_space_cutoff = 9.0
+    p.verlet_cutoff = 11.0
+    return p
+
+
+def test_small_box_uses_per_pair_minimum_image(cuda_lib, oracle_lib):
+    """L/2 - r_cutoff = 3.4 A leaves no room for one minimum-image shift per (cluster, atom): the library launches the
+    pair kernel that shifts every pair (k_pair_tiles<.., false>).  512 molecules, L = 24.9 A: one evaluation + 20 steps."""
+    s = system.build_water_box(8, with_hydronium=True)
+    assert 0.5 * s.box_length - 9.0 < 4.0
+    so = engine.Simulation(s, _small_box_params(n_threads=_threads()), library=oracle_lib)
+    sg = engine.Simulation(s, _small_box_params(), library=cuda_lib)
+    so.ms_evb_calculate_total_force_energy(); sg.ms_evb_calculate_total_force_energy()
+    _compare_evaluation(sg, so, n_force_states=2)
+    so.md_integrate_atomic(20, ms_evb=True); sg.md_integrate_atomic(20, ms_evb=True)
+    _compare_state(sg, so)
+    # and the non-reactive evaluation of the same box
+    so.calculate_total_force_energy(); sg.calculate_total_force_energy()
+    assert rel_rms(sg.forces(), so.forces()) < F_RTOL
+
+
+def test_oversized_cluster_fails_loudly(cuda_lib):
+    """One shift per (cluster, atom) needs r_cutoff + (extent of three consecutive atoms of a molecule) < L/2; the choice is
+    made from the box and verified on the device -- a molecule that violates it stops the step with an error instead of
+    being computed with a wrong image."""
+    from reactive_pb_nn_md_b200._binding import RpbError
+    s = system.build_water_box(10, with_hydronium=False)
+    assert 0.5 * s.box_length - 10.0 > 4.0
+    sim = engine.Simulation(s, small_params(pme_grid=32), library=cuda_lib)
+    sim.calculate_total_force_energy()
+    xyz = s.xyz.copy()
+    xyz[1] = xyz[0] + np.array([0.5 * s.box_length - 10.0 + 0.5, 0.0, 0.0])       # the first water's H, far from its O
+    sim.upload_state(xyz, s.velocity)
+    with pytest.raises(RpbError, match="farther apart than the box allows"):
+        sim.calculate_total_force_energy()
