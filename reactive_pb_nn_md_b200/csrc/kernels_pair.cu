@@ -101,15 +101,14 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 //      radius and are dropped here at the cost of one 32-byte gather and ~20 fp64 operations per NINE pair slots; the
 //      survivors' list words are compacted (ballot + prefix count) into a per-warp ring in shared memory, and the
 //      coordinates / types of their (up to) three atoms are fetched into the ring by asynchronous copies;
-//   2. interaction, one cull iteration behind (the copies have landed) -- ten tiles per round: lane 3t + b takes atom b
-//      of tile t and its three pairs with the atoms of I (three independent dependency chains per lane; b, and with it the
-//      bit positions of the tile mask, are per-lane constants).  A pair that is not listed or outside the cutoff runs the
+//   2. interaction, one cull iteration behind (the copies have landed) -- 32 J atoms per round: a lane takes one atom of
+//      one tile and its three pairs with the atoms of I (three independent dependency chains per lane).  A pair that is not listed or outside the cutoff runs the
 //      same Coulomb arithmetic on harmless operands (r^2 = 1, q_i q_j = 0) instead of diverging: ~77 % of the slots of a
 //      surviving tile are live.
 // One minimum-image shift per (I, J atom) from I's first atom instead of one per pair: identical results whenever
 // r_cutoff + (largest cluster extent) < L/2 (a pair inside the cutoff then has that very shift, and a pair that would
 // need another one is outside the cutoff with either); checked per launch on the device, per-pair shifts otherwise.
-#define PAIR_QT 80               // ring capacity in tiles: < 10 left over + 2 x 32 from two cull iterations
+#define PAIR_QT 80               // ring capacity in tiles: < 11 left over + 2 x 32 from two cull iterations
 struct PairRing { double4 xq[PAIR_QT][3]; int ty[PAIR_QT][4]; unsigned ent[PAIR_QT]; };
 
 template <int TPB_, int MINB, bool SPA>
@@ -133,7 +132,6 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int 
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
-  const int tl = lane / 3, b = lane - 3 * tl;  // phase 2: tile of the round, atom of J
   const double4* pi = sh_pi[threadIdx.x >> 5];
   const int N = d.N;
   const int NC = *d.n_clusters;                // on the device: a committed hop can change it
@@ -190,13 +188,14 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int 
       __syncwarp();
     }
     double f[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    int qh = 0, qn = 0;                        // ring head and fill, in tiles (uniform over the warp)
+    int qh = 0, qn = 0;                        // ring head and fill in SLOTS (a tile = three slots, one per atom of J); uniform over the warp
 
-    // phase 2: (up to) ten tiles of the ring
+    // phase 2: (up to) 32 slots of the ring, one J atom per lane (a tile may straddle two rounds: its atoms are independent)
     auto interact = [&](const int avail) {
-      const int nt = min(avail, 10);
-      const int slot = (qh + tl) % PAIR_QT;
-      const unsigned ent = tl < nt ? Q.ent[slot] : 0u;
+      const int nt = min(avail, 32);
+      const int sl = (qh + lane) % (3 * PAIR_QT);
+      const int slot = sl / 3, b = sl - 3 * slot;
+      const unsigned ent = lane < nt ? Q.ent[slot] : 0u;
       const unsigned mb = (ent >> (23 + b)) & 0x49u;          // bit 3a: pair (a, b) is listed
       double4 pj = make_double4(0.0, 0.0, 0.0, 0.0);
       int tj = 0;
@@ -261,7 +260,7 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int 
       if (live[0] || live[1] || live[2]) {
         atomicAdd(&d.force[3 * g], fjx); atomicAdd(&d.force[3 * g + 1], fjy); atomicAdd(&d.force[3 * g + 2], fjz);
       }
-      qh = (qh + nt) % PAIR_QT; qn -= nt;
+      qh = (qh + nt) % (3 * PAIR_QT); qn -= nt;
     };
 
     // phase 1, software-pipelined: list words two iterations ahead, first-atom gathers one ahead
@@ -270,7 +269,7 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int 
     if (vs + lane < vf) ent_c = L[vs + lane];
     if (vs + 32 + lane < vf) ent_n = L[vs + 32 + lane];
     if (vs + lane < vf) p_c = ldg256(&d.xq[ent_c & 0x7fffffu]);
-    int ready = 0;                             // tiles of the ring whose asynchronous copies have been waited for
+    int ready = 0;                             // slots of the ring whose asynchronous copies have been waited for
     for (int k0 = vs; k0 < vf; k0 += 32) {
       unsigned ent_nn = 0u;
       double4 p_n = make_double4(0.0, 0.0, 0.0, 0.0);
@@ -284,7 +283,7 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int 
       const bool keep = (k0 + lane < vf) && fma(r2, r2, fma(r1, r1, r0 * r0)) < cull2;
       const unsigned m = __ballot_sync(0xffffffffu, keep);
       if (keep) {
-        const int slot = (qh + qn + __popc(m & lt)) % PAIR_QT;
+        const int slot = ((qh + qn) / 3 + __popc(m & lt)) % PAIR_QT;       // (qh + qn is a multiple of 3: tiles are appended whole)
         const int fj = (int)(ent_c & 0x7fffffu);
         Q.ent[slot] = ent_c;
 #pragma unroll
@@ -299,8 +298,8 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int 
       // the copies of the PREVIOUS iterations have landed once all but the newest group are complete
       cp_async_wait<1>();
       __syncwarp();
-      while (ready >= 10) { interact(ready); ready -= 10; }
-      qn += __popc(m);
+      while (ready >= 32) { interact(ready); ready -= 32; }
+      qn += 3 * __popc(m);
       ready = qn;                                // (this iteration's tiles become usable after the next wait)
       ent_c = ent_n; ent_n = ent_nn; p_c = p_n;
     }
