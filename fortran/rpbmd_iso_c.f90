@@ -126,7 +126,7 @@ module rpbmd_iso_c
   ! flat molecule table handed to / returned by the library (molecules are contiguous ascending atom ranges,
   ! general_routines.f90:670-671)
   integer(c_int), allocatable, save :: rpb_mol_first(:), rpb_mol_natom(:), rpb_mol_type(:)
-  real(c_double), allocatable, target, save :: rpb_r_com_store(:,:)
+  real(c_double), allocatable, save :: rpb_r_com_store(:,:)      ! centres of mass as the library returns them, (3, n_mole)
 
 contains
 
@@ -305,18 +305,11 @@ contains
        end if
     end do
     if ( ms_evb_simulation == "yes" .and. hyd > 0 ) hydronium_molecule_index(1) = hyd
-    call rpb_check( rpb_get_r_com(rpb_handle, rpb_r_com_buffer(system_data%n_mole)) )
+    if ( .not. allocated(rpb_r_com_store) ) allocate( rpb_r_com_store(3, system_data%n_mole) )
+    call rpb_check( rpb_get_r_com(rpb_handle, rpb_r_com_store) )      ! (the array itself: a function result would be copied)
     do i = 1, system_data%n_mole
        molecule_data(i)%r_com(:) = rpb_r_com_store(:, i)
     end do
   end subroutine rpb_pull_results
-
-  ! (scratch for the centres of mass; a function so that the buffer is sized on first use)
-  function rpb_r_com_buffer(n) result(buf)
-    integer, intent(in) :: n
-    real(c_double), pointer :: buf(:,:)
-    if ( .not. allocated(rpb_r_com_store) ) allocate( rpb_r_com_store(3, n) )
-    buf => rpb_r_com_store
-  end function rpb_r_com_buffer
 
 end module rpbmd_iso_c
