@@ -84,6 +84,9 @@ __device__ __forceinline__ double warp_sum9(const double (&v)[9], const int lane
 __device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
+__device__ __forceinline__ void cp_async_8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
 __device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
@@ -109,7 +112,10 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // r_cutoff + (largest cluster extent) < L/2 (a pair inside the cutoff then has that very shift, and a pair that would
 // need another one is outside the cutoff with either); checked per launch on the device, per-pair shifts otherwise.
 #define PAIR_QT 80               // ring capacity in tiles: < 11 left over + 2 x 32 from two cull iterations
-struct PairRing { double4 xq[PAIR_QT][3]; int ty[PAIR_QT][4]; unsigned ent[PAIR_QT]; };
+struct PairRing {
+  double4 xq[PAIR_QT][3]; int ty[PAIR_QT][4]; unsigned ent[PAIR_QT];
+  double4 nxt_pi[3]; int nxt_ty[4]; double4 nxt_first[32];    // next piece: its cluster's atoms / types, first atoms of its first cull chunk
+};
 
 template <int TPB_, int MINB, bool SPA>
 __global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int world) {
@@ -119,17 +125,12 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int 
   __shared__ double4 sh_pi[TPB_ / 32][3];      // the warp's cluster I (uniform over the lanes: broadcast reads instead of registers)
   PairRing& Q = reinterpret_cast<PairRing*>(sh_dyn)[threadIdx.x >> 5];
   double* sh_par = reinterpret_cast<double*>(sh_dyn + (TPB_ / 32) * sizeof(PairRing));
+  // the force-field rows travel into shared memory by asynchronous copies while the warps look up their ranges (every
+  // dependent global load at the head of this kernel is ~0.5 us of a ~50 us kernel)
   const int npar = d.nT * d.nT * 6;
-  for (int k = threadIdx.x; k < npar; k += blockDim.x) sh_par[k] = d.vdw_param[k];
-  for (int k = threadIdx.x; k < d.nT * d.nT; k += blockDim.x) {
-    int vt = d.vdw_type[k];
-    if (vt == 1) {
-      const double* P = &d.vdw_param[6 * k];
-      if (P[0] == 0.0 && P[2] == 0.0 && P[3] == 0.0 && P[4] == 0.0 && P[5] == 0.0) vt = 2;
-    }
-    sh_vt[k] = vt;
-  }
-  __syncthreads();
+  for (int k = threadIdx.x; k < npar; k += blockDim.x) cp_async_8(&sh_par[k], &d.vdw_param[k]);
+  for (int k = threadIdx.x; k < d.nT * d.nT; k += blockDim.x) cp_async_4(&sh_vt[k], &d.vdw_type[k]);
+  cp_async_commit();
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
   const double4* pi = sh_pi[threadIdx.x >> 5];
@@ -160,6 +161,15 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int 
   int I0 = c_begin;
   if (t_begin < t_end) {
     int lo = c_begin, hi = c_end;              // tp[PARTS * lo] <= t_begin < tp[PARTS * hi]
+    {
+      // rows of a liquid have similar lengths: 32 probes around the proportional guess usually bracket the answer at once
+      const int guess = c_begin + (int)(((long long)(t_begin - T0) * (c_end - c_begin)) / max(T1 - T0, 1));
+      const int probe = min(max(guess - 15 + lane, c_begin), c_end);
+      const unsigned le = __ballot_sync(0xffffffffu, tp[RPB_TILE_PARTS * probe] <= t_begin);
+      const int nle = __popc(le);
+      if (nle > 0) lo = __shfl_sync(0xffffffffu, probe, nle - 1);
+      if (nle < 32) hi = __shfl_sync(0xffffffffu, probe, nle);
+    }
     while (hi - lo > 1) {
       const int probe = lo + (int)(((long long)(hi - lo) * (lane + 1)) / 33);
       const unsigned le = __ballot_sync(0xffffffffu, tp[RPB_TILE_PARTS * probe] <= t_begin);   // monotone: a prefix of the lanes
@@ -170,23 +180,51 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int 
     }
     I0 = lo;
   }
+  // force-field rows have landed: a SAPT row with all-zero coefficients contributes exactly 0 -> type 2 (skipped)
+  cp_async_wait<0>();
+  __syncthreads();
+  for (int k = threadIdx.x; k < d.nT * d.nT; k += blockDim.x)
+    if (sh_vt[k] == 1) {
+      const double* P = &sh_par[6 * k];
+      if (P[0] == 0.0 && P[2] == 0.0 && P[3] == 0.0 && P[4] == 0.0 && P[5] == 0.0) sh_vt[k] = 2;
+    }
+  __syncthreads();
+  int pf_I = -1, pf_info = 0, pf_re = 0, prev_re = 0;     // header of the NEXT piece, fetched while the current one is processed
+  unsigned pf_ent = 0u;
   for (int I = I0; I < c_end && t_begin < t_end; I++) {
-    const int rs = tp[RPB_TILE_PARTS * I], re = tp[RPB_TILE_PARTS * (I + 1)];
+    const bool pf = pf_I == I;                 // (uniform over the warp)
+    const unsigned pf_ent_cur = pf_ent;
+    int rs, re, info;
+    if (pf) { rs = prev_re; re = pf_re; info = pf_info; }
+    else { rs = tp[RPB_TILE_PARTS * I]; re = tp[RPB_TILE_PARTS * (I + 1)]; info = d.cl_info[I]; }
+    pf_I = -1;
     if (rs >= t_end) break;
     const int vs = max(rs, t_begin), vf = min(re, t_end);
     if (vs >= vf) continue;
-    const int info = d.cl_info[I], fi = info & 0xffffff, ni = info >> 24;
+    const int fi = info & 0xffffff, ni = info >> 24;
     int ti[3];
     {
       double4 hp = make_double4(0.0, 0.0, 0.0, 0.0);
       int ht = 0;
-      if (lane < 3) { const int ia = fi + (lane < ni ? lane : 0); hp = d.xq[ia]; ht = d.type[ia]; }
+      if (lane < 3) {
+        if (pf) { hp = Q.nxt_pi[lane]; ht = Q.nxt_ty[lane]; }
+        else { const int ia = fi + (lane < ni ? lane : 0); hp = d.xq[ia]; ht = d.type[ia]; }
+      }
 #pragma unroll
       for (int a = 0; a < 3; a++) ti[a] = __shfl_sync(0xffffffffu, ht, a) * nT;
       __syncwarp();
       if (lane < 3) sh_pi[threadIdx.x >> 5][lane] = hp;
       __syncwarp();
     }
+    // the next piece (cluster I + 1, if this warp's range goes on): row end, cluster word and the list words of its first
+    // chunk are requested now; the copies that depend on them are issued from the first cull iteration below
+    const bool want_next = I + 1 < c_end && re < t_end;
+    if (want_next) {
+      pf_info = d.cl_info[I + 1];
+      pf_re = tp[RPB_TILE_PARTS * (I + 2)];
+      pf_ent = re + lane < t_end ? L[re + lane] : 0u;
+    }
+    bool next_issued = false;
     double f[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     int qh = 0, qn = 0;                        // ring head and fill in SLOTS (a tile = three slots, one per atom of J); uniform over the warp
 
@@ -266,9 +304,14 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int 
     // phase 1, software-pipelined: list words two iterations ahead, first-atom gathers one ahead
     unsigned ent_c = 0u, ent_n = 0u;
     double4 p_c = make_double4(0.0, 0.0, 0.0, 0.0);
-    if (vs + lane < vf) ent_c = L[vs + lane];
+    if (pf) {                                  // (a prefetched piece starts at its row start: vs == rs)
+      ent_c = vs + lane < vf ? pf_ent_cur : 0u;
+      if (vs + lane < vf) p_c = Q.nxt_first[lane];
+    } else {
+      if (vs + lane < vf) ent_c = L[vs + lane];
+      if (vs + lane < vf) p_c = ldg256(&d.xq[ent_c & 0x7fffffu]);
+    }
     if (vs + 32 + lane < vf) ent_n = L[vs + 32 + lane];
-    if (vs + lane < vf) p_c = ldg256(&d.xq[ent_c & 0x7fffffu]);
     int ready = 0;                             // slots of the ring whose asynchronous copies have been waited for
     for (int k0 = vs; k0 < vf; k0 += 32) {
       unsigned ent_nn = 0u;
@@ -294,6 +337,22 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int 
             cp_async_4(&Q.ty[slot][a], &d.type[fj + a]);
           }
       }
+      if (want_next && !next_issued) {         // (once per piece, in the group of its first iteration: landed long before the switch)
+        next_issued = true;
+        const int nfi = pf_info & 0xffffff, nni = pf_info >> 24;
+        __syncwarp();                            // the previous contents of the slots were consumed at this piece's start
+        if (lane < 3) {
+          const int ia = nfi + (lane < nni ? lane : 0);
+          cp_async_16(&Q.nxt_pi[lane], &d.xq[ia]);
+          cp_async_16(reinterpret_cast<char*>(&Q.nxt_pi[lane]) + 16, reinterpret_cast<const char*>(&d.xq[ia]) + 16);
+          cp_async_4(&Q.nxt_ty[lane], &d.type[ia]);
+        }
+        if (re + lane < min(pf_re, t_end)) {
+          const double4* src = &d.xq[pf_ent & 0x7fffffu];
+          cp_async_16(&Q.nxt_first[lane], src);
+          cp_async_16(reinterpret_cast<char*>(&Q.nxt_first[lane]) + 16, reinterpret_cast<const char*>(src) + 16);
+        }
+      }
       cp_async_commit();
       // the copies of the PREVIOUS iterations have landed once all but the newest group are complete
       cp_async_wait<1>();
@@ -311,6 +370,7 @@ __global__ void __launch_bounds__(TPB_, MINB) k_pair_tiles(Dev d, int rank, int 
     // the PME gather add to d.force concurrently)
     const double mine = warp_sum9(f, lane);
     if (lane < 3 * ni) atomicAdd(&d.force[3 * fi + lane], mine);
+    if (want_next) { pf_I = I + 1; prev_re = re; }
   }
   e_el = block_sum(e_el, sh_red);
   e_vdw = block_sum(e_vdw, sh_red);
