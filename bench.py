@@ -10,11 +10,12 @@ round-robin across the ranks and combined with two all-reduces per s
 total work is fixed -> "scaling": "strong".  `--workload c2|c3|c4` selects the other single-GPU configs.
 
 One "step" = md_integrate_atomic: half-kick/drift, COM+wrap, MS-EVB force (principal diabat, enumeration, all
-diabats' matrix elements with batched PME, Jacobi, Hellmann-Feynman mixing), half-kick, COM momentum removal.
+diabats' matrix elements with the charge-delta algebra for reciprocal space, ground-state solve, Hellmann-Feynman mixing,
+hop commit), half-kick, COM momentum removal -- 35 launches replayed as one CUDA graph, no host decision inside.
 Timing: CUDA events on the library's stream around every step, L2 flushed (256 MiB write) between steps outside
 the timed intervals, barrier + synchronize on both sides, max over ranks.
 
-The headline loop runs the library as shipped (three concurrent streams).  The per-kernel table (`kernels`, `roofline`)
+The headline loop runs the library as shipped (six concurrent streams inside one graph launch per step).  The per-kernel table (`kernels`, `roofline`)
 comes from a second context created with RPB_SERIAL_STREAMS=1 -- every branch on one stream -- so that each kernel's
 CUDA-event time is its own and not inflated by whatever overlapped it; ALGORITHMIC bytes / flops per launch follow
 DESIGN.md section 4.  `roofline` is the dominant kernel of the step (the fp64 real-space pair kernel, against
